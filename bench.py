@@ -1,0 +1,306 @@
+#!/usr/bin/env python
+"""bench.py -- LAS forward hot path on B200: audio-seconds per second (RTFx) + microseconds per decoder step.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--precision bf16|fp32]
+                    [--workload c3|c2|c4]
+
+A "step" is one pass of the hot path (Listener pBLSTM encoder + Speller greedy attention-decoder loop) over one
+synthetic batch.  Workloads are BASELINE.json configs:
+    c3 (default, the one the metric is quoted on): paper LAS (256x3 / 512x2), batch 64 x 1600 frames, 300-char greedy
+    c2: small LAS (128x2 / 256x2), batch 32 x 1600 frames, 300-char greedy
+    c4: paper LAS long-form, batch 16 x 3000 frames, 600-char greedy
+N > 1 (torchrun, one rank per GPU): every rank runs the same per-GPU batch on its own shard of utterances (weak
+scaling, BASELINE.json config 5 = 64 utterances per GPU); there is no data-path collective, NCCL only brackets
+the timed region and reduces the time (MAX) and a token checksum.
+
+One JSON line on rank 0.  `value` = whole-job audio-s/s with inputs resident in HBM (CUDA events, max over ranks);
+`e2e` = same through LAS.forward with pinned-host inputs copied in and the decoded tokens copied out every step;
+`roofline` = dominant launch group against the measured peak; `cpu_baseline` = oracle/las_ref_torch.py (the
+reference's torch op sequence) timed on this box's host cores on a bounded sample.
+`--impl reference` times that CPU path alone (rank 0 only).
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+WORKLOADS = {
+    "c3": dict(cfg="paper", B=64, T=1600, S=300, desc="paper LAS (listener 256x3 pBLSTM, speller 512x2), batch 64 x 1600 frames, 300-char greedy decode"),
+    "c2": dict(cfg="small", B=32, T=1600, S=300, desc="small LAS (listener 128x2, speller 256x2), batch 32 x 1600 frames, 300-char greedy decode"),
+    "c4": dict(cfg="paper", B=16, T=3000, S=600, desc="paper LAS long-form, batch 16 x 3000 frames, 600-char greedy decode"),
+}
+FRAME_SEC = 0.01  # 10 ms frame hop (3000 frames = 30 s)
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], tensor=d["bf16_tflops"], tensor_sustained=d["bf16_tflops_sustained"], source="measured")
+    return dict(hbm=6650.0, tensor=1590.0, tensor_sustained=1400.0, source="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=lambda: [self.lines.append(l) for l in self.proc.stdout], daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for l in self.lines:
+            f = [x.strip() for x in l.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_reference_arm(wl, sample_B, steps, warmup):
+    """The reference's CPU op sequence (oracle/las_ref_torch.py) on the host cores; returns (audio_s_per_s, info)."""
+    import torch
+
+    import las_testlib as tl
+    from oracle.las_ref_torch import RefTorchLAS
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    c = tl.CONFIGS[wl["cfg"]]
+    las = tl.build_model(wl["cfg"], max_label_len=wl["S"], seed=17, gain=3.0)
+    m = RefTorchLAS(tl.state_dict_numpy(las), c["L"], c["sl"])
+    x, _ = tl.make_inputs(sample_B, wl["T"], c["F"], wl["S"], c["V"], seed=17)
+    times, lis_t = [], []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        enc = m.listener(x)
+        t1 = time.perf_counter()
+        m.speller(enc, wl["S"], None, 1)
+        t2 = time.perf_counter()
+        if i >= warmup:
+            times.append(t2 - t0); lis_t.append(t1 - t0)
+    tot = sum(times)
+    audio = sample_B * wl["T"] * FRAME_SEC * len(times)
+    info = dict(cores=torch.get_num_threads(), sample=f"{sample_B} of the workload's {wl['B']} utterances x {wl['T']} frames, full {wl['S']}-step greedy decode, "
+                f"{len(times)} timed runs after {warmup} warm-up", ms_per_step=1e3 * tot / len(times),
+                listener_ms=1e3 * sum(lis_t) / len(times), us_per_decoder_step=1e6 * (tot - sum(lis_t)) / len(times) / wl["S"])
+    return audio / tot, info
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default=None, choices=["bf16", "fp32"])
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
+    ap.add_argument("--cpu-sample", type=int, default=8, help="utterances in the bounded CPU-baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
+    wl = WORKLOADS[args.workload]
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    base = {"metric": "audio-sec/sec (RTFx)", "unit": "audio-s/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "data": "synthetic"}
+
+    # ---------------------------------------------------------------- reference arm: CPU only, rank 0 only
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        val, info = cpu_reference_arm(wl, args.cpu_sample, args.steps, args.warmup)
+        out = dict(base, impl="reference", value=val, ms_per_step=info["ms_per_step"], dtype="f32",
+                   config={"workload": f"{args.workload}: {wl['desc']}", "per_step_sample": info["sample"], "device": "host CPU"},
+                   cpu_baseline={"value": val, "unit": "audio-s/s", "cores": info["cores"], "kind": "port", "sample": info["sample"],
+                                 "us_per_decoder_step": info["us_per_decoder_step"], "listener_ms": info["listener_ms"]},
+                   e2e={"value": val, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, gpu_launches=0)
+        print(json.dumps(out))
+        return
+
+    # ---------------------------------------------------------------- our arm
+    import numpy as np
+    import torch
+
+    import las_testlib as tl
+    from las_pytorch_b200 import _cabi
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl ours needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _cabi.load_library()
+    precision = args.precision or ("bf16" if lib.las_mode_available(_cabi.MODE_BF16) else "fp32")
+    c = tl.CONFIGS[wl["cfg"]]
+    B, T, S = wl["B"], wl["T"], wl["S"]
+    las = tl.build_model(wl["cfg"], max_label_len=S, seed=17, gain=3.0, precision=precision).to(dev)
+    # each rank decodes its own shard of the global batch (different utterances per rank, same shape)
+    x_host, _ = tl.make_inputs(B, T, c["F"], S, c["V"], seed=17 + rank)
+    x_host = x_host.pin_memory()
+    x_dev = x_host.to(dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def one_step(x):
+        enc = las.listener(x)
+        las.speller(enc, None, 0.0)
+        return las.speller.last_tokens
+
+    for _ in range(args.warmup):
+        one_step(x_dev)
+    barrier()
+
+    # ---- timed region 1: device-resident inputs, CUDA events per step, L2 flushed between steps (untimed)
+    sampler = ClockSampler(torch.cuda.current_device() if "CUDA_VISIBLE_DEVICES" not in os.environ else local_rank)
+    lib.las_prof_enable(1)
+    lib.las_launch_count(1)
+    sampler.start()
+    evs = []
+    barrier()
+    for _ in range(args.steps):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        tokens = one_step(x_dev)
+        e1.record()
+        evs.append((e0, e1))
+    barrier()
+    clocks = sampler.stop()
+    launches = int(lib.las_launch_count(0))
+    ms = sum(a.elapsed_time(b) for a, b in evs)
+    ctypes_buf = ctypes.create_string_buffer(1 << 20)
+    _cabi.check(lib.las_prof_report(ctypes_buf, len(ctypes_buf)))
+    lib.las_prof_enable(0)
+    groups = {}
+    for line in ctypes_buf.value.decode().splitlines():
+        name, t, n = line.rsplit(" ", 2)
+        g = groups.setdefault(name, [0.0, 0])
+        g[0] += float(t); g[1] += int(n)
+    t_ms = torch.tensor([ms], dtype=torch.float64, device=dev)
+    chk = torch.tensor([float(tokens.sum())], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(chk, op=dist.ReduceOp.SUM)  # the only data NCCL moves: a scalar checksum of the decoded tokens
+    ms = float(t_ms)
+    audio_per_step = world * B * T * FRAME_SEC
+    value = audio_per_step * args.steps / (ms / 1e3)
+
+    # ---- timed region 2 (e2e): through LAS.forward, pinned-host input copied in, decoded tokens copied out, every step
+    tok_host = torch.empty(S, B, dtype=torch.int32).pin_memory()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        xd = x_host.to(dev, non_blocking=True)
+        las(xd, None, 0.0, is_training=False)
+        tok_host.copy_(las.speller.last_tokens, non_blocking=True)
+        torch.cuda.synchronize()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    t_e2e = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
+    e2e_value = audio_per_step * args.steps / float(t_e2e)
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant launch group (per step averages; algorithmic work from SURVEY.md 8d)
+    peaks = measured_peaks()
+    H, L, E, Hs, V, D, sl, U = c["H"], c["L"], 2 * c["H"], 2 * c["H"], c["V"], c["D"], c["sl"], T >> c["L"]
+    per_step = {k: v[0] / args.steps for k, v in groups.items()}
+    lis_ms = sum(v for k, v in per_step.items() if k.startswith("listener"))
+    spl_ms = sum(v for k, v in per_step.items() if k.startswith("speller"))
+    dom = max(per_step, key=per_step.get) if per_step else None
+    esize = 2 if precision == "bf16" else 4
+    roofline = None
+    if dom is not None:
+        dt = per_step[dom] / 1e3
+        if dom.endswith("input_gemm"):
+            l = int(dom.split(".")[1][1:])
+            M, K = B * (T >> (l + 1)), (2 * c["F"] if l == 0 else 4 * H)
+            fl = 2.0 * M * K * 8 * H
+            roofline = {"kernel": dom, "bound": "tensor", "achieved": fl / dt / 1e12, "peak": peaks["tensor_sustained"], "unit": "TFLOP/s"}
+        elif dom == "speller.steps":
+            by = S * (B * U * (D + E) * esize + 4.0 * B * U + 4.0 * B * V)  # K + enc read once per step, attn + logp written
+            roofline = {"kernel": dom, "bound": "hbm", "achieved": by / dt / 1e9, "peak": peaks["hbm"], "unit": "GB/s"}
+        else:  # recurrence: latency-bound; report the bytes it must move (P read + h written) against HBM
+            l = int(dom.split(".")[1][1:])
+            Tl = T >> (l + 1)
+            by = B * Tl * (8 * H * 4.0 + 2 * H * 4.0)
+            roofline = {"kernel": dom, "bound": "hbm", "achieved": by / dt / 1e9, "peak": peaks["hbm"], "unit": "GB/s",
+                        "us_per_serial_step": per_step[dom] * 1e3 / Tl}
+        roofline["frac"] = roofline["achieved"] / roofline["peak"]
+        roofline["traffic"] = None
+        roofline["peak_source"] = peaks["source"]
+        roofline["ms_per_launch_group"] = per_step[dom]
+
+    out = dict(base, value=value, ms_per_step=ms / args.steps, dtype=("bf16" if precision == "bf16" else "f32"),
+               config={"workload": f"{args.workload}: {wl['desc']}", "per_gpu_batch": B, "frames": T, "decode_steps": S,
+                       "precision": precision, "weights": "random init seed 17, 2-D params x3 (gain-3)",
+                       "l2": "256 MiB buffer written between timed steps (untimed)", "parallelism": f"dp{world} utterance shards, no data-path collective"},
+               us_per_decoder_step=1e3 * spl_ms / S, listener_ms=lis_ms, speller_ms=spl_ms, phase_ms=per_step,
+               clocks=clocks, gpu_launches=launches,
+               e2e={"value": e2e_value, "unit": "audio-s/s", "h2d_bytes_per_step": x_host.numel() * 4, "d2h_bytes_per_step": tok_host.numel() * 4},
+               roofline=roofline, token_checksum=float(chk))
+    if world == 1 and not args.no_cpu_baseline:
+        v, info = cpu_reference_arm(wl, args.cpu_sample, 1, 1)
+        out["cpu_baseline"] = {"value": v, "unit": "audio-s/s", "cores": info["cores"], "kind": "port", "sample": info["sample"],
+                               "us_per_decoder_step": info["us_per_decoder_step"], "listener_ms": info["listener_ms"]}
+    print(json.dumps(out))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,175 @@
+/* las_b200.h -- C ABI of the B200-native LAS forward hot path.
+ *
+ * Drop-in boundary for jiwidi/las-pytorch's `model/las_model.py`.  The reference has no FFI of its own (it is
+ * pure Python over torch); the one call site into the path is `las_model(batch_data, batch_label,
+ * teacher_force_rate, is_training)` at solver/solver.py:65-67.  Each entry point below names the reference
+ * code it replaces; `las_pytorch_b200/las_model.py` binds them with ctypes behind the reference's own
+ * Listener / Speller / LAS / Attention classes (INTEGRATION.md shows the stub).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer on the current CUDA device unless the
+ *     parameter name ends in `_host`;
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, nothing synchronises;
+ *   - tensors are dense row-major fp32 with the reference's shapes unless stated otherwise;
+ *   - every function returns LAS_OK (0) or a negative LAS_E* code; `las_last_error()` returns a thread-local
+ *     message.  The library never aborts and never falls back to the CPU: on a device that is not sm_100 the
+ *     compute entry points return LAS_EDEVICE;
+ *   - entry points are re-entrant; the library keeps no mutable global state except per-device constant
+ *     lookups (SM count), so one thread per GPU replica (nn.DataParallel, train.py:76-78) is safe.
+ */
+#ifndef LAS_B200_H_
+#define LAS_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LAS_B200_ABI_VERSION 1
+
+enum {
+  LAS_OK = 0,
+  LAS_EINVAL = -1,   /* bad shape / null pointer / unsupported configuration */
+  LAS_ECUDA = -2,    /* a CUDA runtime call or launch failed (message has the CUDA error string) */
+  LAS_EDEVICE = -3,  /* current device is not compute capability 10.x */
+  LAS_ENOMEM = -4    /* caller-provided buffer too small */
+};
+
+/* Arithmetic mode (north_star: "fp32 mode" 1e-4 / "bf16-GEMM, fp32-state mode" 2e-2). */
+enum {
+  LAS_MODE_FP32 = 0, /* fp32 operands, fp32 FMA accumulate everywhere */
+  LAS_MODE_BF16 = 1  /* bf16 GEMM operands on tcgen05 tensor cores, fp32 accumulate, fp32 c/h state, fp32 softmax */
+};
+
+/* decode feedback, model/las_model.py:216-234 */
+enum {
+  LAS_DECODE_RAW = 0,    /* decode_mode 0: feed the log-prob vector back */
+  LAS_DECODE_GREEDY = 1  /* decode_mode 1: feed one-hot(argmax) back (ties -> lowest index) */
+};
+
+int las_abi_version(void);
+const char* las_last_error(void);
+/* 0 if the current device can run the kernels (sm_100), LAS_EDEVICE otherwise. */
+int las_device_check(void);
+/* 1 if `mode` (LAS_MODE_*) is compiled into this library, else 0. */
+int las_mode_available(int mode);
+/* number of kernels this library has launched on the calling thread since the last reset (bench.py gpu_launches) */
+int64_t las_launch_count(int reset);
+/* Optional device-side phase timing for bench.py's roofline: when enabled (per calling thread) the library
+ * brackets each named launch group with cudaEvents on the caller's stream.  las_prof_report synchronises those
+ * events and writes one "name milliseconds launches" line per recorded group into buf. */
+int las_prof_enable(int on);
+int las_prof_report(char* buf, size_t buf_bytes);
+
+/* --------------------------------------------------------------------------------------------------------
+ * Listener: pyramidal BLSTM encoder.  Replaces Listener.forward / pBLSTMLayer.forward,
+ * model/las_model.py:81-91,129-134 (torch nn.LSTM call at :90).
+ * ------------------------------------------------------------------------------------------------------ */
+typedef struct las_listener_dims {
+  int32_t B; /* utterances */
+  int32_t T; /* input frames, T % 2^L == 0 (model/las_model.py:86-87 raises otherwise; we return LAS_EINVAL) */
+  int32_t F; /* input feature dim (40) */
+  int32_t H; /* hidden size per direction */
+  int32_t L; /* pyramid layers; output has U = T / 2^L steps of E = 2H features */
+} las_listener_dims;
+
+/* One direction of one layer, in the reference's state_dict layout, gate order i,f,g,o. */
+typedef struct las_lstm_weights {
+  const float* w_ih; /* [4H, K_in]  (K_in = 2F for layer 0, 4H for layers >= 1) */
+  const float* w_hh; /* [4H, H] */
+  const float* b_ih; /* [4H] */
+  const float* b_hh; /* [4H] */
+} las_lstm_weights;
+
+/* Packed (kernel-layout) weights.  `w_host` is a HOST array of 2L entries ordered
+ * layer0.fwd, layer0.reverse, layer1.fwd, ... whose members are device pointers. */
+size_t las_listener_packed_bytes(const las_listener_dims* d, int mode);
+int las_listener_pack(const las_lstm_weights* w_host, const las_listener_dims* d, int mode, void* packed,
+                      size_t packed_bytes, void* stream);
+size_t las_listener_workspace_bytes(const las_listener_dims* d, int mode);
+/* x [B,T,F] fp32 -> enc [B, T/2^L, 2H] fp32 (forward half first).  The pyramid fold (:86-87) is an index
+ * map, never a copy. */
+int las_listener_forward(const float* x, const void* packed, const las_listener_dims* d, int mode, float* enc,
+                         void* workspace, size_t workspace_bytes, void* stream);
+
+/* --------------------------------------------------------------------------------------------------------
+ * Speller: attention decoder step loop.  Replaces Speller.forward / forward_step and Attention.forward,
+ * model/las_model.py:178-238, 275-297, and the one-hot / TimeDistributed helpers utils/functions.py:54-77.
+ * ------------------------------------------------------------------------------------------------------ */
+typedef struct las_speller_dims {
+  int32_t B;  /* utterances */
+  int32_t U;  /* encoder steps */
+  int32_t E;  /* encoder feature dim = 2 * listener hidden */
+  int32_t Hs; /* speller hidden size; the reference requires Hs == E */
+  int32_t sl; /* stacked LSTM layers */
+  int32_t V;  /* vocabulary (label_dim) */
+  int32_t D;  /* attention MLP dim (phi/psi out features) */
+} las_speller_dims;
+
+typedef struct las_speller_weights {
+  const las_lstm_weights* rnn_host; /* HOST array [sl]; layer 0 w_ih is [4Hs, V+E] (one-hot columns first) */
+  const float* w_phi; /* [D, E]  attention.phi  (model/las_model.py:266) */
+  const float* b_phi; /* [D] */
+  const float* w_psi; /* [D, E]  attention.psi  (:267) */
+  const float* b_psi; /* [D] */
+  const float* w_cd;  /* [V, Hs+E] character_distribution (:174) */
+  const float* b_cd;  /* [V] */
+} las_speller_weights;
+
+size_t las_speller_packed_bytes(const las_speller_dims* d, int mode);
+int las_speller_pack(const las_speller_weights* w, const las_speller_dims* d, int mode, void* packed,
+                     size_t packed_bytes, void* stream);
+
+/* psi = act(enc . W_psi^T + b_psi), [B,U,E] -> [B,U,D] fp32.  Replaces the per-step
+ * TimeDistributed(psi, listener_feature) at model/las_model.py:279: it is step-invariant, so it is computed
+ * once per utterance batch.  Takes the reference-layout weights directly (attention.psi.weight [D,E], .bias [D]).
+ * `relu` = 0 for mlp_activate_in_attention == "None". */
+int las_psi_precompute(const float* enc, const float* w_psi, const float* b_psi, int B, int U, int E, int D, int relu,
+                       float* psi, void* stream);
+
+/* One attention evaluation (Attention.forward, :275-297, single head, 'dot'):
+ * state [B,Hs], enc [B,U,E], psi [B,U,D] -> score [B,U], context [B,E].  w_phi [D,Hs] / b_phi [D] are
+ * attention.phi; w_phi == NULL means use_mlp_in_attention=False (q = state, needs D == Hs; pass psi = enc).
+ * enc_lengths (nullable, int32 [B]) is the length-mask extension; NULL reproduces the reference (softmax
+ * over all U). */
+int las_attention_forward(const float* state, const float* enc, const float* psi, const float* w_phi,
+                          const float* b_phi, int B, int U, int E, int Hs, int D, int relu,
+                          const int32_t* enc_lengths, float* score, float* context, void* stream);
+
+typedef struct las_decode_io {
+  /* inputs */
+  const float* enc;           /* [B,U,E] listener features */
+  const float* psi;           /* [B,U,D] from las_psi_precompute, or NULL to have it computed into the workspace */
+  const float* gt_dense;      /* nullable [B,S,V] fp32: teacher forcing, next input = gt[:,step,:] (:216-217) */
+  const int32_t* gt_index;    /* nullable [B,S] int32: same, as label indices (one-hot implied) */
+  int32_t gt_steps;           /* S dimension of gt_dense / gt_index (>= steps) */
+  const int32_t* enc_lengths; /* nullable [B]: attention length mask extension */
+  /* recurrent state, in/out, nullable: NULL = start from zeros / <sos> / enc[:,0,:] (:193-200) */
+  float* h_state;             /* [sl,B,Hs] */
+  float* c_state;             /* [sl,B,Hs] */
+  float* word;                /* [B,V] current input word vector */
+  float* context;             /* [B,E] current context */
+  /* outputs */
+  float* logp;                /* [S,B,V] log-probabilities per step (raw_pred_seq, :213) */
+  float* attn;                /* nullable [S,B,U] attention scores per step (attention_record, :214) */
+  int32_t* tokens;            /* nullable [S,B] argmax of logp per step */
+} las_decode_io;
+
+size_t las_speller_workspace_bytes(const las_speller_dims* d, int steps, int mode);
+/* Runs `steps` decoder steps (Speller.forward loop, :209-236).  relu: attention activation flag. */
+int las_speller_decode(const las_decode_io* io, const void* packed, const las_speller_dims* d, int steps,
+                       int decode_mode, int mode, int relu, void* workspace, size_t workspace_bytes, void* stream);
+
+/* --------------------------------------------------------------------------------------------------------
+ * Solver epilogue ("next" row f1, solver/solver.py:62-92): NLL(ignore_index=0) sums on device.
+ * out[0] = sum over non-ignored targets of -logp[s,b,label], out[1] = number of non-ignored targets.
+ * ------------------------------------------------------------------------------------------------------ */
+int las_nll_sums(const float* logp /*[S,B,V]*/, const int32_t* labels /*[B,S_lab]*/, int S, int S_lab, int B, int V,
+                 int max_label_len, float* out2, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LAS_B200_H_ */

@@ -1,0 +1,421 @@
+// LAS_MODE_FP32 kernels: fp32 operands, fp32 FMA accumulation, precise expf/tanhf.
+// This is the correctness mode (north_star: log-probs within 1e-4 of the reference); it is also the first CUDA
+// path every faster kernel is validated against.  Kernels here are straightforward CUDA-core code.
+#include "las_kernels.cuh"
+
+namespace las {
+
+// =========================================================================================================
+// SGEMM  C = act(A . W^T + bias)     (reference: the x.W_ih^T half of nn.LSTM, model/las_model.py:90, and
+//                                     TimeDistributed(psi), model/las_model.py:279)
+// 128x128x16 tile, 256 threads, 8x8 register micro-tile (split 4+4 so smem reads are float4 and conflict-free).
+// =========================================================================================================
+constexpr int GM = 128, GN = 128, GK = 16;
+
+__global__ void __launch_bounds__(256)
+sgemm_nt_bias_kernel(const float* __restrict__ A, int lda, const float* __restrict__ W, int ldw,
+                     const float* __restrict__ bias, float* __restrict__ C, int ldc, int M, int N, int K, int relu,
+                     int vec_ok) {
+  __shared__ __align__(16) float As[GK][GM + 4];
+  __shared__ __align__(16) float Ws[GK][GN + 4];
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;
+  const int m0 = blockIdx.y * GM, n0 = blockIdx.x * GN;
+
+  float acc[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+
+  for (int k0 = 0; k0 < K; k0 += GK) {
+    // stage A and W tiles (transposed into [k][row])
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int idx = tid + i * 256;
+      const int row = idx >> 2, kq = (idx & 3) * 4;
+      float va[4] = {0.f, 0.f, 0.f, 0.f}, vw[4] = {0.f, 0.f, 0.f, 0.f};
+      const int gm = m0 + row, gn = n0 + row, gk = k0 + kq;
+      if (gm < M) {
+        const float* p = A + (size_t)gm * lda + gk;
+        if (vec_ok && gk + 3 < K) {
+          const float4 t = *reinterpret_cast<const float4*>(p);
+          va[0] = t.x; va[1] = t.y; va[2] = t.z; va[3] = t.w;
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) if (gk + j < K) va[j] = p[j];
+        }
+      }
+      if (gn < N) {
+        const float* p = W + (size_t)gn * ldw + gk;
+        if (vec_ok && gk + 3 < K) {
+          const float4 t = *reinterpret_cast<const float4*>(p);
+          vw[0] = t.x; vw[1] = t.y; vw[2] = t.z; vw[3] = t.w;
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) if (gk + j < K) vw[j] = p[j];
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        As[kq + j][row] = va[j];
+        Ws[kq + j][row] = vw[j];
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < GK; ++kk) {
+      const float4 a0 = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&As[kk][64 + ty * 4]);
+      const float4 b0 = *reinterpret_cast<const float4*>(&Ws[kk][tx * 4]);
+      const float4 b1 = *reinterpret_cast<const float4*>(&Ws[kk][64 + tx * 4]);
+      const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int gm = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
+    if (gm >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int gn = n0 + (j < 4 ? tx * 4 + j : 64 + tx * 4 + (j - 4));
+      if (gn >= N) continue;
+      float v = acc[i][j] + (bias ? bias[gn] : 0.f);
+      if (relu) v = fmaxf(v, 0.f);
+      C[(size_t)gm * ldc + gn] = v;
+    }
+  }
+}
+
+int launch_sgemm_nt_bias(const float* A, int lda, const float* W, int ldw, const float* bias, float* C, int ldc,
+                         int M, int N, int K, bool relu, cudaStream_t st) {
+  if (M <= 0 || N <= 0) return LAS_OK;
+  const int vec_ok = (lda % 4 == 0) && (ldw % 4 == 0) && ((reinterpret_cast<uintptr_t>(A) & 15) == 0) &&
+                     ((reinterpret_cast<uintptr_t>(W) & 15) == 0);
+  dim3 grid((N + GN - 1) / GN, (M + GM - 1) / GM);
+  sgemm_nt_bias_kernel<<<grid, 256, 0, st>>>(A, lda, W, ldw, bias, C, ldc, M, N, K, relu ? 1 : 0, vec_ok);
+  LAS_LAUNCH_OK("sgemm_nt_bias_kernel");
+  return LAS_OK;
+}
+
+// =========================================================================================================
+// LSTM cell step (torch nn.LSTM equations, gate order i,f,g,o).  Used for the listener recurrence
+// (model/las_model.py:90; pre_add = the precomputed input projection, one launch per time step covering both
+// directions) and for the speller's stacked cells (model/las_model.py:179).
+// Tile: 32 batch rows x 8 hidden units (x4 gates), K streamed in chunks of 32 through smem.
+// =========================================================================================================
+constexpr int CB = 32, CJ = 8, CK = 32;
+
+struct CellArgs2 {
+  CellArgs d[2];
+};
+
+__device__ __forceinline__ void cell_accumulate(const float* __restrict__ src, long long src_ld, int K,
+                                                const float* __restrict__ w, int H, int b0, int j0, int B,
+                                                float (&As)[CB][CK + 1], float (&Ws)[4 * CJ][CK + 1], float (&acc)[4]) {
+  const int tid = threadIdx.x;
+  const int tb = tid / CJ, tj = tid % CJ;
+  for (int k0 = 0; k0 < K; k0 += CK) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int idx = tid + i * 256;
+      const int r = idx / CK, cc = idx % CK;
+      const int gk = k0 + cc;
+      const int gb = b0 + r;
+      As[r][cc] = (gb < B && gk < K) ? src[(long long)gb * src_ld + gk] : 0.f;
+      const int g = r / CJ, jj = r % CJ;
+      const int gj = j0 + jj;
+      Ws[r][cc] = (gj < H && gk < K) ? w[(size_t)(g * H + gj) * K + gk] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < CK; ++kk) {
+      const float av = As[tb][kk];
+#pragma unroll
+      for (int g = 0; g < 4; ++g) acc[g] = fmaf(av, Ws[g * CJ + tj][kk], acc[g]);
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(256) lstm_cell_f32_kernel(CellArgs2 args, int B, int H) {
+  const CellArgs& a = args.d[blockIdx.z];
+  __shared__ float As[CB][CK + 1];
+  __shared__ float Ws[4 * CJ][CK + 1];
+  const int j0 = blockIdx.x * CJ, b0 = blockIdx.y * CB;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  if (a.x) cell_accumulate(a.x, a.x_ld, a.Kx, a.w_ih, H, b0, j0, B, As, Ws, acc);
+  if (a.h_prev) cell_accumulate(a.h_prev, a.h_ld, H, a.w_hh, H, b0, j0, B, As, Ws, acc);
+
+  const int tb = threadIdx.x / CJ, tj = threadIdx.x % CJ;
+  const int b = b0 + tb, j = j0 + tj;
+  if (b >= B || j >= H) return;
+  float pre[4];
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    float v = acc[g];
+    if (a.pre_add) v += a.pre_add[(long long)b * a.pre_ld + g * H + j];
+    if (a.b_ih) v += a.b_ih[g * H + j] + a.b_hh[g * H + j];
+    pre[g] = v;
+  }
+  const float ig = sigmoid_precise(pre[0]);
+  const float fg = sigmoid_precise(pre[1]);
+  const float gg = tanhf(pre[2]);
+  const float og = sigmoid_precise(pre[3]);
+  const float c_new = fg * a.c[(size_t)b * H + j] + ig * gg;
+  a.c[(size_t)b * H + j] = c_new;
+  a.h_out[(long long)b * a.hout_ld + j] = og * tanhf(c_new);
+}
+
+int launch_lstm_cell_f32(const CellArgs* args, int ndir, int B, int H, cudaStream_t st) {
+  CellArgs2 a2;
+  a2.d[0] = args[0];
+  a2.d[1] = args[ndir > 1 ? 1 : 0];
+  dim3 grid((H + CJ - 1) / CJ, (B + CB - 1) / CB, ndir);
+  lstm_cell_f32_kernel<<<grid, 256, 0, st>>>(a2, B, H);
+  LAS_LAUNCH_OK("lstm_cell_f32_kernel");
+  return LAS_OK;
+}
+
+// =========================================================================================================
+// Attention + character distribution + feedback for one decoder step; one CTA per utterance.
+// model/las_model.py:276-297 (phi, energy, softmax, context), :181-182 (cat, Linear, LogSoftmax),
+// :216-227 (teacher forcing / raw / greedy feedback), :236 (next input = [word || context]).
+// smem: state[Hs] q[D] score[U] vec[Hs+E] logits[V] red[32]
+// =========================================================================================================
+__device__ __forceinline__ float block_reduce_max(float v, float* red) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  v = warp_max(v);
+  __syncthreads();
+  if (lane == 0) red[wid] = v;
+  __syncthreads();
+  float r = red[0];
+  for (int i = 1; i < nw; ++i) r = fmaxf(r, red[i]);
+  return r;
+}
+__device__ __forceinline__ float block_reduce_sum(float v, float* red) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) red[wid] = v;
+  __syncthreads();
+  float r = 0.f;
+  for (int i = 0; i < nw; ++i) r += red[i];  // fixed order -> deterministic
+  return r;
+}
+
+__global__ void __launch_bounds__(256) attend_f32_kernel(AttendArgs a) {
+  extern __shared__ float sm[];
+  float* s_state = sm;                 // Hs
+  float* s_q = s_state + a.Hs;         // D
+  float* s_score = s_q + a.D;          // U
+  float* s_ctx = s_score + a.U;        // E
+  float* s_logit = s_ctx + a.E;        // V
+  float* s_red = s_logit + a.V;        // 32
+  const int b = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nw = blockDim.x >> 5;
+
+  for (int k = tid; k < a.Hs; k += blockDim.x) s_state[k] = a.state[(size_t)b * a.state_ld + k];
+  __syncthreads();
+
+  // q = act(W_phi . state + b_phi)   (:278)
+  if (!a.w_phi) {  // use_mlp_in_attention=False (:283-285): query is the raw decoder state
+    for (int d = tid; d < a.D; d += blockDim.x) s_q[d] = s_state[d];
+  }
+  for (int d = wid; a.w_phi && d < a.D; d += nw) {
+    const float* wr = a.w_phi + (size_t)d * a.Hs;
+    float p = 0.f;
+    for (int k = lane; k < a.Hs; k += 32) p = fmaf(wr[k], s_state[k], p);
+    p = warp_sum(p);
+    if (lane == 0) {
+      p += a.b_phi[d];
+      s_q[d] = a.relu ? fmaxf(p, 0.f) : p;
+    }
+  }
+  __syncthreads();
+
+  // energy[u] = <q, psi[b,u,:]>   (:289-291)
+  const int ulen = a.enc_lengths ? min(max(a.enc_lengths[b], 1), a.U) : a.U;
+  const float* psib = a.psi + (size_t)b * a.U * a.D;
+  for (int u = wid; u < a.U; u += nw) {
+    const float* pr = psib + (size_t)u * a.D;
+    float p = 0.f;
+    for (int d = lane; d < a.D; d += 32) p = fmaf(s_q[d], pr[d], p);
+    p = warp_sum(p);
+    if (lane == 0) s_score[u] = (u < ulen) ? p : -INFINITY;
+  }
+  __syncthreads();
+
+  // softmax over U   (:292)
+  float m = -INFINITY;
+  for (int u = tid; u < a.U; u += blockDim.x) m = fmaxf(m, s_score[u]);
+  m = block_reduce_max(m, s_red);
+  float ssum = 0.f;
+  for (int u = tid; u < a.U; u += blockDim.x) {
+    const float e = expf(s_score[u] - m);
+    s_score[u] = e;
+    ssum += e;
+  }
+  ssum = block_reduce_sum(ssum, s_red);
+  const float inv = 1.0f / ssum;
+  for (int u = tid; u < a.U; u += blockDim.x) {
+    const float p = s_score[u] * inv;
+    s_score[u] = p;
+    if (a.score_out) a.score_out[(size_t)b * a.U + u] = p;
+  }
+  __syncthreads();
+
+  // context[e] = sum_u score[u] * enc[b,u,e]   (:293-297)
+  const float* encb = a.enc + (size_t)b * a.U * a.E;
+  for (int e = tid; e < a.E; e += blockDim.x) {
+    float acc = 0.f;
+    for (int u = 0; u < a.U; ++u) acc = fmaf(s_score[u], encb[(size_t)u * a.E + e], acc);
+    s_ctx[e] = acc;
+    a.ctx_out[(size_t)b * a.ctx_ld + e] = acc;
+  }
+  if (!a.w_cd) return;
+  __syncthreads();
+
+  // logits = W_cd . [state || context] + b_cd ; log_softmax   (:181-182)
+  const int KC = a.Hs + a.E;
+  for (int v = wid; v < a.V; v += nw) {
+    const float* wr = a.w_cd + (size_t)v * KC;
+    float p = 0.f;
+    for (int k = lane; k < a.Hs; k += 32) p = fmaf(wr[k], s_state[k], p);
+    for (int k = lane; k < a.E; k += 32) p = fmaf(wr[a.Hs + k], s_ctx[k], p);
+    p = warp_sum(p);
+    if (lane == 0) s_logit[v] = p + a.b_cd[v];
+  }
+  __syncthreads();
+  float lm = -INFINITY;
+  for (int v = tid; v < a.V; v += blockDim.x) lm = fmaxf(lm, s_logit[v]);
+  lm = block_reduce_max(lm, s_red);
+  float ls = 0.f;
+  for (int v = tid; v < a.V; v += blockDim.x) ls += expf(s_logit[v] - lm);
+  ls = block_reduce_sum(ls, s_red);
+  const float lse = lm + logf(ls);
+  for (int v = tid; v < a.V; v += blockDim.x) {
+    const float lp = s_logit[v] - lse;
+    s_logit[v] = lp;
+    a.logp_out[(size_t)b * a.V + v] = lp;
+  }
+  __syncthreads();
+
+  // argmax (lowest index wins ties, as torch.topk / argmax do on a row)   (:225)
+  int best = 0;
+  if (wid == 0) {
+    float bv = -INFINITY;
+    int bi = 0x7fffffff;
+    for (int v = lane; v < a.V; v += 32) {
+      const float x = s_logit[v];
+      if (x > bv) { bv = x; bi = v; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+    }
+    best = bi;
+    if (lane == 0) {
+      s_red[0] = __int_as_float(best);
+      if (a.token_out) a.token_out[b] = best;
+    }
+  }
+  __syncthreads();
+  best = __float_as_int(s_red[0]);
+
+  // next input word   (:216-227)
+  if (a.word_out) {
+    float* wo = a.word_out + (size_t)b * a.word_ld;
+    if (a.gt_dense_step) {
+      const float* g = a.gt_dense_step + (long long)b * a.gt_ld;
+      for (int v = tid; v < a.V; v += blockDim.x) wo[v] = g[v];
+    } else if (a.gt_index_step) {
+      const int gi = a.gt_index_step[(size_t)b * a.gt_index_ld];
+      for (int v = tid; v < a.V; v += blockDim.x) wo[v] = (v == gi) ? 1.f : 0.f;
+    } else if (a.decode_mode == LAS_DECODE_RAW) {
+      for (int v = tid; v < a.V; v += blockDim.x) wo[v] = s_logit[v];
+    } else {
+      for (int v = tid; v < a.V; v += blockDim.x) wo[v] = (v == best) ? 1.f : 0.f;
+    }
+  }
+}
+
+int launch_attend_f32(const AttendArgs& a, cudaStream_t st) {
+  const size_t smem = sizeof(float) * ((size_t)a.Hs + a.D + a.U + a.E + a.V + 32);
+  if (smem > 200 * 1024) return fail(LAS_EINVAL, "attention step needs %zu bytes of shared memory (U=%d too long)", smem, a.U);
+  if (smem > 48 * 1024) {
+    LAS_CUDA_OK(cudaFuncSetAttribute(attend_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  }
+  attend_f32_kernel<<<a.B, 256, smem, st>>>(a);
+  LAS_LAUNCH_OK("attend_f32_kernel");
+  return LAS_OK;
+}
+
+// =========================================================================================================
+__global__ void speller_init_kernel(float* xin, int xin_ld, const float* enc, int B, int U, int E, int V) {
+  const int b = blockIdx.x;
+  for (int i = threadIdx.x; i < V + E; i += blockDim.x) {
+    float v;
+    if (i < V) v = (i == 0) ? 1.f : 0.f;              // <sos> one-hot, utils/functions.py:54-63
+    else v = enc[(size_t)b * U * E + (i - V)];         // listener_feature[:, 0, :], model/las_model.py:198
+    xin[(size_t)b * xin_ld + i] = v;
+  }
+}
+int launch_speller_init(float* xin, int xin_ld, const float* enc, int B, int U, int E, int V, cudaStream_t st) {
+  speller_init_kernel<<<B, 128, 0, st>>>(xin, xin_ld, enc, B, U, E, V);
+  LAS_LAUNCH_OK("speller_init_kernel");
+  return LAS_OK;
+}
+
+__global__ void copy2d_kernel(float* dst, long long dst_ld, const float* src, long long src_ld, int rows, int cols) {
+  const long long n = (long long)rows * cols;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / cols, c = i % cols;
+    dst[r * dst_ld + c] = src[r * src_ld + c];
+  }
+}
+int launch_copy2d(float* dst, long long dst_ld, const float* src, long long src_ld, int rows, int cols, cudaStream_t st) {
+  if (rows <= 0 || cols <= 0) return LAS_OK;
+  const long long n = (long long)rows * cols;
+  const int blocks = (int)((n + 255) / 256 < 1184 ? (n + 255) / 256 : 1184);
+  copy2d_kernel<<<blocks, 256, 0, st>>>(dst, dst_ld, src, src_ld, rows, cols);
+  LAS_LAUNCH_OK("copy2d_kernel");
+  return LAS_OK;
+}
+
+// solver/solver.py:62,70-77: NLLLoss(ignore_index=0) numerator / denominator, deterministic single-CTA reduce.
+__global__ void nll_sums_kernel(const float* logp, const int32_t* labels, int S, int S_lab, int B, int V, int L,
+                                float* out2) {
+  __shared__ float red[32];
+  float num = 0.f, den = 0.f;
+  for (int i = threadIdx.x; i < B * L; i += blockDim.x) {
+    const int b = i / L, s = i % L;
+    const int lab = labels[(size_t)b * S_lab + s];
+    if (lab != 0 && lab < V) {
+      num -= logp[((size_t)s * B + b) * V + lab];
+      den += 1.f;
+    }
+  }
+  num = block_reduce_sum(num, red);
+  den = block_reduce_sum(den, red);
+  if (threadIdx.x == 0) { out2[0] = num; out2[1] = den; }
+}
+int launch_nll_sums(const float* logp, const int32_t* labels, int S, int S_lab, int B, int V, int max_label_len,
+                    float* out2, cudaStream_t st) {
+  int L = max_label_len < S ? max_label_len : S;
+  if (S_lab < L) L = S_lab;
+  nll_sums_kernel<<<1, 1024, 0, st>>>(logp, labels, S, S_lab, B, V, L, out2);
+  LAS_LAUNCH_OK("nll_sums_kernel");
+  return LAS_OK;
+}
+
+}  // namespace las

@@ -1,0 +1,517 @@
+// extern "C" entry points of include/las_b200.h: argument validation, buffer carving, kernel sequencing.
+#include "las_kernels.cuh"
+#include "las_fast.cuh"
+
+#include <string.h>
+
+namespace las {
+
+static thread_local char g_err[512] = "";
+static thread_local int64_t g_launches = 0;
+
+char* err_buf() { return g_err; }
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+void count_launch(int n) { g_launches += n; }
+
+// ---- profiling registry (thread-local) ------------------------------------------------------------------
+struct ProfRec {
+  char name[48];
+  cudaEvent_t e0, e1;
+  int64_t launches0, launches1;
+};
+static thread_local bool g_prof_on = false;
+static thread_local ProfRec g_prof[4096];
+static thread_local int g_prof_n = 0;
+
+ProfScope::ProfScope(const char* name, cudaStream_t stream) : st(stream) {
+  if (!g_prof_on || g_prof_n >= 4096) return;
+  ProfRec& r = g_prof[g_prof_n];
+  if (cudaEventCreate(&r.e0) != cudaSuccess || cudaEventCreate(&r.e1) != cudaSuccess) return;
+  snprintf(r.name, sizeof(r.name), "%s", name);
+  r.launches0 = g_launches;
+  cudaEventRecord(r.e0, st);
+  slot = g_prof_n++;
+}
+ProfScope::~ProfScope() {
+  if (slot < 0) return;
+  g_prof[slot].launches1 = g_launches;
+  cudaEventRecord(g_prof[slot].e1, st);
+}
+
+int sm_count() {
+  int dev = 0, n = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+  if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 148;
+  return n;
+}
+
+static int device_ok() {
+  int dev = 0, major = 0;
+  LAS_CUDA_OK(cudaGetDevice(&dev));
+  LAS_CUDA_OK(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+  if (major != 10)
+    return fail(LAS_EDEVICE, "device %d has compute capability %d.x; this library is built for sm_100a only (no fallback)",
+                dev, major);
+  return LAS_OK;
+}
+
+__global__ void bias_sum_kernel(float* out, const float* a, const float* b, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = a[i] + b[i];
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Listener, fp32 mode.  Packed layout per layer: Wcat [8H, K] (fwd rows then reverse rows), bias [8H]
+// (= b_ih + b_hh), Whh [2][4H, H].
+// ---------------------------------------------------------------------------------------------------------
+struct ListenerPackF32 {
+  float* wcat[16];
+  float* bias[16];
+  float* whh[16];
+  size_t bytes;
+};
+static int listener_check(const las_listener_dims* d) {
+  LAS_REQUIRE(d != nullptr, "dims is NULL");
+  LAS_REQUIRE(d->B > 0 && d->T > 0 && d->F > 0 && d->H > 0, "listener dims must be positive (B=%d T=%d F=%d H=%d)", d->B, d->T, d->F, d->H);
+  LAS_REQUIRE(d->L >= 1 && d->L <= 16, "Listener should have at least 1 layer (L=%d)", d->L);
+  LAS_REQUIRE(d->T % (1 << d->L) == 0,
+              "timestep %d is not divisible by 2^%d: the pyramid fold (model/las_model.py:86-87) needs an even length at every layer",
+              d->T, d->L);
+  return LAS_OK;
+}
+static ListenerPackF32 listener_pack_layout_f32(const las_listener_dims* d, void* base) {
+  ListenerPackF32 p;
+  Carver cv(base);
+  for (int l = 0; l < d->L; ++l) {
+    const size_t K = (l == 0) ? 2 * (size_t)d->F : 4 * (size_t)d->H;
+    p.wcat[l] = cv.take<float>(8 * (size_t)d->H * K);
+    p.bias[l] = cv.take<float>(8 * (size_t)d->H);
+    p.whh[l] = cv.take<float>(8 * (size_t)d->H * d->H);
+  }
+  p.bytes = cv.total();
+  return p;
+}
+
+struct ListenerWsF32 {
+  float* P;
+  float* act[2];
+  float* c;
+  size_t bytes;
+};
+static ListenerWsF32 listener_ws_layout_f32(const las_listener_dims* d, void* base) {
+  ListenerWsF32 w;
+  Carver cv(base);
+  const size_t M0 = (size_t)d->B * (d->T / 2);
+  w.P = cv.take<float>(M0 * 8 * d->H);
+  w.act[0] = cv.take<float>(M0 * 2 * d->H);
+  w.act[1] = cv.take<float>(M0 / 2 * 2 * d->H + 16);
+  w.c = cv.take<float>(2 * (size_t)d->B * d->H);
+  w.bytes = cv.total();
+  return w;
+}
+
+static int listener_forward_f32(const float* x, const void* packed, const las_listener_dims* d, float* enc, void* ws,
+                                cudaStream_t st) {
+  const ListenerPackF32 pk = listener_pack_layout_f32(d, const_cast<void*>(packed));
+  const ListenerWsF32 w = listener_ws_layout_f32(d, ws);
+  const int B = d->B, H = d->H;
+  const float* cur = x;
+  int Tin = d->T, Fin = d->F;
+  for (int l = 0; l < d->L; ++l) {
+    const int Tl = Tin / 2, K = 2 * Fin, M = B * Tl;
+    // pyramid fold = reading [B, Tin, Fin] as [B*Tl, 2*Fin]: same memory, lda = 2*Fin (model/las_model.py:86-87)
+    char nm[48];
+    {
+      snprintf(nm, sizeof(nm), "listener.L%d.input_gemm", l);
+      ProfScope ps(nm, st);
+      LAS_TRY(launch_sgemm_nt_bias(cur, K, pk.wcat[l], K, pk.bias[l], w.P, 8 * H, M, 8 * H, K, false, st));
+    }
+    snprintf(nm, sizeof(nm), "listener.L%d.recurrence", l);
+    ProfScope ps(nm, st);
+    float* out = (l == d->L - 1) ? enc : w.act[l & 1];
+    LAS_CUDA_OK(cudaMemsetAsync(w.c, 0, sizeof(float) * 2 * (size_t)B * H, st));
+    const long long row_ld = (long long)Tl * 2 * H;
+    for (int step = 0; step < Tl; ++step) {
+      const int tf = step, tb = Tl - 1 - step;
+      CellArgs a[2];
+      memset(a, 0, sizeof(a));
+      a[0].h_prev = step ? out + (size_t)(tf - 1) * 2 * H : nullptr;
+      a[0].h_ld = row_ld;
+      a[0].w_hh = pk.whh[l];
+      a[0].pre_add = w.P + (size_t)tf * 8 * H;
+      a[0].pre_ld = (long long)Tl * 8 * H;
+      a[0].c = w.c;
+      a[0].h_out = out + (size_t)tf * 2 * H;
+      a[0].hout_ld = row_ld;
+      a[1].h_prev = step ? out + (size_t)(tb + 1) * 2 * H + H : nullptr;
+      a[1].h_ld = row_ld;
+      a[1].w_hh = pk.whh[l] + 4 * (size_t)H * H;
+      a[1].pre_add = w.P + (size_t)tb * 8 * H + 4 * H;
+      a[1].pre_ld = (long long)Tl * 8 * H;
+      a[1].c = w.c + (size_t)B * H;
+      a[1].h_out = out + (size_t)tb * 2 * H + H;
+      a[1].hout_ld = row_ld;
+      LAS_TRY(launch_lstm_cell_f32(a, 2, B, H, st));
+    }
+    cur = out;
+    Tin = Tl;
+    Fin = 2 * H;
+  }
+  return LAS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Speller, fp32 mode.  Packed layout = contiguous fp32 copies in the reference's own shapes.
+// ---------------------------------------------------------------------------------------------------------
+struct SpellerPackF32 {
+  float *w_ih[8], *w_hh[8], *b_ih[8], *b_hh[8];
+  float *w_phi, *b_phi, *w_psi, *b_psi, *w_cd, *b_cd;
+  size_t bytes;
+};
+static int speller_check(const las_speller_dims* d) {
+  LAS_REQUIRE(d != nullptr, "dims is NULL");
+  LAS_REQUIRE(d->B > 0 && d->U > 0 && d->E > 0 && d->Hs > 0 && d->V > 0 && d->D > 0,
+              "speller dims must be positive (B=%d U=%d E=%d Hs=%d V=%d D=%d)", d->B, d->U, d->E, d->Hs, d->V, d->D);
+  LAS_REQUIRE(d->sl >= 1 && d->sl <= 8, "speller layers must be in [1,8] (sl=%d)", d->sl);
+  LAS_REQUIRE(d->Hs == d->E,
+              "speller hidden_size (%d) must equal 2*listener_hidden_size (%d): rnn input is [one-hot || encoder feature] "
+              "(model/las_model.py:165,198)", d->Hs, d->E);
+  return LAS_OK;
+}
+static SpellerPackF32 speller_pack_layout_f32(const las_speller_dims* d, void* base) {
+  SpellerPackF32 p;
+  Carver cv(base);
+  const size_t G = 4 * (size_t)d->Hs;
+  for (int l = 0; l < d->sl; ++l) {
+    const size_t Kx = (l == 0) ? (size_t)d->V + d->E : (size_t)d->Hs;
+    p.w_ih[l] = cv.take<float>(G * Kx);
+    p.w_hh[l] = cv.take<float>(G * d->Hs);
+    p.b_ih[l] = cv.take<float>(G);
+    p.b_hh[l] = cv.take<float>(G);
+  }
+  p.w_phi = cv.take<float>((size_t)d->D * d->Hs);
+  p.b_phi = cv.take<float>(d->D);
+  p.w_psi = cv.take<float>((size_t)d->D * d->E);
+  p.b_psi = cv.take<float>(d->D);
+  p.w_cd = cv.take<float>((size_t)d->V * (d->Hs + d->E));
+  p.b_cd = cv.take<float>(d->V);
+  p.bytes = cv.total();
+  return p;
+}
+
+struct SpellerWsF32 {
+  float* psi;
+  float* xin;
+  float* h[2];
+  float* c;
+  size_t bytes;
+};
+static SpellerWsF32 speller_ws_layout_f32(const las_speller_dims* d, void* base) {
+  SpellerWsF32 w;
+  Carver cv(base);
+  w.psi = cv.take<float>((size_t)d->B * d->U * d->D);
+  w.xin = cv.take<float>((size_t)d->B * (d->V + d->E));
+  w.h[0] = cv.take<float>((size_t)d->sl * d->B * d->Hs);
+  w.h[1] = cv.take<float>((size_t)d->sl * d->B * d->Hs);
+  w.c = cv.take<float>((size_t)d->sl * d->B * d->Hs);
+  w.bytes = cv.total();
+  return w;
+}
+
+static int speller_decode_f32(const las_decode_io* io, const void* packed, const las_speller_dims* d, int steps,
+                              int decode_mode, int relu, void* ws, cudaStream_t st) {
+  const SpellerPackF32 pk = speller_pack_layout_f32(d, const_cast<void*>(packed));
+  const SpellerWsF32 w = speller_ws_layout_f32(d, ws);
+  const int B = d->B, Hs = d->Hs, V = d->V, E = d->E, U = d->U, D = d->D, sl = d->sl;
+  const int xld = V + E;
+  const size_t state_n = (size_t)sl * B * Hs;
+
+  const float* psi = io->psi;
+  if (!psi) {
+    ProfScope ps("speller.psi", st);
+    LAS_TRY(launch_sgemm_nt_bias(io->enc, E, pk.w_psi, E, pk.b_psi, w.psi, D, B * U, D, E, relu != 0, st));
+    psi = w.psi;
+  }
+  if (io->word && io->context) {
+    LAS_TRY(launch_copy2d(w.xin, xld, io->word, V, B, V, st));
+    LAS_TRY(launch_copy2d(w.xin + V, xld, io->context, E, B, E, st));
+  } else {
+    LAS_TRY(launch_speller_init(w.xin, xld, io->enc, B, U, E, V, st));
+  }
+  if (io->h_state && io->c_state) {
+    LAS_CUDA_OK(cudaMemcpyAsync(w.h[0], io->h_state, sizeof(float) * state_n, cudaMemcpyDeviceToDevice, st));
+    LAS_CUDA_OK(cudaMemcpyAsync(w.c, io->c_state, sizeof(float) * state_n, cudaMemcpyDeviceToDevice, st));
+  } else {
+    LAS_CUDA_OK(cudaMemsetAsync(w.h[0], 0, sizeof(float) * state_n, st));
+    LAS_CUDA_OK(cudaMemsetAsync(w.c, 0, sizeof(float) * state_n, st));
+  }
+
+  ProfScope ps_steps("speller.steps", st);
+  for (int s = 0; s < steps; ++s) {
+    float* hp = w.h[s & 1];
+    float* hn = w.h[(s & 1) ^ 1];
+    for (int l = 0; l < sl; ++l) {
+      CellArgs a;
+      memset(&a, 0, sizeof(a));
+      a.x = (l == 0) ? w.xin : hn + (size_t)(l - 1) * B * Hs;
+      a.x_ld = (l == 0) ? xld : Hs;
+      a.Kx = (l == 0) ? xld : Hs;
+      a.w_ih = pk.w_ih[l];
+      a.h_prev = hp + (size_t)l * B * Hs;
+      a.h_ld = Hs;
+      a.w_hh = pk.w_hh[l];
+      a.b_ih = pk.b_ih[l];
+      a.b_hh = pk.b_hh[l];
+      a.c = w.c + (size_t)l * B * Hs;
+      a.h_out = hn + (size_t)l * B * Hs;
+      a.hout_ld = Hs;
+      LAS_TRY(launch_lstm_cell_f32(&a, 1, B, Hs, st));
+    }
+    AttendArgs t;
+    memset(&t, 0, sizeof(t));
+    t.state = hn + (size_t)(sl - 1) * B * Hs;
+    t.state_ld = Hs;
+    t.enc = io->enc;
+    t.psi = psi;
+    t.w_phi = pk.w_phi; t.b_phi = pk.b_phi; t.w_cd = pk.w_cd; t.b_cd = pk.b_cd;
+    t.enc_lengths = io->enc_lengths;
+    t.B = B; t.U = U; t.E = E; t.Hs = Hs; t.V = V; t.D = D;
+    t.relu = relu;
+    t.score_out = io->attn ? io->attn + (size_t)s * B * U : nullptr;
+    t.ctx_out = w.xin + V;
+    t.ctx_ld = xld;
+    t.logp_out = io->logp + (size_t)s * B * V;
+    t.token_out = io->tokens ? io->tokens + (size_t)s * B : nullptr;
+    t.word_out = w.xin;
+    t.word_ld = xld;
+    if (io->gt_dense) {
+      t.gt_dense_step = io->gt_dense + (size_t)s * V;
+      t.gt_ld = (long long)io->gt_steps * V;
+    } else if (io->gt_index) {
+      t.gt_index_step = io->gt_index + s;
+      t.gt_index_ld = io->gt_steps;
+    }
+    t.decode_mode = decode_mode;
+    LAS_TRY(launch_attend_f32(t, st));
+  }
+  if (io->h_state && io->c_state) {
+    LAS_CUDA_OK(cudaMemcpyAsync(io->h_state, w.h[steps & 1], sizeof(float) * state_n, cudaMemcpyDeviceToDevice, st));
+    LAS_CUDA_OK(cudaMemcpyAsync(io->c_state, w.c, sizeof(float) * state_n, cudaMemcpyDeviceToDevice, st));
+  }
+  if (io->word && io->context) {
+    LAS_TRY(launch_copy2d(io->word, V, w.xin, xld, B, V, st));
+    LAS_TRY(launch_copy2d(io->context, E, w.xin + V, xld, B, E, st));
+  }
+  return LAS_OK;
+}
+
+}  // namespace las
+
+using namespace las;
+
+extern "C" {
+
+int las_abi_version(void) { return LAS_B200_ABI_VERSION; }
+const char* las_last_error(void) { return err_buf(); }
+int las_device_check(void) { return device_ok(); }
+int las_mode_available(int mode) { return mode == LAS_MODE_FP32 || (mode == LAS_MODE_BF16 && fast_available()); }
+int las_prof_enable(int on) {
+  for (int i = 0; i < g_prof_n; ++i) {
+    cudaEventDestroy(g_prof[i].e0);
+    cudaEventDestroy(g_prof[i].e1);
+  }
+  g_prof_n = 0;
+  g_prof_on = on != 0;
+  return LAS_OK;
+}
+int las_prof_report(char* buf, size_t buf_bytes) {
+  LAS_REQUIRE(buf && buf_bytes > 0, "null buffer");
+  size_t off = 0;
+  buf[0] = 0;
+  for (int i = 0; i < g_prof_n; ++i) {
+    float ms = 0.f;
+    LAS_CUDA_OK(cudaEventSynchronize(g_prof[i].e1));
+    LAS_CUDA_OK(cudaEventElapsedTime(&ms, g_prof[i].e0, g_prof[i].e1));
+    const int n = snprintf(buf + off, buf_bytes - off, "%s %.6f %lld\n", g_prof[i].name, ms,
+                           (long long)(g_prof[i].launches1 - g_prof[i].launches0));
+    if (n < 0 || (size_t)n >= buf_bytes - off) return fail(LAS_ENOMEM, "report buffer too small");
+    off += n;
+  }
+  return LAS_OK;
+}
+int64_t las_launch_count(int reset) {
+  const int64_t v = g_launches;
+  if (reset) g_launches = 0;
+  return v;
+}
+
+// ---- listener ------------------------------------------------------------------------------------------
+size_t las_listener_packed_bytes(const las_listener_dims* d, int mode) {
+  if (listener_check(d) != LAS_OK) return 0;
+  if (mode == LAS_MODE_BF16) return fast_listener_packed_bytes(d);
+  return listener_pack_layout_f32(d, nullptr).bytes;
+}
+
+int las_listener_pack(const las_lstm_weights* w, const las_listener_dims* d, int mode, void* packed, size_t packed_bytes,
+                      void* stream) {
+  LAS_TRY(listener_check(d));
+  LAS_REQUIRE(w && packed, "null weights / packed buffer");
+  LAS_REQUIRE(mode == LAS_MODE_FP32 || mode == LAS_MODE_BF16, "unknown mode %d", mode);
+  LAS_TRY(device_ok());
+  if (packed_bytes < las_listener_packed_bytes(d, mode))
+    return fail(LAS_ENOMEM, "packed buffer too small: %zu < %zu", packed_bytes, las_listener_packed_bytes(d, mode));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (mode == LAS_MODE_BF16) return fast_listener_pack(w, d, packed, st);
+  const ListenerPackF32 pk = listener_pack_layout_f32(d, packed);
+  const size_t H = d->H;
+  for (int l = 0; l < d->L; ++l) {
+    const size_t K = (l == 0) ? 2 * (size_t)d->F : 4 * H;
+    for (int dir = 0; dir < 2; ++dir) {
+      const las_lstm_weights& s = w[2 * l + dir];
+      LAS_REQUIRE(s.w_ih && s.w_hh && s.b_ih && s.b_hh, "null weight pointer in layer %d dir %d", l, dir);
+      LAS_CUDA_OK(cudaMemcpyAsync(pk.wcat[l] + dir * 4 * H * K, s.w_ih, sizeof(float) * 4 * H * K, cudaMemcpyDeviceToDevice, st));
+      LAS_CUDA_OK(cudaMemcpyAsync(pk.whh[l] + dir * 4 * H * H, s.w_hh, sizeof(float) * 4 * H * H, cudaMemcpyDeviceToDevice, st));
+      bias_sum_kernel<<<(unsigned)((4 * H + 255) / 256), 256, 0, st>>>(pk.bias[l] + dir * 4 * H, s.b_ih, s.b_hh, (int)(4 * H));
+      LAS_LAUNCH_OK("bias_sum_kernel");
+    }
+  }
+  return LAS_OK;
+}
+
+size_t las_listener_workspace_bytes(const las_listener_dims* d, int mode) {
+  if (listener_check(d) != LAS_OK) return 0;
+  if (mode == LAS_MODE_BF16) return fast_listener_workspace_bytes(d);
+  return listener_ws_layout_f32(d, nullptr).bytes;
+}
+
+int las_listener_forward(const float* x, const void* packed, const las_listener_dims* d, int mode, float* enc,
+                         void* workspace, size_t workspace_bytes, void* stream) {
+  LAS_TRY(listener_check(d));
+  LAS_REQUIRE(x && packed && enc && workspace, "null pointer argument");
+  LAS_REQUIRE(mode == LAS_MODE_FP32 || mode == LAS_MODE_BF16, "unknown mode %d", mode);
+  LAS_TRY(device_ok());
+  if (workspace_bytes < las_listener_workspace_bytes(d, mode))
+    return fail(LAS_ENOMEM, "workspace too small: %zu < %zu", workspace_bytes, las_listener_workspace_bytes(d, mode));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (mode == LAS_MODE_BF16) return fast_listener_forward(x, packed, d, enc, workspace, st);
+  return listener_forward_f32(x, packed, d, enc, workspace, st);
+}
+
+// ---- speller -------------------------------------------------------------------------------------------
+size_t las_speller_packed_bytes(const las_speller_dims* d, int mode) {
+  if (speller_check(d) != LAS_OK) return 0;
+  // the bf16 pack keeps the fp32 block first (phi/psi/cd and fallbacks read it), then its own layouts
+  const size_t f32 = speller_pack_layout_f32(d, nullptr).bytes;
+  if (mode == LAS_MODE_BF16) return f32 + fast_speller_packed_bytes(d);
+  return f32;
+}
+
+int las_speller_pack(const las_speller_weights* w, const las_speller_dims* d, int mode, void* packed, size_t packed_bytes,
+                     void* stream) {
+  LAS_TRY(speller_check(d));
+  LAS_REQUIRE(w && packed && w->rnn_host, "null weights / packed buffer");
+  LAS_REQUIRE(mode == LAS_MODE_FP32 || mode == LAS_MODE_BF16, "unknown mode %d", mode);
+  LAS_REQUIRE(w->w_phi && w->b_phi && w->w_psi && w->b_psi && w->w_cd && w->b_cd, "null attention / output weight pointer");
+  LAS_TRY(device_ok());
+  if (packed_bytes < las_speller_packed_bytes(d, mode))
+    return fail(LAS_ENOMEM, "packed buffer too small: %zu < %zu", packed_bytes, las_speller_packed_bytes(d, mode));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const SpellerPackF32 pk = speller_pack_layout_f32(d, packed);
+  const size_t G = 4 * (size_t)d->Hs;
+#define CP(dst, src, n) LAS_CUDA_OK(cudaMemcpyAsync(dst, src, sizeof(float) * (n), cudaMemcpyDeviceToDevice, st))
+  for (int l = 0; l < d->sl; ++l) {
+    const las_lstm_weights& s = w->rnn_host[l];
+    LAS_REQUIRE(s.w_ih && s.w_hh && s.b_ih && s.b_hh, "null weight pointer in speller layer %d", l);
+    const size_t Kx = (l == 0) ? (size_t)d->V + d->E : (size_t)d->Hs;
+    CP(pk.w_ih[l], s.w_ih, G * Kx);
+    CP(pk.w_hh[l], s.w_hh, G * d->Hs);
+    CP(pk.b_ih[l], s.b_ih, G);
+    CP(pk.b_hh[l], s.b_hh, G);
+  }
+  CP(pk.w_phi, w->w_phi, (size_t)d->D * d->Hs);
+  CP(pk.b_phi, w->b_phi, d->D);
+  CP(pk.w_psi, w->w_psi, (size_t)d->D * d->E);
+  CP(pk.b_psi, w->b_psi, d->D);
+  CP(pk.w_cd, w->w_cd, (size_t)d->V * (d->Hs + d->E));
+  CP(pk.b_cd, w->b_cd, d->V);
+#undef CP
+  if (mode == LAS_MODE_BF16) return fast_speller_pack(w, d, static_cast<char*>(packed) + pk.bytes, st);
+  return LAS_OK;
+}
+
+int las_psi_precompute(const float* enc, const float* w_psi, const float* b_psi, int B, int U, int E, int D, int relu,
+                       float* psi, void* stream) {
+  LAS_REQUIRE(enc && w_psi && b_psi && psi, "null pointer argument");
+  LAS_REQUIRE(B > 0 && U > 0 && E > 0 && D > 0, "bad dims (B=%d U=%d E=%d D=%d)", B, U, E, D);
+  LAS_TRY(device_ok());
+  return launch_sgemm_nt_bias(enc, E, w_psi, E, b_psi, psi, D, B * U, D, E, relu != 0, static_cast<cudaStream_t>(stream));
+}
+
+int las_attention_forward(const float* state, const float* enc, const float* psi, const float* w_phi, const float* b_phi,
+                          int B, int U, int E, int Hs, int D, int relu, const int32_t* enc_lengths, float* score,
+                          float* context, void* stream) {
+  LAS_REQUIRE(state && enc && psi && context, "null pointer argument");
+  LAS_REQUIRE(B > 0 && U > 0 && E > 0 && Hs > 0 && D > 0, "bad dims (B=%d U=%d E=%d Hs=%d D=%d)", B, U, E, Hs, D);
+  LAS_REQUIRE(w_phi ? (b_phi != nullptr) : (D == Hs), "without phi the query is the decoder state itself: D (%d) must equal Hs (%d)", D, Hs);
+  LAS_TRY(device_ok());
+  AttendArgs t;
+  memset(&t, 0, sizeof(t));
+  t.state = state; t.state_ld = Hs;
+  t.enc = enc; t.psi = psi;
+  t.w_phi = w_phi; t.b_phi = b_phi;
+  t.enc_lengths = enc_lengths;
+  t.B = B; t.U = U; t.E = E; t.Hs = Hs; t.V = 0; t.D = D;
+  t.relu = relu;
+  t.score_out = score;
+  t.ctx_out = context; t.ctx_ld = E;
+  return launch_attend_f32(t, static_cast<cudaStream_t>(stream));
+}
+
+size_t las_speller_workspace_bytes(const las_speller_dims* d, int steps, int mode) {
+  if (speller_check(d) != LAS_OK || steps < 0) return 0;
+  const size_t f32 = speller_ws_layout_f32(d, nullptr).bytes;
+  if (mode == LAS_MODE_BF16) return f32 + fast_speller_workspace_bytes(d, steps);
+  return f32;
+}
+
+int las_speller_decode(const las_decode_io* io, const void* packed, const las_speller_dims* d, int steps, int decode_mode,
+                       int mode, int relu, void* workspace, size_t workspace_bytes, void* stream) {
+  LAS_TRY(speller_check(d));
+  LAS_REQUIRE(io && packed && workspace, "null pointer argument");
+  LAS_REQUIRE(io->enc && io->logp, "io->enc and io->logp are required");
+  LAS_REQUIRE(steps >= 0, "steps must be >= 0");
+  LAS_REQUIRE(mode == LAS_MODE_FP32 || mode == LAS_MODE_BF16, "unknown mode %d", mode);
+  LAS_REQUIRE(decode_mode == LAS_DECODE_RAW || decode_mode == LAS_DECODE_GREEDY,
+              "decode_mode %d is not supported on the device path (0 = raw, 1 = greedy)", decode_mode);
+  LAS_REQUIRE(!(io->gt_dense || io->gt_index) || io->gt_steps >= steps, "ground truth has %d steps, %d requested", io->gt_steps, steps);
+  LAS_REQUIRE((io->h_state == nullptr) == (io->c_state == nullptr), "h_state and c_state must be given together");
+  LAS_REQUIRE((io->word == nullptr) == (io->context == nullptr), "word and context must be given together");
+  LAS_TRY(device_ok());
+  if (workspace_bytes < las_speller_workspace_bytes(d, steps, mode))
+    return fail(LAS_ENOMEM, "workspace too small: %zu < %zu", workspace_bytes, las_speller_workspace_bytes(d, steps, mode));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (steps == 0) return LAS_OK;
+  if (mode == LAS_MODE_BF16) {
+    const size_t f32p = speller_pack_layout_f32(d, nullptr).bytes;
+    const size_t f32w = speller_ws_layout_f32(d, nullptr).bytes;
+    return fast_speller_decode(io, packed, static_cast<const char*>(packed) + f32p, d, steps, decode_mode, relu, workspace,
+                               static_cast<char*>(workspace) + f32w, st);
+  }
+  return speller_decode_f32(io, packed, d, steps, decode_mode, relu, workspace, st);
+}
+
+int las_nll_sums(const float* logp, const int32_t* labels, int S, int S_lab, int B, int V, int max_label_len, float* out2,
+                 void* stream) {
+  LAS_REQUIRE(logp && labels && out2, "null pointer argument");
+  LAS_REQUIRE(S > 0 && S_lab > 0 && B > 0 && V > 0, "bad dims");
+  LAS_TRY(device_ok());
+  return launch_nll_sums(logp, labels, S, S_lab, B, V, max_label_len, out2, static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

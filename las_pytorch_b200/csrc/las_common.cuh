@@ -1,0 +1,88 @@
+// Shared host/device helpers for the LAS B200 library (internal; the public surface is include/las_b200.h).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+
+#include "las_b200.h"
+
+namespace las {
+
+// ---- error plumbing: thread-local message, integer status (never abort) -------------------------------
+char* err_buf();
+int fail(int code, const char* fmt, ...);
+void count_launch(int n = 1);
+
+#define LAS_CUDA_OK(expr)                                                                       \
+  do {                                                                                          \
+    cudaError_t _e = (expr);                                                                    \
+    if (_e != cudaSuccess)                                                                      \
+      return ::las::fail(LAS_ECUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+  } while (0)
+
+#define LAS_LAUNCH_OK(name)                                                                     \
+  do {                                                                                          \
+    cudaError_t _e = cudaGetLastError();                                                        \
+    if (_e != cudaSuccess)                                                                      \
+      return ::las::fail(LAS_ECUDA, "launch of %s failed: %s (%s:%d)", name, cudaGetErrorString(_e), __FILE__, __LINE__); \
+    ::las::count_launch();                                                                      \
+  } while (0)
+
+#define LAS_REQUIRE(cond, ...)                                 \
+  do {                                                         \
+    if (!(cond)) return ::las::fail(LAS_EINVAL, __VA_ARGS__);  \
+  } while (0)
+
+#define LAS_TRY(expr)            \
+  do {                           \
+    int _s = (expr);             \
+    if (_s != LAS_OK) return _s; \
+  } while (0)
+
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// Carves sub-buffers out of one caller-provided allocation (256-byte aligned pieces).
+struct Carver {
+  char* base;
+  size_t off = 0;
+  explicit Carver(void* p) : base(static_cast<char*>(p)) {}
+  template <typename T>
+  T* take(size_t n) {
+    off = align_up(off, 256);
+    T* p = base ? reinterpret_cast<T*>(base + off) : nullptr;
+    off += n * sizeof(T);
+    return p;
+  }
+  size_t total() const { return align_up(off, 256); }
+};
+
+int sm_count();  // cached per device
+
+// ---- optional per-phase device timing (bench.py roofline): cudaEvent pairs around named launch groups ----
+// Disabled by default (zero overhead beyond one thread-local load).  las_prof_enable(1) turns it on for the
+// calling thread; las_prof_report() synchronises the recorded events and formats "name ms launches" lines.
+struct ProfScope {
+  int slot = -1;
+  cudaStream_t st;
+  ProfScope(const char* name, cudaStream_t stream);
+  ~ProfScope();
+};
+
+// ---- device math ---------------------------------------------------------------------------------------
+__device__ __forceinline__ float sigmoid_precise(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+}  // namespace las

@@ -1,0 +1,22 @@
+// LAS_MODE_BF16 path: tcgen05 / cluster / persistent kernels (fast_*.cu).  Internal interface used by las_api.cu.
+#pragma once
+#include "las_common.cuh"
+
+namespace las {
+
+bool fast_available();
+
+size_t fast_listener_packed_bytes(const las_listener_dims* d);
+int fast_listener_pack(const las_lstm_weights* w_host, const las_listener_dims* d, void* packed, cudaStream_t st);
+size_t fast_listener_workspace_bytes(const las_listener_dims* d);
+int fast_listener_forward(const float* x, const void* packed, const las_listener_dims* d, float* enc, void* ws,
+                          cudaStream_t st);
+
+size_t fast_speller_packed_bytes(const las_speller_dims* d);
+int fast_speller_pack(const las_speller_weights* w, const las_speller_dims* d, void* packed_fast, cudaStream_t st);
+size_t fast_speller_workspace_bytes(const las_speller_dims* d, int steps);
+int fast_speller_decode(const las_decode_io* io, const void* packed_f32, const void* packed_fast,
+                        const las_speller_dims* d, int steps, int decode_mode, int relu, void* ws_f32, void* ws_fast,
+                        cudaStream_t st);
+
+}  // namespace las

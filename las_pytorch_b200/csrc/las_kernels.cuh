@@ -1,0 +1,68 @@
+// Internal launch-function declarations shared between translation units.
+#pragma once
+#include "las_common.cuh"
+
+namespace las {
+
+// ---- fp32 (LAS_MODE_FP32) kernels: kernels_f32.cu ------------------------------------------------------
+
+// C[M,N] = act(A[M,K] . W[N,K]^T + bias[N]);  A row stride lda, W row stride ldw, C row stride ldc.
+int launch_sgemm_nt_bias(const float* A, int lda, const float* W, int ldw, const float* bias, float* C, int ldc,
+                         int M, int N, int K, bool relu, cudaStream_t st);
+
+// One LSTM cell update for a batch: pre = [x . W_ih^T] + [h_prev . W_hh^T] + [pre_add] + [b_ih + b_hh].
+struct CellArgs {
+  const float* x;       // nullable, [B, Kx] row stride x_ld
+  int x_ld, Kx;
+  const float* w_ih;    // [4H, Kx]
+  const float* h_prev;  // nullable (== zeros), [B, H] row stride h_ld
+  long long h_ld;
+  const float* w_hh;    // [4H, H]
+  const float* pre_add; // nullable, [B, 4H] row stride pre_ld (already contains the biases)
+  long long pre_ld;
+  const float* b_ih;    // nullable
+  const float* b_hh;    // nullable
+  float* c;             // [B, H] in/out, dense
+  float* h_out;         // [B, H] row stride hout_ld
+  long long hout_ld;
+};
+int launch_lstm_cell_f32(const CellArgs* args, int ndir, int B, int H, cudaStream_t st);
+
+struct AttendArgs {
+  const float* state;   // [B, Hs] row stride state_ld : top-layer decoder state
+  int state_ld;
+  const float* enc;     // [B, U, E]
+  const float* psi;     // [B, U, D]
+  const float* w_phi;   // [D, Hs]
+  const float* b_phi;
+  const float* w_cd;    // [V, Hs+E]   (nullable => attention only)
+  const float* b_cd;
+  const int32_t* enc_lengths;  // nullable
+  int B, U, E, Hs, V, D;
+  int relu;
+  // outputs
+  float* score_out;     // nullable, [B, U]
+  float* ctx_out;       // [B, E] row stride ctx_ld
+  int ctx_ld;
+  float* logp_out;      // [B, V]     (when w_cd)
+  int32_t* token_out;   // nullable [B]
+  // next-step input word (when w_cd): one of gt_dense row / gt_index / greedy / raw
+  float* word_out;      // nullable [B, V] row stride word_ld
+  int word_ld;
+  const float* gt_dense_step;   // nullable [B, V] row stride gt_ld (already offset to this step)
+  long long gt_ld;
+  const int32_t* gt_index_step; // nullable [B] stride gt_index_ld
+  int gt_index_ld;
+  int decode_mode;
+};
+int launch_attend_f32(const AttendArgs& a, cudaStream_t st);
+
+// xin[b, 0:V] = onehot(0), xin[b, V:V+E] = enc[b, 0, :]   (model/las_model.py:193-198)
+int launch_speller_init(float* xin, int xin_ld, const float* enc, int B, int U, int E, int V, cudaStream_t st);
+// strided 2-D copy of fp32 rows
+int launch_copy2d(float* dst, long long dst_ld, const float* src, long long src_ld, int rows, int cols, cudaStream_t st);
+
+int launch_nll_sums(const float* logp, const int32_t* labels, int S, int S_lab, int B, int V, int max_label_len,
+                    float* out2, cudaStream_t st);
+
+}  // namespace las

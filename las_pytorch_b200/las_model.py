@@ -1,0 +1,420 @@
+"""Host-side mirror of the reference's `model/las_model.py` for the forward hot path.
+
+Same class names, constructor arguments, `forward` signatures, return structures and `state_dict` layout as
+/root/reference/model/las_model.py (LAS :24-63, pBLSTMLayer :66-91, Listener :96-134, Speller :138-238,
+Attention :249-318); the arithmetic is done by the sm_100a kernels behind the C ABI (include/las_b200.h).
+torch is used only for device memory, the current stream and parameter storage.
+
+Extra keyword accepted everywhere the reference swallows **kwargs: `precision` = "fp32" | "bf16"
+(LAS_MODE_FP32 / LAS_MODE_BF16; default from $LAS_B200_PRECISION, else "fp32").
+
+Not on this path (raise NotImplementedError instead of silently running something else): GRU/RNN cells,
+multi_head > 1, decode_mode 2 (sampling), training/backward.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import _cabi
+from ._cabi import DecodeIO, ListenerDims, LstmWeights, SpellerDims, SpellerWeights, check, current_stream_ptr, ptr
+from .params import LinearWeights, LSTMWeights
+
+_MODES = {"fp32": _cabi.MODE_FP32, "bf16": _cabi.MODE_BF16}
+
+
+def _default_precision():
+    return os.environ.get("LAS_B200_PRECISION", "fp32")
+
+
+def _mode_of(precision):
+    if precision not in _MODES:
+        raise ValueError(f"precision must be one of {sorted(_MODES)}, got {precision!r}")
+    return _MODES[precision]
+
+
+def _require_cuda(t, what):
+    if not t.is_cuda:
+        raise RuntimeError(
+            f"{what} is on {t.device}: las_pytorch_b200 runs on a B200 (sm_100a) only and has no CPU fallback"
+        )
+
+
+def _f32c(t):
+    return t.detach().to(torch.float32).contiguous()
+
+
+class _Cache:
+    """Packed-weight / workspace cache keyed on (device, mode, parameter versions and storage)."""
+
+    def __init__(self):
+        self.packed = {}
+        self.work = {}
+
+    @staticmethod
+    def params_key(params, mode):
+        return (mode,) + tuple((p.data_ptr(), p._version, str(p.device)) for p in params)
+
+    def workspace(self, key, nbytes, device):
+        buf = self.work.get(key)
+        if buf is None or buf.numel() < nbytes:
+            buf = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+            self.work[key] = buf
+        return buf
+
+
+def _lstm_weight_array(holder, layers, directions):
+    """Host array of las_lstm_weights (device pointers) + the tensors kept alive."""
+    arr = (LstmWeights * (layers * directions))()
+    keep = []
+    for l in range(layers):
+        for d in range(directions):
+            sfx = "_reverse" if d == 1 else ""
+            ts = [_f32c(getattr(holder, f"{n}_l{l}{sfx}")) for n in ("weight_ih", "weight_hh", "bias_ih", "bias_hh")]
+            keep.extend(ts)
+            e = arr[l * directions + d]
+            e.w_ih, e.w_hh, e.b_ih, e.b_hh = (t.data_ptr() for t in ts)
+    return arr, keep
+
+
+def _run_listener(x, holders, input_feature_dim, hidden_size, mode, cache):
+    """x [B,T,F] -> [B, T/2^L, 2H] through `len(holders)` pyramid layers."""
+    _require_cuda(x, "input_x")
+    lib = _cabi.load_library()
+    x = _f32c(x)
+    b, t, f = x.shape
+    if f != input_feature_dim:
+        raise RuntimeError(f"input feature dim {f} != {input_feature_dim}")
+    nl = len(holders)
+    dims = ListenerDims(b, t, f, hidden_size, nl)
+    if t % (1 << nl) != 0:
+        # the reference fails inside `view` (model/las_model.py:87) with a RuntimeError; so do we
+        raise RuntimeError(
+            f"shape '[{b}, {t >> 1}, {f * 2}]' is invalid: timestep {t} is not divisible by 2^{nl} "
+            "(model/las_model.py:86-87 halves the time axis in every layer)"
+        )
+    with torch.cuda.device(x.device):
+        st = current_stream_ptr(x.device)
+        params = [p for h in holders for p in h.parameters()]
+        key = _Cache.params_key(params, mode)
+        packed = cache.packed.get(key)
+        if packed is None:
+            cache.packed.clear()
+            arr = (LstmWeights * (2 * nl))()
+            keep = []
+            for l, h in enumerate(holders):
+                a1, k1 = _lstm_weight_array(h, 1, 2)
+                keep.extend(k1)
+                for d in range(2):
+                    arr[2 * l + d] = a1[d]
+            nbytes = lib.las_listener_packed_bytes(C.byref(dims), mode)
+            packed = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=x.device)
+            check(lib.las_listener_pack(arr, C.byref(dims), mode, ptr(packed), packed.numel(), st))
+            cache.packed[key] = packed
+            del keep
+        ws_bytes = lib.las_listener_workspace_bytes(C.byref(dims), mode)
+        ws = cache.workspace(("listener", x.device, mode), ws_bytes, x.device)
+        enc = torch.empty(b, t >> nl, 2 * hidden_size, dtype=torch.float32, device=x.device)
+        check(lib.las_listener_forward(ptr(x), ptr(packed), C.byref(dims), mode, ptr(enc), ptr(ws), ws.numel(), st))
+    return enc
+
+
+class LAS(nn.Module):
+    """model/las_model.py:24-63."""
+
+    def __init__(self, listener, speller):
+        super().__init__()
+        self.listener = listener
+        self.speller = speller
+
+    def forward(self, batch_data, batch_label, teacher_force_rate, is_training=True):
+        listener_feature = self.listener(batch_data)
+        if is_training:
+            raw_pred_seq, attention_record = self.speller(
+                listener_feature, ground_truth=batch_label, teacher_force_rate=teacher_force_rate
+            )
+        else:
+            raw_pred_seq, attention_record = self.speller(listener_feature, ground_truth=None, teacher_force_rate=0)
+        return raw_pred_seq, attention_record
+
+    def serialize(self, optimizer, epoch, tr_loss, val_loss):
+        """Checkpoint package with the reference's keys (model/las_model.py:42-63; "etype" is written twice
+        there, the speller's value wins -- reproduced)."""
+        package = {
+            "einput": self.listener.input_feature_dim,
+            "ehidden": self.listener.hidden_size,
+            "elayer": self.listener.num_layers,
+            "edropout": self.listener.dropout_rate,
+            "dvocab_size": self.speller.label_dim,
+            "dhidden": self.speller.hidden_size,
+            "dlayer": self.speller.num_layers,
+            "etype": self.speller.rnn_unit,
+            "state_dict": self.state_dict(),
+            "optim_dict": optimizer.state_dict() if optimizer is not None else None,
+            "epoch": epoch,
+        }
+        if tr_loss is not None:
+            package["tr_loss"] = tr_loss
+            package["val_loss"] = val_loss
+        return package
+
+
+def _check_unit(rnn_unit):
+    if str(rnn_unit).upper() != "LSTM":
+        raise NotImplementedError(
+            f"rnn_unit={rnn_unit!r}: only LSTM cells are implemented on the B200 path (SURVEY.md section 8 row f4)"
+        )
+
+
+class pBLSTMLayer(nn.Module):
+    """model/las_model.py:66-91: halve the time axis by pairing frames, then a bidirectional LSTM."""
+
+    def __init__(self, input_feature_dim, hidden_dim, rnn_unit="LSTM", dropout_rate=0.0, precision=None):
+        super().__init__()
+        _check_unit(rnn_unit)
+        self.rnn_unit = nn.LSTM  # the reference stores the class here (:69)
+        self.input_feature_dim = input_feature_dim
+        self.hidden_dim = hidden_dim
+        self.precision = precision or _default_precision()
+        # same parameter names as nn.LSTM(input_feature_dim*2, hidden_dim, 1, bidirectional=True) (:72-79)
+        self.BLSTM = LSTMWeights(input_feature_dim * 2, hidden_dim, 1, bidirectional=True)
+        self._cache = _Cache()
+
+    def forward(self, input_x):
+        out = _run_listener(input_x, [self.BLSTM], self.input_feature_dim, self.hidden_dim, _mode_of(self.precision), self._cache)
+        h = self.hidden_dim
+        h_n = torch.stack([out[:, -1, :h], out[:, 0, h:]])  # final hidden of each direction
+        return out, (h_n, None)
+
+
+class Listener(nn.Module):
+    """model/las_model.py:96-134: stack of `num_layers` pBLSTM layers, [B,T,F] -> [B, T/2^L, 2H]."""
+
+    def __init__(self, input_feature_dim, hidden_size, num_layers, rnn_unit, use_gpu=True, dropout_rate=0.0, **kwargs):
+        super().__init__()
+        _check_unit(rnn_unit)
+        self.input_feature_dim = input_feature_dim
+        self.hidden_size = hidden_size
+        self.num_layers = num_layers
+        self.rnn_unit = rnn_unit
+        self.dropout_rate = dropout_rate
+        self.precision = kwargs.get("precision") or _default_precision()
+        assert self.num_layers >= 1, "Listener should have at least 1 layer"
+        self.pLSTM_layer0 = pBLSTMLayer(input_feature_dim, hidden_size, rnn_unit=rnn_unit, dropout_rate=dropout_rate)
+        for i in range(1, self.num_layers):
+            setattr(self, "pLSTM_layer" + str(i), pBLSTMLayer(hidden_size * 2, hidden_size, rnn_unit=rnn_unit, dropout_rate=dropout_rate))
+        self._cache = _Cache()
+
+    def forward(self, input_x):
+        holders = [getattr(self, "pLSTM_layer" + str(i)).BLSTM for i in range(self.num_layers)]
+        return _run_listener(input_x, holders, self.input_feature_dim, self.hidden_size, _mode_of(self.precision), self._cache)
+
+
+class Attention(nn.Module):
+    """model/las_model.py:249-318 (single head, 'dot')."""
+
+    def __init__(self, mlp_preprocess_input, preprocess_mlp_dim, activate, mode="dot", input_feature_dim=512, multi_head=1):
+        super().__init__()
+        self.mode = mode.lower()
+        self.mlp_preprocess_input = mlp_preprocess_input
+        self.multi_head = multi_head
+        self.input_feature_dim = input_feature_dim
+        if multi_head != 1:
+            raise NotImplementedError("multi_head > 1 is not implemented on the B200 path (SURVEY.md section 8 row f4)")
+        if self.mode != "dot":
+            raise NotImplementedError("only 'dot' attention exists in the reference (model/las_model.py:315-317)")
+        if mlp_preprocess_input:
+            self.preprocess_mlp_dim = preprocess_mlp_dim
+            self.phi = LinearWeights(input_feature_dim, preprocess_mlp_dim * multi_head)
+            self.psi = LinearWeights(input_feature_dim, preprocess_mlp_dim)
+            if activate != "None":
+                if activate != "relu":
+                    raise NotImplementedError(f"mlp_activate_in_attention={activate!r}: only 'relu' and 'None' are implemented")
+                self.activate = "relu"
+            else:
+                self.activate = None
+
+    @property
+    def relu_flag(self):
+        return 1 if (self.mlp_preprocess_input and self.activate) else 0
+
+    @property
+    def mlp_dim(self):
+        return self.preprocess_mlp_dim if self.mlp_preprocess_input else self.input_feature_dim
+
+    def project_listener_feature(self, listener_feature):
+        """psi(listener_feature) with activation -- the step-invariant half of :276-285, computed once."""
+        enc = _f32c(listener_feature)
+        if not self.mlp_preprocess_input:
+            return enc
+        _require_cuda(enc, "listener_feature")
+        lib = _cabi.load_library()
+        b, u, e = enc.shape
+        d = self.preprocess_mlp_dim
+        psi = torch.empty(b, u, d, dtype=torch.float32, device=enc.device)
+        with torch.cuda.device(enc.device):
+            w, bias = _f32c(self.psi.weight), _f32c(self.psi.bias)
+            check(lib.las_psi_precompute(ptr(enc), ptr(w), ptr(bias), b, u, e, d, self.relu_flag, ptr(psi), current_stream_ptr(enc.device)))
+        return psi
+
+    def forward(self, decoder_state, listener_feature):
+        _require_cuda(listener_feature, "listener_feature")
+        lib = _cabi.load_library()
+        enc = _f32c(listener_feature)
+        state = _f32c(decoder_state).reshape(decoder_state.size(0), -1)
+        b, u, e = enc.shape
+        hs = state.size(1)
+        psi = self.project_listener_feature(enc)
+        score = torch.empty(b, u, dtype=torch.float32, device=enc.device)
+        context = torch.empty(b, e, dtype=torch.float32, device=enc.device)
+        with torch.cuda.device(enc.device):
+            if self.mlp_preprocess_input:
+                w, bias = _f32c(self.phi.weight), _f32c(self.phi.bias)
+            else:
+                w = bias = None
+            check(lib.las_attention_forward(ptr(state), ptr(enc), ptr(psi), ptr(w), ptr(bias), b, u, e, hs, self.mlp_dim,
+                                            self.relu_flag, None, ptr(score), ptr(context), current_stream_ptr(enc.device)))
+        return [score], context
+
+
+class Speller(nn.Module):
+    """model/las_model.py:138-238: attention decoder; the whole step loop runs on the device."""
+
+    def __init__(self, vocab_size, hidden_size, rnn_unit, num_layers, max_label_len, use_mlp_in_attention,
+                 mlp_dim_in_attention, mlp_activate_in_attention, listener_hidden_size, multi_head, decode_mode,
+                 use_gpu=True, **kwargs):
+        super().__init__()
+        _check_unit(rnn_unit)
+        self.rnn_unit = nn.LSTM  # the reference stores the class (:156); serialize() writes it under "etype"
+        self.hidden_size = hidden_size
+        self.num_layers = num_layers
+        self.max_label_len = max_label_len
+        self.decode_mode = decode_mode
+        self.use_gpu = use_gpu
+        self.float_type = torch.cuda.FloatTensor if use_gpu else torch.FloatTensor
+        self.label_dim = vocab_size
+        self.precision = kwargs.get("precision") or _default_precision()
+        if decode_mode not in (0, 1):
+            raise NotImplementedError("decode_mode 2 (sampling, model/las_model.py:229-234) is not implemented on the B200 path")
+        if not use_mlp_in_attention:
+            raise NotImplementedError("use_mlp_in_attention=False is only available through the standalone Attention module")
+        if hidden_size != 2 * listener_hidden_size:
+            raise ValueError(
+                f"hidden_size ({hidden_size}) must equal 2*listener_hidden_size ({2 * listener_hidden_size}): the rnn input is "
+                "[one-hot || encoder feature] (model/las_model.py:165,198)"
+            )
+        self.rnn_layer = LSTMWeights(vocab_size + hidden_size, hidden_size, num_layers=num_layers)
+        self.attention = Attention(
+            mlp_preprocess_input=use_mlp_in_attention,
+            preprocess_mlp_dim=mlp_dim_in_attention,
+            activate=mlp_activate_in_attention,
+            input_feature_dim=2 * listener_hidden_size,
+            multi_head=multi_head,
+        )
+        self.character_distribution = LinearWeights(hidden_size * 2, vocab_size)
+        self._cache = _Cache()
+
+    # ---- device plumbing -------------------------------------------------------------------------------
+    def _dims(self, b, u, e):
+        return SpellerDims(b, u, e, self.hidden_size, self.num_layers, self.label_dim, self.attention.preprocess_mlp_dim)
+
+    def _packed(self, lib, dims, mode, device, st):
+        params = list(self.parameters())
+        key = _Cache.params_key(params, mode)
+        packed = self._cache.packed.get(key)
+        if packed is None:
+            self._cache.packed.clear()
+            arr, keep = _lstm_weight_array(self.rnn_layer, self.num_layers, 1)
+            at, cd = self.attention, self.character_distribution
+            ts = [_f32c(t) for t in (at.phi.weight, at.phi.bias, at.psi.weight, at.psi.bias, cd.weight, cd.bias)]
+            w = SpellerWeights()
+            w.rnn_host = C.cast(arr, C.POINTER(LstmWeights))
+            w.w_phi, w.b_phi, w.w_psi, w.b_psi, w.w_cd, w.b_cd = (t.data_ptr() for t in ts)
+            nbytes = lib.las_speller_packed_bytes(C.byref(dims), mode)
+            packed = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=device)
+            check(lib.las_speller_pack(C.byref(w), C.byref(dims), mode, ptr(packed), packed.numel(), st))
+            self._cache.packed[key] = packed
+            del keep, ts
+        return packed
+
+    def _decode(self, enc, steps, gt_dense=None, gt_index=None, state=None, word=None, context=None, enc_lengths=None,
+                want_attn=True):
+        """Runs `steps` decoder steps.  Returns (logp [S,B,V], attn [S,B,U] | None, tokens [S,B])."""
+        _require_cuda(enc, "listener_feature")
+        lib = _cabi.load_library()
+        enc = _f32c(enc)
+        b, u, e = enc.shape
+        mode = _mode_of(self.precision)
+        dims = self._dims(b, u, e)
+        dev = enc.device
+        with torch.cuda.device(dev):
+            st = current_stream_ptr(dev)
+            packed = self._packed(lib, dims, mode, dev, st)
+            ws_bytes = lib.las_speller_workspace_bytes(C.byref(dims), steps, mode)
+            ws = self._cache.workspace(("speller", dev, mode), ws_bytes, dev)
+            logp = torch.empty(steps, b, self.label_dim, dtype=torch.float32, device=dev)
+            attn = torch.empty(steps, b, u, dtype=torch.float32, device=dev) if want_attn else None
+            tokens = torch.empty(steps, b, dtype=torch.int32, device=dev)
+            io = DecodeIO()
+            io.enc = enc.data_ptr()
+            io.psi = None
+            io.gt_steps = 0
+            if gt_dense is not None:
+                io.gt_dense = gt_dense.data_ptr()
+                io.gt_steps = gt_dense.size(1)
+            if gt_index is not None:
+                io.gt_index = gt_index.data_ptr()
+                io.gt_steps = gt_index.size(1)
+            if enc_lengths is not None:
+                io.enc_lengths = enc_lengths.data_ptr()
+            if state is not None:
+                io.h_state, io.c_state = state[0].data_ptr(), state[1].data_ptr()
+            if word is not None:
+                io.word, io.context = word.data_ptr(), context.data_ptr()
+            io.logp = logp.data_ptr()
+            io.attn = attn.data_ptr() if attn is not None else None
+            io.tokens = tokens.data_ptr()
+            check(lib.las_speller_decode(C.byref(io), ptr(packed), C.byref(dims), steps, int(self.decode_mode), mode,
+                                         self.attention.relu_flag, ptr(ws), ws.numel(), st))
+        return logp, attn, tokens
+
+    # ---- reference API ---------------------------------------------------------------------------------
+    def forward_step(self, input_word, last_hidden_state, listener_feature):
+        """One decoder step (model/las_model.py:178-184).  input_word [B,1,V+E]; last_hidden_state (h,c) or None."""
+        b = input_word.size(0)
+        v = self.label_dim
+        flat = _f32c(input_word).reshape(b, -1)
+        word = flat[:, :v].contiguous()
+        context = flat[:, v:].contiguous()
+        if last_hidden_state is None:
+            h = torch.zeros(self.num_layers, b, self.hidden_size, dtype=torch.float32, device=flat.device)
+            c = torch.zeros_like(h)
+        else:
+            h, c = (_f32c(t).clone() for t in last_hidden_state)
+        logp, attn, _ = self._decode(listener_feature, 1, state=(h, c), word=word, context=context)
+        return logp[0], (h, c), context, [attn[0]]
+
+    def forward(self, listener_feature, ground_truth=None, teacher_force_rate=0.9, enc_lengths=None):
+        if ground_truth is None:
+            teacher_force_rate = 0
+        # one draw from numpy's global RNG per call, exactly like the reference (:189)
+        teacher_force = True if np.random.random_sample() < teacher_force_rate else False
+
+        gt_dense = None
+        if (ground_truth is None) or (not teacher_force):
+            max_step = self.max_label_len
+        else:
+            max_step = ground_truth.size()[1]
+            # `.type(self.float_type)` in the reference (:217): the label tensor is consumed as dense floats
+            gt_dense = ground_truth.to(device=listener_feature.device, dtype=torch.float32).contiguous()
+        if enc_lengths is not None:
+            enc_lengths = enc_lengths.to(device=listener_feature.device, dtype=torch.int32).contiguous()
+        logp, attn, tokens = self._decode(listener_feature, max_step, gt_dense=gt_dense, enc_lengths=enc_lengths)
+        self.last_tokens = tokens  # [S,B] int32 argmax per step (device); not part of the reference API
+        raw_pred_seq = list(logp.unbind(0))
+        attention_record = [[a] for a in attn.unbind(0)]
+        return raw_pred_seq, attention_record

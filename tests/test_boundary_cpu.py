@@ -1,0 +1,120 @@
+"""Host-side boundary checks that need no GPU: ABI surface, state_dict layout, error behaviour."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+import las_testlib as tl
+import las_pytorch_b200 as lp
+from las_pytorch_b200 import _cabi
+
+
+def header_functions():
+    src = open(os.path.join(tl.ROOT, "include", "las_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(las_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _cabi.load_library()
+    names = header_functions()
+    assert len(names) >= 14
+    for n in names:
+        assert hasattr(lib, n), f"{n} is declared in include/las_b200.h but not exported by liblas_b200.so"
+    assert sorted(_cabi.PROTOTYPES) == names, "ctypes prototypes and header declarations differ"
+    assert lib.las_abi_version() == 1
+
+
+def test_size_queries_run_on_host():
+    lib = _cabi.load_library()
+    d = _cabi.ListenerDims(64, 1600, 40, 256, 3)
+    for mode in (_cabi.MODE_FP32,):
+        assert lib.las_listener_packed_bytes(ctypes.byref(d), mode) >= 4 * (2048 * 80 + 2 * 2048 * 1024 + 3 * 2048 * 256)
+        assert lib.las_listener_workspace_bytes(ctypes.byref(d), mode) >= 4 * 64 * 800 * 2048
+    bad = _cabi.ListenerDims(2, 62, 40, 16, 2)  # 62 is not divisible by 4
+    assert lib.las_listener_packed_bytes(ctypes.byref(bad), 0) == 0
+    assert b"not divisible" in lib.las_last_error()
+    s = _cabi.SpellerDims(64, 200, 512, 512, 2, 30, 64)
+    assert lib.las_speller_packed_bytes(ctypes.byref(s), 0) >= 4 * 4_260_000
+    bad_s = _cabi.SpellerDims(4, 10, 64, 48, 2, 30, 16)  # Hs != E
+    assert lib.las_speller_packed_bytes(ctypes.byref(bad_s), 0) == 0
+    assert b"must equal" in lib.las_last_error()
+
+
+@pytest.mark.parametrize("cfg,count", [("small", 2_004_126), ("paper", 10_303_646)])
+def test_state_dict_layout_matches_reference(cfg, count):
+    """key names, order within an LSTM, shapes and parameter counts."""
+    c = tl.CONFIGS[cfg]
+    las = tl.build_model(cfg, max_label_len=10)
+    sd = las.state_dict()
+    assert sum(v.numel() for v in sd.values()) == count
+    H, V, D = c["H"], c["V"], c["D"]
+    keys = list(sd)
+    assert keys[:8] == [f"listener.pLSTM_layer0.BLSTM.{n}" for n in (
+        "weight_ih_l0", "weight_hh_l0", "bias_ih_l0", "bias_hh_l0",
+        "weight_ih_l0_reverse", "weight_hh_l0_reverse", "bias_ih_l0_reverse", "bias_hh_l0_reverse")]
+    assert sd["listener.pLSTM_layer0.BLSTM.weight_ih_l0"].shape == (4 * H, 80)
+    assert sd["listener.pLSTM_layer1.BLSTM.weight_ih_l0_reverse"].shape == (4 * H, 4 * H)
+    assert sd["speller.rnn_layer.weight_ih_l0"].shape == (8 * H, V + 2 * H)
+    assert sd["speller.rnn_layer.weight_ih_l1"].shape == (8 * H, 2 * H)
+    assert sd["speller.attention.phi.weight"].shape == (D, 2 * H)
+    assert sd["speller.attention.psi.bias"].shape == (D,)
+    assert sd["speller.character_distribution.weight"].shape == (V, 4 * H)
+    assert all(v.dtype == torch.float32 for v in sd.values())
+
+
+def test_loads_reference_state_dict_strictly():
+    g = np.load(os.path.join(tl.GOLDEN_DIR, "tiny_tf_g3.npz"))
+    sd = {k[2:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("w:")}
+    las = tl.build_model("tiny", max_label_len=6, seed=1)
+    las.load_state_dict(sd, strict=True)
+    assert torch.equal(las.speller.rnn_layer.weight_hh_l1, sd["speller.rnn_layer.weight_hh_l1"])
+    pkg = las.serialize(None, epoch=3, tr_loss=1.0, val_loss=2.0)
+    assert set(pkg) == {"einput", "ehidden", "elayer", "edropout", "etype", "dvocab_size", "dhidden", "dlayer",
+                        "state_dict", "optim_dict", "epoch", "tr_loss", "val_loss"}
+    assert pkg["etype"] is torch.nn.LSTM and pkg["dvocab_size"] == 30
+
+
+def test_constructor_contract():
+    # kwargs splatted from the YAML are swallowed (model/las_model.py:105,153)
+    lis = lp.Listener(input_feature_dim=40, hidden_size=16, num_layers=2, rnn_unit="LSTM", use_gpu=True, dropout=0.0, bidirectional=True)
+    assert (lis.input_feature_dim, lis.hidden_size, lis.num_layers, lis.rnn_unit, lis.dropout_rate) == (40, 16, 2, "LSTM", 0.0)
+    sp = lp.Speller(30, 32, "LSTM", 2, 7, True, 16, "relu", 16, 1, 1, use_gpu=False, bidirectional=True)
+    assert (sp.label_dim, sp.hidden_size, sp.num_layers, sp.max_label_len, sp.decode_mode) == (30, 32, 2, 7, 1)
+    assert sp.float_type is torch.FloatTensor
+    with pytest.raises(AssertionError):
+        lp.Listener(40, 16, 0, "LSTM", True)
+    with pytest.raises(ValueError):
+        lp.Speller(30, 48, "LSTM", 2, 7, True, 16, "relu", 16, 1, 1)  # Hs != 2H
+    with pytest.raises(NotImplementedError):
+        lp.Listener(40, 16, 2, "GRU", True)
+
+
+def test_no_cpu_fallback_and_single_rng_draw():
+    las = tl.build_model("tiny", max_label_len=4)
+    x = torch.randn(2, 16, 40)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        las.listener(x)
+    enc = torch.randn(2, 4, 32)
+    np.random.seed(5)
+    expect = np.random.RandomState(5)
+    expect.random_sample()
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        las.speller(enc, ground_truth=None, teacher_force_rate=0.9)
+    # exactly one draw from numpy's global RNG per Speller.forward call (model/las_model.py:189)
+    assert np.random.random_sample() == expect.random_sample()
+
+
+def test_missing_library_fails_loudly(tmp_path):
+    with pytest.raises(_cabi.LasB200Error, match="no CPU fallback"):
+        _cabi.load_library(str(tmp_path / "nope.so"))
+
+
+def test_product_does_not_import_oracle():
+    for root, _, files in os.walk(os.path.join(tl.ROOT, "las_pytorch_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh")):
+                assert "oracle" not in open(os.path.join(root, f)).read(), f"{f} references oracle/"
