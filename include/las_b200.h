@@ -169,6 +169,16 @@ int las_speller_decode(const las_decode_io* io, const void* packed, const las_sp
 int las_nll_sums(const float* logp /*[S,B,V]*/, const int32_t* labels /*[B,S_lab]*/, int S, int S_lab, int B, int V,
                  int max_label_len, float* out2, void* stream);
 
+/* --------------------------------------------------------------------------------------------------------
+ * Test hooks (used by tests/ only): exercise single kernels through the same ABI.
+ * ------------------------------------------------------------------------------------------------------ */
+/* C[M,N] fp32 = A[M,K] . W[N,K]^T + bias[N]; A, W bf16 row-major device buffers (the tcgen05 input-projection GEMM). */
+int las_debug_gemm_bf16(const void* a_bf16, const void* w_bf16, const float* bias, float* c, int M, int N, int K, void* stream);
+/* One CTA: D[128,N] fp32 = A[128,K] . B[N,K]^T through shared-memory operands laid out by the library's UMMA
+ * layout helpers (a_sw128 / b_sw128: 0 = interleaved core matrices, 1 = 128-byte swizzle). */
+int las_debug_umma_probe(const void* a_bf16, const void* b_bf16, float* d, int N, int K, int a_sw128, int b_sw128, int variant,
+                         void* stream);
+
 #ifdef __cplusplus
 }
 #endif

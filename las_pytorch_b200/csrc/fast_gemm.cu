@@ -1,0 +1,304 @@
+// Listener input projection on the 5th-gen tensor cores:
+//     P[M, N] = A[M, K] . W[N, K]^T + bias[N]        A, W bf16 (K-major), P fp32, fp32 accumulation in TMEM
+// Replaces the x.W_ih^T half of the nn.LSTM call at model/las_model.py:90 for all timesteps and both directions
+// at once (N = 8H).  The pyramid fold (:86-87) costs nothing: [B, 2Tl, Fin] and [B*Tl, 2Fin] are the same memory,
+// so the fold is just the tensor map's shape.
+//
+// Structure (one CTA per SM, persistent over 128x256 output tiles):
+//   warp 0     TMA producer: cp.async.bulk.tensor 2-D loads of A (128x64) and W (256x64) tiles, SWIZZLE_128B,
+//              4-stage mbarrier ring; K / M / N tails are TMA out-of-bounds zero fill
+//   warp 1     TMEM allocator + single-thread tcgen05.mma issuer (M=128, N=256, K=16 per instruction),
+//              tcgen05.commit releases smem stages and publishes finished accumulators
+//   warps 2-5  epilogue: tcgen05.ld accumulator rows -> +bias -> 128-byte row segments to global;
+//              two 256-column accumulators in TMEM so the epilogue of tile i overlaps the MMAs of tile i+1
+#include <cuda.h>
+
+#include "las_fast.cuh"
+#include "umma.cuh"
+
+namespace las {
+
+namespace {
+
+constexpr int BM = 128, BN = 256, BK = 64, STAGES = 4;
+constexpr int A_TILE_BYTES = BM * BK * 2, B_TILE_BYTES = BN * BK * 2;
+constexpr int GEMM_THREADS = 192;
+
+struct __align__(1024) GemmSmem {
+  uint8_t a[STAGES][A_TILE_BYTES];
+  uint8_t b[STAGES][B_TILE_BYTES];
+  uint64_t full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2];
+  uint32_t tmem_base;
+};
+
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
+                    const float* __restrict__ bias, float* __restrict__ C, long long ldc, int M, int N, int K) {
+  extern __shared__ uint8_t smem_raw[];
+  GemmSmem& s = *reinterpret_cast<GemmSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m_tiles = (M + BM - 1) / BM, n_tiles = (N + BN - 1) / BN, k_blocks = (K + BK - 1) / BK;
+  const int num_tiles = m_tiles * n_tiles;
+
+  if (threadIdx.x == 0) {
+    ptx::prefetch_tensormap(&tm_a);
+    ptx::prefetch_tensormap(&tm_b);
+    for (int i = 0; i < STAGES; ++i) {
+      ptx::mbar_init(&s.full[i], 1);
+      ptx::mbar_init(&s.empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(&s.tmem_full[i], 1);
+      ptx::mbar_init(&s.tmem_empty[i], 128);
+    }
+    ptx::fence_mbar_init();
+  }
+  if (warp == 1) ptx::tmem_alloc(&s.tmem_base, 512);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = s.tmem_base;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m0 = (tile / n_tiles) * BM, n0 = (tile % n_tiles) * BN;
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          ptx::mbar_wait(&s.empty[stage], phase ^ 1);
+          ptx::mbar_arrive_expect_tx(&s.full[stage], A_TILE_BYTES + B_TILE_BYTES);
+          ptx::tma_load_2d(s.a[stage], &tm_a, &s.full[stage], kb * BK, m0);
+          ptx::tma_load_2d(s.b[stage], &tm_b, &s.full[stage], kb * BK, n0);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const UmmaLayout la{1, 0, 1024, A_TILE_BYTES}, lb{1, 0, 1024, B_TILE_BYTES};
+      const uint32_t idesc = umma_idesc_bf16(BM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        ptx::mbar_wait(&s.tmem_empty[acc], acc_phase ^ 1);
+        ptx::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          ptx::mbar_wait(&s.full[stage], phase);
+          ptx::tc_fence_after();
+          const uint32_t a_addr = ptx::smem_u32(s.a[stage]), b_addr = ptx::smem_u32(s.b[stage]);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k)
+            ptx::umma_bf16(d_tmem, umma_smem_desc(la, a_addr, k * 16), umma_smem_desc(lb, b_addr, k * 16), idesc, (kb | k) != 0);
+          ptx::umma_commit(&s.empty[stage]);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        ptx::umma_commit(&s.tmem_full[acc]);
+      }
+    }
+  } else {
+    const int q = warp & 3;  // TMEM lane quadrant this warp may access
+    const bool vec_ok = (ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0);
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      const int m0 = (tile / n_tiles) * BM, n0 = (tile % n_tiles) * BN;
+      ptx::mbar_wait(&s.tmem_full[acc], acc_phase);
+      ptx::tc_fence_after();
+      const int row = m0 + q * 32 + lane;
+      float* crow = C + (long long)row * ldc;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t v[32];
+        ptx::tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + c0, v);
+        ptx::tmem_ld_wait();
+        const int col0 = n0 + c0;
+        if (row < M && col0 < N) {
+          if (vec_ok && col0 + 32 <= N) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 bv = *reinterpret_cast<const float4*>(bias + col0 + j);
+              float4 o;
+              o.x = __uint_as_float(v[j]) + bv.x;
+              o.y = __uint_as_float(v[j + 1]) + bv.y;
+              o.z = __uint_as_float(v[j + 2]) + bv.z;
+              o.w = __uint_as_float(v[j + 3]) + bv.w;
+              *reinterpret_cast<float4*>(crow + col0 + j) = o;
+            }
+          } else {
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < N) crow[col0 + j] = __uint_as_float(v[j]) + bias[col0 + j];
+          }
+        }
+      }
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(&s.tmem_empty[acc]);
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) ptx::tmem_dealloc(tmem_base, 512);
+}
+
+// ---- host: tensor maps ---------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int get_encode_fn(EncodeTiledFn* out) {
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  LAS_CUDA_OK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+  if (!fn || qres != cudaDriverEntryPointSuccess) return fail(LAS_ECUDA, "cuTensorMapEncodeTiled is not available from the driver");
+  *out = reinterpret_cast<EncodeTiledFn>(fn);
+  return LAS_OK;
+}
+
+// row-major bf16 matrix [rows, cols] with row pitch `ld` elements; box = {64 cols, box_rows}, 128-byte swizzle
+int make_tmap_bf16(CUtensorMap* tm, const void* base, long long rows, long long cols, long long ld, int box_rows) {
+  EncodeTiledFn enc;
+  LAS_TRY(get_encode_fn(&enc));
+  LAS_REQUIRE((ld * 2) % 16 == 0 && (reinterpret_cast<uintptr_t>(base) & 15) == 0,
+              "TMA needs 16-byte aligned rows (ld=%lld elements)", ld);
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t gstr[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  const CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstr, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(LAS_ECUDA, "cuTensorMapEncodeTiled failed with CUresult %d (rows=%lld cols=%lld ld=%lld)", (int)r, rows, cols, ld);
+  return LAS_OK;
+}
+
+}  // namespace
+
+int launch_gemm_bf16_tc(const __nv_bfloat16* A, long long lda, const __nv_bfloat16* W, long long ldw, const float* bias, float* C,
+                        long long ldc, int M, int N, int K, cudaStream_t st) {
+  LAS_REQUIRE(M > 0 && N > 0 && K > 0, "bad GEMM shape %dx%dx%d", M, N, K);
+  CUtensorMap tm_a, tm_b;
+  LAS_TRY(make_tmap_bf16(&tm_a, A, M, K, lda, BM));
+  LAS_TRY(make_tmap_bf16(&tm_b, W, N, K, ldw, BN));
+  const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
+  const int grid = tiles < sm_count() ? tiles : sm_count();
+  const size_t smem = sizeof(GemmSmem) + 1024;
+  static thread_local bool attr_set = false;
+  if (!attr_set) {
+    LAS_CUDA_OK(cudaFuncSetAttribute(gemm_bf16_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  gemm_bf16_tc_kernel<<<grid, GEMM_THREADS, smem, st>>>(tm_a, tm_b, bias, C, ldc, M, N, K);
+  LAS_LAUNCH_OK("gemm_bf16_tc_kernel");
+  return LAS_OK;
+}
+
+// =========================================================================================================
+// UMMA probe (test hook): one CTA stages A[M=128,K] and B[N,K] into shared memory with the layout helpers of
+// umma.cuh, runs the K/16 tcgen05.mma chain and dumps the TMEM accumulator.  tests/ use it to pin the descriptor
+// conventions every other tensor-core kernel here relies on.
+// =========================================================================================================
+__global__ void __launch_bounds__(128, 1)
+umma_probe_kernel(const __nv_bfloat16* __restrict__ A, const __nv_bfloat16* __restrict__ B, float* __restrict__ D, int N, int K,
+                  UmmaLayout la, UmmaLayout lb, uint32_t a_bytes, int variant) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sa = base;
+  uint8_t* sb = base + a_bytes;
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_slot;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    ptx::mbar_init(&bar, 1);
+    ptx::fence_mbar_init();
+  }
+  if (warp == 0) ptx::tmem_alloc(&tmem_slot, 256);
+  for (int i = threadIdx.x; i < 128 * K; i += blockDim.x) {
+    const int r = i / K, k = i % K;
+    *reinterpret_cast<__nv_bfloat16*>(sa + umma_offset(la, r, k)) = A[i];
+  }
+  for (int i = threadIdx.x; i < N * K; i += blockDim.x) {
+    const int r = i / K, k = i % K;
+    *reinterpret_cast<__nv_bfloat16*>(sb + umma_offset(lb, r, k)) = B[i];
+  }
+  ptx::fence_proxy_async();
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+  if (threadIdx.x == 0) {
+    const uint32_t idesc = umma_idesc_bf16(128, N);
+    auto swap_fields = [](uint64_t d) {  // hypothesis test: LBO / SBO meanings swapped
+      const uint64_t l = (d >> 16) & 0x3FFF, s2 = (d >> 32) & 0x3FFF;
+      d &= ~((0x3FFFull << 16) | (0x3FFFull << 32));
+      return d | (s2 << 16) | (l << 32);
+    };
+    for (int k0 = 0; k0 < K; k0 += 16) {
+      uint64_t da = umma_smem_desc(la, ptx::smem_u32(sa), k0), db = umma_smem_desc(lb, ptx::smem_u32(sb), k0);
+      if (variant & 1) {
+        if (!la.sw128) da = swap_fields(da);
+        if (!lb.sw128) db = swap_fields(db);
+      }
+      ptx::umma_bf16(tmem, da, db, idesc, k0 != 0);
+    }
+    ptx::umma_commit(&bar);
+  }
+  ptx::mbar_wait(&bar, 0);
+  ptx::tc_fence_after();
+  const int row = warp * 32 + lane;
+  for (int c0 = 0; c0 < N; c0 += 8) {
+    uint32_t v[8];
+    ptx::tmem_ld_32x32b_x8(tmem + ((uint32_t)(warp * 32) << 16) + c0, v);
+    ptx::tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 8; ++j) D[(size_t)row * N + c0 + j] = __uint_as_float(v[j]);
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) ptx::tmem_dealloc(tmem, 256);
+}
+
+int launch_umma_probe(const void* A, const void* B, float* D, int N, int K, int a_sw128, int b_sw128, int variant, cudaStream_t st) {
+  LAS_REQUIRE(N >= 16 && N <= 256 && N % 16 == 0, "probe needs N in [16,256], multiple of 16 (N=%d)", N);
+  LAS_REQUIRE(K >= 16 && K % 16 == 0 && K <= 256, "probe needs K in [16,256], multiple of 16 (K=%d)", K);
+  LAS_REQUIRE(!(a_sw128 || b_sw128) || K % 64 == 0, "SW128 probe needs K %% 64 == 0");
+  UmmaLayout la, lb;
+  if (a_sw128) la = UmmaLayout{1, 0, 1024, 128u * 128u};
+  else la = UmmaLayout{0, (128u / 8) * 128u, 128, 0};
+  if (b_sw128) lb = UmmaLayout{1, 0, 1024, (uint32_t)N * 128u};
+  else lb = UmmaLayout{0, ((uint32_t)N / 8) * 128u, 128, 0};
+  const uint32_t a_bytes = 128u * K * 2, b_bytes = (uint32_t)N * K * 2;
+  const size_t smem = (size_t)a_bytes + b_bytes + 2048;
+  LAS_CUDA_OK(cudaFuncSetAttribute(umma_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  umma_probe_kernel<<<1, 128, smem, st>>>(static_cast<const __nv_bfloat16*>(A), static_cast<const __nv_bfloat16*>(B), D, N, K, la, lb,
+                                          (a_bytes + 1023) & ~1023u, variant);
+  LAS_LAUNCH_OK("umma_probe_kernel");
+  return LAS_OK;
+}
+
+// fp32 -> bf16 (round to nearest even), dense
+__global__ void f32_to_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, size_t n) {
+  for (size_t i = (blockIdx.x * (size_t)blockDim.x + threadIdx.x) * 4; i < n; i += (size_t)gridDim.x * blockDim.x * 4) {
+    if (i + 3 < n) {
+      const float4 v = *reinterpret_cast<const float4*>(src + i);
+      *reinterpret_cast<__nv_bfloat162*>(dst + i) = __floats2bfloat162_rn(v.x, v.y);
+      *reinterpret_cast<__nv_bfloat162*>(dst + i + 2) = __floats2bfloat162_rn(v.z, v.w);
+    } else {
+      for (size_t j = i; j < n; ++j) dst[j] = __float2bfloat16_rn(src[j]);
+    }
+  }
+}
+int launch_f32_to_bf16(const float* src, __nv_bfloat16* dst, size_t n, cudaStream_t st) {
+  if (n == 0) return LAS_OK;
+  LAS_REQUIRE((reinterpret_cast<uintptr_t>(src) & 15) == 0 && (reinterpret_cast<uintptr_t>(dst) & 7) == 0, "unaligned cast buffers");
+  const size_t blocks = (n / 4 + 255) / 256;
+  f32_to_bf16_kernel<<<(unsigned)(blocks < 2368 ? (blocks ? blocks : 1) : 2368), 256, 0, st>>>(src, dst, n);
+  LAS_LAUNCH_OK("f32_to_bf16_kernel");
+  return LAS_OK;
+}
+
+}  // namespace las

@@ -514,4 +514,16 @@ int las_nll_sums(const float* logp, const int32_t* labels, int S, int S_lab, int
   return launch_nll_sums(logp, labels, S, S_lab, B, V, max_label_len, out2, static_cast<cudaStream_t>(stream));
 }
 
+int las_debug_gemm_bf16(const void* a, const void* w, const float* bias, float* c, int M, int N, int K, void* stream) {
+  LAS_REQUIRE(a && w && bias && c, "null pointer argument");
+  LAS_TRY(device_ok());
+  return launch_gemm_bf16_tc(static_cast<const __nv_bfloat16*>(a), K, static_cast<const __nv_bfloat16*>(w), K, bias, c, N, M, N, K,
+                             static_cast<cudaStream_t>(stream));
+}
+int las_debug_umma_probe(const void* a, const void* b, float* d, int N, int K, int a_sw128, int b_sw128, int variant, void* stream) {
+  LAS_REQUIRE(a && b && d, "null pointer argument");
+  LAS_TRY(device_ok());
+  return launch_umma_probe(a, b, d, N, K, a_sw128, b_sw128, variant, static_cast<cudaStream_t>(stream));
+}
+
 }  // extern "C"

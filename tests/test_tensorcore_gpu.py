@@ -1,0 +1,35 @@
+"""tcgen05 building blocks through the C ABI test hooks: UMMA descriptor conventions and the input-projection GEMM."""
+import pytest
+import torch
+
+from las_pytorch_b200 import _cabi
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("a_sw,b_sw", [(0, 0), (1, 1), (1, 0), (0, 1)])
+@pytest.mark.parametrize("N,K", [(16, 256), (64, 128), (256, 64)])
+def test_umma_layouts(N, K, a_sw, b_sw):
+    lib = _cabi.load_library()
+    g = torch.Generator().manual_seed(N * 1000 + K)
+    a = torch.randn(128, K, generator=g).cuda().to(torch.bfloat16)
+    b = torch.randn(N, K, generator=g).cuda().to(torch.bfloat16)
+    d = torch.full((128, N), float("nan"), device="cuda")
+    _cabi.check(lib.las_debug_umma_probe(_cabi.ptr(a), _cabi.ptr(b), _cabi.ptr(d), N, K, a_sw, b_sw, 0, _cabi.current_stream_ptr()))
+    torch.cuda.synchronize()
+    ref = a.float() @ b.float().t()
+    assert float((d - ref).abs().max()) <= 1e-3 * float(ref.abs().max())
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (300, 128, 80), (1000, 2048, 1024), (389, 280, 96), (2048, 1024, 512)])
+def test_input_projection_gemm(M, N, K):
+    lib = _cabi.load_library()
+    g = torch.Generator().manual_seed(M + N + K)
+    a = torch.randn(M, K, generator=g).cuda().to(torch.bfloat16)
+    w = (torch.randn(N, K, generator=g) / K ** 0.5).cuda().to(torch.bfloat16)
+    bias = torch.randn(N, generator=g).cuda()
+    c = torch.full((M, N), float("nan"), device="cuda")
+    _cabi.check(lib.las_debug_gemm_bf16(_cabi.ptr(a), _cabi.ptr(w), _cabi.ptr(bias), _cabi.ptr(c), M, N, K, _cabi.current_stream_ptr()))
+    torch.cuda.synchronize()
+    ref = a.float() @ w.float().t() + bias
+    assert float((c - ref).abs().max()) <= 2e-3
