@@ -18,7 +18,7 @@ def main():
         a = torch.randn(128, K, generator=g).to(dev).to(torch.bfloat16)
         b = torch.randn(N, K, generator=g).to(dev).to(torch.bfloat16)
         ref = a.float() @ b.float().t()
-        for a_sw, b_sw, variant in itertools.product((0, 1), (0, 1), (0, 1)):
+        for a_sw, b_sw, variant in itertools.product((0, 1), (0, 1), (0,)):
             if variant and a_sw and b_sw:
                 continue
             d = torch.full((128, N), float("nan"), device=dev)
