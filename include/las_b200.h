@@ -179,6 +179,11 @@ int las_debug_gemm_bf16(const void* a_bf16, const void* w_bf16, const float* bia
 int las_debug_umma_probe(const void* a_bf16, const void* b_bf16, float* d, int N, int K, int a_sw128, int b_sw128, int variant,
                          void* stream);
 
+/* Device buffer of 64*8 int64 that the layer-0 recurrence kernel fills with clock64 stamps (NULL disables). */
+int las_debug_set_trace(void* dev_buf);
+/* Kernel variant switches for A/B tests: key 1 = recurrence keeps W_hh in tensor memory (1, default) or shared memory (0). */
+int las_debug_set_option(int key, int value);
+
 #ifdef __cplusplus
 }
 #endif

@@ -73,6 +73,8 @@ PROTOTYPES = {
     "las_speller_decode": (C.c_int, [C.POINTER(DecodeIO), C.c_void_p, C.POINTER(SpellerDims), C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]),
     "las_debug_gemm_bf16": (C.c_int, [C.c_void_p] * 4 + [C.c_int] * 3 + [C.c_void_p]),
     "las_debug_umma_probe": (C.c_int, [C.c_void_p] * 3 + [C.c_int] * 5 + [C.c_void_p]),
+    "las_debug_set_trace": (C.c_int, [C.c_void_p]),
+    "las_debug_set_option": (C.c_int, [C.c_int, C.c_int]),
     "las_nll_sums": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
 }
 

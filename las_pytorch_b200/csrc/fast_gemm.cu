@@ -217,9 +217,12 @@ umma_probe_kernel(const __nv_bfloat16* __restrict__ A, const __nv_bfloat16* __re
     ptx::fence_mbar_init();
   }
   if (warp == 0) ptx::tmem_alloc(&tmem_slot, 256);
-  for (int i = threadIdx.x; i < 128 * K; i += blockDim.x) {
-    const int r = i / K, k = i % K;
-    *reinterpret_cast<__nv_bfloat16*>(sa + umma_offset(la, r, k)) = A[i];
+  const bool a_tmem = (variant & 2) != 0;  // A operand staged in tensor memory (columns 128..) instead of smem
+  if (!a_tmem) {
+    for (int i = threadIdx.x; i < 128 * K; i += blockDim.x) {
+      const int r = i / K, k = i % K;
+      *reinterpret_cast<__nv_bfloat16*>(sa + umma_offset(la, r, k)) = A[i];
+    }
   }
   for (int i = threadIdx.x; i < N * K; i += blockDim.x) {
     const int r = i / K, k = i % K;
@@ -230,6 +233,20 @@ umma_probe_kernel(const __nv_bfloat16* __restrict__ A, const __nv_bfloat16* __re
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem = tmem_slot;
+  if (a_tmem) {
+    const int row = warp * 32 + lane;
+    for (int k0 = 0; k0 < K; k0 += 16) {
+      uint32_t v[8];
+      const uint4 q0 = *reinterpret_cast<const uint4*>(A + (size_t)row * K + k0);
+      const uint4 q1 = *reinterpret_cast<const uint4*>(A + (size_t)row * K + k0 + 8);
+      v[0] = q0.x; v[1] = q0.y; v[2] = q0.z; v[3] = q0.w; v[4] = q1.x; v[5] = q1.y; v[6] = q1.z; v[7] = q1.w;
+      ptx::tmem_st_32x32b_x8(tmem + ((uint32_t)(warp * 32) << 16) + 128 + k0 / 2, v);
+    }
+    ptx::tmem_st_wait();
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+  }
   if (threadIdx.x == 0) {
     const uint32_t idesc = umma_idesc_bf16(128, N);
     auto swap_fields = [](uint64_t d) {  // hypothesis test: LBO / SBO meanings swapped
@@ -243,7 +260,8 @@ umma_probe_kernel(const __nv_bfloat16* __restrict__ A, const __nv_bfloat16* __re
         if (!la.sw128) da = swap_fields(da);
         if (!lb.sw128) db = swap_fields(db);
       }
-      ptx::umma_bf16(tmem, da, db, idesc, k0 != 0);
+      if (a_tmem) ptx::umma_bf16_ts(tmem, tmem + 128 + k0 / 2, db, idesc, k0 != 0);
+      else ptx::umma_bf16(tmem, da, db, idesc, k0 != 0);
     }
     ptx::umma_commit(&bar);
   }
@@ -266,6 +284,7 @@ int launch_umma_probe(const void* A, const void* B, float* D, int N, int K, int 
   LAS_REQUIRE(N >= 16 && N <= 256 && N % 16 == 0, "probe needs N in [16,256], multiple of 16 (N=%d)", N);
   LAS_REQUIRE(K >= 16 && K % 16 == 0 && K <= 256, "probe needs K in [16,256], multiple of 16 (K=%d)", K);
   LAS_REQUIRE(!(a_sw128 || b_sw128) || K % 64 == 0, "SW128 probe needs K %% 64 == 0");
+  LAS_REQUIRE(!(variant & 2) || N <= 128, "A-in-TMEM probe needs N <= 128");
   UmmaLayout la, lb;
   if (a_sw128) la = UmmaLayout{1, 0, 1024, 128u * 128u};
   else la = UmmaLayout{0, (128u / 8) * 128u, 128, 0};

@@ -1,0 +1,512 @@
+// LAS_MODE_BF16 listener: tcgen05 input-projection GEMM (fast_gemm.cu) + cluster-resident LSTM recurrence.
+//
+// Recurrence kernel (the h.W_hh^T + gates half of the nn.LSTM call at model/las_model.py:90):
+//   * one thread-block CLUSTER per (direction, batch chunk of Bc utterances); forward and backward directions and
+//     all batch chunks run concurrently in one launch;
+//   * the cluster's CS CTAs split the hidden units 32 per CTA; each CTA keeps its [4 gates x 32 units, H] slice of
+//     W_hh (bf16) resident in shared memory for the whole sequence, as the A operand of a "swap-AB" UMMA:
+//         D[128 gate rows, Bc] (TMEM, fp32) = W_slice[128, H] . h_{t-1}^T[H, Bc]
+//   * h_{t-1} (bf16, the B operand) lives in every CTA's shared memory; after the gate math each CTA pushes its
+//     32-unit slice of h_t into all CS CTAs' buffers with st.shared::cluster (DSMEM) and arrives on their mbarriers;
+//   * c_t and the gate math stay fp32 in registers; the input projection P (from the GEMM, biases included) is
+//     prefetched one step ahead.
+// Gate rows are ordered unit-major / gate-minor (row = 4*unit + gate), so the four gates of a unit sit in four
+// adjacent lanes of one warp after tcgen05.ld and are exchanged with warp shuffles.  The GEMM's weight rows are
+// permuted the same way at pack time, so P[b,t] holds (i,f,g,o) of a unit as one float4.
+#include "las_fast.cuh"
+#include "las_kernels.cuh"
+#include "umma.cuh"
+
+namespace las {
+
+namespace {
+
+constexpr int REC_THREADS = 160;  // warps 0-3: epilogue (one TMEM lane quadrant each); warp 4: MMA issuer
+
+struct RecParams {
+  const float* P;               // [B*Tl, NP] fp32; column = dir*4Hp + r*128 + jj*4 + gate
+  const uint8_t* whh_img;       // [2][CS] shared-memory images of the W_hh slices (128 x Hp bf16, INTERLEAVE layout)
+  float* out_f32;               // nullable [B, Tl, 2H]
+  __nv_bfloat16* out_bf16;      // nullable [B, Tl, 2H]
+  int B, Tl, H, Hp, CS, nchunks;
+  int a_tmem;                   // 1: W_hh slice lives in tensor memory (UMMA .ts form); 0: in shared memory
+  long long* trace;             // nullable test hook: [64 steps][8] clock64 stamps from CTA 0
+};
+
+#define REC_TRACE(slot) do { if (p.trace && blockIdx.x == 0 && s < 64) p.trace[s * 8 + (slot)] = clock64(); } while (0)
+
+__device__ __forceinline__ float tanh_fast(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float sigmoid_fast(float x) { return fmaf(tanh_fast(0.5f * x), 0.5f, 0.5f); }
+__device__ __forceinline__ float sel4(float a0, float a1, float a2, float a3, int i) {
+  return i == 0 ? a0 : (i == 1 ? a1 : (i == 2 ? a2 : a3));
+}
+
+// W_hh slice operand: 128 rows x Hp, INTERLEAVE: K-adjacent core matrices 2048 B apart, 8-row groups 128 B apart
+__host__ __device__ inline UmmaLayout whh_layout() { return UmmaLayout{0, 2048, 128, 0}; }
+// h operand: Bc rows x Hp, INTERLEAVE: [coreK][coreN][8 rows][16 B]
+__host__ __device__ inline UmmaLayout h_layout(int Bc) { return UmmaLayout{0, (uint32_t)Bc * 16u, 128, 0}; }
+
+__host__ __device__ inline uint32_t rec_tmem_cols(int Hp, int BC, int a_tmem) {
+  uint32_t need = (uint32_t)BC + (a_tmem ? (uint32_t)Hp / 2 : 0u), c = 32;
+  while (c < need) c <<= 1;
+  return c;
+}
+
+template <int BC>
+__global__ void __launch_bounds__(REC_THREADS, 1) lstm_recurrence_cluster_kernel(RecParams p) {
+  constexpr int NB = BC / 4;  // cells per epilogue thread
+  // Dependent UMMAs into one accumulator serialise on the tensor core's accumulate latency (~80 cycles each, far more
+  // than the 8-32 issue cycles of an N=16..64 instruction), so the K loop is spread round-robin over NACC independent
+  // accumulators that the epilogue sums.
+  constexpr int NACC = BC == 16 ? 4 : (BC == 32 ? 2 : 1);
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int Hp = p.Hp;
+  const uint32_t a_bytes = 128u * Hp * 2u, h_bytes = (uint32_t)BC * Hp * 2u;
+  const uint32_t a_smem_bytes = p.a_tmem ? 0u : a_bytes;
+  uint8_t* sA = base;
+  uint8_t* sH0 = base + a_smem_bytes;                         // two h buffers of h_bytes each
+  uint8_t* sStage = sH0 + 2 * h_bytes;                        // [2 parities] x (4 coreK x BC x 16 bytes)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sStage + 2 * 4 * BC * 16);
+  uint64_t* h_full = bars;        // [2]
+  uint64_t* mma_done = bars + 2;  // [1]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t r = ptx::cluster_ctarank();
+  const int CS = p.CS;
+  const int cluster_id = blockIdx.x / CS;
+  const int dir = cluster_id / p.nchunks, chunk = cluster_id % p.nchunks;
+  const int b_base = chunk * BC;
+  const uint32_t tcols = rec_tmem_cols(Hp, BC * NACC, p.a_tmem);
+  const uint8_t* w_img = p.whh_img + ((size_t)dir * CS + r) * a_bytes;
+
+  // ---- one-time setup: barriers, TMEM, resident W_hh slice
+  if (threadIdx.x == 0) {
+    ptx::mbar_init(&h_full[0], 1);  // one local arrive.expect_tx per phase; the peers' bulk copies complete the bytes
+    ptx::mbar_init(&h_full[1], 1);
+    ptx::mbar_init(mma_done, 1);
+    ptx::fence_mbar_init();
+    // arm the first use of each h buffer (steps 1 and 2) before any peer can send
+    if (p.Tl > 1) ptx::mbar_arrive_expect_tx(&h_full[1], h_bytes);
+    if (p.Tl > 2) ptx::mbar_arrive_expect_tx(&h_full[0], h_bytes);
+  }
+  if (warp == 4) ptx::tmem_alloc(tmem_slot, tcols);
+  if (!p.a_tmem) {
+    const uint4* src = reinterpret_cast<const uint4*>(w_img);
+    uint4* dst = reinterpret_cast<uint4*>(sA);
+    for (uint32_t i = threadIdx.x; i < a_bytes / 16; i += REC_THREADS) dst[i] = src[i];
+  }
+  ptx::fence_proxy_async();
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  // TMEM map: A operand (W_hh slice, lane = gate row, 2 bf16 per column) in columns [0, Hp/2), accumulator behind it
+  const uint32_t d_col = p.a_tmem ? (uint32_t)Hp / 2 : 0u;
+  if (p.a_tmem && warp < 4) {
+    const UmmaLayout la = whh_layout();
+    const int row = threadIdx.x;
+    for (int k0 = 0; k0 < Hp; k0 += 16) {
+      const uint4 q0 = *reinterpret_cast<const uint4*>(w_img + umma_offset(la, row, k0));
+      const uint4 q1 = *reinterpret_cast<const uint4*>(w_img + umma_offset(la, row, k0 + 8));
+      const uint32_t v[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+      ptx::tmem_st_32x32b_x8(tmem + ((uint32_t)(warp * 32) << 16) + k0 / 2, v);
+    }
+    ptx::tmem_st_wait();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::cluster_sync();  // every CTA's barriers are initialised (and armed) before anyone sends
+  ptx::tc_fence_after();
+  const int Tl = p.Tl;
+
+  if (warp == 4) {
+    // ================================ MMA issuer ================================
+    // The whole warp walks the loop with warp-uniform values (descriptors end up in uniform registers); only the
+    // tcgen05 / mbarrier-arrive instructions are predicated on one elected lane.
+    const UmmaLayout la = whh_layout(), lb = h_layout(BC);
+    const uint32_t idesc = umma_idesc_bf16(128, BC);
+    const uint32_t a_addr = ptx::smem_u32(sA);
+    const uint32_t h0_addr = ptx::smem_u32(sH0);
+    if (ptx::elect_one()) ptx::mbar_arrive(mma_done);  // step 0: h_{-1} = 0, nothing to multiply
+    __syncwarp();
+    for (int s = 1; s < Tl; ++s) {
+      ptx::mbar_wait(&h_full[s & 1], (uint32_t)((((s + 1) >> 1) - 1) & 1));
+      if (lane == 0) REC_TRACE(0);
+      ptx::tc_fence_after();
+      const uint32_t b_addr = h0_addr + (uint32_t)(s & 1) * h_bytes;
+      if (ptx::elect_one()) {
+        if (s + 2 < Tl) ptx::mbar_arrive_expect_tx(&h_full[s & 1], h_bytes);  // re-arm for step s+2
+        if (p.a_tmem) {
+#pragma unroll 4
+          for (int ki = 0; ki < Hp / 16; ++ki)
+            ptx::umma_bf16_ts(tmem + d_col + (ki % NACC) * BC, tmem + ki * 8, umma_smem_desc(lb, b_addr, ki * 16), idesc, ki >= NACC);
+        } else {
+#pragma unroll 4
+          for (int ki = 0; ki < Hp / 16; ++ki)
+            ptx::umma_bf16(tmem + d_col + (ki % NACC) * BC, umma_smem_desc(la, a_addr, ki * 16), umma_smem_desc(lb, b_addr, ki * 16), idesc,
+                           ki >= NACC);
+        }
+        ptx::umma_commit(mma_done);
+      }
+      __syncwarp();
+      if (lane == 0) REC_TRACE(1);
+    }
+  } else {
+    // ================================ gate math + h exchange ================================
+    const int tid = threadIdx.x;
+    const int jj = tid >> 2, g = tid & 3;  // TMEM lane = gate row = 4*jj + g
+    const bool bit0 = (g & 1) != 0, bit1 = (g & 2) != 0;
+    const int j = (int)r * 32 + jj;        // hidden unit
+    const int NP = 8 * Hp;
+    const float* pcol = p.P + (size_t)dir * 4 * Hp + (size_t)r * 128 + jj * 4;
+    float c[NB];
+    float4 pnext[NB];
+#pragma unroll
+    for (int m = 0; m < NB; ++m) c[m] = 0.f;
+    {
+      const int t0 = dir ? Tl - 1 : 0;
+#pragma unroll
+      for (int m = 0; m < NB; ++m) {
+        const int b = b_base + 4 * m + g;
+        pnext[m] = (b < p.B) ? *reinterpret_cast<const float4*>(pcol + ((size_t)b * Tl + t0) * NP) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+    const uint32_t stage0 = ptx::smem_u32(sStage);
+    const uint32_t h0_addr = ptx::smem_u32(sH0);
+    const int dst_per_warp = (CS + 3) / 4;  // destination CTAs each warp serves
+    for (int s = 0; s < Tl; ++s) {
+      const int t = dir ? Tl - 1 - s : s;
+      float4 pc[NB];
+#pragma unroll
+      for (int m = 0; m < NB; ++m) pc[m] = pnext[m];
+      if (s + 1 < Tl) {
+        const int tn = dir ? t - 1 : t + 1;
+#pragma unroll
+        for (int m = 0; m < NB; ++m) {
+          const int b = b_base + 4 * m + g;
+          if (b < p.B) pnext[m] = *reinterpret_cast<const float4*>(pcol + ((size_t)b * Tl + tn) * NP);
+        }
+        if (s + 2 < Tl) {  // pull the step after that into L2 so the register prefetch above never sees DRAM latency
+          const int tnn = dir ? t - 2 : t + 2;
+#pragma unroll
+          for (int m = 0; m < NB; ++m) {
+            const int b = b_base + 4 * m + g;
+            if (b < p.B) asm volatile("prefetch.global.L2 [%0];" ::"l"(pcol + ((size_t)b * Tl + tnn) * NP));
+          }
+        }
+      }
+      ptx::mbar_wait(mma_done, (uint32_t)(s & 1));
+      if (tid == 0) REC_TRACE(2);
+      uint32_t v[BC];
+      if (s > 0) {
+        ptx::tc_fence_after();
+        uint32_t part[NACC > 1 ? NACC - 1 : 1][BC];
+#pragma unroll
+        for (int c0 = 0; c0 < BC; c0 += 16) {
+          uint32_t t16[16];
+          ptx::tmem_ld_32x32b_x16(tmem + ((uint32_t)(warp * 32) << 16) + d_col + c0, t16);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[c0 + i] = t16[i];
+#pragma unroll
+          for (int a = 1; a < NACC; ++a) {
+            ptx::tmem_ld_32x32b_x16(tmem + ((uint32_t)(warp * 32) << 16) + d_col + a * BC + c0, t16);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) part[a - 1][c0 + i] = t16[i];
+          }
+        }
+        ptx::tmem_ld_wait();
+        ptx::tc_fence_before();
+#pragma unroll
+        for (int a = 1; a < NACC; ++a) {
+          if (a < Hp / 16) {  // accumulator `a` was written this step (Hp = 32 has only two K steps)
+#pragma unroll
+            for (int i = 0; i < BC; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) + __uint_as_float(part[a - 1][i]));
+          }
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < BC; ++i) v[i] = 0u;
+      }
+      if (tid == 0) REC_TRACE(3);
+      float hval[NB];
+#pragma unroll
+      for (int m = 0; m < NB; ++m) {
+        // 4x4 transpose inside the 4-lane group (two butterfly stages, branch-free): lane g starts with its gate's
+        // pre-activations for batches 4m..4m+3 and ends with all four gates (i,f,g,o) of batch 4m+g.
+        float v0 = __uint_as_float(v[4 * m]), v1 = __uint_as_float(v[4 * m + 1]), v2 = __uint_as_float(v[4 * m + 2]),
+              v3 = __uint_as_float(v[4 * m + 3]);
+        {
+          const float s01 = bit0 ? v0 : v1, s23 = bit0 ? v2 : v3;
+          const float r01 = __shfl_xor_sync(0xffffffffu, s01, 1), r23 = __shfl_xor_sync(0xffffffffu, s23, 1);
+          v0 = bit0 ? r01 : v0; v1 = bit0 ? v1 : r01;
+          v2 = bit0 ? r23 : v2; v3 = bit0 ? v3 : r23;
+        }
+        {
+          const float s02 = bit1 ? v0 : v2, s13 = bit1 ? v1 : v3;
+          const float r02 = __shfl_xor_sync(0xffffffffu, s02, 2), r13 = __shfl_xor_sync(0xffffffffu, s13, 2);
+          v0 = bit1 ? r02 : v0; v2 = bit1 ? v2 : r02;
+          v1 = bit1 ? r13 : v1; v3 = bit1 ? v3 : r13;
+        }
+        const float a_i = v0 + pc[m].x, a_f = v1 + pc[m].y, a_g = v2 + pc[m].z, a_o = v3 + pc[m].w;
+        const float cn = sigmoid_fast(a_f) * c[m] + sigmoid_fast(a_i) * tanh_fast(a_g);
+        c[m] = cn;
+        hval[m] = sigmoid_fast(a_o) * tanh_fast(cn);
+      }
+      if (tid == 0) REC_TRACE(4);
+      // ---- h_t slice -> every CTA of the cluster (B operand of step s+1)
+      if (s + 1 < Tl) {
+        // stage the CTA's 32-unit slice as 4 core-matrix columns (coreK = 4r + warp): [coreK][coreN][8 rows][8 k] bf16.
+        // Double-buffered by step parity: the bulk copies issued at step s have landed in every peer before any CTA
+        // can reach the epilogue of step s+2 (each peer needs them to finish its own step s+1).
+        const uint32_t sb = stage0 + (uint32_t)(s & 1) * (4u * BC * 16u);
+#pragma unroll
+        for (int m = 0; m < NB; ++m) {
+          const int bl = 4 * m + g;  // batch row within the chunk
+          const uint32_t off = (uint32_t)warp * (BC * 16u) + (uint32_t)(bl >> 3) * 128u + (uint32_t)(bl & 7) * 16u + (uint32_t)(jj & 7) * 2u;
+          const __nv_bfloat16 hb = __float2bfloat16_rn(hval[m]);
+          asm volatile("st.shared.b16 [%0], %1;" ::"r"(sb + off), "h"(*reinterpret_cast<const unsigned short*>(&hb)) : "memory");
+        }
+        ptx::fence_proxy_async_smem();  // generic-proxy staging writes -> visible to the bulk-copy (async proxy) reads
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (tid == 0) REC_TRACE(6);
+        const int d = warp * dst_per_warp + lane;
+        if (lane < dst_per_warp && d < CS) {
+          // one DSMEM bulk copy of the whole slice per destination CTA; completes its bytes on that CTA's h_full barrier
+          const uint32_t nb = (uint32_t)((s + 1) & 1);
+          const uint32_t dst_rank = (r + d) % CS;
+          const uint32_t dst_off = h0_addr + nb * h_bytes + ((uint32_t)(4 * r) * BC) * 16u;
+          ptx::bulk_copy_to_cluster(ptx::mapa(dst_off, dst_rank), sb, 4u * BC * 16u, ptx::mapa(ptx::smem_u32(&h_full[nb]), dst_rank));
+        }
+        if (tid == 0) REC_TRACE(7);
+      }
+      // ---- outputs to global (off the critical path: after the exchange has been issued)
+      if (j < p.H) {
+#pragma unroll
+        for (int m = 0; m < NB; ++m) {
+          const int b = b_base + 4 * m + g;
+          if (b < p.B) {
+            const size_t o = ((size_t)b * Tl + t) * 2 * p.H + (size_t)dir * p.H + j;
+            if (p.out_f32) p.out_f32[o] = hval[m];
+            if (p.out_bf16) p.out_bf16[o] = __float2bfloat16_rn(hval[m]);
+          }
+        }
+      }
+      if (tid == 0) REC_TRACE(5);
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::cluster_sync();  // no CTA leaves while a peer could still address its shared memory
+  if (warp == 4) ptx::tmem_dealloc(tmem, tcols);
+}
+
+// ---- pack kernels ------------------------------------------------------------------------------------------
+// W_ih rows permuted to the recurrence's gate-row order, converted to bf16: dst [8Hp, K]
+__global__ void pack_wih_kernel(const float* w_fwd, const float* w_rev, __nv_bfloat16* dst, int H, int Hp, int K) {
+  const size_t n = (size_t)8 * Hp * K;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const int k = (int)(i % K);
+    const int row = (int)(i / K);
+    const int dir = row / (4 * Hp), rem = row % (4 * Hp);
+    const int unit = rem >> 2, gate = rem & 3;  // rem = r*128 + jj*4 + gate with unit = r*32 + jj
+    const float* w = dir ? w_rev : w_fwd;
+    dst[i] = __float2bfloat16_rn(unit < H ? w[(size_t)(gate * H + unit) * K + k] : 0.f);
+  }
+}
+__global__ void pack_bias_kernel(const float* bi_f, const float* bh_f, const float* bi_r, const float* bh_r, float* dst, int H, int Hp) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 8 * Hp) return;
+  const int dir = i / (4 * Hp), rem = i % (4 * Hp);
+  const int unit = rem >> 2, gate = rem & 3;
+  const float* bi = dir ? bi_r : bi_f;
+  const float* bh = dir ? bh_r : bh_f;
+  dst[i] = unit < H ? bi[gate * H + unit] + bh[gate * H + unit] : 0.f;
+}
+// W_hh -> per (dir, rank) shared-memory images of the 128 x Hp A operand
+__global__ void pack_whh_kernel(const float* w_fwd, const float* w_rev, uint8_t* img, int H, int Hp, int CS) {
+  const size_t per = (size_t)128 * Hp;
+  const size_t n = 2 * (size_t)CS * per;
+  const UmmaLayout la = whh_layout();
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const int k = (int)(i % Hp);
+    const int row = (int)((i / Hp) % 128);
+    const int rk = (int)((i / per) % CS);
+    const int dir = (int)(i / (per * CS));
+    const int unit = rk * 32 + (row >> 2), gate = row & 3;
+    const float* w = dir ? w_rev : w_fwd;
+    const float val = (unit < H && k < H) ? w[(size_t)(gate * H + unit) * H + k] : 0.f;
+    *reinterpret_cast<__nv_bfloat16*>(img + ((size_t)dir * CS + rk) * per * 2 + umma_offset(la, row, k)) = __float2bfloat16_rn(val);
+  }
+}
+
+long long* g_rec_trace = nullptr;  // set through las_debug_set_trace (test hook)
+int g_rec_a_tmem = 1;              // las_debug_set_option(1, v)
+
+struct Geo {
+  int Hp, CS;
+  bool ok;
+};
+Geo geometry(int H) {
+  Geo g;
+  g.CS = (H + 31) / 32;
+  g.Hp = g.CS * 32;
+  g.ok = (g.CS == 1 || g.CS == 2 || g.CS == 4 || g.CS == 8 || g.CS == 16) && (H <= 32 || H % 32 == 0);
+  return g;
+}
+int pick_bc(int B, int CS) {
+  // batch chunk per cluster (the UMMA N): multiples of 16; grow it only when the clusters would not fit the chip
+  const int max_clusters = sm_count() / CS > 0 ? sm_count() / CS : 1;
+  int bc = 16;
+  while (bc < 64 && 2 * ((B + bc - 1) / bc) > max_clusters) bc *= 2;
+  return bc;
+}
+
+struct ListenerPackFast {
+  __nv_bfloat16* wih[16];
+  float* bias[16];
+  uint8_t* whh[16];
+  size_t bytes;
+};
+ListenerPackFast pack_layout(const las_listener_dims* d, void* base) {
+  ListenerPackFast p;
+  const Geo g = geometry(d->H);
+  Carver cv(base);
+  for (int l = 0; l < d->L; ++l) {
+    const size_t K = (l == 0) ? 2 * (size_t)d->F : 4 * (size_t)d->H;
+    p.wih[l] = cv.take<__nv_bfloat16>(8 * (size_t)g.Hp * K);
+    p.bias[l] = cv.take<float>(8 * (size_t)g.Hp);
+    p.whh[l] = cv.take<uint8_t>(2 * (size_t)g.CS * 128 * g.Hp * 2);
+  }
+  p.bytes = cv.total();
+  return p;
+}
+struct ListenerWsFast {
+  __nv_bfloat16* xb;
+  float* P;
+  __nv_bfloat16* act[2];
+  size_t bytes;
+};
+ListenerWsFast ws_layout(const las_listener_dims* d, void* base) {
+  ListenerWsFast w;
+  const Geo g = geometry(d->H);
+  Carver cv(base);
+  const size_t M0 = (size_t)d->B * (d->T / 2);
+  w.xb = cv.take<__nv_bfloat16>((size_t)d->B * d->T * d->F);
+  w.P = cv.take<float>(M0 * 8 * g.Hp);
+  w.act[0] = cv.take<__nv_bfloat16>(M0 * 2 * d->H);
+  w.act[1] = cv.take<__nv_bfloat16>(M0 / 2 * 2 * d->H + 64);
+  w.bytes = cv.total();
+  return w;
+}
+
+int shape_ok(const las_listener_dims* d) {
+  const Geo g = geometry(d->H);
+  LAS_REQUIRE(g.ok, "LAS_MODE_BF16 listener supports hidden sizes <= 32 or 64/128/256/512 (H=%d); use LAS_MODE_FP32", d->H);
+  LAS_REQUIRE((2 * d->F) % 8 == 0 && (4 * d->H) % 8 == 0,
+              "LAS_MODE_BF16 needs 16-byte aligned bf16 rows for TMA: 2F (%d) and 4H (%d) must be multiples of 8", 2 * d->F, 4 * d->H);
+  return LAS_OK;
+}
+
+template <int BC>
+int launch_rec(const RecParams& p, cudaStream_t st) {
+  const size_t smem = 1024 + (p.a_tmem ? 0u : 128u * p.Hp * 2) + 2u * BC * p.Hp * 2 + 2 * 4 * BC * 16 + 64;
+  LAS_CUDA_OK(cudaFuncSetAttribute(lstm_recurrence_cluster_kernel<BC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (p.CS > 8) LAS_CUDA_OK(cudaFuncSetAttribute(lstm_recurrence_cluster_kernel<BC>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(p.CS * 2 * p.nchunks);
+  cfg.blockDim = dim3(REC_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = p.CS;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  LAS_CUDA_OK(cudaLaunchKernelEx(&cfg, lstm_recurrence_cluster_kernel<BC>, p));
+  count_launch();
+  return LAS_OK;
+}
+
+}  // namespace
+
+
+
+void fast_set_trace(long long* p) { g_rec_trace = p; }
+void fast_set_option(int key, int value) {
+  if (key == 1) g_rec_a_tmem = value;
+}
+
+size_t fast_listener_packed_bytes(const las_listener_dims* d) { return pack_layout(d, nullptr).bytes; }
+size_t fast_listener_workspace_bytes(const las_listener_dims* d) { return ws_layout(d, nullptr).bytes; }
+
+int fast_listener_pack(const las_lstm_weights* w, const las_listener_dims* d, void* packed, cudaStream_t st) {
+  LAS_TRY(shape_ok(d));
+  const Geo g = geometry(d->H);
+  const ListenerPackFast pk = pack_layout(d, packed);
+  for (int l = 0; l < d->L; ++l) {
+    const int K = (l == 0) ? 2 * d->F : 4 * d->H;
+    const las_lstm_weights &f = w[2 * l], &r = w[2 * l + 1];
+    LAS_REQUIRE(f.w_ih && f.w_hh && f.b_ih && f.b_hh && r.w_ih && r.w_hh && r.b_ih && r.b_hh, "null weight pointer in layer %d", l);
+    pack_wih_kernel<<<592, 256, 0, st>>>(f.w_ih, r.w_ih, pk.wih[l], d->H, g.Hp, K);
+    LAS_LAUNCH_OK("pack_wih_kernel");
+    pack_bias_kernel<<<(8 * g.Hp + 255) / 256, 256, 0, st>>>(f.b_ih, f.b_hh, r.b_ih, r.b_hh, pk.bias[l], d->H, g.Hp);
+    LAS_LAUNCH_OK("pack_bias_kernel");
+    pack_whh_kernel<<<592, 256, 0, st>>>(f.w_hh, r.w_hh, pk.whh[l], d->H, g.Hp, g.CS);
+    LAS_LAUNCH_OK("pack_whh_kernel");
+  }
+  return LAS_OK;
+}
+
+int fast_listener_forward(const float* x, const void* packed, const las_listener_dims* d, float* enc, void* ws, cudaStream_t st) {
+  LAS_TRY(shape_ok(d));
+  const Geo g = geometry(d->H);
+  const ListenerPackFast pk = pack_layout(d, const_cast<void*>(packed));
+  const ListenerWsFast w = ws_layout(d, ws);
+  const int B = d->B, H = d->H;
+  {
+    ProfScope ps("listener.cast_bf16", st);
+    LAS_TRY(launch_f32_to_bf16(x, w.xb, (size_t)B * d->T * d->F, st));
+  }
+  const __nv_bfloat16* cur = w.xb;
+  int Tin = d->T, Fin = d->F;
+  for (int l = 0; l < d->L; ++l) {
+    const int Tl = Tin / 2, K = 2 * Fin, M = B * Tl, NP = 8 * g.Hp;
+    char nm[48];
+    {
+      snprintf(nm, sizeof(nm), "listener.L%d.input_gemm", l);
+      ProfScope ps(nm, st);
+      // pyramid fold = reading [B, Tin, Fin] as [B*Tl, 2*Fin] (model/las_model.py:86-87): only the tensor map changes
+      LAS_TRY(launch_gemm_bf16_tc(cur, K, pk.wih[l], K, pk.bias[l], w.P, NP, M, NP, K, st));
+    }
+    snprintf(nm, sizeof(nm), "listener.L%d.recurrence", l);
+    ProfScope ps(nm, st);
+    const bool last = (l == d->L - 1);
+    RecParams rp;
+    rp.P = w.P;
+    rp.whh_img = pk.whh[l];
+    rp.out_f32 = last ? enc : nullptr;
+    rp.out_bf16 = last ? nullptr : w.act[l & 1];
+    rp.B = B; rp.Tl = Tl; rp.H = H; rp.Hp = g.Hp; rp.CS = g.CS;
+    rp.trace = (l == 0) ? g_rec_trace : nullptr;
+    rp.a_tmem = g_rec_a_tmem;
+    const int bc = pick_bc(B, g.CS);
+    rp.nchunks = (B + bc - 1) / bc;
+    if (bc == 16) LAS_TRY(launch_rec<16>(rp, st));
+    else if (bc == 32) LAS_TRY(launch_rec<32>(rp, st));
+    else LAS_TRY(launch_rec<64>(rp, st));
+    cur = w.act[l & 1];
+    Tin = Tl;
+    Fin = 2 * H;
+  }
+  return LAS_OK;
+}
+
+}  // namespace las

@@ -520,6 +520,14 @@ int las_debug_gemm_bf16(const void* a, const void* w, const float* bias, float* 
   return launch_gemm_bf16_tc(static_cast<const __nv_bfloat16*>(a), K, static_cast<const __nv_bfloat16*>(w), K, bias, c, N, M, N, K,
                              static_cast<cudaStream_t>(stream));
 }
+int las_debug_set_option(int key, int value) {
+  fast_set_option(key, value);
+  return LAS_OK;
+}
+int las_debug_set_trace(void* dev_buf) {
+  fast_set_trace(static_cast<long long*>(dev_buf));
+  return LAS_OK;
+}
 int las_debug_umma_probe(const void* a, const void* b, float* d, int N, int K, int a_sw128, int b_sw128, int variant, void* stream) {
   LAS_REQUIRE(a && b && d, "null pointer argument");
   LAS_TRY(device_ok());

@@ -19,6 +19,9 @@ int fast_speller_decode(const las_decode_io* io, const void* packed_f32, const v
                         const las_speller_dims* d, int steps, int decode_mode, int relu, void* ws_f32, void* ws_fast,
                         cudaStream_t st);
 
+void fast_set_option(int key, int value);  // test hook: 1 = recurrence A operand in TMEM (default 1)
+void fast_set_trace(long long* dev_buf);  // test hook: recurrence kernel timeline (64 steps x 8 clock64 stamps)
+
 // fast_gemm.cu
 int launch_gemm_bf16_tc(const __nv_bfloat16* A, long long lda, const __nv_bfloat16* W, long long ldw, const float* bias, float* C,
                         long long ldc, int M, int N, int K, cudaStream_t st);
