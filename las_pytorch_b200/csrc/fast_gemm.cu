@@ -178,6 +178,10 @@ int make_tmap_bf16(CUtensorMap* tm, const void* base, long long rows, long long 
 
 }  // namespace
 
+int make_tmap_bf16_box(CUtensorMap* tm, const void* base, long long rows, long long cols, long long ld, int box_rows) {
+  return make_tmap_bf16(tm, base, rows, cols, ld, box_rows);
+}
+
 int launch_gemm_bf16_tc(const __nv_bfloat16* A, long long lda, const __nv_bfloat16* W, long long ldw, const float* bias, float* C,
                         long long ldc, int M, int N, int K, cudaStream_t st) {
   LAS_REQUIRE(M > 0 && N > 0 && K > 0, "bad GEMM shape %dx%dx%d", M, N, K);

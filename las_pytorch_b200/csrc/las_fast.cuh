@@ -20,7 +20,8 @@ int fast_speller_decode(const las_decode_io* io, const void* packed_f32, const v
                         cudaStream_t st);
 
 void fast_set_option(int key, int value);  // test hook: 1 = recurrence A operand in TMEM (default 1)
-void fast_set_trace(long long* dev_buf);  // test hook: recurrence kernel timeline (64 steps x 8 clock64 stamps)
+void fast_set_trace(long long* dev_buf);
+long long* fast_get_trace();  // test hook: recurrence kernel timeline (64 steps x 8 clock64 stamps)
 
 // fast_gemm.cu
 int launch_gemm_bf16_tc(const __nv_bfloat16* A, long long lda, const __nv_bfloat16* W, long long ldw, const float* bias, float* C,

@@ -1,0 +1,50 @@
+"""Decoder-only timing + cross-role timeline (globaltimer) on the GPU."""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import las_testlib as tl  # noqa: E402
+from las_pytorch_b200 import _cabi  # noqa: E402
+
+
+def main():
+    lib = _cabi.load_library()
+    cfgname, B, T, S = "paper", 64, 1600, 300
+    c = tl.CONFIGS[cfgname]
+    las = tl.build_model(cfgname, max_label_len=S, seed=17, gain=3.0, precision="bf16").cuda()
+    x, _ = tl.make_inputs(B, T, c["F"], S, c["V"], seed=17)
+    enc = las.listener(x.cuda())
+    for _ in range(2):
+        las.speller(enc, None, 0.0)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(3):
+        las.speller(enc, None, 0.0)
+    e1.record()
+    torch.cuda.synchronize()
+    print(f"speller c3 bf16: {e0.elapsed_time(e1) / 3:.3f} ms  ({e0.elapsed_time(e1) / 3 / S * 1e3:.2f} us/step)")
+    buf = torch.zeros(512 + 3 * 32 * 8, dtype=torch.int64, device="cuda")
+    lib.las_debug_set_trace(_cabi.ptr(buf))
+    las.speller(enc, None, 0.0)
+    torch.cuda.synchronize()
+    lib.las_debug_set_trace(None)
+    t = buf.cpu().numpy()[512:].reshape(3, 32, 8)
+    names = [["in ready", "tma issued", "mma issued", "tmem_full", "stored", "signalled", "h-part mma", "-"],
+             ["in ready", "tma issued", "mma issued", "tmem_full", "stored", "signalled", "h-part mma", "-"],
+             ["h ready", "q", "energy", "softmax", "ctx", "logits+lsm", "signalled", "-"]]
+    for s in range(4, 9):
+        base = t[0, s, 0]
+        print(f"step {s} (ns relative to layer-0 'input ready'):")
+        for role, rn in enumerate(["L0 cta0", "L1 cta0", "att cta0"]):
+            print(f"   {rn}: " + "  ".join(f"{names[role][i]}={int(t[role, s, i] - base)}" for i in range(7)))
+        print(f"   next step L0 input ready at +{int(t[0, s + 1, 0] - base)} ns")
+
+
+if __name__ == "__main__":
+    main()
