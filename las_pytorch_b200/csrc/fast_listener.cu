@@ -441,8 +441,10 @@ int launch_rec(const RecParams& p, cudaStream_t st) {
 
 void fast_set_trace(long long* p) { g_rec_trace = p; }
 long long* fast_get_trace() { return g_rec_trace; }
+void fast_set_option_speller(int key, int value);
 void fast_set_option(int key, int value) {
   if (key == 1) g_rec_a_tmem = value;
+  fast_set_option_speller(key, value);
 }
 
 size_t fast_listener_packed_bytes(const las_listener_dims* d) { return pack_layout(d, nullptr).bytes; }

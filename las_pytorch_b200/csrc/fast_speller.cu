@@ -28,7 +28,7 @@ namespace {
 
 constexpr int DEC_NW = 64;        // gate columns per LSTM CTA (16 hidden units x 4 gates)
 constexpr int DEC_UNITS = DEC_NW / 4;
-constexpr int DEC_MAX_STAGES = 12;
+constexpr int DEC_MAX_STAGES = 16;
 constexpr int DEC_THREADS = 512;
 constexpr int DEC_VP = 64;        // one-hot / word columns padded to one 64-wide K atom
 constexpr int WATOM_BYTES = DEC_NW * 128;  // B atom: 64 gate columns x 64 bf16
@@ -64,6 +64,7 @@ struct DecParams {
   int Bfull;  // batch pitch of the caller's tensors; this launch covers utterances [b0, b0 + B)
   int b0;
   int U, E, Hs, sl, V, D, steps, decode_mode, relu, gt_steps, ncl, k_in_smem;
+  int ctx_tmem;  // 1: enc[b]^T is resident in the attention CTA's tensor memory and the context is a UMMA
   int nstages, stage_bytes;  // activation ring: stage = [box_rows (64 or 128) batch rows x 64 bf16], 128-byte swizzled
   long long* trace;  // nullable test hook: [3 roles][32 steps][8] globaltimer stamps (layer-0 CTA 0, top-layer CTA 0, attention CTA 0)
 };
@@ -135,27 +136,25 @@ __device__ void lstm_role(const DecParams& p, uint8_t* smem, int l, int nb) {
   const int nh = (p.Hs + 63) / 64;
   const int nx = (l == 0) ? (DEC_VP + p.E + 63) / 64 : (p.Hs + 63) / 64;
   const int natoms = nh + nx;
-  const int NST = p.nstages, STAGE_BYTES = p.stage_bytes;
-  // activation ring first, weights right behind it: with 64-row stages the UMMA (M = 128) also reads the 8 KB that
-  // follow a stage (the next stage or the first weight atom); those rows only feed accumulator lanes >= 64, which are
-  // never read
-  uint8_t* ring = smem;                                  // NST x STAGE_BYTES
-  uint8_t* wsm = ring + (size_t)NST * STAGE_BYTES;       // natoms x 8 KB
+  const int NBUF = p.nstages, STAGE_BYTES = p.stage_bytes;  // NBUF >= max(nh, nx): one slot per atom of a part
+  // Activation buffer first, weights right behind it: with 64-row slots the UMMA (M = 128) also reads the 8 KB that
+  // follow a slot (the next slot or the first weight atom); those rows only feed accumulator lanes >= 64, never read.
+  uint8_t* abuf = smem;                                  // NBUF x STAGE_BYTES
+  uint8_t* wsm = abuf + (size_t)NBUF * STAGE_BYTES;      // natoms x 8 KB
   float* bias_s = reinterpret_cast<float*>(wsm + (size_t)natoms * WATOM_BYTES);
   uint64_t* bars = reinterpret_cast<uint64_t*>(bias_s + DEC_NW);
-  uint64_t* full = bars;                     // [NST]
-  uint64_t* empty = bars + DEC_MAX_STAGES;   // [NST]
-  uint64_t* tmem_full = bars + 2 * DEC_MAX_STAGES;
+  uint64_t* full = bars;                         // [NBUF] one per slot: TMA bytes landed
+  uint64_t* part_empty = bars + DEC_MAX_STAGES;  // all MMAs of the previous part have read the buffer
+  uint64_t* tmem_full = part_empty + 1;
   uint64_t* tmem_empty = tmem_full + 1;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 1);
+  constexpr int EPI_WARPS = 8, EPI_THREADS = EPI_WARPS * 32;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < NST; ++i) {
-      ptx::mbar_init(&full[i], 1);
-      ptx::mbar_init(&empty[i], 1);
-    }
+    for (int i = 0; i < NBUF; ++i) ptx::mbar_init(&full[i], 1);
+    ptx::mbar_init(part_empty, 1);
     ptx::mbar_init(tmem_full, 1);
-    ptx::mbar_init(tmem_empty, 128);
+    ptx::mbar_init(tmem_empty, EPI_THREADS);
     ptx::fence_mbar_init();
   }
   if (warp == 1) ptx::tmem_alloc(tmem_slot, 128);
@@ -176,137 +175,135 @@ __device__ void lstm_role(const DecParams& p, uint8_t* smem, int l, int nb) {
 
   if (warp == 0) {
     // ============================ TMA producer ============================
-    int stage = 0;
-    uint32_t phase = 0;
+    // Each step has two parts: (0) the layer's own h_{s-1}, complete once every CTA of this layer finished step s-1
+    // (available long before it is needed), and (1) the critical input: [word | context] of step s-1 for layer 0, the
+    // lower layer's h of THIS step otherwise.  All atoms of a part are issued back to back into their own slots.
     const uint32_t* own_ctr = counter(p, l);
     const uint32_t* in_ctr = (l == 0) ? counter(p, MAX_SL) : counter(p, l - 1);
+    int n = 0;  // running part index
     for (int s = 0; s < S; ++s) {
       const int par = s & 1;
-      // (1) the layer's own h_{s-1}: complete once every CTA of this layer has finished step s-1
-      if (lane == 0) wait_counter(own_ctr, (uint32_t)s * p.ncl);
-      __syncwarp();
-      fence_proxy_async_global();  // other SMs' generic-proxy stores (acquired above) -> this warp's TMA reads
-      for (int i = 0; i < nh; ++i) {
-        ptx::mbar_wait(&empty[stage], phase ^ 1);
-        if (ptx::elect_one()) {
-          ptx::mbar_arrive_expect_tx(&full[stage], STAGE_BYTES);
-          ptx::tma_load_2d(ring + stage * STAGE_BYTES, &p.tm_h[l][par], &full[stage], i * 64, 0);
+      for (int part = 0; part < 2; ++part, ++n) {
+        if (n > 0) ptx::mbar_wait(part_empty, (uint32_t)((n - 1) & 1));
+        if (lane == 0) {
+          if (part == 0) wait_counter(own_ctr, (uint32_t)s * p.ncl);
+          else wait_counter(in_ctr, (l == 0) ? (uint32_t)s * p.B : (uint32_t)(s + 1) * p.ncl);
+          if (part == 1 && trole >= 0) DEC_TRACE(trole, 0);
         }
         __syncwarp();
-        if (++stage == NST) { stage = 0; phase ^= 1; }
-      }
-      // (2) the critical input: [word | context] of step s-1 (layer 0) or the lower layer's h of THIS step
-      if (lane == 0) wait_counter(in_ctr, (l == 0) ? (uint32_t)s * p.B : (uint32_t)(s + 1) * p.ncl);
-      if (lane == 0 && trole >= 0) DEC_TRACE(trole, 0);
-      __syncwarp();
-      fence_proxy_async_global();
-      const CUtensorMap* tm_in = (l == 0) ? &p.tm_x[par] : &p.tm_h[l - 1][par ^ 1];
-      for (int i = 0; i < nx; ++i) {
-        ptx::mbar_wait(&empty[stage], phase ^ 1);
+        fence_proxy_async_global();  // other SMs' generic-proxy stores (acquired above) -> this warp's TMA reads
+        const CUtensorMap* tm = (part == 0) ? &p.tm_h[l][par] : ((l == 0) ? &p.tm_x[par] : &p.tm_h[l - 1][par ^ 1]);
+        const int na = part == 0 ? nh : nx;
         if (ptx::elect_one()) {
-          ptx::mbar_arrive_expect_tx(&full[stage], STAGE_BYTES);
-          ptx::tma_load_2d(ring + stage * STAGE_BYTES, tm_in, &full[stage], i * 64, 0);
+          for (int i = 0; i < na; ++i) {
+            ptx::mbar_arrive_expect_tx(&full[i], STAGE_BYTES);
+            ptx::tma_load_2d(abuf + (size_t)i * STAGE_BYTES, tm, &full[i], i * 64, 0);
+          }
         }
         __syncwarp();
-        if (++stage == NST) { stage = 0; phase ^= 1; }
+        if (part == 1 && lane == 0 && trole >= 0) DEC_TRACE(trole, 1);
       }
-      if (lane == 0 && trole >= 0) DEC_TRACE(trole, 1);
     }
   } else if (warp == 1) {
     // ============================ MMA issuer ============================
     const UmmaLayout la{1, 0, 1024, (uint32_t)STAGE_BYTES}, lb{1, 0, 1024, WATOM_BYTES};
     const uint32_t idesc = umma_idesc_bf16(128, DEC_NW);
-    const uint32_t ring_addr = ptx::smem_u32(ring), w_addr = ptx::smem_u32(wsm);
-    int stage = 0;
-    uint32_t phase = 0;
+    const uint32_t a0 = ptx::smem_u32(abuf), w_addr = ptx::smem_u32(wsm);
+    uint32_t phase_bits = 0;  // per-slot phase parity
     for (int s = 0; s < S; ++s) {
       ptx::mbar_wait(tmem_empty, (uint32_t)((s & 1) ^ 1));
       ptx::tc_fence_after();
-      for (int i = 0; i < natoms; ++i) {
-        ptx::mbar_wait(&full[stage], phase);
-        ptx::tc_fence_after();
-        if (ptx::elect_one()) {
-          const uint32_t d = tmem + (i < nh ? 0u : (uint32_t)DEC_NW);  // separate accumulators for the two parts
-          const bool first = (i == 0) || (i == nh);
-          const uint32_t a_addr = ring_addr + stage * STAGE_BYTES, b_addr = w_addr + i * WATOM_BYTES;
+      for (int part = 0; part < 2; ++part) {
+        const int na = part == 0 ? nh : nx;
+        const uint32_t d = tmem + (part == 0 ? 0u : (uint32_t)DEC_NW);  // separate accumulators for the two parts
+        for (int i = 0; i < na; ++i) {
+          ptx::mbar_wait(&full[i], (phase_bits >> i) & 1u);
+          phase_bits ^= 1u << i;
+          ptx::tc_fence_after();
+          if (ptx::elect_one()) {
+            const uint32_t a_addr = a0 + i * STAGE_BYTES, b_addr = w_addr + (part == 0 ? i : nh + i) * WATOM_BYTES;
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            ptx::umma_bf16(d, umma_smem_desc(la, a_addr, k * 16), umma_smem_desc(lb, b_addr, k * 16), idesc, !(first && k == 0));
-          ptx::umma_commit(&empty[stage]);
-          if (i == natoms - 1) ptx::umma_commit(tmem_full);
+            for (int k = 0; k < 4; ++k)
+              ptx::umma_bf16(d, umma_smem_desc(la, a_addr, k * 16), umma_smem_desc(lb, b_addr, k * 16), idesc, !(i == 0 && k == 0));
+            if (i == na - 1) {
+              ptx::umma_commit(part_empty);
+              if (part == 1) ptx::umma_commit(tmem_full);
+            }
+          }
+          __syncwarp();
         }
-        __syncwarp();
-        if (i == nh - 1 && lane == 0 && trole >= 0) DEC_TRACE(trole, 6);
-        if (++stage == NST) { stage = 0; phase ^= 1; }
+        if (part == 0 && lane == 0 && trole >= 0) DEC_TRACE(trole, 6);
       }
       if (lane == 0 && trole >= 0) DEC_TRACE(trole, 2);
     }
-  } else if (warp < 6) {
+  } else if (warp < 2 + EPI_WARPS) {
     // ============================ epilogue: gates, cell state, h ============================
-    const int q = warp & 3;
-    const int b = q * 32 + lane;          // batch row = TMEM lane
-    const int u0 = nb * DEC_UNITS;        // first hidden unit of this CTA
+    // 8 warps: TMEM lane quadrant = warp & 3 (batch rows), column half = (warp - 2) / 4 (8 of the CTA's 16 units each)
+    const int q = warp & 3, half = (warp - 2) >> 2;
+    const int b = q * 32 + lane;                       // batch row = TMEM lane
+    const int u0 = nb * DEC_UNITS + half * 8;          // first hidden unit of this thread
+    const int c0 = half * 32;                          // first accumulator column
     const bool live = b < p.B;
-    float c[DEC_UNITS];
+    const bool warp_live = q * 32 < p.B;
+    float c[8];
 #pragma unroll
-    for (int i = 0; i < DEC_UNITS; ++i)
-      c[i] = (live && p.c_init) ? p.c_init[((size_t)l * p.Bfull + p.b0 + b) * p.Hs + u0 + i] : 0.f;
+    for (int i = 0; i < 8; ++i) c[i] = (live && p.c_init) ? p.c_init[((size_t)l * p.Bfull + p.b0 + b) * p.Hs + u0 + i] : 0.f;
     const bool top = (l == p.sl - 1);
     for (int s = 0; s < S; ++s) {
       ptx::mbar_wait(tmem_full, (uint32_t)(s & 1));
       if (warp == 2 && lane == 0 && trole >= 0) DEC_TRACE(trole, 3);
       ptx::tc_fence_after();
-      float h[DEC_UNITS];
+      float h[8];
+      if (warp_live) {
 #pragma unroll
-      for (int ch = 0; ch < 4; ++ch) {
-        uint32_t a0[16], a1[16];
-        ptx::tmem_ld_32x32b_x16(tmem + ((uint32_t)(q * 32) << 16) + ch * 16, a0);
-        ptx::tmem_ld_32x32b_x16(tmem + ((uint32_t)(q * 32) << 16) + DEC_NW + ch * 16, a1);
-        ptx::tmem_ld_wait();
+        for (int ch = 0; ch < 2; ++ch) {
+          uint32_t a0[16], a1[16];
+          ptx::tmem_ld_32x32b_x16(tmem + ((uint32_t)(q * 32) << 16) + c0 + ch * 16, a0);
+          ptx::tmem_ld_32x32b_x16(tmem + ((uint32_t)(q * 32) << 16) + DEC_NW + c0 + ch * 16, a1);
+          ptx::tmem_ld_wait();
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int col = ch * 16 + u * 4;
-          const float pi = __uint_as_float(a0[u * 4 + 0]) + __uint_as_float(a1[u * 4 + 0]) + bias_s[col + 0];
-          const float pf = __uint_as_float(a0[u * 4 + 1]) + __uint_as_float(a1[u * 4 + 1]) + bias_s[col + 1];
-          const float pg = __uint_as_float(a0[u * 4 + 2]) + __uint_as_float(a1[u * 4 + 2]) + bias_s[col + 2];
-          const float po = __uint_as_float(a0[u * 4 + 3]) + __uint_as_float(a1[u * 4 + 3]) + bias_s[col + 3];
-          const int ui = ch * 4 + u;
-          const float cn = sigmoid_fast(pf) * c[ui] + sigmoid_fast(pi) * tanh_fast(pg);
-          c[ui] = cn;
-          h[ui] = sigmoid_fast(po) * tanh_fast(cn);
+          for (int u = 0; u < 4; ++u) {
+            const int col = c0 + ch * 16 + u * 4;
+            const float pi = __uint_as_float(a0[u * 4 + 0]) + __uint_as_float(a1[u * 4 + 0]) + bias_s[col + 0];
+            const float pf = __uint_as_float(a0[u * 4 + 1]) + __uint_as_float(a1[u * 4 + 1]) + bias_s[col + 1];
+            const float pg = __uint_as_float(a0[u * 4 + 2]) + __uint_as_float(a1[u * 4 + 2]) + bias_s[col + 2];
+            const float po = __uint_as_float(a0[u * 4 + 3]) + __uint_as_float(a1[u * 4 + 3]) + bias_s[col + 3];
+            const int ui = ch * 4 + u;
+            const float cn = sigmoid_fast(pf) * c[ui] + sigmoid_fast(pi) * tanh_fast(pg);
+            c[ui] = cn;
+            h[ui] = sigmoid_fast(po) * tanh_fast(cn);
+          }
         }
       }
       ptx::tc_fence_before();
       ptx::mbar_arrive(tmem_empty);
       if (live) {
         const int np = (s + 1) & 1;
-        uint32_t pk[DEC_UNITS / 2];
+        uint32_t pk[4];
 #pragma unroll
-        for (int i = 0; i < DEC_UNITS / 2; ++i) {
+        for (int i = 0; i < 4; ++i) {
           const __nv_bfloat162 t = __floats2bfloat162_rn(h[2 * i], h[2 * i + 1]);
           pk[i] = *reinterpret_cast<const uint32_t*>(&t);
         }
-        uint4* dst = reinterpret_cast<uint4*>(p.hbuf[l][np] + (size_t)b * p.Hs + u0);
-        dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-        dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+        *reinterpret_cast<uint4*>(p.hbuf[l][np] + (size_t)b * p.Hs + u0) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
         if (top) {
           float4* df = reinterpret_cast<float4*>(p.hf32[np] + (size_t)b * p.Hs + u0);
-#pragma unroll
-          for (int i = 0; i < DEC_UNITS / 4; ++i) df[i] = make_float4(h[4 * i], h[4 * i + 1], h[4 * i + 2], h[4 * i + 3]);
+          df[0] = make_float4(h[0], h[1], h[2], h[3]);
+          df[1] = make_float4(h[4], h[5], h[6], h[7]);
         }
         if (s == S - 1) {
           if (p.h_out) {
 #pragma unroll
-            for (int i = 0; i < DEC_UNITS; ++i) p.h_out[((size_t)l * p.Bfull + p.b0 + b) * p.Hs + u0 + i] = h[i];
+            for (int i = 0; i < 8; ++i) p.h_out[((size_t)l * p.Bfull + p.b0 + b) * p.Hs + u0 + i] = h[i];
           }
           if (p.c_out) {
 #pragma unroll
-            for (int i = 0; i < DEC_UNITS; ++i) p.c_out[((size_t)l * p.Bfull + p.b0 + b) * p.Hs + u0 + i] = c[i];
+            for (int i = 0; i < 8; ++i) p.c_out[((size_t)l * p.Bfull + p.b0 + b) * p.Hs + u0 + i] = c[i];
           }
         }
       }
       if (warp == 2 && lane == 0 && trole >= 0) DEC_TRACE(trole, 4);
-      asm volatile("bar.sync 1, 128;" ::: "memory");  // all rows stored; the release below is cumulative over the barrier
+      asm volatile("bar.sync 1, 256;" ::: "memory");  // all rows stored; the release below is cumulative over the barrier
       if (warp == 2 && lane == 0) {
         red_release_add(my_ready, 1u);
         if (trole >= 0) DEC_TRACE(trole, 5);
@@ -346,6 +343,14 @@ __device__ void attention_role(const DecParams& p, uint8_t* smem, int b) {
   float* s_k = s_part + 4096;       // [U][KS] when k_in_smem
   const int ncg = E / 8;            // 8-column groups of enc
   const int nrg = DEC_THREADS / ncg;  // row groups working in parallel
+  // tensor-memory context path: s_part's space holds the mbarrier, the TMEM slot and the score operand instead
+  uint64_t* ctx_bar = reinterpret_cast<uint64_t*>(s_part);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_part + 2);
+  uint8_t* s_bop = reinterpret_cast<uint8_t*>(s_part + 4);   // [2*nks core-K][2][8 rows][16 B]: row 0 = scores (bf16)
+  float* s_lh = s_logit;                                      // h-part of the logits is accumulated in place
+  const int nks = (U + 15) / 16;                              // UMMA K steps over the encoder axis
+  const int CU = nks * 8;                                     // TMEM columns of one 128-feature tile of enc^T
+  const int NT = E / 128;                                     // feature tiles
 
   for (int i = tid; i < D * Hs; i += DEC_THREADS) s_wphi[(size_t)(i / Hs) * WPS + (i % Hs)] = p.w_phi[i];
   for (int i = tid; i < V * KC; i += DEC_THREADS) s_wcd[(size_t)(i / KC) * WCS + (i % KC)] = p.w_cd[i];
@@ -364,7 +369,40 @@ __device__ void attention_role(const DecParams& p, uint8_t* smem, int b) {
   const uint32_t* h_ctr = counter(p, p.sl - 1);
   uint32_t* ctx_ctr = counter(p, MAX_SL);
   const int dchunk = ((D + 3) / 4 + 3) & ~3;  // psi columns per lane of a 4-lane row team, multiple of 4
+  uint32_t tmem = 0;
+  if (p.ctx_tmem) {
+    // enc[b]^T -> tensor memory, once: tile t holds features [128t, 128t+128) as TMEM lanes, encoder steps along the
+    // columns (two bf16 per 32-bit column) = the A operand of  ctx^T[E,1] = enc^T[E,U] . score[U,1]
+    if (tid == 0) {
+      ptx::mbar_init(ctx_bar, 1);
+      ptx::fence_mbar_init();
+    }
+    if (warp == 0) ptx::tmem_alloc(tmem_slot, 512);
+    for (int i = tid; i < nks * 512 / 16; i += DEC_THREADS) reinterpret_cast<uint4*>(s_bop)[i] = make_uint4(0, 0, 0, 0);
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    tmem = *tmem_slot;
+    const int qd = warp & 3;
+    for (int t = warp >> 2; t < NT; t += NWARP / 4) {
+      const __nv_bfloat16* col = encb + t * 128 + qd * 32 + lane;
+      for (int ks = 0; ks < nks; ++ks) {
+        uint32_t v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int u0 = ks * 16 + 2 * i;
+          const unsigned short lo = u0 < U ? *reinterpret_cast<const unsigned short*>(col + (size_t)u0 * E) : 0;
+          const unsigned short hi = u0 + 1 < U ? *reinterpret_cast<const unsigned short*>(col + (size_t)(u0 + 1) * E) : 0;
+          v[i] = (uint32_t)lo | ((uint32_t)hi << 16);
+        }
+        ptx::tmem_st_32x32b_x8(tmem + ((uint32_t)(qd * 32) << 16) + t * CU + ks * 8, v);
+      }
+    }
+    ptx::tmem_st_wait();
+    ptx::tc_fence_before();
+  }
   __syncthreads();
+  ptx::tc_fence_after();
 
   for (int s = 0; s < p.steps; ++s) {
     const int np = (s + 1) & 1;
@@ -461,58 +499,124 @@ __device__ void attention_role(const DecParams& p, uint8_t* smem, int b) {
     __syncthreads();
     if (tid == 0 && b == 0) DEC_TRACE(2, 3);
 
-    // context[e] = sum_u score[u] * enc[b,u,e]  (:293-297): 16-byte bf16 loads, nrg row groups in parallel, 8 loads in flight
-    {
-      const int rg = tid / ncg, cg = tid % ncg;
-      float acc[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-      if (rg < nrg) {
-        const uint4* col = reinterpret_cast<const uint4*>(encb + cg * 8);
-        const int rstride = E / 8;  // uint4 per row
-        for (int u = rg; u < ulen; u += 8 * nrg) {
-          uint4 v[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const int uu = u + j * nrg;
-            v[j] = (uu < ulen) ? __ldg(col + (size_t)uu * rstride) : make_uint4(0, 0, 0, 0);
-          }
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const int uu = u + j * nrg;
-            const float a = (uu < ulen) ? s_score[uu] : 0.f;
-            const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&v[j]);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const float2 f = __bfloat1622float2(h2[i]);
-              acc[2 * i] = fmaf(a, f.x, acc[2 * i]);
-              acc[2 * i + 1] = fmaf(a, f.y, acc[2 * i + 1]);
+    if (p.ctx_tmem) {
+      // context via the tensor core: scores (bf16) are row 0 of a 16-row K-major operand in shared memory,
+      // D_t[128 features, 16] = enc^T tile (TMEM) . scores^T ; column 0 of each accumulator is the context
+      for (int u = tid; u < U; u += DEC_THREADS) {
+        const __nv_bfloat16 a = __float2bfloat16_rn(s_score[u]);
+        *reinterpret_cast<__nv_bfloat16*>(s_bop + (u >> 3) * 256 + (u & 7) * 2) = a;
+      }
+      ptx::fence_proxy_async_smem();
+      __syncthreads();
+      if (warp == 0) {
+        ptx::tc_fence_after();
+        if (ptx::elect_one()) {
+          const UmmaLayout lb{0, 256, 128, 0};
+          const uint32_t idesc = umma_idesc_bf16(128, 16);
+          const uint32_t bop = ptx::smem_u32(s_bop);
+          for (int t = 0; t < NT; ++t)
+            for (int ks = 0; ks < nks; ++ks)
+              ptx::umma_bf16_ts(tmem + NT * CU + t * 16, tmem + t * CU + ks * 8, umma_smem_desc(lb, bop, ks * 16), idesc, ks != 0);
+          ptx::umma_commit(ctx_bar);
+        }
+        __syncwarp();
+      }
+      // meanwhile: the h half of the character distribution, W_cd[:, :Hs] . h  (16 lanes per output)
+      {
+        const int part = tid & 15;
+        const float2* xv = reinterpret_cast<const float2*>(s_h);
+        for (int v = tid >> 4; v < ((V + 1) & ~1); v += DEC_THREADS / 16) {
+          float a0 = 0.f, a1 = 0.f;
+          if (v < V) {
+            const __nv_bfloat162* wr = reinterpret_cast<const __nv_bfloat162*>(s_wcd + (size_t)v * WCS);
+            int kp = part;
+            for (; kp + 16 < Hs / 2; kp += 32) {
+              const float2 w0 = __bfloat1622float2(wr[kp]), w1 = __bfloat1622float2(wr[kp + 16]);
+              const float2 x0 = xv[kp], x1 = xv[kp + 16];
+              a0 = fmaf(w0.x, x0.x, a0); a0 = fmaf(w0.y, x0.y, a0);
+              a1 = fmaf(w1.x, x1.x, a1); a1 = fmaf(w1.y, x1.y, a1);
+            }
+            for (; kp < Hs / 2; kp += 16) {
+              const float2 w0 = __bfloat1622float2(wr[kp]);
+              const float2 x0 = xv[kp];
+              a0 = fmaf(w0.x, x0.x, a0); a0 = fmaf(w0.y, x0.y, a0);
             }
           }
+          float acc = a0 + a1;
+          acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+          acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+          acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+          acc += __shfl_xor_sync(0xffffffffu, acc, 8);
+          if (part == 0 && v < V) s_lh[v] = acc + s_bcd[v];
         }
-        float4* dst = reinterpret_cast<float4*>(s_part + (size_t)rg * E + cg * 8);
-        dst[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
-        dst[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
       }
+      ptx::mbar_wait(ctx_bar, (uint32_t)(s & 1));
+      ptx::tc_fence_after();
+      {
+        const int qd = warp & 3;
+        for (int t = warp >> 2; t < NT; t += NWARP / 4) {
+          const uint32_t r = ptx::tmem_ld_32x32b_x1(tmem + ((uint32_t)(qd * 32) << 16) + NT * CU + t * 16);
+          ptx::tmem_ld_wait();
+          s_ctx[t * 128 + qd * 32 + lane] = __uint_as_float(r);
+        }
+      }
+      ptx::tc_fence_before();
+      __syncthreads();
+    } else {
+      // context[e] = sum_u score[u] * enc[b,u,e]  (:293-297): 16-byte bf16 loads, nrg row groups in parallel, 8 loads in flight
+      {
+        const int rg = tid / ncg, cg = tid % ncg;
+        float acc[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+        if (rg < nrg) {
+          const uint4* col = reinterpret_cast<const uint4*>(encb + cg * 8);
+          const int rstride = E / 8;  // uint4 per row
+          for (int u = rg; u < ulen; u += 8 * nrg) {
+            uint4 v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const int uu = u + j * nrg;
+              v[j] = (uu < ulen) ? __ldg(col + (size_t)uu * rstride) : make_uint4(0, 0, 0, 0);
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const int uu = u + j * nrg;
+              const float a = (uu < ulen) ? s_score[uu] : 0.f;
+              const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&v[j]);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const float2 f = __bfloat1622float2(h2[i]);
+                acc[2 * i] = fmaf(a, f.x, acc[2 * i]);
+                acc[2 * i + 1] = fmaf(a, f.y, acc[2 * i + 1]);
+              }
+            }
+          }
+          float4* dst = reinterpret_cast<float4*>(s_part + (size_t)rg * E + cg * 8);
+          dst[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+          dst[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+        }
+      }
+      __syncthreads();
+      for (int e = tid; e < E; e += DEC_THREADS) {
+        float acc = 0.f;
+        for (int rg = 0; rg < nrg; ++rg) acc += s_part[(size_t)rg * E + e];
+        s_ctx[e] = acc;
+      }
+      __syncthreads();
     }
-    __syncthreads();
-    for (int e = tid; e < E; e += DEC_THREADS) {
-      float acc = 0.f;
-      for (int rg = 0; rg < nrg; ++rg) acc += s_part[(size_t)rg * E + e];
-      s_ctx[e] = acc;
-    }
-    __syncthreads();
     if (tid == 0 && b == 0) DEC_TRACE(2, 4);
 
     // logits = W_cd . [h || context] + b_cd ; log_softmax  (:181-182)
-    {  // 16 lanes per output, interleaved 4-byte columns
+    {  // 16 lanes per output, interleaved 4-byte columns.  Tensor-memory path: only the context half is left to add.
       const int part = tid & 15;
+      const int k_lo = p.ctx_tmem ? Hs / 2 : 0;
       const float2* xv = reinterpret_cast<const float2*>(s_h);  // s_h and s_ctx are contiguous: [h || context]
       for (int v = tid >> 4; v < ((V + 1) & ~1); v += DEC_THREADS / 16) {
         float a0 = 0.f, a1 = 0.f;
         if (v < V) {
           const __nv_bfloat162* wr = reinterpret_cast<const __nv_bfloat162*>(s_wcd + (size_t)v * WCS);
-          int kp = part;
+          int kp = k_lo + part;
           for (; kp + 16 < KC / 2; kp += 32) {
             const float2 w0 = __bfloat1622float2(wr[kp]), w1 = __bfloat1622float2(wr[kp + 16]);
             const float2 x0 = xv[kp], x1 = xv[kp + 16];
@@ -530,7 +634,7 @@ __device__ void attention_role(const DecParams& p, uint8_t* smem, int b) {
         acc += __shfl_xor_sync(0xffffffffu, acc, 2);
         acc += __shfl_xor_sync(0xffffffffu, acc, 4);
         acc += __shfl_xor_sync(0xffffffffu, acc, 8);
-        if (part == 0 && v < V) s_logit[v] = acc + s_bcd[v];
+        if (part == 0 && v < V) s_logit[v] = p.ctx_tmem ? s_lh[v] + acc : acc + s_bcd[v];
       }
     }
     __syncthreads();
@@ -585,6 +689,11 @@ __device__ void attention_role(const DecParams& p, uint8_t* smem, int b) {
       red_release_add(ctx_ctr, 1u);
       if (b == 0) DEC_TRACE(2, 6);
     }
+  }
+  if (p.ctx_tmem) {
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 0) ptx::tmem_dealloc(tmem, 512);
   }
 }
 
@@ -652,6 +761,8 @@ __global__ void dec_init_kernel(DecParams p, const float* enc_f32, const float* 
       p.hbuf[l][0][(size_t)b * p.Hs + i] = __float2bfloat16_rn(h_in ? h_in[((size_t)l * p.Bfull + gb) * p.Hs + i] : 0.f);
 }
 
+int g_dec_ctx_tmem = 1;  // las_debug_set_option(2, v)
+
 struct Shape {
   int ncl, natoms[MAX_SL];
   size_t w_bytes[MAX_SL];
@@ -678,14 +789,16 @@ RingCfg ring_cfg(const las_speller_dims* d, int rows) {
   int mx = 0;
   for (int l = 0; l < d->sl; ++l) mx = s.natoms[l] > mx ? s.natoms[l] : mx;
   RingCfg r;
-  r.box_rows = rows <= 64 ? 64 : 128;
+  (void)rows;
+  r.box_rows = 64;
   r.stage_bytes = r.box_rows * 128;
-  const size_t fixed = (size_t)mx * WATOM_BYTES + DEC_NW * 4 + (2 * DEC_MAX_STAGES + 4) * 8 + 64;
-  const size_t budget = 222 * 1024;
-  long long n = fixed < budget ? (long long)((budget - fixed) / r.stage_bytes) : 0;
-  if (n > DEC_MAX_STAGES) n = DEC_MAX_STAGES;
-  r.nstages = (int)n;
-  r.smem = fixed + (size_t)r.nstages * r.stage_bytes;
+  const size_t fixed = (size_t)mx * WATOM_BYTES + DEC_NW * 4 + (DEC_MAX_STAGES + 4) * 8 + 64;
+  // one slot per atom of the larger part (own-h part: ceil(Hs/64); input part: (64 + E)/64 for layer 0)
+  int need = (d->Hs + 63) / 64;
+  const int nx0 = (DEC_VP + d->E + 63) / 64;
+  if (nx0 > need) need = nx0;
+  r.nstages = need;
+  r.smem = fixed + (size_t)r.nstages * r.stage_bytes + (r.box_rows == 64 ? 0 : 0);
   return r;
 }
 size_t att_smem(const las_speller_dims* d, bool k_in) {
@@ -700,7 +813,8 @@ int supported(const las_speller_dims* d) {
   LAS_REQUIRE(d->Hs % 16 == 0 && d->Hs <= 512, "LAS_MODE_BF16 speller needs hidden_size %% 16 == 0 and <= 512 (Hs=%d); use LAS_MODE_FP32", d->Hs);
   LAS_REQUIRE(d->V <= DEC_VP, "LAS_MODE_BF16 speller supports vocabularies up to %d (V=%d)", DEC_VP, d->V);
   LAS_REQUIRE(d->E % 8 == 0 && d->E / 8 <= DEC_THREADS, "LAS_MODE_BF16 speller needs E %% 8 == 0 and E <= 4096 (E=%d)", d->E);
-  LAS_REQUIRE(att_smem(d, false) <= 220 * 1024 && ring_cfg(d, 128).nstages >= 2, "LAS_MODE_BF16 speller: model does not fit shared memory (U=%d)", d->U);
+  LAS_REQUIRE(att_smem(d, false) <= 220 * 1024 && ring_cfg(d, 64).smem <= 224 * 1024 && ring_cfg(d, 64).nstages <= DEC_MAX_STAGES,
+              "LAS_MODE_BF16 speller: model does not fit shared memory (U=%d, Hs=%d)", d->U, d->Hs);
   return LAS_OK;
 }
 
@@ -748,6 +862,9 @@ SpellerWsFast ws_layout(const las_speller_dims* d, void* base) {
 }  // namespace
 
 bool fast_available() { return true; }
+void fast_set_option_speller(int key, int value) {
+  if (key == 2) g_dec_ctx_tmem = value;
+}
 
 size_t fast_speller_packed_bytes(const las_speller_dims* d) { return pack_layout(d, nullptr).bytes; }
 size_t fast_speller_workspace_bytes(const las_speller_dims* d, int) { return ws_layout(d, nullptr).bytes; }
@@ -775,7 +892,8 @@ int fast_speller_decode(const las_decode_io* io, const void* packed_f32, const v
   const int n_lstm = d->sl * s.ncl;
   const int nsm = sm_count();
   LAS_REQUIRE(n_lstm + 1 <= nsm, "LAS_MODE_BF16 speller: %d LSTM CTAs do not fit %d SMs", n_lstm, nsm);
-  const int max_b = nsm - n_lstm;  // utterances per persistent launch (one attention CTA each)
+  // utterances per persistent launch: one attention CTA each, and at most 64 (activation slots hold 64 batch rows)
+  const int max_b = (nsm - n_lstm) < 64 ? (nsm - n_lstm) : 64;
   const SpellerPackFast pk = pack_layout(d, const_cast<void*>(packed_fast));
   // fp32 block of the pack (las_api.cu layout): psi / phi / cd weights and biases in the reference's own shapes
   struct F32View { const float *w_psi, *b_psi, *b_phi, *b_cd; } fv;
@@ -811,6 +929,10 @@ int fast_speller_decode(const las_decode_io* io, const void* packed_f32, const v
     p.B = Bc; p.U = d->U; p.E = d->E; p.Hs = d->Hs; p.sl = d->sl; p.V = d->V; p.D = d->D;
     p.steps = steps; p.decode_mode = decode_mode; p.relu = relu; p.gt_steps = io->gt_steps; p.ncl = s.ncl;
     p.k_in_smem = att_smem(d, true) <= 220 * 1024;
+    {
+      const int nks = (d->U + 15) / 16, NT = d->E / 128;
+      p.ctx_tmem = (d->E % 128 == 0) && (NT * (nks * 8 + 16) <= 512) && (nks * 512 + 16 <= 4096 * 4) && g_dec_ctx_tmem;
+    }
     const RingCfg rc = ring_cfg(d, Bc);
     p.nstages = rc.nstages;
     p.stage_bytes = rc.stage_bytes;
