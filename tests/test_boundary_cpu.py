@@ -118,3 +118,19 @@ def test_product_does_not_import_oracle():
         for f in files:
             if f.endswith((".py", ".cu", ".cuh")):
                 assert "oracle" not in open(os.path.join(root, f)).read(), f"{f} references oracle/"
+
+
+def test_checkpoint_package_roundtrip(tmp_path):
+    """reference-format package (train.py:83-90,181-201), incl. a DataParallel `module.` prefix."""
+    from las_pytorch_b200 import checkpoint
+
+    las = tl.build_model("tiny", max_label_len=9, seed=5)
+    path = str(tmp_path / "las-epoch3.pth.tar")
+    checkpoint.save_package(las, path, optimizer=None, epoch=3, tr_loss=1.5, val_loss=2.5)
+    las2, pkg = checkpoint.load_package(path, mlp_dim_in_attention=16, max_label_len=9)
+    assert pkg["epoch"] == 3 and pkg["ehidden"] == 16 and pkg["dhidden"] == 32
+    for (k1, v1), (k2, v2) in zip(las.state_dict().items(), las2.state_dict().items()):
+        assert k1 == k2 and torch.equal(v1, v2)
+    pkg["state_dict"] = {"module." + k: v for k, v in pkg["state_dict"].items()}
+    las3, _ = checkpoint.load_package(pkg, las=tl.build_model("tiny", max_label_len=9, seed=1))
+    assert torch.equal(las3.listener.pLSTM_layer1.BLSTM.weight_hh_l0_reverse, las.listener.pLSTM_layer1.BLSTM.weight_hh_l0_reverse)

@@ -206,3 +206,24 @@ def test_nll_sums_match_solver_loss():
     _cabi.check(lib.las_nll_sums(_cabi.ptr(logp), _cabi.ptr(labels), S, S, B, V, S, _cabi.ptr(out), _cabi.current_stream_ptr()))
     ref = O.nll_loss_ignore0(logp.permute(1, 0, 2).cpu().numpy().astype(np.float64), labels.cpu().numpy())
     assert abs(float(out[0] / out[1]) - ref) < 1e-5
+
+
+def test_solver_batch_iterator_matches_oracle():
+    """'next' row f1: solver.batch_iterator(is_training=False) -> (NLL(ignore_index=0) loss, per-utterance LER)."""
+    from las_pytorch_b200.solver import batch_iterator
+
+    c = tl.CONFIGS["small"]
+    B, T, S = 5, 128, 20
+    las = tl.build_model("small", max_label_len=S, seed=11, gain=3.0)
+    sd = tl.state_dict_numpy(las)
+    x, labels = tl.make_inputs(B, T, c["F"], S, c["V"], seed=11)
+    labels[:, -3:] = 0  # padded tail, as collate_fn produces (utils/data.py:133-136)
+    labels[:, -4] = 1   # <eos>
+    ref = O.las_forward(x.numpy(), sd, c["L"], c["sl"], S, dtype=np.float64)
+    ref_loss = O.nll_loss_ignore0(ref["logp"].transpose(1, 0, 2), labels.numpy())
+    ref_ler = O.letter_error_rate(ref["tokens"].T, labels.numpy())
+    loss, ler = batch_iterator(x.cuda(), tl.onehot(labels, c["V"]).cuda(), las.cuda(), None, 0.0, False, S, 0.1)
+    assert abs(float(loss) - ref_loss) < 1e-4
+    assert np.allclose(ler, ref_ler, atol=1e-12)
+    with pytest.raises(NotImplementedError):
+        batch_iterator(x.cuda(), tl.onehot(labels, c["V"]).cuda(), las, None, 0.9, True, S, 0.1)
