@@ -35,7 +35,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                     const float* __restrict__ bias, float* __restrict__ C, long long ldc, int M, int N, int K) {
   extern __shared__ uint8_t smem_raw[];
-  GemmSmem& s = *reinterpret_cast<GemmSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  GemmSmem& s = *reinterpret_cast<GemmSmem*>(smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u));  // offset from the __shared__ symbol keeps the address space
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m_tiles = (M + BM - 1) / BM, n_tiles = (N + BN - 1) / BN, k_blocks = (K + BK - 1) / BK;
   const int num_tiles = m_tiles * n_tiles;
@@ -210,7 +210,7 @@ __global__ void __launch_bounds__(128, 1)
 umma_probe_kernel(const __nv_bfloat16* __restrict__ A, const __nv_bfloat16* __restrict__ B, float* __restrict__ D, int N, int K,
                   UmmaLayout la, UmmaLayout lb, uint32_t a_bytes, int variant) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* base = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);  // offset from the __shared__ symbol keeps the address space
   uint8_t* sa = base;
   uint8_t* sb = base + a_bytes;
   __shared__ uint64_t bar;

@@ -64,7 +64,7 @@ __global__ void __launch_bounds__(REC_THREADS, 1) lstm_recurrence_cluster_kernel
   // accumulators that the epilogue sums.
   constexpr int NACC = BC == 16 ? 4 : (BC == 32 ? 2 : 1);
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* base = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);  // offset from the __shared__ symbol keeps the address space
   const int Hp = p.Hp;
   const uint32_t a_bytes = 128u * Hp * 2u, h_bytes = (uint32_t)BC * Hp * 2u;
   const uint32_t a_smem_bytes = p.a_tmem ? 0u : a_bytes;

@@ -3,16 +3,26 @@
 //
 // CTA roles (one CTA per SM, all co-resident; cudaLaunchAttributeCooperative guarantees it):
 //   * LSTM CTAs: layer l, block nb owns 16 hidden units (64 gate columns, unit-major / gate-minor).  Its slice of
-//     [W_hh | W_ih] (bf16, 128-byte-swizzled K-major atoms) stays in shared memory for all S steps as the B operand;
-//     the A operand is the activation matrix [batch (M = 128 TMEM lanes), K] streamed per step by TMA through a
-//     4-stage ring: first the layer's own h_{s-1} (available early), then the critical input ([word | context] for
-//     layer 0, the lower layer's fresh h otherwise).  tcgen05.mma accumulates both parts in TMEM; the epilogue thread
-//     of batch row b holds that row's cell state c in registers (fp32) and writes h (bf16 operand copy + fp32 copy).
-//   * attention CTAs: one per utterance.  W_phi, W_cd (bf16) and psi(enc)[b] (fp32) are resident in shared memory;
-//     per step: q = relu(W_phi h + b), energies, length-masked softmax, context (streams enc[b] as bf16, 16-byte
-//     loads), character distribution, log-softmax, argmax / teacher forcing, and the next LSTM input row.
-// Hand-off between roles is through global-memory buffers (double-buffered by step parity) and monotonically
-// increasing release/acquire counters; TMA reads of freshly written activations are ordered by fence.proxy.async.
+//     [W_hh | W_word | W_in] (bf16, 128-byte-swizzled K-major atoms) stays in shared memory for all S steps as the B
+//     operand; the A operand is the activation matrix [batch (M = 128 TMEM lanes), K] streamed per step by TMA:
+//       part 0   the layer's own h_{s-1}            (ready long before it is needed; accumulator 0)
+//       part 1a  the critical input: the context of step s-1 (layer 0) / the lower layer's fresh h (accumulator 1)
+//       part 1b  layer 0 only, and only when the fed-back word is a dense vector (decode_mode 0, dense teacher
+//                forcing, the first step): the word atom.  For greedy decoding / index teacher forcing the word is
+//                an index, and the epilogue adds the matching column of W_word straight from the resident atom.
+//     tcgen05.mma accumulates in TMEM; the epilogue thread of batch row b holds that row's cell state c in registers
+//     (fp32) and writes h (bf16 operand copy for the TMA consumers; fp32 flag-in-data copy for the attention CTAs).
+//   * attention CTAs: one per utterance.  W_phi, W_cd (bf16) and psi(enc)[b] (fp32) are resident in shared memory,
+//     enc[b]^T in tensor memory; per step: q = relu(W_phi h + b), energies, length-masked softmax, context (UMMA with
+//     the scores as the B operand), publish the context, then character distribution, log-softmax, argmax / teacher
+//     forcing, publish the word.  The context is published BEFORE the character distribution is evaluated, so layer 0's
+//     context GEMM of the next step overlaps the logits of this one.
+// Hand-offs (measured in tools/microbench.cu: a release/acquire counter hop costs ~1.0 us + ~0.8 us of TMA, a
+// self-validating store ~0.5 us):
+//   * matrix hand-offs consumed by TMA (h -> LSTM CTAs, context / dense word -> layer 0): global buffers double-buffered
+//     by step parity + monotonically increasing release/acquire counters; fence.proxy.async orders the TMA reads;
+//   * top-layer h -> attention CTA and greedy token -> layer 0: 8-byte {value, step tag} slots written with one store
+//     and polled by the consumer itself (no fence, no counter): the data is its own flag.
 #include <cuda.h>
 #include <string.h>
 
@@ -33,15 +43,19 @@ constexpr int DEC_THREADS = 512;
 constexpr int DEC_VP = 64;        // one-hot / word columns padded to one 64-wide K atom
 constexpr int WATOM_BYTES = DEC_NW * 128;  // B atom: 64 gate columns x 64 bf16
 constexpr int MAX_SL = 4;
+constexpr int CTR_CTX = MAX_SL, CTR_WORD = MAX_SL + 1, N_CTR = MAX_SL + 2;
+constexpr int ATT_MAXP = 3;       // encoder steps per attention CTA <= ATT_MAXP * 256
+typedef unsigned long long u64;
 
 struct DecParams {
   CUtensorMap tm_h[MAX_SL][2];  // hbuf[l][parity]  bf16 [B, Hs]
-  CUtensorMap tm_x[2];          // xbuf[parity]     bf16 [B, VP + E]
-  const uint8_t* w_img[MAX_SL]; // [ncl][atoms_l] swizzled 64x64 bf16 atoms: h part first, then input part
+  CUtensorMap tm_x[2];          // xbuf[parity]     bf16 [B, VP + E]  (word atom first, then the context)
+  const uint8_t* w_img[MAX_SL]; // [ncl][atoms_l] swizzled 64x64 bf16 atoms: h part, (layer 0: word atom), input part
   const float* bias[MAX_SL];    // [ncl*64] b_ih + b_hh in CTA column order
   __nv_bfloat16* hbuf[MAX_SL][2];
-  float* hf32[2];               // top layer h, fp32 [B, Hs]
   __nv_bfloat16* xbuf[2];
+  u64* h_ll;                    // [B, Hs] {fp32 h of the top layer, step tag}
+  u64* tok_ll;                  // [B]     {token fed back, step tag}
   const float* c_init;          // nullable [sl, B, Hs]
   float* h_out;                 // nullable [sl, B, Hs]
   float* c_out;                 // nullable [sl, B, Hs]
@@ -59,13 +73,14 @@ struct DecParams {
   int32_t* tokens;              // nullable [S, B]
   float* word_out;              // nullable [B, V]
   float* ctx_out;               // nullable [B, E]
-  uint32_t* sync;               // counters, 32 uint32 apart: [l] = h_ready[l], [MAX_SL] = ctx_ready
+  uint32_t* sync;               // counters, 32 uint32 apart: [l] = h_ready[l], [CTR_CTX], [CTR_WORD]
   int B;      // utterances handled by this launch (one attention CTA each)
   int Bfull;  // batch pitch of the caller's tensors; this launch covers utterances [b0, b0 + B)
   int b0;
   int U, E, Hs, sl, V, D, steps, decode_mode, relu, gt_steps, ncl, k_in_smem;
-  int ctx_tmem;  // 1: enc[b]^T is resident in the attention CTA's tensor memory and the context is a UMMA
-  int nstages, stage_bytes;  // activation ring: stage = [box_rows (64 or 128) batch rows x 64 bf16], 128-byte swizzled
+  int word_gather;  // 1: the fed-back word is an index (greedy argmax / gt_index); 0: a dense vector (part 1b)
+  int ctx_tmem;     // 1: enc[b]^T is resident in the attention CTA's tensor memory and the context is a UMMA
+  int nstages, stage_bytes;  // activation slots: [64 batch rows x 64 bf16], 128-byte swizzled; last slot = word atom
   long long* trace;  // nullable test hook: [3 roles][32 steps][8] globaltimer stamps (layer-0 CTA 0, top-layer CTA 0, attention CTA 0)
 };
 
@@ -96,7 +111,8 @@ __device__ __forceinline__ uint32_t ld_relaxed(const uint32_t* p) {
   asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
-// spin with relaxed loads (an acquire load also invalidates L1 on every poll), then one acquire load to synchronise
+// spin with relaxed loads, then one acquire load to synchronise (tools/microbench.cu: the cheapest correct pairing
+// with red.release on this part)
 __device__ __forceinline__ void wait_counter(const uint32_t* ctr, uint32_t target) {
   while (ld_relaxed(ctr) < target) {
   }
@@ -105,27 +121,45 @@ __device__ __forceinline__ void wait_counter(const uint32_t* ctr, uint32_t targe
 __device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
 __device__ __forceinline__ uint32_t* counter(const DecParams& p, int idx) { return p.sync + idx * 32; }
 
-__device__ __forceinline__ float block_max_512(float v, float* red) {
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  v = warp_max(v);
-  __syncthreads();
-  if (lane == 0) red[wid] = v;
-  __syncthreads();
-  float r = red[0];
-#pragma unroll
-  for (int i = 1; i < DEC_THREADS / 32; ++i) r = fmaxf(r, red[i]);
-  return r;
+// flag-in-data slots: one aligned 8-byte store carries the value and the step tag, so the consumer needs no fence
+__device__ __forceinline__ u64 ll_pack(uint32_t value, uint32_t tag) { return ((u64)tag << 32) | value; }
+__device__ __forceinline__ u64 ll_load(const u64* p) {
+  u64 v;
+  asm volatile("ld.relaxed.gpu.global.b64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
 }
-__device__ __forceinline__ float block_sum_512(float v, float* red) {
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  v = warp_sum(v);
-  __syncthreads();
-  if (lane == 0) red[wid] = v;
-  __syncthreads();
-  float r = 0.f;
-#pragma unroll
-  for (int i = 0; i < DEC_THREADS / 32; ++i) r += red[i];
-  return r;
+__device__ __forceinline__ void ll_store(u64* p, u64 v) { asm volatile("st.relaxed.gpu.global.b64 [%0], %1;" ::"l"(p), "l"(v) : "memory"); }
+__device__ __forceinline__ void ll_store2(u64* p, u64 a, u64 b) {
+  asm volatile("st.relaxed.gpu.global.v2.b64 [%0], {%1, %2};" ::"l"(p), "l"(a), "l"(b) : "memory");
+}
+__device__ __forceinline__ uint32_t ll_wait(const u64* p, uint32_t tag) {
+  u64 v;
+  do {
+    v = ll_load(p);
+  } while ((uint32_t)(v >> 32) != tag);
+  return (uint32_t)v;
+}
+
+// Activation vectors read by the GEMV phases (h, context) are stored permuted: the 8 floats that go with the 16-byte
+// weight chunk cc sit as two float4 at float4 index (cc / 8) * 16 + (cc % 8) and 8 float4 further on, so that the lanes
+// of a quarter warp (consecutive chunks) read consecutive float4 -- one conflict-free wavefront per load.
+__device__ __forceinline__ int xpos(int k) {
+  const int cc = k >> 3, w = k & 7;
+  return ((((cc >> 3) << 4) + ((w >> 2) << 3) + (cc & 7)) << 2) + (w & 3);
+}
+__device__ __forceinline__ const float4* xchunk(const float* xb, int cc) { return reinterpret_cast<const float4*>(xb) + ((cc >> 3) << 4) + (cc & 7); }
+__device__ __forceinline__ uint4 lds128(const void* ptr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(ptx::smem_u32(ptr)));
+  return v;
+}
+// dot product of 8 bf16 weights (one 16-byte chunk) with 8 fp32 activations
+__device__ __forceinline__ float dot8(const uint4& w, const float4& x0, const float4& x1, float acc) {
+  const __nv_bfloat162* w2 = reinterpret_cast<const __nv_bfloat162*>(&w);
+  const float2 a = __bfloat1622float2(w2[0]), b = __bfloat1622float2(w2[1]), c = __bfloat1622float2(w2[2]), d = __bfloat1622float2(w2[3]);
+  acc = fmaf(a.x, x0.x, acc); acc = fmaf(a.y, x0.y, acc); acc = fmaf(b.x, x0.z, acc); acc = fmaf(b.y, x0.w, acc);
+  acc = fmaf(c.x, x1.x, acc); acc = fmaf(c.y, x1.y, acc); acc = fmaf(d.x, x1.z, acc); acc = fmaf(d.y, x1.w, acc);
+  return acc;
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -133,10 +167,13 @@ __device__ __forceinline__ float block_sum_512(float v, float* red) {
 // ------------------------------------------------------------------------------------------------------------
 __device__ void lstm_role(const DecParams& p, uint8_t* smem, int l, int nb) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int nh = (p.Hs + 63) / 64;
-  const int nx = (l == 0) ? (DEC_VP + p.E + 63) / 64 : (p.Hs + 63) / 64;
-  const int natoms = nh + nx;
-  const int NBUF = p.nstages, STAGE_BYTES = p.stage_bytes;  // NBUF >= max(nh, nx): one slot per atom of a part
+  const bool first = (l == 0), top = (l == p.sl - 1);
+  const int nh = (p.Hs + 63) / 64;                                 // atoms of the layer's own h
+  const int nc = first ? (p.E + 63) / 64 : (p.Hs + 63) / 64;      // atoms of the critical input
+  const int nwd = first ? 1 : 0;                                   // word atom
+  const int natoms = nh + nwd + nc;
+  const int NBUF = p.nstages, STAGE_BYTES = p.stage_bytes;         // NBUF = max(nh, nc) + 1; the last slot holds the word atom
+  const int wslot = NBUF - 1;
   // Activation buffer first, weights right behind it: with 64-row slots the UMMA (M = 128) also reads the 8 KB that
   // follow a slot (the next slot or the first weight atom); those rows only feed accumulator lanes >= 64, never read.
   uint8_t* abuf = smem;                                  // NBUF x STAGE_BYTES
@@ -144,11 +181,14 @@ __device__ void lstm_role(const DecParams& p, uint8_t* smem, int l, int nb) {
   float* bias_s = reinterpret_cast<float*>(wsm + (size_t)natoms * WATOM_BYTES);
   uint64_t* bars = reinterpret_cast<uint64_t*>(bias_s + DEC_NW);
   uint64_t* full = bars;                         // [NBUF] one per slot: TMA bytes landed
-  uint64_t* part_empty = bars + DEC_MAX_STAGES;  // all MMAs of the previous part have read the buffer
+  uint64_t* part_empty = bars + DEC_MAX_STAGES;  // all MMAs issued so far have read their slots
   uint64_t* tmem_full = part_empty + 1;
   uint64_t* tmem_empty = tmem_full + 1;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 1);
-  constexpr int EPI_WARPS = 8, EPI_THREADS = EPI_WARPS * 32;
+  // Warp roles.  A launch covers at most 64 utterances, so only TMEM lane quadrants 0 and 1 (batch rows 0..63) carry
+  // data; the eight warps that can read them (warp % 4 < 2) form the epilogue, four per quadrant with four hidden
+  // units each.  The producer and the MMA issuer sit on the two idle quadrants.
+  constexpr int EPI_WARPS = 8, EPI_THREADS = EPI_WARPS * 32, PROD_WARP = 2, MMA_WARP = 3;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < NBUF; ++i) ptx::mbar_init(&full[i], 1);
@@ -157,7 +197,7 @@ __device__ void lstm_role(const DecParams& p, uint8_t* smem, int l, int nb) {
     ptx::mbar_init(tmem_empty, EPI_THREADS);
     ptx::fence_mbar_init();
   }
-  if (warp == 1) ptx::tmem_alloc(tmem_slot, 128);
+  if (warp == MMA_WARP) ptx::tmem_alloc(tmem_slot, 128);
   {  // resident weight slice + bias
     const uint4* src = reinterpret_cast<const uint4*>(p.w_img[l] + (size_t)nb * natoms * WATOM_BYTES);
     uint4* dst = reinterpret_cast<uint4*>(wsm);
@@ -171,61 +211,85 @@ __device__ void lstm_role(const DecParams& p, uint8_t* smem, int l, int nb) {
   const uint32_t tmem = *tmem_slot;
   const int S = p.steps;
   uint32_t* my_ready = counter(p, l);
-  const int trole = (nb == 0 && l == 0) ? 0 : ((nb == 0 && l == p.sl - 1) ? 1 : -1);
+  const int trole = (nb == 0 && l == 0) ? 0 : ((nb == 0 && top) ? 1 : -1);
 
-  if (warp == 0) {
+  if (warp == PROD_WARP) {
     // ============================ TMA producer ============================
-    // Each step has two parts: (0) the layer's own h_{s-1}, complete once every CTA of this layer finished step s-1
-    // (available long before it is needed), and (1) the critical input: [word | context] of step s-1 for layer 0, the
-    // lower layer's h of THIS step otherwise.  All atoms of a part are issued back to back into their own slots.
     const uint32_t* own_ctr = counter(p, l);
-    const uint32_t* in_ctr = (l == 0) ? counter(p, MAX_SL) : counter(p, l - 1);
-    int n = 0;  // running part index
+    const uint32_t* in_ctr = first ? counter(p, CTR_CTX) : counter(p, l - 1);
+    const uint32_t* word_ctr = counter(p, CTR_WORD);
+    int n = 0;  // commits on part_empty waited for so far
     for (int s = 0; s < S; ++s) {
       const int par = s & 1;
-      for (int part = 0; part < 2; ++part, ++n) {
-        if (n > 0) ptx::mbar_wait(part_empty, (uint32_t)((n - 1) & 1));
-        if (lane == 0) {
-          if (part == 0) wait_counter(own_ctr, (uint32_t)s * p.ncl);
-          else wait_counter(in_ctr, (l == 0) ? (uint32_t)s * p.B : (uint32_t)(s + 1) * p.ncl);
-          if (part == 1 && trole >= 0) DEC_TRACE(trole, 0);
+      // ---- part 0: own h_{s-1}, complete once every CTA of this layer finished step s-1
+      if (n > 0) ptx::mbar_wait(part_empty, (uint32_t)((n - 1) & 1));
+      ++n;
+      if (lane == 0) wait_counter(own_ctr, (uint32_t)s * p.ncl);
+      __syncwarp();
+      fence_proxy_async_global();  // other SMs' generic-proxy stores (acquired above) -> this warp's TMA reads
+      if (ptx::elect_one()) {
+        for (int i = 0; i < nh; ++i) {
+          ptx::mbar_arrive_expect_tx(&full[i], STAGE_BYTES);
+          ptx::tma_load_2d(abuf + (size_t)i * STAGE_BYTES, &p.tm_h[l][par], &full[i], i * 64, 0);
         }
-        __syncwarp();
-        fence_proxy_async_global();  // other SMs' generic-proxy stores (acquired above) -> this warp's TMA reads
-        const CUtensorMap* tm = (part == 0) ? &p.tm_h[l][par] : ((l == 0) ? &p.tm_x[par] : &p.tm_h[l - 1][par ^ 1]);
-        const int na = part == 0 ? nh : nx;
+      }
+      __syncwarp();
+      // ---- part 1a: context of step s-1 (layer 0) / the lower layer's h of THIS step
+      ptx::mbar_wait(part_empty, (uint32_t)((n - 1) & 1));
+      ++n;
+      if (lane == 0) {
+        wait_counter(in_ctr, first ? (uint32_t)s * p.B : (uint32_t)(s + 1) * p.ncl);
+        if (trole >= 0) DEC_TRACE(trole, 0);
+      }
+      __syncwarp();
+      fence_proxy_async_global();
+      {
+        const CUtensorMap* tm = first ? &p.tm_x[par] : &p.tm_h[l - 1][par ^ 1];
+        const int col0 = first ? DEC_VP : 0;
         if (ptx::elect_one()) {
-          for (int i = 0; i < na; ++i) {
+          for (int i = 0; i < nc; ++i) {
             ptx::mbar_arrive_expect_tx(&full[i], STAGE_BYTES);
-            ptx::tma_load_2d(abuf + (size_t)i * STAGE_BYTES, tm, &full[i], i * 64, 0);
+            ptx::tma_load_2d(abuf + (size_t)i * STAGE_BYTES, tm, &full[i], col0 + i * 64, 0);
           }
         }
         __syncwarp();
-        if (part == 1 && lane == 0 && trole >= 0) DEC_TRACE(trole, 1);
+      }
+      if (lane == 0 && trole >= 0) DEC_TRACE(trole, 1);
+      // ---- part 1b: dense word vector of step s-1
+      if (first && (s == 0 || !p.word_gather)) {
+        if (lane == 0) wait_counter(word_ctr, (uint32_t)s * p.B);
+        __syncwarp();
+        fence_proxy_async_global();
+        if (ptx::elect_one()) {
+          ptx::mbar_arrive_expect_tx(&full[wslot], STAGE_BYTES);
+          ptx::tma_load_2d(abuf + (size_t)wslot * STAGE_BYTES, &p.tm_x[par], &full[wslot], 0, 0);
+        }
+        __syncwarp();
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == MMA_WARP) {
     // ============================ MMA issuer ============================
     const UmmaLayout la{1, 0, 1024, (uint32_t)STAGE_BYTES}, lb{1, 0, 1024, WATOM_BYTES};
     const uint32_t idesc = umma_idesc_bf16(128, DEC_NW);
     const uint32_t a0 = ptx::smem_u32(abuf), w_addr = ptx::smem_u32(wsm);
     uint32_t phase_bits = 0;  // per-slot phase parity
     for (int s = 0; s < S; ++s) {
+      const bool wd = first && (s == 0 || !p.word_gather);
       ptx::mbar_wait(tmem_empty, (uint32_t)((s & 1) ^ 1));
       ptx::tc_fence_after();
       for (int part = 0; part < 2; ++part) {
-        const int na = part == 0 ? nh : nx;
+        const int na = part == 0 ? nh : nc;
         const uint32_t d = tmem + (part == 0 ? 0u : (uint32_t)DEC_NW);  // separate accumulators for the two parts
         for (int i = 0; i < na; ++i) {
           ptx::mbar_wait(&full[i], (phase_bits >> i) & 1u);
           phase_bits ^= 1u << i;
           ptx::tc_fence_after();
           if (ptx::elect_one()) {
-            const uint32_t a_addr = a0 + i * STAGE_BYTES, b_addr = w_addr + (part == 0 ? i : nh + i) * WATOM_BYTES;
+            const uint32_t a_addr = a0 + i * STAGE_BYTES, b_addr = w_addr + (part == 0 ? i : nh + nwd + i) * WATOM_BYTES;
 #pragma unroll
             for (int k = 0; k < 4; ++k)
               ptx::umma_bf16(d, umma_smem_desc(la, a_addr, k * 16), umma_smem_desc(lb, b_addr, k * 16), idesc, !(i == 0 && k == 0));
-            if (i == na - 1) {
+            if (i == na - 1 && (part == 0 || !wd)) {
               ptx::umma_commit(part_empty);
               if (part == 1) ptx::umma_commit(tmem_full);
             }
@@ -234,77 +298,105 @@ __device__ void lstm_role(const DecParams& p, uint8_t* smem, int l, int nb) {
         }
         if (part == 0 && lane == 0 && trole >= 0) DEC_TRACE(trole, 6);
       }
+      if (wd) {
+        ptx::mbar_wait(&full[wslot], (phase_bits >> wslot) & 1u);
+        phase_bits ^= 1u << wslot;
+        ptx::tc_fence_after();
+        if (ptx::elect_one()) {
+          const uint32_t a_addr = a0 + wslot * STAGE_BYTES, b_addr = w_addr + nh * WATOM_BYTES;
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            ptx::umma_bf16(tmem + (uint32_t)DEC_NW, umma_smem_desc(la, a_addr, k * 16), umma_smem_desc(lb, b_addr, k * 16), idesc, 1u);
+          ptx::umma_commit(part_empty);
+          ptx::umma_commit(tmem_full);
+        }
+        __syncwarp();
+      }
       if (lane == 0 && trole >= 0) DEC_TRACE(trole, 2);
     }
-  } else if (warp < 2 + EPI_WARPS) {
+  } else if ((warp & 3) < 2) {
     // ============================ epilogue: gates, cell state, h ============================
-    // 8 warps: TMEM lane quadrant = warp & 3 (batch rows), column half = (warp - 2) / 4 (8 of the CTA's 16 units each)
-    const int q = warp & 3, half = (warp - 2) >> 2;
+    const int q = warp & 3, cs = warp >> 2;            // TMEM lane quadrant (batch rows), column slice (4 units = 16 columns)
     const int b = q * 32 + lane;                       // batch row = TMEM lane
-    const int u0 = nb * DEC_UNITS + half * 8;          // first hidden unit of this thread
-    const int c0 = half * 32;                          // first accumulator column
+    const int u0 = nb * DEC_UNITS + cs * 4;            // first hidden unit of this thread
+    const int c0 = cs * 16;                            // first accumulator column
     const bool live = b < p.B;
     const bool warp_live = q * 32 < p.B;
-    float c[8];
+    const bool lead = (warp == 0 && lane == 0);
+    const int gb = p.b0 + b;
+    float c[4];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) c[i] = (live && p.c_init) ? p.c_init[((size_t)l * p.Bfull + p.b0 + b) * p.Hs + u0 + i] : 0.f;
-    const bool top = (l == p.sl - 1);
+    for (int i = 0; i < 4; ++i) c[i] = (live && p.c_init) ? p.c_init[((size_t)l * p.Bfull + gb) * p.Hs + u0 + i] : 0.f;
+    float bias_r[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) bias_r[i] = bias_s[c0 + i];
+    const uint8_t* watom = wsm + (size_t)nh * WATOM_BYTES;  // layer 0: resident word atom [64 gate columns x 64 vocabulary entries]
     for (int s = 0; s < S; ++s) {
-      ptx::mbar_wait(tmem_full, (uint32_t)(s & 1));
-      if (warp == 2 && lane == 0 && trole >= 0) DEC_TRACE(trole, 3);
-      ptx::tc_fence_after();
-      float h[8];
-      if (warp_live) {
+      // Word contribution first: for an index word (greedy / index teacher forcing) the token is known about a microsecond
+      // before the context GEMM finishes, so its column of W_word is added to the bias while the MMAs are still running.
+      float pb[16];
 #pragma unroll
-        for (int ch = 0; ch < 2; ++ch) {
-          uint32_t a0[16], a1[16];
-          ptx::tmem_ld_32x32b_x16(tmem + ((uint32_t)(q * 32) << 16) + c0 + ch * 16, a0);
-          ptx::tmem_ld_32x32b_x16(tmem + ((uint32_t)(q * 32) << 16) + DEC_NW + c0 + ch * 16, a1);
-          ptx::tmem_ld_wait();
+      for (int i = 0; i < 16; ++i) pb[i] = bias_r[i];
+      if (first && s > 0 && p.word_gather && live) {
+        int tok = p.gt_index ? p.gt_index[(size_t)gb * p.gt_steps + (s - 1)] : (int)ll_wait(p.tok_ll + b, (uint32_t)s);
+        if (tok >= 0 && tok < p.V) {
+          const uint32_t tok_off = (uint32_t)(tok & 7) * 2u, tok_chunk = (uint32_t)(tok >> 3);
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int col = c0 + ch * 16 + u * 4;
-            const float pi = __uint_as_float(a0[u * 4 + 0]) + __uint_as_float(a1[u * 4 + 0]) + bias_s[col + 0];
-            const float pf = __uint_as_float(a0[u * 4 + 1]) + __uint_as_float(a1[u * 4 + 1]) + bias_s[col + 1];
-            const float pg = __uint_as_float(a0[u * 4 + 2]) + __uint_as_float(a1[u * 4 + 2]) + bias_s[col + 2];
-            const float po = __uint_as_float(a0[u * 4 + 3]) + __uint_as_float(a1[u * 4 + 3]) + bias_s[col + 3];
-            const int ui = ch * 4 + u;
-            const float cn = sigmoid_fast(pf) * c[ui] + sigmoid_fast(pi) * tanh_fast(pg);
-            c[ui] = cn;
-            h[ui] = sigmoid_fast(po) * tanh_fast(cn);
+          for (int i = 0; i < 16; ++i) {  // + W_word[c0 + i, tok]: the one-hot word times the word atom, without the GEMM
+            const uint32_t rr = (uint32_t)(c0 + i);
+            const uint32_t off = (rr >> 3) * 1024u + (rr & 7u) * 128u + (((tok_chunk ^ (rr & 7u)) & 7u) << 4) + tok_off;
+            pb[i] += __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(watom + off));
           }
+        }
+      }
+      if (lead && trole == 0) DEC_TRACE(4, 1);
+      ptx::mbar_wait(tmem_full, (uint32_t)(s & 1));
+      if (lead && trole >= 0) DEC_TRACE(trole, 3);
+      ptx::tc_fence_after();
+      float h[4];
+      if (warp_live) {
+        uint32_t a0[16], a1[16];
+        ptx::tmem_ld_32x32b_x16(tmem + ((uint32_t)(q * 32) << 16) + c0, a0);
+        ptx::tmem_ld_32x32b_x16(tmem + ((uint32_t)(q * 32) << 16) + DEC_NW + c0, a1);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const float pi = __uint_as_float(a0[u * 4 + 0]) + __uint_as_float(a1[u * 4 + 0]) + pb[u * 4 + 0];
+          const float pf = __uint_as_float(a0[u * 4 + 1]) + __uint_as_float(a1[u * 4 + 1]) + pb[u * 4 + 1];
+          const float pg = __uint_as_float(a0[u * 4 + 2]) + __uint_as_float(a1[u * 4 + 2]) + pb[u * 4 + 2];
+          const float po = __uint_as_float(a0[u * 4 + 3]) + __uint_as_float(a1[u * 4 + 3]) + pb[u * 4 + 3];
+          const float cn = sigmoid_fast(pf) * c[u] + sigmoid_fast(pi) * tanh_fast(pg);
+          c[u] = cn;
+          h[u] = sigmoid_fast(po) * tanh_fast(cn);
         }
       }
       ptx::tc_fence_before();
       ptx::mbar_arrive(tmem_empty);
       if (live) {
         const int np = (s + 1) & 1;
-        uint32_t pk[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const __nv_bfloat162 t = __floats2bfloat162_rn(h[2 * i], h[2 * i + 1]);
-          pk[i] = *reinterpret_cast<const uint32_t*>(&t);
+        if (top) {  // attention CTA b polls these slots directly
+          const uint32_t tag = (uint32_t)(s + 1);
+          u64* dst = p.h_ll + (size_t)b * p.Hs + u0;
+          ll_store2(dst, ll_pack(__float_as_uint(h[0]), tag), ll_pack(__float_as_uint(h[1]), tag));
+          ll_store2(dst + 2, ll_pack(__float_as_uint(h[2]), tag), ll_pack(__float_as_uint(h[3]), tag));
         }
-        *reinterpret_cast<uint4*>(p.hbuf[l][np] + (size_t)b * p.Hs + u0) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-        if (top) {
-          float4* df = reinterpret_cast<float4*>(p.hf32[np] + (size_t)b * p.Hs + u0);
-          df[0] = make_float4(h[0], h[1], h[2], h[3]);
-          df[1] = make_float4(h[4], h[5], h[6], h[7]);
-        }
+        const __nv_bfloat162 t0 = __floats2bfloat162_rn(h[0], h[1]), t1 = __floats2bfloat162_rn(h[2], h[3]);
+        *reinterpret_cast<uint2*>(p.hbuf[l][np] + (size_t)b * p.Hs + u0) =
+            make_uint2(*reinterpret_cast<const uint32_t*>(&t0), *reinterpret_cast<const uint32_t*>(&t1));
         if (s == S - 1) {
           if (p.h_out) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) p.h_out[((size_t)l * p.Bfull + p.b0 + b) * p.Hs + u0 + i] = h[i];
+            for (int i = 0; i < 4; ++i) p.h_out[((size_t)l * p.Bfull + gb) * p.Hs + u0 + i] = h[i];
           }
           if (p.c_out) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) p.c_out[((size_t)l * p.Bfull + p.b0 + b) * p.Hs + u0 + i] = c[i];
+            for (int i = 0; i < 4; ++i) p.c_out[((size_t)l * p.Bfull + gb) * p.Hs + u0 + i] = c[i];
           }
         }
       }
-      if (warp == 2 && lane == 0 && trole >= 0) DEC_TRACE(trole, 4);
+      if (lead && trole >= 0) DEC_TRACE(trole, 4);
       asm volatile("bar.sync 1, 256;" ::: "memory");  // all rows stored; the release below is cumulative over the barrier
-      if (warp == 2 && lane == 0) {
+      if (lead) {
         red_release_add(my_ready, 1u);
         if (trole >= 0) DEC_TRACE(trole, 5);
       }
@@ -312,42 +404,72 @@ __device__ void lstm_role(const DecParams& p, uint8_t* smem, int l, int nb) {
   }
   ptx::tc_fence_before();
   __syncthreads();
-  if (warp == 1) ptx::tmem_dealloc(tmem, 128);
+  if (warp == MMA_WARP) ptx::tmem_dealloc(tmem, 128);
 }
 
 // ------------------------------------------------------------------------------------------------------------
 // attention role (one utterance)
 // ------------------------------------------------------------------------------------------------------------
-__host__ __device__ inline int att_kstride(int D) { return ((D + 3) & ~3) + 4; }  // padded psi row (floats), 16-byte multiple
+// padded psi row (floats): KS % 32 == 8, so that the 8 lanes of a quarter warp (4 encoder steps x 2 halves, 16-byte
+// chunks interleaved between the halves) hit 8 different 16-byte bank groups
+__host__ __device__ inline int att_kstride(int D) {
+  int ks = (D + 3) & ~3;
+  while (ks % 32 != 8) ks += 4;
+  return ks;
+}
+struct AttLayout {
+  int WPS, WCS, KS, Up;
+  size_t o_wcd, o_h, o_q, o_score, o_logit, o_bphi, o_bcd, o_red, o_part, o_k, total;
+};
+__host__ __device__ inline AttLayout att_layout(int Hs, int E, int U, int D, int V, bool k_in) {
+  AttLayout a;
+  a.WPS = Hs + 8;          // bf16 row strides: multiples of 8 keep every 16-byte chunk aligned
+  a.WCS = Hs + E + 8;
+  a.KS = att_kstride(D);
+  a.Up = (U + 3) & ~3;
+  size_t o = 0;
+  auto take = [&](size_t bytes) { const size_t at = o; o = (o + bytes + 15) & ~(size_t)15; return at; };
+  take((size_t)D * a.WPS * 2);                         // W_phi at offset 0
+  a.o_wcd = take((size_t)V * a.WCS * 2);
+  a.o_h = take((size_t)(((Hs + 63) & ~63) + ((E + 63) & ~63)) * 4);  // h, then ctx, each permuted (xpos) and padded to 64 floats
+  a.o_q = take((size_t)a.KS * 4);
+  a.o_score = take((size_t)a.Up * 4);
+  a.o_logit = take(64 * 4);
+  a.o_bphi = take((size_t)((D + 3) & ~3) * 4);
+  a.o_bcd = take(64 * 4);
+  a.o_red = take(64 * 4);
+  a.o_part = take(4096 * 4);                           // context partial sums, or {mbarrier, TMEM slot, score operand}
+  a.o_k = o;
+  if (k_in) take((size_t)U * a.KS * 4);
+  a.total = o;
+  return a;
+}
 
 __device__ void attention_role(const DecParams& p, uint8_t* smem, int b) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr int NWARP = DEC_THREADS / 32;
   const int Hs = p.Hs, E = p.E, U = p.U, D = p.D, V = p.V, KC = p.Hs + p.E;
-  const int KS = att_kstride(D);
+  const AttLayout L = att_layout(Hs, E, U, D, V, p.k_in_smem != 0);
+  const int KS = L.KS, WPS = L.WPS, WCS = L.WCS;
   const int gb = p.b0 + b;  // utterance index in the caller's tensors
-  // ---- shared-memory carve-up
-  const int WPS = Hs + 16, WCS = KC + 32;  // padded row strides (bf16): shift consecutive rows by 32 / 64 bytes across the banks
-  __nv_bfloat16* s_wphi = reinterpret_cast<__nv_bfloat16*>(smem);             // [D][WPS]
-  __nv_bfloat16* s_wcd = s_wphi + (size_t)D * WPS;                             // [V][WCS]
-  float* s_f = reinterpret_cast<float*>(s_wcd + (((size_t)V * WCS + 7) & ~(size_t)7));
-  float* s_h = s_f;                 // [Hs]
-  float* s_ctx = s_h + Hs;          // [E]   (contiguous after s_h: [h | ctx] is the character-distribution input)
-  float* s_q = s_ctx + E;           // [KS] (zero padded)
-  float* s_score = s_q + KS;        // [U]
-  float* s_logit = s_score + U;     // [V]
-  float* s_bphi = s_logit + V;      // [D]
-  float* s_bcd = s_bphi + D;        // [V]
-  float* s_red = s_bcd + V;         // [32]
-  float* s_part = s_f + (((size_t)Hs + E + KS + D + U + 2 * V + 32 + 3) & ~(size_t)3);  // [nrg][E] <= 4096 floats, 16-byte aligned
-  float* s_k = s_part + 4096;       // [U][KS] when k_in_smem
-  const int ncg = E / 8;            // 8-column groups of enc
+  __nv_bfloat16* s_wphi = reinterpret_cast<__nv_bfloat16*>(smem);               // [D][WPS]
+  __nv_bfloat16* s_wcd = reinterpret_cast<__nv_bfloat16*>(smem + L.o_wcd);      // [V][WCS]
+  float* s_h = reinterpret_cast<float*>(smem + L.o_h);      // [Hs]
+  float* s_ctx = s_h + ((Hs + 63) & ~63);                   // [E]
+  float* s_q = reinterpret_cast<float*>(smem + L.o_q);      // [KS] (zero padded)
+  float* s_score = reinterpret_cast<float*>(smem + L.o_score);  // [U]
+  float* s_logit = reinterpret_cast<float*>(smem + L.o_logit);  // [V]
+  float* s_bphi = reinterpret_cast<float*>(smem + L.o_bphi);
+  float* s_bcd = reinterpret_cast<float*>(smem + L.o_bcd);
+  float* s_red = reinterpret_cast<float*>(smem + L.o_red);      // [0,16): warp maxima, [16,32): warp sums
+  float* s_part = reinterpret_cast<float*>(smem + L.o_part);
+  float* s_k = reinterpret_cast<float*>(smem + L.o_k);          // [U][KS] when k_in_smem
+  const int ncg = E / 8;              // 8-column groups of enc (non-TMEM context path)
   const int nrg = DEC_THREADS / ncg;  // row groups working in parallel
   // tensor-memory context path: s_part's space holds the mbarrier, the TMEM slot and the score operand instead
   uint64_t* ctx_bar = reinterpret_cast<uint64_t*>(s_part);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_part + 2);
   uint8_t* s_bop = reinterpret_cast<uint8_t*>(s_part + 4);   // [2*nks core-K][2][8 rows][16 B]: row 0 = scores (bf16)
-  float* s_lh = s_logit;                                      // h-part of the logits is accumulated in place
   const int nks = (U + 15) / 16;                              // UMMA K steps over the encoder axis
   const int CU = nks * 8;                                     // TMEM columns of one 128-feature tile of enc^T
   const int NT = E / 128;                                     // feature tiles
@@ -366,9 +488,8 @@ __device__ void attention_role(const DecParams& p, uint8_t* smem, int b) {
   }
   const int ulen = p.enc_lengths ? min(max(p.enc_lengths[gb], 1), U) : U;
   const __nv_bfloat16* encb = p.enc + (size_t)b * U * E;
-  const uint32_t* h_ctr = counter(p, p.sl - 1);
-  uint32_t* ctx_ctr = counter(p, MAX_SL);
-  const int dchunk = ((D + 3) / 4 + 3) & ~3;  // psi columns per lane of a 4-lane row team, multiple of 4
+  uint32_t* ctx_ctr = counter(p, CTR_CTX);
+  uint32_t* word_ctr = counter(p, CTR_WORD);
   uint32_t tmem = 0;
   if (p.ctx_tmem) {
     // enc[b]^T -> tensor memory, once: tile t holds features [128t, 128t+128) as TMEM lanes, encoder steps along the
@@ -404,41 +525,36 @@ __device__ void attention_role(const DecParams& p, uint8_t* smem, int b) {
   __syncthreads();
   ptx::tc_fence_after();
 
+  const int hchunks = Hs >> 3, kchunks = KC >> 3;  // 16-byte chunks (8 bf16) of a W_phi row / W_cd row
+  const int Dp = (D + 3) & ~3, Vp = (V + 1) & ~1;
+  const int nd4 = (D + 3) >> 2;                    // float4 chunks of a psi row
+
   for (int s = 0; s < p.steps; ++s) {
     const int np = (s + 1) & 1;
-    if (tid == 0) {
-      wait_counter(h_ctr, (uint32_t)(s + 1) * p.ncl);  // acquire; the CTA barrier below extends it to the other threads
-      if (b == 0) DEC_TRACE(2, 0);
-    }
+    const bool last = (s == p.steps - 1);
+    // ---- A: this step's top-layer h, polled straight out of the LSTM epilogue's flag-in-data slots
+    if (tid < Hs) s_h[xpos(tid)] = __uint_as_float(ll_wait(p.h_ll + (size_t)b * Hs + tid, (uint32_t)(s + 1)));
     __syncthreads();
-    for (int k = tid; k < Hs; k += DEC_THREADS) s_h[k] = __ldcg(p.hf32[np] + (size_t)b * Hs + k);
-    __syncthreads();
+    if (tid == 0 && b == 0) { DEC_TRACE(2, 0); DEC_TRACE(3, 0); if (p.trace && s < 32) p.trace[(2 * 32 + s) * 8 + 7] = clock64(); }
 
-    // q = act(W_phi . h + b_phi)   (model/las_model.py:278): 8 lanes per output, interleaved 4-byte columns
+    // ---- B: q = act(W_phi . h + b_phi)   (model/las_model.py:278): 8 lanes per output, interleaved 16-byte chunks
     {
       const int part = tid & 7;
-      const float2* hv = reinterpret_cast<const float2*>(s_h);
-      for (int d = tid >> 3; d < ((D + 3) & ~3); d += DEC_THREADS / 8) {
-        float a0 = 0.f, a1 = 0.f;
+      for (int d = tid >> 3; d < Dp; d += DEC_THREADS / 8) {
+        float acc = 0.f;
         if (d < D) {
-          const __nv_bfloat162* wr = reinterpret_cast<const __nv_bfloat162*>(s_wphi + (size_t)d * WPS);
-          int kp = part;
-          for (; kp + 8 < Hs / 2; kp += 16) {
-            const float2 w0 = __bfloat1622float2(wr[kp]), w1 = __bfloat1622float2(wr[kp + 8]);
-            const float2 x0 = hv[kp], x1 = hv[kp + 8];
-            a0 = fmaf(w0.x, x0.x, a0); a0 = fmaf(w0.y, x0.y, a0);
-            a1 = fmaf(w1.x, x1.x, a1); a1 = fmaf(w1.y, x1.y, a1);
-          }
-          for (; kp < Hs / 2; kp += 8) {
-            const float2 w0 = __bfloat1622float2(wr[kp]);
-            const float2 x0 = hv[kp];
-            a0 = fmaf(w0.x, x0.x, a0); a0 = fmaf(w0.y, x0.y, a0);
+          const uint4* wr = reinterpret_cast<const uint4*>(s_wphi + (size_t)d * WPS);
+#pragma unroll 4
+          for (int c = part; c < hchunks; c += 8) {
+            const float4* xv = xchunk(s_h, c);
+            acc = dot8(lds128(wr + c), xv[0], xv[8], acc);
           }
         }
-        float acc = a0 + a1;
+        if (tid == 0 && b == 0) DEC_TRACE(3, 1);
         acc += __shfl_xor_sync(0xffffffffu, acc, 1);
         acc += __shfl_xor_sync(0xffffffffu, acc, 2);
         acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+        if (tid == 0 && b == 0) DEC_TRACE(3, 2);
         if (part == 0 && d < D) {
           acc += s_bphi[d];
           s_q[d] = p.relu ? fmaxf(acc, 0.f) : acc;
@@ -446,69 +562,94 @@ __device__ void attention_role(const DecParams& p, uint8_t* smem, int b) {
       }
     }
     __syncthreads();
-    if (tid == 0 && b == 0) DEC_TRACE(2, 1);
+    if (tid == 0 && b == 0) { DEC_TRACE(2, 1); DEC_TRACE(3, 3); }
 
-    // energy[u] = <q, psi[b,u,:]>  (:289-291).  A team of 4 lanes (lane, lane^8, lane^16, lane^24) shares one encoder
-    // step, each lane taking a contiguous quarter of the D columns with 16-byte loads; a warp covers 8 steps per pass
-    // and the 8 lanes of a quarter-warp hit 8 different rows -> conflict-free with the padded row stride.
+    // ---- C: energy[u] = <q, psi[b,u,:]>  (:289-291), two lanes per encoder step, then a softmax over the encoder
+    //         steps (:292) with one exchange of warp maxima and one of warp sums
+    float ev[ATT_MAXP];
+    float lmax = -INFINITY;
     {
-      const int urow = lane & 7, part = lane >> 3;
-      const int d0 = part * dchunk;
-      for (int ub = warp * 8; ub < U; ub += NWARP * 8) {
-        const int u = ub + urow;
-        float acc = 0.f;
-        if (u < U) {
-          if (p.k_in_smem) {
-            const float* kr = s_k + (size_t)u * KS;
-            float acc2 = 0.f;
-            for (int d = d0; d < d0 + dchunk && d < KS - 4; d += 4) {  // q and psi rows are zero padded to KS
-              const float4 kv = *reinterpret_cast<const float4*>(kr + d);
-              const float4 qv = *reinterpret_cast<const float4*>(s_q + d);
-              acc = fmaf(qv.x, kv.x, acc); acc2 = fmaf(qv.y, kv.y, acc2); acc = fmaf(qv.z, kv.z, acc); acc2 = fmaf(qv.w, kv.w, acc2);
+      const int half = tid & 1;
+#pragma unroll
+      for (int ps = 0; ps < ATT_MAXP; ++ps) {
+        ev[ps] = -INFINITY;
+        if (ps * 256 < U) {
+          const int u = ps * 256 + (tid >> 1);
+          float acc = 0.f;
+          if (u < ulen) {
+            if (p.k_in_smem) {
+              const float4* kr = reinterpret_cast<const float4*>(s_k + (size_t)u * KS);
+              const float4* qv = reinterpret_cast<const float4*>(s_q);
+              float acc2 = 0.f;
+#pragma unroll 4
+              for (int c = half; c < nd4; c += 2) {  // q and the psi rows are zero padded to KS
+                const float4 kv = kr[c], q4 = qv[c];
+                acc = fmaf(q4.x, kv.x, acc); acc2 = fmaf(q4.y, kv.y, acc2); acc = fmaf(q4.z, kv.z, acc); acc2 = fmaf(q4.w, kv.w, acc2);
+              }
+              acc += acc2;
+            } else {
+              const float* kr = psib + (size_t)u * D;
+              for (int d = half; d < D; d += 2) acc = fmaf(s_q[d], kr[d], acc);
             }
-            acc += acc2;
-          } else {
-            const float* kr = psib + (size_t)u * D;
-            for (int d = d0; d < d0 + dchunk && d < D; ++d) acc = fmaf(s_q[d], kr[d], acc);
+          }
+          acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+          if (u < ulen) ev[ps] = acc;
+          lmax = fmaxf(lmax, ev[ps]);
+        }
+      }
+      if (tid == 0 && b == 0) DEC_TRACE(3, 4);
+      lmax = warp_max(lmax);
+      if (lane == 0) s_red[warp] = lmax;
+      __syncthreads();
+      if (tid == 0 && b == 0) DEC_TRACE(3, 5);
+      float m;
+      {
+        const float4* r4 = reinterpret_cast<const float4*>(s_red);
+        const float4 a = r4[0], b4 = r4[1], c4 = r4[2], d4 = r4[3];
+        m = fmaxf(fmaxf(fmaxf(a.x, a.y), fmaxf(a.z, a.w)), fmaxf(fmaxf(b4.x, b4.y), fmaxf(b4.z, b4.w)));
+        m = fmaxf(m, fmaxf(fmaxf(fmaxf(c4.x, c4.y), fmaxf(c4.z, c4.w)), fmaxf(fmaxf(d4.x, d4.y), fmaxf(d4.z, d4.w))));
+      }
+      float lsum = 0.f;
+#pragma unroll
+      for (int ps = 0; ps < ATT_MAXP; ++ps) {
+        ev[ps] = (ev[ps] == -INFINITY) ? 0.f : __expf(ev[ps] - m);
+        if (half == 0) lsum += ev[ps];
+      }
+      lsum = warp_sum(lsum);
+      if (lane == 0) s_red[16 + warp] = lsum;
+      __syncthreads();
+      if (tid == 0 && b == 0) DEC_TRACE(3, 6);
+      float tot;
+      {
+        const float4* r4 = reinterpret_cast<const float4*>(s_red + 16);
+        const float4 a = r4[0], b4 = r4[1], c4 = r4[2], d4 = r4[3];
+        tot = ((a.x + a.y) + (a.z + a.w)) + ((b4.x + b4.y) + (b4.z + b4.w)) + ((c4.x + c4.y) + (c4.z + c4.w)) + ((d4.x + d4.y) + (d4.z + d4.w));
+      }
+      const float inv = 1.0f / tot;
+      if (half == 0) {
+#pragma unroll
+        for (int ps = 0; ps < ATT_MAXP; ++ps) {
+          const int u = ps * 256 + (tid >> 1);
+          if (u < U) {
+            const float a = ev[ps] * inv;
+            if (p.attn) p.attn[((size_t)s * p.Bfull + gb) * U + u] = a;
+            if (p.ctx_tmem) *reinterpret_cast<__nv_bfloat16*>(s_bop + (u >> 3) * 256 + (u & 7) * 2) = __float2bfloat16_rn(a);
+            else s_score[u] = a;
           }
         }
-        acc += __shfl_xor_sync(0xffffffffu, acc, 8);
-        acc += __shfl_xor_sync(0xffffffffu, acc, 16);
-        if (part == 0 && u < U) s_score[u] = (u < ulen) ? acc : -INFINITY;
       }
     }
+    if (tid == 0 && b == 0) DEC_TRACE(3, 7);
+    if (p.ctx_tmem) ptx::fence_proxy_async_smem();
     __syncthreads();
     if (tid == 0 && b == 0) DEC_TRACE(2, 2);
 
-    // softmax over encoder steps (:292): every warp reduces max / sum redundantly with shuffles (no CTA barriers)
-    {
-      float m = -INFINITY;
-      for (int u = lane; u < U; u += 32) m = fmaxf(m, s_score[u]);
-      m = warp_max(m);
-      float ssum = 0.f;
-      for (int u = lane; u < U; u += 32) ssum += __expf(s_score[u] - m);
-      ssum = warp_sum(ssum);
-      const float inv = 1.0f / ssum;
-      __syncthreads();  // everyone has read the raw energies
-      for (int u = tid; u < U; u += DEC_THREADS) {
-        const float a = __expf(s_score[u] - m) * inv;
-        s_score[u] = a;
-        if (p.attn) p.attn[((size_t)s * p.Bfull + gb) * U + u] = a;
-      }
-    }
-    __syncthreads();
-    if (tid == 0 && b == 0) DEC_TRACE(2, 3);
-
-    if (p.ctx_tmem) {
-      // context via the tensor core: scores (bf16) are row 0 of a 16-row K-major operand in shared memory,
-      // D_t[128 features, 16] = enc^T tile (TMEM) . scores^T ; column 0 of each accumulator is the context
-      for (int u = tid; u < U; u += DEC_THREADS) {
-        const __nv_bfloat16 a = __float2bfloat16_rn(s_score[u]);
-        *reinterpret_cast<__nv_bfloat16*>(s_bop + (u >> 3) * 256 + (u & 7) * 2) = a;
-      }
-      ptx::fence_proxy_async_smem();
-      __syncthreads();
-      if (warp == 0) {
+    // ---- D: context[e] = sum_u score[u] * enc[b,u,e]  (:293-297); warps 1.. meanwhile evaluate the h half of the
+    //         character distribution, W_cd[:, :Hs] . h + b_cd  (16 lanes per output)
+    if (warp == 0) {
+      if (p.ctx_tmem) {
+        // scores (bf16) are row 0 of a 16-row K-major operand in shared memory:
+        // D_t[128 features, 16] = enc^T tile (TMEM) . scores^T ; column 0 of each accumulator is the context
         ptx::tc_fence_after();
         if (ptx::elect_one()) {
           const UmmaLayout lb{0, 256, 128, 0};
@@ -521,49 +662,43 @@ __device__ void attention_role(const DecParams& p, uint8_t* smem, int b) {
         }
         __syncwarp();
       }
-      // meanwhile: the h half of the character distribution, W_cd[:, :Hs] . h  (16 lanes per output)
-      {
-        const int part = tid & 15;
-        const float2* xv = reinterpret_cast<const float2*>(s_h);
-        for (int v = tid >> 4; v < ((V + 1) & ~1); v += DEC_THREADS / 16) {
-          float a0 = 0.f, a1 = 0.f;
-          if (v < V) {
-            const __nv_bfloat162* wr = reinterpret_cast<const __nv_bfloat162*>(s_wcd + (size_t)v * WCS);
-            int kp = part;
-            for (; kp + 16 < Hs / 2; kp += 32) {
-              const float2 w0 = __bfloat1622float2(wr[kp]), w1 = __bfloat1622float2(wr[kp + 16]);
-              const float2 x0 = xv[kp], x1 = xv[kp + 16];
-              a0 = fmaf(w0.x, x0.x, a0); a0 = fmaf(w0.y, x0.y, a0);
-              a1 = fmaf(w1.x, x1.x, a1); a1 = fmaf(w1.y, x1.y, a1);
-            }
-            for (; kp < Hs / 2; kp += 16) {
-              const float2 w0 = __bfloat1622float2(wr[kp]);
-              const float2 x0 = xv[kp];
-              a0 = fmaf(w0.x, x0.x, a0); a0 = fmaf(w0.y, x0.y, a0);
-            }
+    } else {
+      const int part = tid & 15;
+      for (int v = (tid - 32) >> 4; v < Vp; v += (DEC_THREADS - 32) / 16) {
+        float acc = 0.f;
+        if (v < V) {
+          const uint4* wr = reinterpret_cast<const uint4*>(s_wcd + (size_t)v * WCS);
+#pragma unroll 4
+          for (int c = part; c < hchunks; c += 16) {
+            const float4* xv = xchunk(s_h, c);
+            acc = dot8(lds128(wr + c), xv[0], xv[8], acc);
           }
-          float acc = a0 + a1;
-          acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-          acc += __shfl_xor_sync(0xffffffffu, acc, 2);
-          acc += __shfl_xor_sync(0xffffffffu, acc, 4);
-          acc += __shfl_xor_sync(0xffffffffu, acc, 8);
-          if (part == 0 && v < V) s_lh[v] = acc + s_bcd[v];
         }
+        acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+        acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+        acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+        acc += __shfl_xor_sync(0xffffffffu, acc, 8);
+        if (part == 0 && v < V) s_logit[v] = acc + s_bcd[v];
       }
+    }
+    __nv_bfloat16* xr = p.xbuf[np] + (size_t)b * (DEC_VP + E);  // next LSTM input row: [word (padded to 64) | context]
+    if (p.ctx_tmem) {
       ptx::mbar_wait(ctx_bar, (uint32_t)(s & 1));
       ptx::tc_fence_after();
-      {
-        const int qd = warp & 3;
-        for (int t = warp >> 2; t < NT; t += NWARP / 4) {
-          const uint32_t r = ptx::tmem_ld_32x32b_x1(tmem + ((uint32_t)(qd * 32) << 16) + NT * CU + t * 16);
-          ptx::tmem_ld_wait();
-          s_ctx[t * 128 + qd * 32 + lane] = __uint_as_float(r);
-        }
+      if (tid == 0 && b == 0) DEC_TRACE(2, 3);
+      const int qd = warp & 3;
+      for (int t = warp >> 2; t < NT; t += NWARP / 4) {
+        const uint32_t r = ptx::tmem_ld_32x32b_x1(tmem + ((uint32_t)(qd * 32) << 16) + NT * CU + t * 16);
+        ptx::tmem_ld_wait();
+        const int e = t * 128 + qd * 32 + lane;
+        const float cv = __uint_as_float(r);
+        s_ctx[xpos(e)] = cv;
+        xr[DEC_VP + e] = __float2bfloat16_rn(cv);
+        if (last && p.ctx_out) p.ctx_out[(size_t)gb * E + e] = cv;
       }
       ptx::tc_fence_before();
-      __syncthreads();
     } else {
-      // context[e] = sum_u score[u] * enc[b,u,e]  (:293-297): 16-byte bf16 loads, nrg row groups in parallel, 8 loads in flight
+      // 16-byte bf16 loads of enc[b] (L2 resident), nrg row groups in parallel, 8 loads in flight
       {
         const int rg = tid / ncg, cg = tid % ncg;
         float acc[8];
@@ -598,49 +733,47 @@ __device__ void attention_role(const DecParams& p, uint8_t* smem, int b) {
         }
       }
       __syncthreads();
+      if (tid == 0 && b == 0) DEC_TRACE(2, 3);
       for (int e = tid; e < E; e += DEC_THREADS) {
         float acc = 0.f;
         for (int rg = 0; rg < nrg; ++rg) acc += s_part[(size_t)rg * E + e];
-        s_ctx[e] = acc;
+        s_ctx[xpos(e)] = acc;
+        xr[DEC_VP + e] = __float2bfloat16_rn(acc);
+        if (last && p.ctx_out) p.ctx_out[(size_t)gb * E + e] = acc;
       }
-      __syncthreads();
     }
-    if (tid == 0 && b == 0) DEC_TRACE(2, 4);
+    __syncthreads();  // context row written by every thread; the release below is cumulative over the barrier
+    if (tid == 0) {
+      red_release_add(ctx_ctr, 1u);  // layer 0 starts its context GEMM while the character distribution is evaluated here
+      if (b == 0) DEC_TRACE(2, 4);
+    }
 
-    // logits = W_cd . [h || context] + b_cd ; log_softmax  (:181-182)
-    {  // 16 lanes per output, interleaved 4-byte columns.  Tensor-memory path: only the context half is left to add.
+    // ---- E: logits = W_cd . [h || context] + b_cd: the context half, 16 lanes per output  (:181)
+    {
       const int part = tid & 15;
-      const int k_lo = p.ctx_tmem ? Hs / 2 : 0;
-      const float2* xv = reinterpret_cast<const float2*>(s_h);  // s_h and s_ctx are contiguous: [h || context]
-      for (int v = tid >> 4; v < ((V + 1) & ~1); v += DEC_THREADS / 16) {
-        float a0 = 0.f, a1 = 0.f;
+      for (int v = tid >> 4; v < Vp; v += DEC_THREADS / 16) {
+        float acc = 0.f;
         if (v < V) {
-          const __nv_bfloat162* wr = reinterpret_cast<const __nv_bfloat162*>(s_wcd + (size_t)v * WCS);
-          int kp = k_lo + part;
-          for (; kp + 16 < KC / 2; kp += 32) {
-            const float2 w0 = __bfloat1622float2(wr[kp]), w1 = __bfloat1622float2(wr[kp + 16]);
-            const float2 x0 = xv[kp], x1 = xv[kp + 16];
-            a0 = fmaf(w0.x, x0.x, a0); a0 = fmaf(w0.y, x0.y, a0);
-            a1 = fmaf(w1.x, x1.x, a1); a1 = fmaf(w1.y, x1.y, a1);
-          }
-          for (; kp < KC / 2; kp += 16) {
-            const float2 w0 = __bfloat1622float2(wr[kp]);
-            const float2 x0 = xv[kp];
-            a0 = fmaf(w0.x, x0.x, a0); a0 = fmaf(w0.y, x0.y, a0);
+          const uint4* wr = reinterpret_cast<const uint4*>(s_wcd + (size_t)v * WCS);
+#pragma unroll 4
+          for (int c = part; c < kchunks - hchunks; c += 16) {
+            const float4* xv = xchunk(s_ctx, c);
+            acc = dot8(lds128(wr + hchunks + c), xv[0], xv[8], acc);
           }
         }
-        float acc = a0 + a1;
         acc += __shfl_xor_sync(0xffffffffu, acc, 1);
         acc += __shfl_xor_sync(0xffffffffu, acc, 2);
         acc += __shfl_xor_sync(0xffffffffu, acc, 4);
         acc += __shfl_xor_sync(0xffffffffu, acc, 8);
-        if (part == 0 && v < V) s_logit[v] = p.ctx_tmem ? s_lh[v] + acc : acc + s_bcd[v];
+        if (part == 0 && v < V) s_logit[v] += acc;
       }
     }
     __syncthreads();
-    // every warp computes the log-sum-exp and the argmax redundantly (shuffles only); warp 0 writes the outputs
-    int best;
-    {
+    if (tid == 0 && b == 0) DEC_TRACE(2, 5);
+
+    // ---- F: warp 0: log_softmax (:182), argmax / teacher forcing (:216-227), the word fed back (:236).  The other
+    //         warps go straight on to poll for the next step's h.
+    if (warp == 0) {
       float lm = -INFINITY;
       for (int v = lane; v < V; v += 32) lm = fmaxf(lm, s_logit[v]);
       lm = warp_max(lm);
@@ -652,7 +785,7 @@ __device__ void attention_role(const DecParams& p, uint8_t* smem, int b) {
       int bi = 0x7fffffff;
       for (int v = lane; v < V; v += 32) {
         const float lp = s_logit[v] - lse;
-        if (warp == 0) p.logp[((size_t)s * p.Bfull + gb) * V + v] = lp;
+        p.logp[((size_t)s * p.Bfull + gb) * V + v] = lp;
         if (lp > bv) { bv = lp; bi = v; }
       }
 #pragma unroll
@@ -661,33 +794,28 @@ __device__ void attention_role(const DecParams& p, uint8_t* smem, int b) {
         const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
         if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
       }
-      best = bi;
-      if (tid == 0 && p.tokens) p.tokens[(size_t)s * p.Bfull + gb] = bi;
-      if (tid == 0 && b == 0) DEC_TRACE(2, 5);
-
-      // next LSTM input row: [word (padded to 64) | context], bf16  (:216-227, :236)
-      __nv_bfloat16* xr = p.xbuf[np] + (size_t)b * (DEC_VP + E);
-      const bool last = (s == p.steps - 1);
-      for (int i = tid; i < DEC_VP + E; i += DEC_THREADS) {
-        float val;
-        if (i < DEC_VP) {
-          if (i >= V) val = 0.f;
-          else if (p.gt_dense) val = p.gt_dense[((size_t)gb * p.gt_steps + s) * V + i];
-          else if (p.gt_index) val = (p.gt_index[(size_t)gb * p.gt_steps + s] == i) ? 1.f : 0.f;
-          else if (p.decode_mode == LAS_DECODE_RAW) val = s_logit[i] - lse;
-          else val = (i == best) ? 1.f : 0.f;
-          if (last && p.word_out && i < V) p.word_out[(size_t)gb * V + i] = val;
-        } else {
-          val = s_ctx[i - DEC_VP];
-          if (last && p.ctx_out) p.ctx_out[(size_t)gb * E + (i - DEC_VP)] = val;
+      if (lane == 0 && p.tokens) p.tokens[(size_t)s * p.Bfull + gb] = bi;
+      if (p.word_gather) {
+        // the word is an index: layer 0's epilogue adds the matching column of W_word itself
+        const int fed = p.gt_index ? p.gt_index[(size_t)gb * p.gt_steps + s] : bi;
+        if (lane == 0 && !p.gt_index) ll_store(p.tok_ll + b, ll_pack((uint32_t)fed, (uint32_t)(s + 1)));
+        if (last && p.word_out)
+          for (int i = lane; i < V; i += 32) p.word_out[(size_t)gb * V + i] = (i == fed) ? 1.f : 0.f;
+      } else {
+        for (int i = lane; i < DEC_VP; i += 32) {
+          float val = 0.f;
+          if (i < V) {
+            if (p.gt_dense) val = p.gt_dense[((size_t)gb * p.gt_steps + s) * V + i];
+            else if (p.decode_mode == LAS_DECODE_RAW) val = s_logit[i] - lse;
+            else val = (i == bi) ? 1.f : 0.f;
+            if (last && p.word_out) p.word_out[(size_t)gb * V + i] = val;
+          }
+          xr[i] = __float2bfloat16_rn(val);
         }
-        xr[i] = __float2bfloat16_rn(val);
+        __syncwarp();
+        if (lane == 0) red_release_add(word_ctr, 1u);
       }
-    }
-    __syncthreads();  // all rows written (and s_logit / s_ctx no longer needed); the release below is cumulative over it
-    if (tid == 0) {
-      red_release_add(ctx_ctr, 1u);
-      if (b == 0) DEC_TRACE(2, 6);
+      if (lane == 0 && b == 0) DEC_TRACE(2, 6);
     }
   }
   if (p.ctx_tmem) {
@@ -699,7 +827,9 @@ __device__ void attention_role(const DecParams& p, uint8_t* smem, int b) {
 
 __global__ void __launch_bounds__(DEC_THREADS, 1) speller_decode_persistent_kernel(const __grid_constant__ DecParams p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1024-byte alignment (SWIZZLE_128B atoms) as an offset from the __shared__ symbol, so that the compiler keeps the
+  // address space and emits LDS/STS instead of generic loads
+  uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
   const int n_lstm = p.sl * p.ncl;
   if ((int)blockIdx.x < n_lstm) lstm_role(p, smem, blockIdx.x / p.ncl, blockIdx.x % p.ncl);
   else attention_role(p, smem, blockIdx.x - n_lstm);
@@ -793,26 +923,21 @@ RingCfg ring_cfg(const las_speller_dims* d, int rows) {
   r.box_rows = 64;
   r.stage_bytes = r.box_rows * 128;
   const size_t fixed = (size_t)mx * WATOM_BYTES + DEC_NW * 4 + (DEC_MAX_STAGES + 4) * 8 + 64;
-  // one slot per atom of the larger part (own-h part: ceil(Hs/64); input part: (64 + E)/64 for layer 0)
+  // one slot per atom of the larger shared part (own h: ceil(Hs/64); context / lower h: ceil(E/64)) + the word slot
   int need = (d->Hs + 63) / 64;
-  const int nx0 = (DEC_VP + d->E + 63) / 64;
-  if (nx0 > need) need = nx0;
-  r.nstages = need;
+  const int nc0 = (d->E + 63) / 64;
+  if (nc0 > need) need = nc0;
+  r.nstages = need + 1;
   r.smem = fixed + (size_t)r.nstages * r.stage_bytes + (r.box_rows == 64 ? 0 : 0);
   return r;
 }
-size_t att_smem(const las_speller_dims* d, bool k_in) {
-  const size_t KC = (size_t)d->Hs + d->E;
-  size_t b = (size_t)d->D * (d->Hs + 16) * 2 + ((size_t)d->V * (KC + 32) + 8) * 2;
-  b += 4 * ((size_t)d->Hs + d->E + att_kstride(d->D) + d->D + d->U + 2 * d->V + 32 + 4 + 4096);
-  if (k_in) b += 4 * (size_t)d->U * att_kstride(d->D);
-  return b + 64;
-}
+size_t att_smem(const las_speller_dims* d, bool k_in) { return att_layout(d->Hs, d->E, d->U, d->D, d->V, k_in).total + 64; }
 int supported(const las_speller_dims* d) {
   LAS_REQUIRE(d->sl <= MAX_SL, "LAS_MODE_BF16 speller supports at most %d layers (sl=%d)", MAX_SL, d->sl);
   LAS_REQUIRE(d->Hs % 16 == 0 && d->Hs <= 512, "LAS_MODE_BF16 speller needs hidden_size %% 16 == 0 and <= 512 (Hs=%d); use LAS_MODE_FP32", d->Hs);
   LAS_REQUIRE(d->V <= DEC_VP, "LAS_MODE_BF16 speller supports vocabularies up to %d (V=%d)", DEC_VP, d->V);
   LAS_REQUIRE(d->E % 8 == 0 && d->E / 8 <= DEC_THREADS, "LAS_MODE_BF16 speller needs E %% 8 == 0 and E <= 4096 (E=%d)", d->E);
+  LAS_REQUIRE(d->U <= ATT_MAXP * 256, "LAS_MODE_BF16 speller supports at most %d encoder steps (U=%d)", ATT_MAXP * 256, d->U);
   LAS_REQUIRE(att_smem(d, false) <= 220 * 1024 && ring_cfg(d, 64).smem <= 224 * 1024 && ring_cfg(d, 64).nstages <= DEC_MAX_STAGES,
               "LAS_MODE_BF16 speller: model does not fit shared memory (U=%d, Hs=%d)", d->U, d->Hs);
   return LAS_OK;
@@ -841,9 +966,12 @@ SpellerPackFast pack_layout(const las_speller_dims* d, void* base) {
 struct SpellerWsFast {
   __nv_bfloat16* enc_bf16;
   __nv_bfloat16* hbuf[MAX_SL][2];
-  float* hf32[2];
   __nv_bfloat16* xbuf[2];
+  uint8_t* flags;      // one block cleared per launch: counters, token slots, h slots
+  size_t flag_bytes;
   uint32_t* sync;
+  u64* tok_ll;
+  u64* h_ll;
   size_t bytes;
 };
 SpellerWsFast ws_layout(const las_speller_dims* d, void* base) {
@@ -852,9 +980,13 @@ SpellerWsFast ws_layout(const las_speller_dims* d, void* base) {
   w.enc_bf16 = cv.take<__nv_bfloat16>((size_t)d->B * d->U * d->E);
   for (int l = 0; l < MAX_SL; ++l)
     for (int k = 0; k < 2; ++k) w.hbuf[l][k] = cv.take<__nv_bfloat16>((size_t)d->B * d->Hs);
-  for (int k = 0; k < 2; ++k) w.hf32[k] = cv.take<float>((size_t)d->B * d->Hs);
   for (int k = 0; k < 2; ++k) w.xbuf[k] = cv.take<__nv_bfloat16>((size_t)d->B * (DEC_VP + d->E));
-  w.sync = cv.take<uint32_t>(32 * (MAX_SL + 1));
+  const size_t sync_bytes = sizeof(uint32_t) * 32 * N_CTR, tok_bytes = align_up(sizeof(u64) * (size_t)d->B, 256);
+  w.flag_bytes = sync_bytes + tok_bytes + sizeof(u64) * (size_t)d->B * d->Hs;
+  w.flags = cv.take<uint8_t>(w.flag_bytes);
+  w.sync = reinterpret_cast<uint32_t*>(w.flags);
+  w.tok_ll = reinterpret_cast<u64*>(w.flags ? w.flags + sync_bytes : nullptr);
+  w.h_ll = reinterpret_cast<u64*>(w.flags ? w.flags + sync_bytes + tok_bytes : nullptr);
   w.bytes = cv.total();
   return w;
 }
@@ -945,7 +1077,6 @@ int fast_speller_decode(const las_decode_io* io, const void* packed_f32, const v
       }
     }
     for (int k = 0; k < 2; ++k) {
-      p.hf32[k] = w.hf32[k];
       p.xbuf[k] = w.xbuf[k];
       LAS_TRY(make_tmap_bf16_box(&p.tm_x[k], w.xbuf[k], Bc, DEC_VP + d->E, DEC_VP + d->E, rc.box_rows));
     }
@@ -964,12 +1095,16 @@ int fast_speller_decode(const las_decode_io* io, const void* packed_f32, const v
     p.logp = io->logp; p.attn = io->attn; p.tokens = io->tokens;
     p.word_out = io->word; p.ctx_out = io->context;
     p.sync = w.sync;
-    p.trace = fast_get_trace() ? fast_get_trace() + 512 : nullptr;
+    p.h_ll = w.h_ll;
+    p.tok_ll = w.tok_ll;
+    // the fed-back word is an index (greedy argmax / index teacher forcing) unless a dense vector is asked for
+    p.word_gather = io->gt_dense ? 0 : (io->gt_index ? 1 : (decode_mode == LAS_DECODE_GREEDY ? 1 : 0));
+    p.trace = fast_get_trace() ? fast_get_trace() + 512 : nullptr;  // needs 5 roles x 32 steps x 8 stamps behind the recurrence trace
 
     {
       ProfScope ps("speller.prepare", st);
       LAS_TRY(launch_f32_to_bf16(io->enc + so * d->U * d->E, w.enc_bf16, (size_t)Bc * d->U * d->E, st));
-      LAS_CUDA_OK(cudaMemsetAsync(w.sync, 0, sizeof(uint32_t) * 32 * (MAX_SL + 1), st));
+      LAS_CUDA_OK(cudaMemsetAsync(w.flags, 0, w.flag_bytes, st));
       dec_init_kernel<<<Bc, 256, 0, st>>>(p, io->enc, io->word, io->context, io->h_state);
       LAS_LAUNCH_OK("dec_init_kernel");
     }

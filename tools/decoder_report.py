@@ -29,21 +29,27 @@ def main():
     e1.record()
     torch.cuda.synchronize()
     print(f"speller c3 bf16: {e0.elapsed_time(e1) / 3:.3f} ms  ({e0.elapsed_time(e1) / 3 / S * 1e3:.2f} us/step)")
-    buf = torch.zeros(512 + 3 * 32 * 8, dtype=torch.int64, device="cuda")
+    buf = torch.zeros(512 + 5 * 32 * 8, dtype=torch.int64, device="cuda")
     lib.las_debug_set_trace(_cabi.ptr(buf))
     las.speller(enc, None, 0.0)
     torch.cuda.synchronize()
     lib.las_debug_set_trace(None)
-    t = buf.cpu().numpy()[512:].reshape(3, 32, 8)
+    t = buf.cpu().numpy()[512:].reshape(5, 32, 8)
     names = [["in ready", "tma issued", "mma issued", "tmem_full", "stored", "signalled", "h-part mma", "-"],
              ["in ready", "tma issued", "mma issued", "tmem_full", "stored", "signalled", "h-part mma", "-"],
-             ["h ready", "q", "energy", "softmax", "ctx", "logits+lsm", "signalled", "-"]]
+             ["h arrived", "q", "softmax", "ctx mma", "ctx published", "logits", "word published", "-"]]
     for s in range(4, 9):
         base = t[0, s, 0]
         print(f"step {s} (ns relative to layer-0 'input ready'):")
         for role, rn in enumerate(["L0 cta0", "L1 cta0", "att cta0"]):
             print(f"   {rn}: " + "  ".join(f"{names[role][i]}={int(t[role, s, i] - base)}" for i in range(7)))
         print(f"   next step L0 input ready at +{int(t[0, s + 1, 0] - base)} ns")
+        print("   att fine (rel. h arrived): " + "  ".join(f"{n}={int(t[3, s, i] - t[3, s, 0])}" for i, n in enumerate(
+            ["h", "dot", "shfl", "q sync", "energy", "max sync", "sum sync", "attn written"])))
+        print("   L0 epilogue warp 4 (rel. in ready): " + "  ".join(f"{n}={int(t[4, s, i] - base)}" for i, n in enumerate(
+            ["-", "word gathered"])))
+        print(f"   attention CTA 0: {int(t[2, s + 1, 7] - t[2, s, 7])} SM cycles in {int(t[2, s + 1, 0] - t[2, s, 0])} ns "
+              f"-> {1e3 * (t[2, s + 1, 7] - t[2, s, 7]) / max(1, (t[2, s + 1, 0] - t[2, s, 0])):.0f} MHz")
 
 
 if __name__ == "__main__":
