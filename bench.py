@@ -255,35 +255,52 @@ def main():
             dist.destroy_process_group()
         return
 
-    # ---- roofline of the dominant launch group (per step averages; algorithmic work from SURVEY.md 8d)
+    # ---- rooflines per launch group (per step averages; algorithmic work from SURVEY.md 8d); `roofline` = the dominant one
     peaks = measured_peaks()
     H, L, E, Hs, V, D, sl, U = c["H"], c["L"], 2 * c["H"], 2 * c["H"], c["V"], c["D"], c["sl"], T >> c["L"]
     per_step = {k: v[0] / args.steps for k, v in groups.items()}
     lis_ms = sum(v for k, v in per_step.items() if k.startswith("listener"))
     spl_ms = sum(v for k, v in per_step.items() if k.startswith("speller"))
-    dom = max(per_step, key=per_step.get) if per_step else None
     esize = 2 if precision == "bf16" else 4
-    roofline = None
-    if dom is not None:
-        dt = per_step[dom] / 1e3
-        if dom.endswith("input_gemm"):
-            l = int(dom.split(".")[1][1:])
+    traffic = {}
+    tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")  # dram bytes per launch from `ncu --set full` (tools/ncu_traffic.py)
+    if os.path.exists(tp):
+        traffic = json.load(open(tp)).get(f"{args.workload}:{precision}", {})
+
+    def roof(name):
+        dt = per_step[name] / 1e3
+        if dt <= 0:
+            return None
+        if name.endswith("input_gemm"):
+            l = int(name.split(".")[1][1:])
             M, K = B * (T >> (l + 1)), (2 * c["F"] if l == 0 else 4 * H)
-            fl = 2.0 * M * K * 8 * H
-            roofline = {"kernel": dom, "bound": "tensor", "achieved": fl / dt / 1e12, "peak": peaks["tensor_sustained"], "unit": "TFLOP/s"}
-        elif dom == "speller.steps":
+            fl, by = 2.0 * M * K * 8 * H, esize * M * K + esize * 8 * H * K + 4.0 * M * 8 * H
+            if l == 0 or precision != "bf16":  # K = 2F: arithmetic intensity below the ridge -> bound by the fp32 output write
+                r = {"bound": "hbm", "achieved": by / dt / 1e9, "peak": peaks["hbm"], "unit": "GB/s", "tflops": fl / dt / 1e12}
+            else:
+                r = {"bound": "tensor", "achieved": fl / dt / 1e12, "peak": peaks["tensor_sustained"], "unit": "TFLOP/s"}
+        elif name == "speller.steps":
             by = S * (B * U * (D + E) * esize + 4.0 * B * U + 4.0 * B * V)  # K + enc read once per step, attn + logp written
-            roofline = {"kernel": dom, "bound": "hbm", "achieved": by / dt / 1e9, "peak": peaks["hbm"], "unit": "GB/s"}
-        else:  # recurrence: latency-bound; report the bytes it must move (P read + h written) against HBM
-            l = int(dom.split(".")[1][1:])
+            r = {"bound": "hbm", "achieved": by / dt / 1e9, "peak": peaks["hbm"], "unit": "GB/s", "us_per_decoder_step": per_step[name] * 1e3 / S}
+        elif name.endswith("recurrence"):  # serial chain: report the bytes it must move (P read + h written) against HBM, and us / serial step
+            l = int(name.split(".")[1][1:])
             Tl = T >> (l + 1)
             by = B * Tl * (8 * H * 4.0 + 2 * H * 4.0)
-            roofline = {"kernel": dom, "bound": "hbm", "achieved": by / dt / 1e9, "peak": peaks["hbm"], "unit": "GB/s",
-                        "us_per_serial_step": per_step[dom] * 1e3 / Tl}
-        roofline["frac"] = roofline["achieved"] / roofline["peak"]
-        roofline["traffic"] = None
-        roofline["peak_source"] = peaks["source"]
-        roofline["ms_per_launch_group"] = per_step[dom]
+            r = {"bound": "hbm", "achieved": by / dt / 1e9, "peak": peaks["hbm"], "unit": "GB/s", "us_per_serial_step": per_step[name] * 1e3 / Tl}
+        elif name == "speller.psi":
+            by = B * U * (E * 4.0 + D * 4.0) + D * E * 4.0
+            r = {"bound": "hbm", "achieved": by / dt / 1e9, "peak": peaks["hbm"], "unit": "GB/s"}
+        else:
+            return None
+        r = dict({"kernel": name}, **r)
+        r["frac"] = r["achieved"] / r["peak"]
+        r["traffic"] = traffic.get(name)
+        r["peak_source"] = peaks["source"]
+        r["ms_per_launch_group"] = per_step[name]
+        return r
+
+    rooflines = [r for r in (roof(k) for k in sorted(per_step, key=per_step.get, reverse=True)) if r]
+    roofline = rooflines[0] if rooflines else None
 
     out = dict(base, value=value, ms_per_step=ms / args.steps, dtype=("bf16" if precision == "bf16" else "f32"),
                config={"workload": f"{args.workload}: {wl['desc']}", "per_gpu_batch": B, "frames": T, "decode_steps": S,
@@ -292,7 +309,7 @@ def main():
                us_per_decoder_step=1e3 * spl_ms / S, listener_ms=lis_ms, speller_ms=spl_ms, phase_ms=per_step,
                clocks=clocks, gpu_launches=launches,
                e2e={"value": e2e_value, "unit": "audio-s/s", "h2d_bytes_per_step": x_host.numel() * 4, "d2h_bytes_per_step": tok_host.numel() * 4},
-               roofline=roofline, token_checksum=float(chk))
+               roofline=roofline, rooflines=rooflines, token_checksum=float(chk))
     if world == 1 and not args.no_cpu_baseline:
         v, info = cpu_reference_arm(wl, args.cpu_sample, 1, 1)
         out["cpu_baseline"] = {"value": v, "unit": "audio-s/s", "cores": info["cores"], "kind": "port", "sample": info["sample"],

@@ -55,7 +55,7 @@ struct DecParams {
   __nv_bfloat16* hbuf[MAX_SL][2];
   __nv_bfloat16* xbuf[2];
   u64* h_ll;                    // [B, Hs] {fp32 h of the top layer, step tag}
-  u64* tok_ll;                  // [B]     {token fed back, step tag}
+  u64* tok_ll;                  // [ncl, B] {token fed back, step tag}: one private copy per layer-0 CTA (no polling hot spot)
   const float* c_init;          // nullable [sl, B, Hs]
   float* h_out;                 // nullable [sl, B, Hs]
   float* c_out;                 // nullable [sl, B, Hs]
@@ -89,6 +89,8 @@ __device__ __forceinline__ long long gtimer() {
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
+// per-CTA stamps of step 8 (spread across CTAs): behind the 5 x 32 x 8 role trace, [gridDim][8]
+#define DEC_TRACE_ALL(slot) do { if (p.trace && s == 8) p.trace[5 * 32 * 8 + blockIdx.x * 8 + (slot)] = gtimer(); } while (0)
 #define DEC_TRACE(role, slot) do { if (p.trace && s < 32) p.trace[((role) * 32 + s) * 8 + (slot)] = gtimer(); } while (0)
 
 __device__ __forceinline__ float tanh_fast(float x) {
@@ -237,9 +239,13 @@ __device__ void lstm_role(const DecParams& p, uint8_t* smem, int l, int nb) {
       // ---- part 1a: context of step s-1 (layer 0) / the lower layer's h of THIS step
       ptx::mbar_wait(part_empty, (uint32_t)((n - 1) & 1));
       ++n;
+      if (ptx::elect_one())  // slots are free: arm their barriers now, so that only the copies are left to issue once the input is there
+        for (int i = 0; i < nc; ++i) ptx::mbar_arrive_expect_tx(&full[i], STAGE_BYTES);
+      __syncwarp();
       if (lane == 0) {
         wait_counter(in_ctr, first ? (uint32_t)s * p.B : (uint32_t)(s + 1) * p.ncl);
         if (trole >= 0) DEC_TRACE(trole, 0);
+        DEC_TRACE_ALL(0);
       }
       __syncwarp();
       fence_proxy_async_global();
@@ -247,10 +253,7 @@ __device__ void lstm_role(const DecParams& p, uint8_t* smem, int l, int nb) {
         const CUtensorMap* tm = first ? &p.tm_x[par] : &p.tm_h[l - 1][par ^ 1];
         const int col0 = first ? DEC_VP : 0;
         if (ptx::elect_one()) {
-          for (int i = 0; i < nc; ++i) {
-            ptx::mbar_arrive_expect_tx(&full[i], STAGE_BYTES);
-            ptx::tma_load_2d(abuf + (size_t)i * STAGE_BYTES, tm, &full[i], col0 + i * 64, 0);
-          }
+          for (int i = 0; i < nc; ++i) ptx::tma_load_2d(abuf + (size_t)i * STAGE_BYTES, tm, &full[i], col0 + i * 64, 0);
         }
         __syncwarp();
       }
@@ -338,7 +341,7 @@ __device__ void lstm_role(const DecParams& p, uint8_t* smem, int l, int nb) {
 #pragma unroll
       for (int i = 0; i < 16; ++i) pb[i] = bias_r[i];
       if (first && s > 0 && p.word_gather && live) {
-        int tok = p.gt_index ? p.gt_index[(size_t)gb * p.gt_steps + (s - 1)] : (int)ll_wait(p.tok_ll + b, (uint32_t)s);
+        int tok = p.gt_index ? p.gt_index[(size_t)gb * p.gt_steps + (s - 1)] : (int)ll_wait(p.tok_ll + (size_t)nb * p.B + b, (uint32_t)s);
         if (tok >= 0 && tok < p.V) {
           const uint32_t tok_off = (uint32_t)(tok & 7) * 2u, tok_chunk = (uint32_t)(tok >> 3);
 #pragma unroll
@@ -352,6 +355,7 @@ __device__ void lstm_role(const DecParams& p, uint8_t* smem, int l, int nb) {
       if (lead && trole == 0) DEC_TRACE(4, 1);
       ptx::mbar_wait(tmem_full, (uint32_t)(s & 1));
       if (lead && trole >= 0) DEC_TRACE(trole, 3);
+      if (lead) DEC_TRACE_ALL(1);
       ptx::tc_fence_after();
       float h[4];
       if (warp_live) {
@@ -395,10 +399,12 @@ __device__ void lstm_role(const DecParams& p, uint8_t* smem, int l, int nb) {
         }
       }
       if (lead && trole >= 0) DEC_TRACE(trole, 4);
+      if (lead) DEC_TRACE_ALL(2);
       asm volatile("bar.sync 1, 256;" ::: "memory");  // all rows stored; the release below is cumulative over the barrier
       if (lead) {
         red_release_add(my_ready, 1u);
         if (trole >= 0) DEC_TRACE(trole, 5);
+        DEC_TRACE_ALL(3);
       }
     }
   }
@@ -535,6 +541,7 @@ __device__ void attention_role(const DecParams& p, uint8_t* smem, int b) {
     // ---- A: this step's top-layer h, polled straight out of the LSTM epilogue's flag-in-data slots
     if (tid < Hs) s_h[xpos(tid)] = __uint_as_float(ll_wait(p.h_ll + (size_t)b * Hs + tid, (uint32_t)(s + 1)));
     __syncthreads();
+    if (tid == 0) DEC_TRACE_ALL(0);
     if (tid == 0 && b == 0) { DEC_TRACE(2, 0); DEC_TRACE(3, 0); if (p.trace && s < 32) p.trace[(2 * 32 + s) * 8 + 7] = clock64(); }
 
     // ---- B: q = act(W_phi . h + b_phi)   (model/las_model.py:278): 8 lanes per output, interleaved 16-byte chunks
@@ -609,40 +616,34 @@ __device__ void attention_role(const DecParams& p, uint8_t* smem, int b) {
         m = fmaxf(fmaxf(fmaxf(a.x, a.y), fmaxf(a.z, a.w)), fmaxf(fmaxf(b4.x, b4.y), fmaxf(b4.z, b4.w)));
         m = fmaxf(m, fmaxf(fmaxf(fmaxf(c4.x, c4.y), fmaxf(c4.z, c4.w)), fmaxf(fmaxf(d4.x, d4.y), fmaxf(d4.z, d4.w))));
       }
+      // p[u] = exp(e[u] - max) goes to the context reduction unnormalised (bf16 operand of the UMMA / fp32 for the
+      // CUDA-core path); the sum arrives through the same barrier and the 1/sum scaling is applied to the context
       float lsum = 0.f;
 #pragma unroll
       for (int ps = 0; ps < ATT_MAXP; ++ps) {
         ev[ps] = (ev[ps] == -INFINITY) ? 0.f : __expf(ev[ps] - m);
-        if (half == 0) lsum += ev[ps];
-      }
-      lsum = warp_sum(lsum);
-      if (lane == 0) s_red[16 + warp] = lsum;
-      __syncthreads();
-      if (tid == 0 && b == 0) DEC_TRACE(3, 6);
-      float tot;
-      {
-        const float4* r4 = reinterpret_cast<const float4*>(s_red + 16);
-        const float4 a = r4[0], b4 = r4[1], c4 = r4[2], d4 = r4[3];
-        tot = ((a.x + a.y) + (a.z + a.w)) + ((b4.x + b4.y) + (b4.z + b4.w)) + ((c4.x + c4.y) + (c4.z + c4.w)) + ((d4.x + d4.y) + (d4.z + d4.w));
-      }
-      const float inv = 1.0f / tot;
-      if (half == 0) {
-#pragma unroll
-        for (int ps = 0; ps < ATT_MAXP; ++ps) {
+        if (half == 0) {
+          lsum += ev[ps];
           const int u = ps * 256 + (tid >> 1);
           if (u < U) {
-            const float a = ev[ps] * inv;
-            if (p.attn) p.attn[((size_t)s * p.Bfull + gb) * U + u] = a;
-            if (p.ctx_tmem) *reinterpret_cast<__nv_bfloat16*>(s_bop + (u >> 3) * 256 + (u & 7) * 2) = __float2bfloat16_rn(a);
-            else s_score[u] = a;
+            if (p.ctx_tmem) *reinterpret_cast<__nv_bfloat16*>(s_bop + (u >> 3) * 256 + (u & 7) * 2) = __float2bfloat16_rn(ev[ps]);
+            else s_score[u] = ev[ps];
           }
         }
       }
+      lsum = warp_sum(lsum);
+      if (lane == 0) s_red[16 + warp] = lsum;
     }
-    if (tid == 0 && b == 0) DEC_TRACE(3, 7);
     if (p.ctx_tmem) ptx::fence_proxy_async_smem();
     __syncthreads();
-    if (tid == 0 && b == 0) DEC_TRACE(2, 2);
+    if (tid == 0 && b == 0) { DEC_TRACE(3, 6); DEC_TRACE(2, 2); }
+    if (tid == 0) DEC_TRACE_ALL(1);
+    float inv;
+    {
+      const float4* r4 = reinterpret_cast<const float4*>(s_red + 16);
+      const float4 a = r4[0], b4 = r4[1], c4 = r4[2], d4 = r4[3];
+      inv = 1.0f / (((a.x + a.y) + (a.z + a.w)) + ((b4.x + b4.y) + (b4.z + b4.w)) + ((c4.x + c4.y) + (c4.z + c4.w)) + ((d4.x + d4.y) + (d4.z + d4.w)));
+    }
 
     // ---- D: context[e] = sum_u score[u] * enc[b,u,e]  (:293-297); warps 1.. meanwhile evaluate the h half of the
     //         character distribution, W_cd[:, :Hs] . h + b_cd  (16 lanes per output)
@@ -662,7 +663,15 @@ __device__ void attention_role(const DecParams& p, uint8_t* smem, int b) {
         }
         __syncwarp();
       }
-    } else {
+    }
+    if (p.attn && (tid & 1) == 0) {  // attention record (:292, returned to the caller): off the critical path
+#pragma unroll
+      for (int ps = 0; ps < ATT_MAXP; ++ps) {
+        const int u = ps * 256 + (tid >> 1);
+        if (u < U) p.attn[((size_t)s * p.Bfull + gb) * U + u] = ev[ps] * inv;
+      }
+    }
+    if (warp != 0) {
       const int part = tid & 15;
       for (int v = (tid - 32) >> 4; v < Vp; v += (DEC_THREADS - 32) / 16) {
         float acc = 0.f;
@@ -691,9 +700,8 @@ __device__ void attention_role(const DecParams& p, uint8_t* smem, int b) {
         const uint32_t r = ptx::tmem_ld_32x32b_x1(tmem + ((uint32_t)(qd * 32) << 16) + NT * CU + t * 16);
         ptx::tmem_ld_wait();
         const int e = t * 128 + qd * 32 + lane;
-        const float cv = __uint_as_float(r);
+        const float cv = __uint_as_float(r) * inv;
         s_ctx[xpos(e)] = cv;
-        xr[DEC_VP + e] = __float2bfloat16_rn(cv);
         if (last && p.ctx_out) p.ctx_out[(size_t)gb * E + e] = cv;
       }
       ptx::tc_fence_before();
@@ -717,7 +725,7 @@ __device__ void attention_role(const DecParams& p, uint8_t* smem, int b) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               const int uu = u + j * nrg;
-              const float a = (uu < ulen) ? s_score[uu] : 0.f;
+              const float a = (uu < ulen) ? s_score[uu] : 0.f;  // unnormalised exp(e - max)
               const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&v[j]);
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
@@ -737,15 +745,34 @@ __device__ void attention_role(const DecParams& p, uint8_t* smem, int b) {
       for (int e = tid; e < E; e += DEC_THREADS) {
         float acc = 0.f;
         for (int rg = 0; rg < nrg; ++rg) acc += s_part[(size_t)rg * E + e];
+        acc *= inv;
         s_ctx[xpos(e)] = acc;
-        xr[DEC_VP + e] = __float2bfloat16_rn(acc);
         if (last && p.ctx_out) p.ctx_out[(size_t)gb * E + e] = acc;
       }
     }
-    __syncthreads();  // context row written by every thread; the release below is cumulative over the barrier
-    if (tid == 0) {
-      red_release_add(ctx_ctr, 1u);  // layer 0 starts its context GEMM while the character distribution is evaluated here
-      if (b == 0) DEC_TRACE(2, 4);
+    __syncthreads();
+    // publish the context row (bf16) with 16-byte stores from the first E/8 threads -- few, sector-filling writes keep the
+    // release short -- then release: layer 0 starts its context GEMM while the character distribution is evaluated here
+    {
+      const int npub = E >> 3, nsync = (npub + 31) & ~31;
+      if (tid < nsync) {
+        if (tid < npub) {
+          const float4* xv = xchunk(s_ctx, tid);
+          const float4 lo = xv[0], hi = xv[8];
+          const __nv_bfloat162 p0 = __floats2bfloat162_rn(lo.x, lo.y), p1 = __floats2bfloat162_rn(lo.z, lo.w);
+          const __nv_bfloat162 p2 = __floats2bfloat162_rn(hi.x, hi.y), p3 = __floats2bfloat162_rn(hi.z, hi.w);
+          *reinterpret_cast<uint4*>(xr + DEC_VP + 8 * tid) =
+              make_uint4(*reinterpret_cast<const uint32_t*>(&p0), *reinterpret_cast<const uint32_t*>(&p1),
+                         *reinterpret_cast<const uint32_t*>(&p2), *reinterpret_cast<const uint32_t*>(&p3));
+        }
+        if (nsync > 32) asm volatile("bar.sync 2, %0;" ::"r"(nsync) : "memory");
+        else __syncwarp();
+        if (tid == 0) {
+          red_release_add(ctx_ctr, 1u);
+          DEC_TRACE_ALL(3);
+          if (b == 0) DEC_TRACE(2, 4);
+        }
+      }
     }
 
     // ---- E: logits = W_cd . [h || context] + b_cd: the context half, 16 lanes per output  (:181)
@@ -798,7 +825,8 @@ __device__ void attention_role(const DecParams& p, uint8_t* smem, int b) {
       if (p.word_gather) {
         // the word is an index: layer 0's epilogue adds the matching column of W_word itself
         const int fed = p.gt_index ? p.gt_index[(size_t)gb * p.gt_steps + s] : bi;
-        if (lane == 0 && !p.gt_index) ll_store(p.tok_ll + b, ll_pack((uint32_t)fed, (uint32_t)(s + 1)));
+        if (!p.gt_index)
+          for (int i = lane; i < p.ncl; i += 32) ll_store(p.tok_ll + (size_t)i * p.B + b, ll_pack((uint32_t)fed, (uint32_t)(s + 1)));
         if (last && p.word_out)
           for (int i = lane; i < V; i += 32) p.word_out[(size_t)gb * V + i] = (i == fed) ? 1.f : 0.f;
       } else {
@@ -981,7 +1009,7 @@ SpellerWsFast ws_layout(const las_speller_dims* d, void* base) {
   for (int l = 0; l < MAX_SL; ++l)
     for (int k = 0; k < 2; ++k) w.hbuf[l][k] = cv.take<__nv_bfloat16>((size_t)d->B * d->Hs);
   for (int k = 0; k < 2; ++k) w.xbuf[k] = cv.take<__nv_bfloat16>((size_t)d->B * (DEC_VP + d->E));
-  const size_t sync_bytes = sizeof(uint32_t) * 32 * N_CTR, tok_bytes = align_up(sizeof(u64) * (size_t)d->B, 256);
+  const size_t sync_bytes = sizeof(uint32_t) * 32 * N_CTR, tok_bytes = align_up(sizeof(u64) * (size_t)d->B * (d->Hs / DEC_UNITS), 256);
   w.flag_bytes = sync_bytes + tok_bytes + sizeof(u64) * (size_t)d->B * d->Hs;
   w.flags = cv.take<uint8_t>(w.flag_bytes);
   w.sync = reinterpret_cast<uint32_t*>(w.flags);

@@ -29,12 +29,14 @@ def main():
     e1.record()
     torch.cuda.synchronize()
     print(f"speller c3 bf16: {e0.elapsed_time(e1) / 3:.3f} ms  ({e0.elapsed_time(e1) / 3 / S * 1e3:.2f} us/step)")
-    buf = torch.zeros(512 + 5 * 32 * 8, dtype=torch.int64, device="cuda")
+    buf = torch.zeros(512 + 5 * 32 * 8 + 148 * 8, dtype=torch.int64, device="cuda")
     lib.las_debug_set_trace(_cabi.ptr(buf))
     las.speller(enc, None, 0.0)
     torch.cuda.synchronize()
     lib.las_debug_set_trace(None)
-    t = buf.cpu().numpy()[512:].reshape(5, 32, 8)
+    raw = buf.cpu().numpy()
+    t = raw[512:512 + 5 * 32 * 8].reshape(5, 32, 8)
+    allc = raw[512 + 5 * 32 * 8:].reshape(148, 8)
     names = [["in ready", "tma issued", "mma issued", "tmem_full", "stored", "signalled", "h-part mma", "-"],
              ["in ready", "tma issued", "mma issued", "tmem_full", "stored", "signalled", "h-part mma", "-"],
              ["h arrived", "q", "softmax", "ctx mma", "ctx published", "logits", "word published", "-"]]
@@ -45,11 +47,24 @@ def main():
             print(f"   {rn}: " + "  ".join(f"{names[role][i]}={int(t[role, s, i] - base)}" for i in range(7)))
         print(f"   next step L0 input ready at +{int(t[0, s + 1, 0] - base)} ns")
         print("   att fine (rel. h arrived): " + "  ".join(f"{n}={int(t[3, s, i] - t[3, s, 0])}" for i, n in enumerate(
-            ["h", "dot", "shfl", "q sync", "energy", "max sync", "sum sync", "attn written"])))
-        print("   L0 epilogue warp 4 (rel. in ready): " + "  ".join(f"{n}={int(t[4, s, i] - base)}" for i, n in enumerate(
-            ["-", "word gathered"])))
+            ["h", "dot", "shfl", "q sync", "energy", "max sync", "sum sync"])))
+        print(f"   L0 epilogue: word column gathered at +{int(t[4, s, 1] - base)} ns")
+        if s == 8:
+            spread(allc, base)
         print(f"   attention CTA 0: {int(t[2, s + 1, 7] - t[2, s, 7])} SM cycles in {int(t[2, s + 1, 0] - t[2, s, 0])} ns "
               f"-> {1e3 * (t[2, s + 1, 7] - t[2, s, 7]) / max(1, (t[2, s + 1, 0] - t[2, s, 0])):.0f} MHz")
+
+
+def spread(allc, base):
+    """Step 8, every CTA: min / max of each stamp relative to layer-0 CTA 0's 'input ready'."""
+    def mm(rows, slot):
+        v = allc[rows, slot] - base
+        return f"{int(v.min())}..{int(v.max())}"
+    print("step 8 spread over CTAs (ns, min..max):")
+    for name, rows in (("L0", slice(0, 32)), ("L1", slice(32, 64))):
+        print(f"   {name}: in ready {mm(rows, 0)}  tmem_full {mm(rows, 1)}  stored {mm(rows, 2)}  signalled {mm(rows, 3)}")
+    rows = slice(64, 128)
+    print(f"   att: h arrived {mm(rows, 0)}  softmax {mm(rows, 1)}  ctx published {mm(rows, 3)}")
 
 
 if __name__ == "__main__":
