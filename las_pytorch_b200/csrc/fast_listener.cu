@@ -56,13 +56,12 @@ __host__ __device__ inline uint32_t rec_tmem_cols(int Hp, int BC, int a_tmem) {
   return c;
 }
 
-template <int BC>
+template <int BC, int NACC>
 __global__ void __launch_bounds__(REC_THREADS, 1) lstm_recurrence_cluster_kernel(RecParams p) {
   constexpr int NB = BC / 4;  // cells per epilogue thread
-  // Dependent UMMAs into one accumulator serialise on the tensor core's accumulate latency (~80 cycles each, far more
-  // than the 8-32 issue cycles of an N=16..64 instruction), so the K loop is spread round-robin over NACC independent
-  // accumulators that the epilogue sums.
-  constexpr int NACC = BC == 16 ? 4 : (BC == 32 ? 2 : 1);
+  // The K loop can be spread round-robin over NACC independent accumulators that the epilogue sums (test hook:
+  // las_debug_set_option(4, n)).  tools/microbench.cu: a tcgen05.mma with the A operand in TMEM issues every ~33 cycles
+  // whatever N is and whether or not consecutive instructions share an accumulator, so NACC = 1 is the default.
   extern __shared__ uint8_t smem_raw[];
   uint8_t* base = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);  // offset from the __shared__ symbol keeps the address space
   const int Hp = p.Hp;
@@ -347,6 +346,7 @@ __global__ void pack_whh_kernel(const float* w_fwd, const float* w_rev, uint8_t*
 
 long long* g_rec_trace = nullptr;  // set through las_debug_set_trace (test hook)
 int g_rec_a_tmem = 1;              // las_debug_set_option(1, v)
+int g_rec_nacc = 0;                // las_debug_set_option(4, v): independent accumulators the K loop is spread over (0 = default)
 
 struct Geo {
   int Hp, CS;
@@ -413,11 +413,11 @@ int shape_ok(const las_listener_dims* d) {
   return LAS_OK;
 }
 
-template <int BC>
+template <int BC, int NACC>
 int launch_rec(const RecParams& p, cudaStream_t st) {
   const size_t smem = 1024 + (p.a_tmem ? 0u : 128u * p.Hp * 2) + 2u * BC * p.Hp * 2 + 2 * 4 * BC * 16 + 64;
-  LAS_CUDA_OK(cudaFuncSetAttribute(lstm_recurrence_cluster_kernel<BC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  if (p.CS > 8) LAS_CUDA_OK(cudaFuncSetAttribute(lstm_recurrence_cluster_kernel<BC>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+  LAS_CUDA_OK(cudaFuncSetAttribute(lstm_recurrence_cluster_kernel<BC, NACC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (p.CS > 8) LAS_CUDA_OK(cudaFuncSetAttribute(lstm_recurrence_cluster_kernel<BC, NACC>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(p.CS * 2 * p.nchunks);
   cfg.blockDim = dim3(REC_THREADS);
@@ -430,7 +430,7 @@ int launch_rec(const RecParams& p, cudaStream_t st) {
   at[0].val.clusterDim.z = 1;
   cfg.attrs = at;
   cfg.numAttrs = 1;
-  LAS_CUDA_OK(cudaLaunchKernelEx(&cfg, lstm_recurrence_cluster_kernel<BC>, p));
+  LAS_CUDA_OK(cudaLaunchKernelEx(&cfg, lstm_recurrence_cluster_kernel<BC, NACC>, p));
   count_launch();
   return LAS_OK;
 }
@@ -444,6 +444,7 @@ long long* fast_get_trace() { return g_rec_trace; }
 void fast_set_option_speller(int key, int value);
 void fast_set_option(int key, int value) {
   if (key == 1) g_rec_a_tmem = value;
+  if (key == 4) g_rec_nacc = value;
   fast_set_option_speller(key, value);
 }
 
@@ -502,9 +503,16 @@ int fast_listener_forward(const float* x, const void* packed, const las_listener
     rp.a_tmem = g_rec_a_tmem;
     const int bc = pick_bc(B, g.CS);
     rp.nchunks = (B + bc - 1) / bc;
-    if (bc == 16) LAS_TRY(launch_rec<16>(rp, st));
-    else if (bc == 32) LAS_TRY(launch_rec<32>(rp, st));
-    else LAS_TRY(launch_rec<64>(rp, st));
+    if (bc == 16) {
+      const int nacc = g_rec_nacc ? g_rec_nacc : 1;  // measured: one accumulator chain is fastest with the A operand in TMEM
+      if (nacc == 1) LAS_TRY((launch_rec<16, 1>(rp, st)));
+      else if (nacc == 2) LAS_TRY((launch_rec<16, 2>(rp, st)));
+      else LAS_TRY((launch_rec<16, 4>(rp, st)));
+    } else if (bc == 32) {
+      LAS_TRY((launch_rec<32, 2>(rp, st)));
+    } else {
+      LAS_TRY((launch_rec<64, 1>(rp, st)));
+    }
     cur = w.act[l & 1];
     Tin = Tl;
     Fin = 2 * H;

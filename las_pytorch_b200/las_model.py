@@ -404,16 +404,21 @@ class Speller(nn.Module):
         # one draw from numpy's global RNG per call, exactly like the reference (:189)
         teacher_force = True if np.random.random_sample() < teacher_force_rate else False
 
-        gt_dense = None
+        gt_dense = gt_index = None
         if (ground_truth is None) or (not teacher_force):
             max_step = self.max_label_len
         else:
             max_step = ground_truth.size()[1]
-            # `.type(self.float_type)` in the reference (:217): the label tensor is consumed as dense floats
-            gt_dense = ground_truth.to(device=listener_feature.device, dtype=torch.float32).contiguous()
+            if ground_truth.dim() == 2:
+                # extension: [B,S] label indices instead of the reference's [B,S,V] one-hot
+                # tensor -- V times less host-to-device traffic; index v feeds one_hot(v), a negative index the zero vector
+                gt_index = ground_truth.to(device=listener_feature.device, dtype=torch.int32).contiguous()
+            else:
+                # `.type(self.float_type)` in the reference (:217): the label tensor is consumed as dense floats
+                gt_dense = ground_truth.to(device=listener_feature.device, dtype=torch.float32).contiguous()
         if enc_lengths is not None:
             enc_lengths = enc_lengths.to(device=listener_feature.device, dtype=torch.int32).contiguous()
-        logp, attn, tokens = self._decode(listener_feature, max_step, gt_dense=gt_dense, enc_lengths=enc_lengths)
+        logp, attn, tokens = self._decode(listener_feature, max_step, gt_dense=gt_dense, gt_index=gt_index, enc_lengths=enc_lengths)
         self.last_tokens = tokens  # [S,B] int32 argmax per step (device); not part of the reference API
         raw_pred_seq = list(logp.unbind(0))
         attention_record = [[a] for a in attn.unbind(0)]

@@ -142,6 +142,82 @@ def test_full_size_properties(precision):
         assert float((sharded - logp).abs().max()) < 2e-2
 
 
+@pytest.mark.parametrize("name", ["paper_greedy_g3", "small_greedy_g3"])
+def test_bf16_greedy_agreement_on_named_shapes(name):
+    """north_star: free-running greedy token sequences agree with the reference on >= 99 % of characters, also in the
+    bf16-GEMM mode, at the shapes the benchmark names (paper / small LAS)."""
+    if "bf16" not in precisions():
+        pytest.skip("bf16 mode not built")
+    g, cfg, las, mode = load_case(name, "bf16")
+    _, logp, _ = run_ours(las, torch.from_numpy(g["x"]), torch.from_numpy(g["labels"]).long(), cfg["V"], mode)
+    agree = (logp.argmax(-1) == g["logp_f64"].argmax(-1)).mean()
+    assert agree >= 0.99, f"greedy agreement {agree:.4f}"
+
+
+@pytest.mark.parametrize("precision", precisions())
+@pytest.mark.parametrize("cfgname", ["small", "odd"])
+def test_index_teacher_forcing_equals_onehot(cfgname, precision):
+    """Row f2 extension: [B,S] label indices feed the same decoder as the reference's one-hot tensor.  In bf16 mode the index
+    path adds the word column of W_ih in the LSTM epilogue instead of multiplying a one-hot atom on the tensor core."""
+    c = tl.CONFIGS[cfgname]
+    B, T, S = 5, 64, 12
+    las = tl.build_model(cfgname, max_label_len=S, seed=29, gain=3.0, precision=precision)
+    sd = tl.state_dict_numpy(las)
+    x, labels = tl.make_inputs(B, T, c["F"], S, c["V"], seed=29)
+    ref = O.las_forward(x.numpy(), sd, c["L"], c["sl"], S, ground_truth=labels.numpy(), teacher_forced=True, dtype=np.float64)
+    las = las.cuda()
+    np.random.seed(0)
+    p_idx, _ = las(x.cuda(), labels.cuda(), 1.1, is_training=True)
+    np.random.seed(0)
+    p_hot, _ = las(x.cuda(), tl.onehot(labels, c["V"]).cuda(), 1.1, is_training=True)
+    p_idx, p_hot = torch.stack(p_idx).cpu().numpy(), torch.stack(p_hot).cpu().numpy()
+    tol = TOL[precision]["logp"]
+    assert np.abs(p_idx - ref["logp"]).max() <= tol and np.abs(p_hot - ref["logp"]).max() <= tol
+    assert np.abs(p_idx - p_hot).max() <= (1e-5 if precision == "fp32" else 2e-3)  # same numbers up to fp32 summation order
+
+
+def test_bf16_forward_step_state_roundtrip():
+    """Speller.forward_step in bf16 mode: state / word / context handed in and out step by step equals one fused decode."""
+    if "bf16" not in precisions():
+        pytest.skip("bf16 mode not built")
+    c = tl.CONFIGS["small"]
+    S = 4
+    las = tl.build_model("small", max_label_len=S, seed=31, gain=3.0, precision="bf16")
+    sd = tl.state_dict_numpy(las)
+    las = las.cuda()
+    enc = torch.tanh(torch.randn(3, 16, 2 * c["H"], generator=torch.Generator().manual_seed(4)))
+    ref = O.speller_forward(enc.numpy(), sd, c["sl"], S, dtype=np.float64)
+    encd = enc.cuda()
+    fused, _ = las.speller(encd, None, 0.0)
+    word = torch.zeros(3, 1, c["V"], device="cuda")
+    word[:, :, 0] = 1
+    rnn_in = torch.cat([word, encd[:, 0:1, :]], dim=-1)
+    hidden = None
+    for s in range(S):
+        raw_pred, hidden, context, score = las.speller.forward_step(rnn_in, hidden, encd)
+        assert np.abs(raw_pred.cpu().numpy() - ref["logp"][s]).max() <= 2e-2
+        assert float((raw_pred - fused[s]).abs().max()) <= 5e-3  # the state leaves / re-enters through fp32 and bf16 copies
+        nxt = torch.nn.functional.one_hot(raw_pred.argmax(-1), c["V"]).float().unsqueeze(1)
+        rnn_in = torch.cat([nxt, context.unsqueeze(1)], dim=-1)
+
+
+def test_bf16_length_mask():
+    if "bf16" not in precisions():
+        pytest.skip("bf16 mode not built")
+    c = tl.CONFIGS["small"]
+    las = tl.build_model("small", max_label_len=6, seed=3, gain=3.0, precision="bf16")
+    sd = tl.state_dict_numpy(las)
+    las = las.cuda()
+    enc = torch.tanh(torch.randn(4, 24, 2 * c["H"], generator=torch.Generator().manual_seed(2)))
+    lens = torch.tensor([24, 17, 5, 1])
+    ref = O.speller_forward(enc.numpy(), sd, c["sl"], 6, dtype=np.float64, enc_lengths=lens.numpy())
+    preds, attns = las.speller(enc.cuda(), None, 0.0, enc_lengths=lens)
+    attn = torch.stack([a[0] for a in attns]).cpu().numpy()
+    assert np.abs(torch.stack(preds).cpu().numpy() - ref["logp"]).max() <= 2e-2
+    assert np.array_equal(attn[:, 2, 5:], np.zeros_like(attn[:, 2, 5:]))  # masked steps get exactly zero weight
+    assert np.abs(attn.sum(-1) - 1).max() < 1e-4
+
+
 def test_forward_step_and_attention_api():
     """Speller.forward_step / Attention.forward (model/las_model.py:178-184, 275-297) against the oracle."""
     c = tl.CONFIGS["tiny"]

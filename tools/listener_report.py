@@ -76,7 +76,9 @@ def trace():
     import sys as _s
     opt = int(_s.argv[2]) if len(_s.argv) > 2 else 1
     lib.las_debug_set_option(1, opt)
-    print(f"recurrence A operand in TMEM: {opt}")
+    nacc = int(_s.argv[3]) if len(_s.argv) > 3 else 0
+    lib.las_debug_set_option(4, nacc)
+    print(f"recurrence A operand in TMEM: {opt}; accumulators: {nacc or 'default'}")
     ref = tl.build_model("paper", max_label_len=4, seed=17, gain=3.0, precision="fp32").listener.cuda()(x)
     out = lis(x)
     print(f"bf16 vs fp32 listener max err {float((out - ref).abs().max()):.3e}")
