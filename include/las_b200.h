@@ -94,6 +94,16 @@ size_t las_listener_workspace_bytes(const las_listener_dims* d, int mode);
 int las_listener_forward(const float* x, const void* packed, const las_listener_dims* d, int mode, float* enc,
                          void* workspace, size_t workspace_bytes, void* stream);
 
+/* Length-mask extension (north_star: "padding is handled by length masks"; SURVEY.md section 8 row f2: the reference's
+ * collate_fn computes inputs_length, utils/data.py:146, and train.py:117 drops it).  x_lengths [B] int32 = valid frames per
+ * utterance (nullable: NULL reproduces the reference, which runs the BLSTMs over the zero padding).  Layer l keeps
+ * len_l = ceil(len_{l-1} / 2) steps: each direction runs over the valid prefix only, exactly as torch's
+ * pack_padded_sequence -> nn.LSTM -> pad_packed_sequence does, and outputs past len_l are zero.  enc_lengths [B] int32
+ * (nullable) receives len_{L-1}, the attention mask for las_speller_decode. */
+int las_listener_forward_masked(const float* x, const int32_t* x_lengths, const void* packed, const las_listener_dims* d,
+                                int mode, float* enc, int32_t* enc_lengths, void* workspace, size_t workspace_bytes,
+                                void* stream);
+
 /* --------------------------------------------------------------------------------------------------------
  * Speller: attention decoder step loop.  Replaces Speller.forward / forward_step and Attention.forward,
  * model/las_model.py:178-238, 275-297, and the one-hot / TimeDistributed helpers utils/functions.py:54-77.

@@ -65,6 +65,8 @@ PROTOTYPES = {
     "las_listener_pack": (C.c_int, [C.POINTER(LstmWeights), C.POINTER(ListenerDims), C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]),
     "las_listener_workspace_bytes": (C.c_size_t, [C.POINTER(ListenerDims), C.c_int]),
     "las_listener_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(ListenerDims), C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "las_listener_forward_masked": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(ListenerDims), C.c_int, C.c_void_p, C.c_void_p,
+                                              C.c_void_p, C.c_size_t, C.c_void_p]),
     "las_speller_packed_bytes": (C.c_size_t, [C.POINTER(SpellerDims), C.c_int]),
     "las_speller_pack": (C.c_int, [C.POINTER(SpellerWeights), C.POINTER(SpellerDims), C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]),
     "las_psi_precompute": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),

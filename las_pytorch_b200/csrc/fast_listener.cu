@@ -28,6 +28,7 @@ struct RecParams {
   const uint8_t* whh_img;       // [2][CS] shared-memory images of the W_hh slices (128 x Hp bf16, INTERLEAVE layout)
   float* out_f32;               // nullable [B, Tl, 2H]
   __nv_bfloat16* out_bf16;      // nullable [B, Tl, 2H]
+  const int32_t* lengths;       // nullable [B]: valid steps of this layer (length-mask extension)
   int B, Tl, H, Hp, CS, nchunks;
   int a_tmem;                   // 1: W_hh slice lives in tensor memory (UMMA .ts form); 0: in shared memory
   long long* trace;             // nullable test hook: [64 steps][8] clock64 stamps from CTA 0
@@ -166,8 +167,13 @@ __global__ void __launch_bounds__(REC_THREADS, 1) lstm_recurrence_cluster_kernel
     const float* pcol = p.P + (size_t)dir * 4 * Hp + (size_t)r * 128 + jj * 4;
     float c[NB];
     float4 pnext[NB];
+    int len[NB];  // valid steps of this thread's utterances: past them the cell keeps its state and emits h = 0
 #pragma unroll
-    for (int m = 0; m < NB; ++m) c[m] = 0.f;
+    for (int m = 0; m < NB; ++m) {
+      c[m] = 0.f;
+      const int b = b_base + 4 * m + g;
+      len[m] = (p.lengths && b < p.B) ? p.lengths[b] : Tl;
+    }
     {
       const int t0 = dir ? Tl - 1 : 0;
 #pragma unroll
@@ -254,8 +260,9 @@ __global__ void __launch_bounds__(REC_THREADS, 1) lstm_recurrence_cluster_kernel
         }
         const float a_i = v0 + pc[m].x, a_f = v1 + pc[m].y, a_g = v2 + pc[m].z, a_o = v3 + pc[m].w;
         const float cn = sigmoid_fast(a_f) * c[m] + sigmoid_fast(a_i) * tanh_fast(a_g);
-        c[m] = cn;
-        hval[m] = sigmoid_fast(a_o) * tanh_fast(cn);
+        const bool on = t < len[m];
+        c[m] = on ? cn : c[m];
+        hval[m] = on ? sigmoid_fast(a_o) * tanh_fast(cn) : 0.f;
       }
       if (tid == 0) REC_TRACE(4);
       // ---- h_t slice -> every CTA of the cluster (B operand of step s+1)
@@ -390,6 +397,7 @@ struct ListenerWsFast {
   __nv_bfloat16* xb;
   float* P;
   __nv_bfloat16* act[2];
+  int32_t* len;  // [L][B]
   size_t bytes;
 };
 ListenerWsFast ws_layout(const las_listener_dims* d, void* base) {
@@ -401,6 +409,7 @@ ListenerWsFast ws_layout(const las_listener_dims* d, void* base) {
   w.P = cv.take<float>(M0 * 8 * g.Hp);
   w.act[0] = cv.take<__nv_bfloat16>(M0 * 2 * d->H);
   w.act[1] = cv.take<__nv_bfloat16>(M0 / 2 * 2 * d->H + 64);
+  w.len = cv.take<int32_t>((size_t)d->L * d->B);
   w.bytes = cv.total();
   return w;
 }
@@ -469,7 +478,8 @@ int fast_listener_pack(const las_lstm_weights* w, const las_listener_dims* d, vo
   return LAS_OK;
 }
 
-int fast_listener_forward(const float* x, const void* packed, const las_listener_dims* d, float* enc, void* ws, cudaStream_t st) {
+int fast_listener_forward(const float* x, const int32_t* x_lengths, const void* packed, const las_listener_dims* d, float* enc,
+                          int32_t* enc_lengths, void* ws, cudaStream_t st) {
   LAS_TRY(shape_ok(d));
   const Geo g = geometry(d->H);
   const ListenerPackFast pk = pack_layout(d, const_cast<void*>(packed));
@@ -483,6 +493,11 @@ int fast_listener_forward(const float* x, const void* packed, const las_listener
   int Tin = d->T, Fin = d->F;
   for (int l = 0; l < d->L; ++l) {
     const int Tl = Tin / 2, K = 2 * Fin, M = B * Tl, NP = 8 * g.Hp;
+    const int32_t* len_l = nullptr;
+    if (x_lengths) {
+      LAS_TRY(launch_pyramid_lengths(l == 0 ? x_lengths : w.len + (size_t)(l - 1) * B, w.len + (size_t)l * B, B, Tl, st));
+      len_l = w.len + (size_t)l * B;
+    }
     char nm[48];
     {
       snprintf(nm, sizeof(nm), "listener.L%d.input_gemm", l);
@@ -498,6 +513,7 @@ int fast_listener_forward(const float* x, const void* packed, const las_listener
     rp.whh_img = pk.whh[l];
     rp.out_f32 = last ? enc : nullptr;
     rp.out_bf16 = last ? nullptr : w.act[l & 1];
+    rp.lengths = len_l;
     rp.B = B; rp.Tl = Tl; rp.H = H; rp.Hp = g.Hp; rp.CS = g.CS;
     rp.trace = (l == 0) ? g_rec_trace : nullptr;
     rp.a_tmem = g_rec_a_tmem;
@@ -517,6 +533,8 @@ int fast_listener_forward(const float* x, const void* packed, const las_listener
     Tin = Tl;
     Fin = 2 * H;
   }
+  if (x_lengths && enc_lengths)
+    LAS_CUDA_OK(cudaMemcpyAsync(enc_lengths, w.len + (size_t)(d->L - 1) * B, sizeof(int32_t) * B, cudaMemcpyDeviceToDevice, st));
   return LAS_OK;
 }
 

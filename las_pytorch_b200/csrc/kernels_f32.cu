@@ -157,6 +157,10 @@ __global__ void __launch_bounds__(256) lstm_cell_f32_kernel(CellArgs2 args, int 
   const int tb = threadIdx.x / CJ, tj = threadIdx.x % CJ;
   const int b = b0 + tb, j = j0 + tj;
   if (b >= B || j >= H) return;
+  if (a.lengths && a.t >= a.lengths[b]) {  // padded step: state untouched, output zero
+    a.h_out[(long long)b * a.hout_ld + j] = 0.f;
+    return;
+  }
   float pre[4];
 #pragma unroll
   for (int g = 0; g < 4; ++g) {
@@ -172,6 +176,16 @@ __global__ void __launch_bounds__(256) lstm_cell_f32_kernel(CellArgs2 args, int 
   const float c_new = fg * a.c[(size_t)b * H + j] + ig * gg;
   a.c[(size_t)b * H + j] = c_new;
   a.h_out[(long long)b * a.hout_ld + j] = og * tanhf(c_new);
+}
+
+__global__ void pyramid_lengths_kernel(const int32_t* in, int32_t* out, int B, int cap) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b < B) out[b] = min(max((in[b] + 1) / 2, 0), cap);
+}
+int launch_pyramid_lengths(const int32_t* in, int32_t* out, int B, int cap, cudaStream_t st) {
+  pyramid_lengths_kernel<<<(B + 127) / 128, 128, 0, st>>>(in, out, B, cap);
+  LAS_LAUNCH_OK("pyramid_lengths_kernel");
+  return LAS_OK;
 }
 
 int launch_lstm_cell_f32(const CellArgs* args, int ndir, int B, int H, cudaStream_t st) {

@@ -102,6 +102,7 @@ struct ListenerWsF32 {
   float* P;
   float* act[2];
   float* c;
+  int32_t* len;  // [L][B] valid steps per layer (length-mask extension)
   size_t bytes;
 };
 static ListenerWsF32 listener_ws_layout_f32(const las_listener_dims* d, void* base) {
@@ -112,12 +113,13 @@ static ListenerWsF32 listener_ws_layout_f32(const las_listener_dims* d, void* ba
   w.act[0] = cv.take<float>(M0 * 2 * d->H);
   w.act[1] = cv.take<float>(M0 / 2 * 2 * d->H + 16);
   w.c = cv.take<float>(2 * (size_t)d->B * d->H);
+  w.len = cv.take<int32_t>((size_t)d->L * d->B);
   w.bytes = cv.total();
   return w;
 }
 
-static int listener_forward_f32(const float* x, const void* packed, const las_listener_dims* d, float* enc, void* ws,
-                                cudaStream_t st) {
+static int listener_forward_f32(const float* x, const int32_t* x_lengths, const void* packed, const las_listener_dims* d, float* enc,
+                                int32_t* enc_lengths, void* ws, cudaStream_t st) {
   const ListenerPackF32 pk = listener_pack_layout_f32(d, const_cast<void*>(packed));
   const ListenerWsF32 w = listener_ws_layout_f32(d, ws);
   const int B = d->B, H = d->H;
@@ -125,6 +127,11 @@ static int listener_forward_f32(const float* x, const void* packed, const las_li
   int Tin = d->T, Fin = d->F;
   for (int l = 0; l < d->L; ++l) {
     const int Tl = Tin / 2, K = 2 * Fin, M = B * Tl;
+    const int32_t* len_l = nullptr;
+    if (x_lengths) {
+      LAS_TRY(launch_pyramid_lengths(l == 0 ? x_lengths : w.len + (size_t)(l - 1) * B, w.len + (size_t)l * B, B, Tl, st));
+      len_l = w.len + (size_t)l * B;
+    }
     // pyramid fold = reading [B, Tin, Fin] as [B*Tl, 2*Fin]: same memory, lda = 2*Fin (model/las_model.py:86-87)
     char nm[48];
     {
@@ -149,6 +156,10 @@ static int listener_forward_f32(const float* x, const void* packed, const las_li
       a[0].c = w.c;
       a[0].h_out = out + (size_t)tf * 2 * H;
       a[0].hout_ld = row_ld;
+      a[0].lengths = len_l;
+      a[0].t = tf;
+      a[1].lengths = len_l;
+      a[1].t = tb;
       a[1].h_prev = step ? out + (size_t)(tb + 1) * 2 * H + H : nullptr;
       a[1].h_ld = row_ld;
       a[1].w_hh = pk.whh[l] + 4 * (size_t)H * H;
@@ -163,6 +174,8 @@ static int listener_forward_f32(const float* x, const void* packed, const las_li
     Tin = Tl;
     Fin = 2 * H;
   }
+  if (x_lengths && enc_lengths)
+    LAS_CUDA_OK(cudaMemcpyAsync(enc_lengths, w.len + (size_t)(d->L - 1) * B, sizeof(int32_t) * B, cudaMemcpyDeviceToDevice, st));
   return LAS_OK;
 }
 
@@ -392,6 +405,12 @@ size_t las_listener_workspace_bytes(const las_listener_dims* d, int mode) {
 
 int las_listener_forward(const float* x, const void* packed, const las_listener_dims* d, int mode, float* enc,
                          void* workspace, size_t workspace_bytes, void* stream) {
+  return las_listener_forward_masked(x, nullptr, packed, d, mode, enc, nullptr, workspace, workspace_bytes, stream);
+}
+
+int las_listener_forward_masked(const float* x, const int32_t* x_lengths, const void* packed, const las_listener_dims* d,
+                                int mode, float* enc, int32_t* enc_lengths, void* workspace, size_t workspace_bytes,
+                                void* stream) {
   LAS_TRY(listener_check(d));
   LAS_REQUIRE(x && packed && enc && workspace, "null pointer argument");
   LAS_REQUIRE(mode == LAS_MODE_FP32 || mode == LAS_MODE_BF16, "unknown mode %d", mode);
@@ -399,8 +418,8 @@ int las_listener_forward(const float* x, const void* packed, const las_listener_
   if (workspace_bytes < las_listener_workspace_bytes(d, mode))
     return fail(LAS_ENOMEM, "workspace too small: %zu < %zu", workspace_bytes, las_listener_workspace_bytes(d, mode));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (mode == LAS_MODE_BF16) return fast_listener_forward(x, packed, d, enc, workspace, st);
-  return listener_forward_f32(x, packed, d, enc, workspace, st);
+  if (mode == LAS_MODE_BF16) return fast_listener_forward(x, x_lengths, packed, d, enc, enc_lengths, workspace, st);
+  return listener_forward_f32(x, x_lengths, packed, d, enc, enc_lengths, workspace, st);
 }
 
 // ---- speller -------------------------------------------------------------------------------------------

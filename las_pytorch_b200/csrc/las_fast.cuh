@@ -9,8 +9,8 @@ bool fast_available();
 size_t fast_listener_packed_bytes(const las_listener_dims* d);
 int fast_listener_pack(const las_lstm_weights* w_host, const las_listener_dims* d, void* packed, cudaStream_t st);
 size_t fast_listener_workspace_bytes(const las_listener_dims* d);
-int fast_listener_forward(const float* x, const void* packed, const las_listener_dims* d, float* enc, void* ws,
-                          cudaStream_t st);
+int fast_listener_forward(const float* x, const int32_t* x_lengths, const void* packed, const las_listener_dims* d, float* enc,
+                          int32_t* enc_lengths, void* ws, cudaStream_t st);
 
 size_t fast_speller_packed_bytes(const las_speller_dims* d);
 int fast_speller_pack(const las_speller_weights* w, const las_speller_dims* d, void* packed_fast, cudaStream_t st);

@@ -25,6 +25,8 @@ struct CellArgs {
   float* c;             // [B, H] in/out, dense
   float* h_out;         // [B, H] row stride hout_ld
   long long hout_ld;
+  const int32_t* lengths;  // nullable [B]: rows with t >= lengths[b] keep c and write h = 0 (length-mask extension)
+  int t;
 };
 int launch_lstm_cell_f32(const CellArgs* args, int ndir, int B, int H, cudaStream_t st);
 
@@ -61,6 +63,9 @@ int launch_attend_f32(const AttendArgs& a, cudaStream_t st);
 int launch_speller_init(float* xin, int xin_ld, const float* enc, int B, int U, int E, int V, cudaStream_t st);
 // strided 2-D copy of fp32 rows
 int launch_copy2d(float* dst, long long dst_ld, const float* src, long long src_ld, int rows, int cols, cudaStream_t st);
+
+// out[b] = (in[b] + 1) / 2, clamped to [0, cap]: valid steps of the next pyramid layer
+int launch_pyramid_lengths(const int32_t* in, int32_t* out, int B, int cap, cudaStream_t st);
 
 int launch_nll_sums(const float* logp, const int32_t* labels, int S, int S_lab, int B, int V, int max_label_len,
                     float* out2, cudaStream_t st);

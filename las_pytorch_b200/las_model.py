@@ -81,8 +81,9 @@ def _lstm_weight_array(holder, layers, directions):
     return arr, keep
 
 
-def _run_listener(x, holders, input_feature_dim, hidden_size, mode, cache):
-    """x [B,T,F] -> [B, T/2^L, 2H] through `len(holders)` pyramid layers."""
+def _run_listener(x, holders, input_feature_dim, hidden_size, mode, cache, lengths=None):
+    """x [B,T,F] -> [B, T/2^L, 2H] through `len(holders)` pyramid layers.  With `lengths` ([B] valid frames; extension)
+    returns (enc, enc_lengths [B] int32)."""
     _require_cuda(x, "input_x")
     lib = _cabi.load_library()
     x = _f32c(x)
@@ -119,8 +120,16 @@ def _run_listener(x, holders, input_feature_dim, hidden_size, mode, cache):
         ws_bytes = lib.las_listener_workspace_bytes(C.byref(dims), mode)
         ws = cache.workspace(("listener", x.device, mode), ws_bytes, x.device)
         enc = torch.empty(b, t >> nl, 2 * hidden_size, dtype=torch.float32, device=x.device)
-        check(lib.las_listener_forward(ptr(x), ptr(packed), C.byref(dims), mode, ptr(enc), ptr(ws), ws.numel(), st))
-    return enc
+        if lengths is None:
+            check(lib.las_listener_forward(ptr(x), ptr(packed), C.byref(dims), mode, ptr(enc), ptr(ws), ws.numel(), st))
+            return enc
+        if lengths.numel() != b:
+            raise RuntimeError(f"input_lengths has {lengths.numel()} entries for a batch of {b}")
+        lens = lengths.to(device=x.device, dtype=torch.int32).contiguous()
+        enc_lens = torch.empty(b, dtype=torch.int32, device=x.device)
+        check(lib.las_listener_forward_masked(ptr(x), ptr(lens), ptr(packed), C.byref(dims), mode, ptr(enc), ptr(enc_lens), ptr(ws),
+                                              ws.numel(), st))
+    return enc, enc_lens
 
 
 class LAS(nn.Module):
@@ -131,14 +140,21 @@ class LAS(nn.Module):
         self.listener = listener
         self.speller = speller
 
-    def forward(self, batch_data, batch_label, teacher_force_rate, is_training=True):
-        listener_feature = self.listener(batch_data)
+    def forward(self, batch_data, batch_label, teacher_force_rate, is_training=True, input_lengths=None):
+        """`input_lengths` ([B] valid frames per utterance) is an extension: the reference's collate_fn computes it
+        (utils/data.py:146) and train.py:117 drops it.  When given, the BLSTMs and the attention skip the padding."""
+        enc_lengths = None
+        if input_lengths is None:
+            listener_feature = self.listener(batch_data)
+        else:
+            listener_feature, enc_lengths = self.listener(batch_data, input_lengths=input_lengths)
         if is_training:
             raw_pred_seq, attention_record = self.speller(
-                listener_feature, ground_truth=batch_label, teacher_force_rate=teacher_force_rate
+                listener_feature, ground_truth=batch_label, teacher_force_rate=teacher_force_rate, enc_lengths=enc_lengths
             )
         else:
-            raw_pred_seq, attention_record = self.speller(listener_feature, ground_truth=None, teacher_force_rate=0)
+            raw_pred_seq, attention_record = self.speller(listener_feature, ground_truth=None, teacher_force_rate=0,
+                                                          enc_lengths=enc_lengths)
         return raw_pred_seq, attention_record
 
     def serialize(self, optimizer, epoch, tr_loss, val_loss):
@@ -209,9 +225,12 @@ class Listener(nn.Module):
             setattr(self, "pLSTM_layer" + str(i), pBLSTMLayer(hidden_size * 2, hidden_size, rnn_unit=rnn_unit, dropout_rate=dropout_rate))
         self._cache = _Cache()
 
-    def forward(self, input_x):
+    def forward(self, input_x, input_lengths=None):
+        """`input_lengths=None` is the reference behaviour (padding is processed as data); with lengths the call returns
+        (listener_feature, enc_lengths)."""
         holders = [getattr(self, "pLSTM_layer" + str(i)).BLSTM for i in range(self.num_layers)]
-        return _run_listener(input_x, holders, self.input_feature_dim, self.hidden_size, _mode_of(self.precision), self._cache)
+        return _run_listener(input_x, holders, self.input_feature_dim, self.hidden_size, _mode_of(self.precision), self._cache,
+                             lengths=input_lengths)
 
 
 class Attention(nn.Module):

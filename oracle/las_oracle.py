@@ -98,6 +98,26 @@ def listener_forward(x, sd, num_layers, dtype=np.float32, prefix="listener"):
     return out
 
 
+def listener_forward_masked(x, lengths, sd, num_layers, dtype=np.float32, prefix="listener"):
+    """Length-mask EXTENSION (not in the reference, which runs over the zero padding -- SURVEY.md A.5.2; the lengths are
+    the `inputs_length` that utils/data.py:146 computes and train.py:117 drops).  Layer l keeps len_l = ceil(len_{l-1}/2)
+    steps; each direction runs over the valid prefix only and outputs past it are zero -- the semantics of torch's
+    pack_padded_sequence -> nn.LSTM -> pad_packed_sequence, which tests/test_oracle_golden.py pins this function to.
+    Returns (enc [B,U,2H], enc_lengths [B])."""
+    out = np.asarray(x, dtype=dtype)
+    lens = np.asarray(lengths, dtype=np.int64)
+    for layer in range(num_layers):
+        xr = pyramid_fold(out)
+        lens = np.minimum((lens + 1) // 2, xr.shape[1])
+        nxt = np.zeros((xr.shape[0], xr.shape[1], 2 * sd[f"{prefix}.pLSTM_layer{layer}.BLSTM.weight_hh_l0"].shape[1]), dtype=dtype)
+        for b in range(xr.shape[0]):
+            n = int(lens[b])
+            if n > 0:  # utterance b alone, truncated to its valid steps
+                nxt[b, :n] = pblstm_layer(out[b:b + 1, :2 * n], sd, f"{prefix}.pLSTM_layer{layer}", dtype)[0]
+        out = nxt
+    return out, lens
+
+
 def psi_project(enc, sd, dtype=np.float32, prefix="speller", activate=True):
     """relu(TimeDistributed(psi, enc)) -- model/las_model.py:279 + utils/functions.py:72-77.
 

@@ -89,3 +89,35 @@ def test_solver_epilogue_restatement():
     assert O.letter_error_rate([[2, 3, 0, 4, 1, 5]], [[2, 3, 4, 1, 0, 0]]) == [0.0]
     assert O.letter_error_rate([[2, 2, 1]], [[2, 3, 4, 1]]) == [2 / 3]
     assert O.levenshtein("kitten", "sitting") == 3
+
+
+def test_masked_listener_oracle_equals_torch_packed_sequence():
+    """The length-mask extension's oracle is pinned to torch itself: per layer, pack_padded_sequence -> nn.LSTM ->
+    pad_packed_sequence with lengths ceil-halved, which is what `listener_forward_masked` restates."""
+    import torch
+    from torch.nn.utils.rnn import pack_padded_sequence, pad_packed_sequence
+
+    torch.manual_seed(7)
+    B, T, F, H, L = 5, 32, 40, 12, 3
+    lstms = [torch.nn.LSTM((F if l == 0 else 2 * H) * 2, H, 1, bidirectional=True, batch_first=True).double() for l in range(L)]
+    sd = {}
+    for l, m in enumerate(lstms):
+        for k, v in m.state_dict().items():
+            sd[f"listener.pLSTM_layer{l}.BLSTM.{k}"] = v.numpy()
+    x = torch.randn(B, T, F, dtype=torch.float64)
+    lengths = torch.tensor([32, 27, 17, 8, 3])
+    for b in range(B):
+        x[b, lengths[b]:] = 0  # zero padding as utils/data.py:132
+    out, lens = x, lengths.clone()
+    with torch.no_grad():
+        for m in lstms:
+            xr = out.reshape(B, out.size(1) // 2, 2 * out.size(2))
+            lens = (lens + 1) // 2
+            packed = pack_padded_sequence(xr, lens, batch_first=True, enforce_sorted=False)
+            out, _ = pad_packed_sequence(m(packed)[0], batch_first=True, total_length=xr.size(1))
+    enc, enc_lens = O.listener_forward_masked(x.numpy(), lengths.numpy(), sd, L, dtype=np.float64)
+    assert np.array_equal(enc_lens, lens.numpy())
+    assert np.abs(enc - out.numpy()).max() < 1e-12
+    # full lengths reproduce the unmasked (reference) listener exactly
+    full, _ = O.listener_forward_masked(x.numpy(), np.full(B, T), sd, L, dtype=np.float64)
+    assert np.abs(full - O.listener_forward(x.numpy(), sd, L, dtype=np.float64)).max() < 1e-13  # BLAS batch-size rounding only

@@ -218,6 +218,40 @@ def test_bf16_length_mask():
     assert np.abs(attn.sum(-1) - 1).max() < 1e-4
 
 
+@pytest.mark.parametrize("precision", precisions())
+@pytest.mark.parametrize("cfgname", ["small", "odd"])
+def test_listener_length_masks(cfgname, precision):
+    """Length-mask extension (north_star): BLSTMs and attention skip the padding; the oracle is pinned to torch's
+    packed-sequence LSTM on CPU.  An utterance's result no longer depends on how much padding follows it."""
+    c = tl.CONFIGS[cfgname]
+    B, T, S = 6, 64, 6
+    las = tl.build_model(cfgname, max_label_len=S, seed=41, gain=3.0, precision=precision)
+    sd = tl.state_dict_numpy(las)
+    x, _ = tl.make_inputs(B, T, c["F"], S, c["V"], seed=41)
+    lengths = torch.tensor([64, 57, 40, 33, 9, 2])
+    for b in range(B):
+        x[b, lengths[b]:] = 0
+    ref_enc, ref_lens = O.listener_forward_masked(x.numpy(), lengths.numpy(), sd, c["L"], dtype=np.float64)
+    ref = O.speller_forward(ref_enc, sd, c["sl"], S, dtype=np.float64, enc_lengths=ref_lens)
+    las = las.cuda()
+    enc, enc_lens = las.listener(x.cuda(), input_lengths=lengths)
+    tol = TOL[precision]
+    assert np.array_equal(enc_lens.cpu().numpy(), ref_lens)  # mask indices bit-exact
+    assert np.abs(enc.cpu().numpy() - ref_enc).max() <= tol["enc"]
+    for b in range(B):  # outputs past the valid length are exactly zero
+        assert float(enc[b, int(ref_lens[b]):].abs().max() if int(ref_lens[b]) < enc.size(1) else 0.0) == 0.0
+    preds, attns = las(x.cuda(), None, 0.0, is_training=False, input_lengths=lengths)
+    assert np.abs(torch.stack(preds).cpu().numpy() - ref["logp"]).max() <= tol["logp"]
+    # padding invariance: the same utterances with 32 more padded frames give the same valid outputs
+    xp = torch.cat([x, torch.zeros(B, 32, c["F"])], dim=1)
+    enc2, enc_lens2 = las.listener(xp.cuda(), input_lengths=lengths)
+    assert torch.equal(enc_lens2, enc_lens)
+    assert torch.equal(enc2[:, : enc.size(1)], enc) and float(enc2[:, enc.size(1):].abs().max()) == 0.0
+    # lengths == T reproduce the reference (unmasked) path bit for bit
+    enc_full, _ = las.listener(x.cuda(), input_lengths=torch.full((B,), T))
+    assert torch.equal(enc_full, las.listener(x.cuda()))
+
+
 def test_forward_step_and_attention_api():
     """Speller.forward_step / Attention.forward (model/las_model.py:178-184, 275-297) against the oracle."""
     c = tl.CONFIGS["tiny"]
