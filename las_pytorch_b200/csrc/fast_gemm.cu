@@ -33,7 +33,7 @@ struct __align__(1024) GemmSmem {
 
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
-                    const float* __restrict__ bias, float* __restrict__ C, long long ldc, int M, int N, int K) {
+                    const float* __restrict__ bias, float* __restrict__ C, long long ldc, int M, int N, int K, int relu) {
   extern __shared__ uint8_t smem_raw[];
   GemmSmem& s = *reinterpret_cast<GemmSmem*>(smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u));  // offset from the __shared__ symbol keeps the address space
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -128,11 +128,15 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
               o.y = __uint_as_float(v[j + 1]) + bv.y;
               o.z = __uint_as_float(v[j + 2]) + bv.z;
               o.w = __uint_as_float(v[j + 3]) + bv.w;
+              if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
               *reinterpret_cast<float4*>(crow + col0 + j) = o;
             }
           } else {
             for (int j = 0; j < 32; ++j)
-              if (col0 + j < N) crow[col0 + j] = __uint_as_float(v[j]) + bias[col0 + j];
+              if (col0 + j < N) {
+                const float o = __uint_as_float(v[j]) + bias[col0 + j];
+                crow[col0 + j] = relu ? fmaxf(o, 0.f) : o;
+              }
           }
         }
       }
@@ -183,7 +187,7 @@ int make_tmap_bf16_box(CUtensorMap* tm, const void* base, long long rows, long l
 }
 
 int launch_gemm_bf16_tc(const __nv_bfloat16* A, long long lda, const __nv_bfloat16* W, long long ldw, const float* bias, float* C,
-                        long long ldc, int M, int N, int K, cudaStream_t st) {
+                        long long ldc, int M, int N, int K, cudaStream_t st, bool relu) {
   LAS_REQUIRE(M > 0 && N > 0 && K > 0, "bad GEMM shape %dx%dx%d", M, N, K);
   CUtensorMap tm_a, tm_b;
   LAS_TRY(make_tmap_bf16(&tm_a, A, M, K, lda, BM));
@@ -196,7 +200,7 @@ int launch_gemm_bf16_tc(const __nv_bfloat16* A, long long lda, const __nv_bfloat
     LAS_CUDA_OK(cudaFuncSetAttribute(gemm_bf16_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
   }
-  gemm_bf16_tc_kernel<<<grid, GEMM_THREADS, smem, st>>>(tm_a, tm_b, bias, C, ldc, M, N, K);
+  gemm_bf16_tc_kernel<<<grid, GEMM_THREADS, smem, st>>>(tm_a, tm_b, bias, C, ldc, M, N, K, relu ? 1 : 0);
   LAS_LAUNCH_OK("gemm_bf16_tc_kernel");
   return LAS_OK;
 }

@@ -78,6 +78,7 @@ struct DecParams {
   int Bfull;  // batch pitch of the caller's tensors; this launch covers utterances [b0, b0 + B)
   int b0;
   int U, E, Hs, sl, V, D, steps, decode_mode, relu, gt_steps, ncl, k_in_smem;
+  int ab_flags;     // test hook (las_debug_set_option(5, v)): bit 0 = W_phi from shared memory instead of registers
   int word_gather;  // 1: the fed-back word is an index (greedy argmax / gt_index); 0: a dense vector (part 1b)
   int ctx_tmem;     // 1: enc[b]^T is resident in the attention CTA's tensor memory and the context is a UMMA
   int nstages, stage_bytes;  // activation slots: [64 batch rows x 64 bf16], 128-byte swizzled; last slot = word atom
@@ -532,6 +533,16 @@ __device__ void attention_role(const DecParams& p, uint8_t* smem, int b) {
   ptx::tc_fence_after();
 
   const int hchunks = Hs >> 3, kchunks = KC >> 3;  // 16-byte chunks (8 bf16) of a W_phi row / W_cd row
+  // W_phi in registers: thread (d = tid / 8, part = tid % 8) keeps the chunks part, part + 8, ... of row d (32 registers)
+  // for all S steps, so the query GEMV reads only h from shared memory (the 64 KB of W_phi would otherwise be half of
+  // the step's shared-memory wavefronts).  Falls back to the shared-memory copy for D > 64 or Hs > 512.
+  const bool wreg = (D <= DEC_THREADS / 8) && (hchunks <= 64) && !(p.ab_flags & 1);
+  uint4 wq[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int d = tid >> 3, c = (tid & 7) + 8 * j;
+    wq[j] = (wreg && d < D && c < hchunks) ? *reinterpret_cast<const uint4*>(s_wphi + (size_t)d * WPS + 8 * c) : make_uint4(0, 0, 0, 0);
+  }
   const int Dp = (D + 3) & ~3, Vp = (V + 1) & ~1;
   const int nd4 = (D + 3) >> 2;                    // float4 chunks of a psi row
 
@@ -549,7 +560,21 @@ __device__ void attention_role(const DecParams& p, uint8_t* smem, int b) {
       const int part = tid & 7;
       for (int d = tid >> 3; d < Dp; d += DEC_THREADS / 8) {
         float acc = 0.f;
-        if (d < D) {
+        if (wreg) {
+          float acc2 = 0.f;
+#pragma unroll
+          for (int j = 0; j < 8; j += 2) {
+            if (part + 8 * j < hchunks) {
+              const float4* xv = xchunk(s_h, part + 8 * j);
+              acc = dot8(wq[j], xv[0], xv[8], acc);
+            }
+            if (part + 8 * (j + 1) < hchunks) {
+              const float4* xv = xchunk(s_h, part + 8 * (j + 1));
+              acc2 = dot8(wq[j + 1], xv[0], xv[8], acc2);
+            }
+          }
+          acc += acc2;
+        } else if (d < D) {
           const uint4* wr = reinterpret_cast<const uint4*>(s_wphi + (size_t)d * WPS);
 #pragma unroll 4
           for (int c = part; c < hchunks; c += 8) {
@@ -920,6 +945,7 @@ __global__ void dec_init_kernel(DecParams p, const float* enc_f32, const float* 
 }
 
 int g_dec_ctx_tmem = 1;  // las_debug_set_option(2, v)
+int g_dec_ab_flags = 0;  // las_debug_set_option(5, v)
 
 struct Shape {
   int ncl, natoms[MAX_SL];
@@ -976,6 +1002,7 @@ struct SpellerPackFast {
   float* bias[MAX_SL];
   __nv_bfloat16* w_phi;
   __nv_bfloat16* w_cd;
+  __nv_bfloat16* w_psi;
   size_t bytes;
 };
 SpellerPackFast pack_layout(const las_speller_dims* d, void* base) {
@@ -988,6 +1015,7 @@ SpellerPackFast pack_layout(const las_speller_dims* d, void* base) {
   }
   p.w_phi = cv.take<__nv_bfloat16>((size_t)d->D * d->Hs);
   p.w_cd = cv.take<__nv_bfloat16>((size_t)d->V * (d->Hs + d->E) + 8);
+  p.w_psi = cv.take<__nv_bfloat16>((size_t)d->D * d->E);
   p.bytes = cv.total();
   return p;
 }
@@ -1024,6 +1052,7 @@ SpellerWsFast ws_layout(const las_speller_dims* d, void* base) {
 bool fast_available() { return true; }
 void fast_set_option_speller(int key, int value) {
   if (key == 2) g_dec_ctx_tmem = value;
+  if (key == 5) g_dec_ab_flags = value;
 }
 
 size_t fast_speller_packed_bytes(const las_speller_dims* d) { return pack_layout(d, nullptr).bytes; }
@@ -1042,6 +1071,7 @@ int fast_speller_pack(const las_speller_weights* w, const las_speller_dims* d, v
   }
   LAS_TRY(launch_f32_to_bf16(w->w_phi, pk.w_phi, (size_t)d->D * d->Hs, st));
   LAS_TRY(launch_f32_to_bf16(w->w_cd, pk.w_cd, (size_t)d->V * (d->Hs + d->E), st));
+  LAS_TRY(launch_f32_to_bf16(w->w_psi, pk.w_psi, (size_t)d->D * d->E, st));
   return LAS_OK;
 }
 
@@ -1072,12 +1102,7 @@ int fast_speller_decode(const las_decode_io* io, const void* packed_f32, const v
     fv.b_cd = cv.take<float>(d->V);
   }
   float* psi_ws = static_cast<float*>(ws_f32);  // first buffer of the fp32 workspace layout: psi [B,U,D]
-  const float* psi = io->psi;
-  if (!psi) {
-    ProfScope ps("speller.psi", st);
-    LAS_TRY(launch_sgemm_nt_bias(io->enc, d->E, fv.w_psi, d->E, fv.b_psi, psi_ws, d->D, d->B * d->U, d->D, d->E, relu != 0, st));
-    psi = psi_ws;
-  }
+  const float* psi = io->psi ? io->psi : psi_ws;
 
   for (int b0 = 0; b0 < d->B; b0 += max_b) {
     const int Bc = (d->B - b0) < max_b ? (d->B - b0) : max_b;
@@ -1126,6 +1151,7 @@ int fast_speller_decode(const las_decode_io* io, const void* packed_f32, const v
     p.h_ll = w.h_ll;
     p.tok_ll = w.tok_ll;
     // the fed-back word is an index (greedy argmax / index teacher forcing) unless a dense vector is asked for
+    p.ab_flags = g_dec_ab_flags;
     p.word_gather = io->gt_dense ? 0 : (io->gt_index ? 1 : (decode_mode == LAS_DECODE_GREEDY ? 1 : 0));
     p.trace = fast_get_trace() ? fast_get_trace() + 512 : nullptr;  // needs 5 roles x 32 steps x 8 stamps behind the recurrence trace
 
@@ -1135,6 +1161,13 @@ int fast_speller_decode(const las_decode_io* io, const void* packed_f32, const v
       LAS_CUDA_OK(cudaMemsetAsync(w.flags, 0, w.flag_bytes, st));
       dec_init_kernel<<<Bc, 256, 0, st>>>(p, io->enc, io->word, io->context, io->h_state);
       LAS_LAUNCH_OK("dec_init_kernel");
+    }
+    if (!io->psi) {
+      // psi(enc) once per utterance (model/las_model.py:279 recomputes it every step): the same tcgen05 GEMM as the
+      // listener's input projection, bf16 operands (the enc copy made above), fp32 accumulate + bias + relu
+      ProfScope pp("speller.psi", st);
+      LAS_TRY(launch_gemm_bf16_tc(w.enc_bf16, d->E, pk.w_psi, d->E, fv.b_psi, psi_ws + so * d->U * d->D, d->D, Bc * d->U, d->D, d->E, st,
+                                  relu != 0));
     }
     ProfScope ps("speller.steps", st);
     const size_t smem_l = rc.smem, smem_a = att_smem(d, p.k_in_smem != 0);

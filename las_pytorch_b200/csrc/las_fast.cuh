@@ -25,7 +25,7 @@ long long* fast_get_trace();  // test hook: recurrence kernel timeline (64 steps
 
 // fast_gemm.cu
 int launch_gemm_bf16_tc(const __nv_bfloat16* A, long long lda, const __nv_bfloat16* W, long long ldw, const float* bias, float* C,
-                        long long ldc, int M, int N, int K, cudaStream_t st);
+                        long long ldc, int M, int N, int K, cudaStream_t st, bool relu = false);
 int launch_umma_probe(const void* A, const void* B, float* D, int N, int K, int a_sw128, int b_sw128, int variant, cudaStream_t st);
 int launch_f32_to_bf16(const float* src, __nv_bfloat16* dst, size_t n, cudaStream_t st);
 
