@@ -21,7 +21,8 @@ namespace las {
 
 namespace {
 
-constexpr int REC_THREADS = 160;  // warps 0-3: epilogue (one TMEM lane quadrant each); warp 4: MMA issuer
+constexpr int REC_THREADS = 288;  // warps 0-7: epilogue (TMEM lane quadrant = warp % 4, batch half = warp / 4); warp 8: MMA issuer
+constexpr int REC_MMA_WARP = 8, REC_EPI_THREADS = 256;
 
 struct RecParams {
   const float* P;               // [B*Tl, NP] fp32; column = dir*4Hp + r*128 + jj*4 + gate
@@ -59,7 +60,8 @@ __host__ __device__ inline uint32_t rec_tmem_cols(int Hp, int BC, int a_tmem) {
 
 template <int BC, int NACC>
 __global__ void __launch_bounds__(REC_THREADS, 1) lstm_recurrence_cluster_kernel(RecParams p) {
-  constexpr int NB = BC / 4;  // cells per epilogue thread
+  constexpr int NB = BC / 8;  // cells per epilogue thread
+  constexpr int HB = BC / 2;  // batch columns per epilogue warp (two warps share a TMEM lane quadrant)
   // The K loop can be spread round-robin over NACC independent accumulators that the epilogue sums (test hook:
   // las_debug_set_option(4, n)).  tools/microbench.cu: a tcgen05.mma with the A operand in TMEM issues every ~33 cycles
   // whatever N is and whether or not consecutive instructions share an accumulator, so NACC = 1 is the default.
@@ -95,7 +97,7 @@ __global__ void __launch_bounds__(REC_THREADS, 1) lstm_recurrence_cluster_kernel
     if (p.Tl > 1) ptx::mbar_arrive_expect_tx(&h_full[1], h_bytes);
     if (p.Tl > 2) ptx::mbar_arrive_expect_tx(&h_full[0], h_bytes);
   }
-  if (warp == 4) ptx::tmem_alloc(tmem_slot, tcols);
+  if (warp == REC_MMA_WARP) ptx::tmem_alloc(tmem_slot, tcols);
   if (!p.a_tmem) {
     const uint4* src = reinterpret_cast<const uint4*>(w_img);
     uint4* dst = reinterpret_cast<uint4*>(sA);
@@ -125,7 +127,7 @@ __global__ void __launch_bounds__(REC_THREADS, 1) lstm_recurrence_cluster_kernel
   ptx::tc_fence_after();
   const int Tl = p.Tl;
 
-  if (warp == 4) {
+  if (warp == REC_MMA_WARP) {
     // ================================ MMA issuer ================================
     // The whole warp walks the loop with warp-uniform values (descriptors end up in uniform registers); only the
     // tcgen05 / mbarrier-arrive instructions are predicated on one elected lane.
@@ -160,7 +162,9 @@ __global__ void __launch_bounds__(REC_THREADS, 1) lstm_recurrence_cluster_kernel
   } else {
     // ================================ gate math + h exchange ================================
     const int tid = threadIdx.x;
-    const int jj = tid >> 2, g = tid & 3;  // TMEM lane = gate row = 4*jj + g
+    const int wq = warp & 3, hb = warp >> 2;     // TMEM lane quadrant; batch half [hb*HB, hb*HB + HB) of the chunk
+    const int row = wq * 32 + lane;              // TMEM lane = gate row = 4*jj + g
+    const int jj = row >> 2, g = row & 3;
     const bool bit0 = (g & 1) != 0, bit1 = (g & 2) != 0;
     const int j = (int)r * 32 + jj;        // hidden unit
     const int NP = 8 * Hp;
@@ -171,20 +175,20 @@ __global__ void __launch_bounds__(REC_THREADS, 1) lstm_recurrence_cluster_kernel
 #pragma unroll
     for (int m = 0; m < NB; ++m) {
       c[m] = 0.f;
-      const int b = b_base + 4 * m + g;
+      const int b = b_base + hb * HB + 4 * m + g;
       len[m] = (p.lengths && b < p.B) ? p.lengths[b] : Tl;
     }
     {
       const int t0 = dir ? Tl - 1 : 0;
 #pragma unroll
       for (int m = 0; m < NB; ++m) {
-        const int b = b_base + 4 * m + g;
+        const int b = b_base + hb * HB + 4 * m + g;
         pnext[m] = (b < p.B) ? *reinterpret_cast<const float4*>(pcol + ((size_t)b * Tl + t0) * NP) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
     }
     const uint32_t stage0 = ptx::smem_u32(sStage);
     const uint32_t h0_addr = ptx::smem_u32(sH0);
-    const int dst_per_warp = (CS + 3) / 4;  // destination CTAs each warp serves
+    const int dst_per_warp = (CS + 7) / 8;  // destination CTAs each warp serves
     for (int s = 0; s < Tl; ++s) {
       const int t = dir ? Tl - 1 - s : s;
       float4 pc[NB];
@@ -194,49 +198,43 @@ __global__ void __launch_bounds__(REC_THREADS, 1) lstm_recurrence_cluster_kernel
         const int tn = dir ? t - 1 : t + 1;
 #pragma unroll
         for (int m = 0; m < NB; ++m) {
-          const int b = b_base + 4 * m + g;
+          const int b = b_base + hb * HB + 4 * m + g;
           if (b < p.B) pnext[m] = *reinterpret_cast<const float4*>(pcol + ((size_t)b * Tl + tn) * NP);
         }
         if (s + 2 < Tl) {  // pull the step after that into L2 so the register prefetch above never sees DRAM latency
           const int tnn = dir ? t - 2 : t + 2;
 #pragma unroll
           for (int m = 0; m < NB; ++m) {
-            const int b = b_base + 4 * m + g;
+            const int b = b_base + hb * HB + 4 * m + g;
             if (b < p.B) asm volatile("prefetch.global.L2 [%0];" ::"l"(pcol + ((size_t)b * Tl + tnn) * NP));
           }
         }
       }
       ptx::mbar_wait(mma_done, (uint32_t)(s & 1));
       if (tid == 0) REC_TRACE(2);
-      uint32_t v[BC];
+      uint32_t v[HB];
       if (s > 0) {
         ptx::tc_fence_after();
-        uint32_t part[NACC > 1 ? NACC - 1 : 1][BC];
+        constexpr int LDW = HB < 16 ? HB : 16;  // columns per tcgen05.ld
 #pragma unroll
-        for (int c0 = 0; c0 < BC; c0 += 16) {
-          uint32_t t16[16];
-          ptx::tmem_ld_32x32b_x16(tmem + ((uint32_t)(warp * 32) << 16) + d_col + c0, t16);
+        for (int a = 0; a < NACC; ++a) {
+          if (a == 0 || a < Hp / 16) {  // accumulator `a` was written this step (Hp = 32 has only two K steps)
 #pragma unroll
-          for (int i = 0; i < 16; ++i) v[c0 + i] = t16[i];
+            for (int c0 = 0; c0 < HB; c0 += LDW) {
+              uint32_t t[LDW];
+              const uint32_t addr = tmem + ((uint32_t)(wq * 32) << 16) + d_col + a * BC + hb * HB + c0;
+              if constexpr (LDW == 16) ptx::tmem_ld_32x32b_x16(addr, *reinterpret_cast<uint32_t(*)[16]>(t));
+              else ptx::tmem_ld_32x32b_x8(addr, *reinterpret_cast<uint32_t(*)[8]>(t));
+              ptx::tmem_ld_wait();
 #pragma unroll
-          for (int a = 1; a < NACC; ++a) {
-            ptx::tmem_ld_32x32b_x16(tmem + ((uint32_t)(warp * 32) << 16) + d_col + a * BC + c0, t16);
-#pragma unroll
-            for (int i = 0; i < 16; ++i) part[a - 1][c0 + i] = t16[i];
+              for (int i = 0; i < LDW; ++i) v[c0 + i] = (a == 0) ? t[i] : __float_as_uint(__uint_as_float(v[c0 + i]) + __uint_as_float(t[i]));
+            }
           }
         }
-        ptx::tmem_ld_wait();
         ptx::tc_fence_before();
-#pragma unroll
-        for (int a = 1; a < NACC; ++a) {
-          if (a < Hp / 16) {  // accumulator `a` was written this step (Hp = 32 has only two K steps)
-#pragma unroll
-            for (int i = 0; i < BC; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) + __uint_as_float(part[a - 1][i]));
-          }
-        }
       } else {
 #pragma unroll
-        for (int i = 0; i < BC; ++i) v[i] = 0u;
+        for (int i = 0; i < HB; ++i) v[i] = 0u;
       }
       if (tid == 0) REC_TRACE(3);
       float hval[NB];
@@ -273,13 +271,13 @@ __global__ void __launch_bounds__(REC_THREADS, 1) lstm_recurrence_cluster_kernel
         const uint32_t sb = stage0 + (uint32_t)(s & 1) * (4u * BC * 16u);
 #pragma unroll
         for (int m = 0; m < NB; ++m) {
-          const int bl = 4 * m + g;  // batch row within the chunk
-          const uint32_t off = (uint32_t)warp * (BC * 16u) + (uint32_t)(bl >> 3) * 128u + (uint32_t)(bl & 7) * 16u + (uint32_t)(jj & 7) * 2u;
+          const int bl = hb * HB + 4 * m + g;  // batch row within the chunk
+          const uint32_t off = (uint32_t)wq * (BC * 16u) + (uint32_t)(bl >> 3) * 128u + (uint32_t)(bl & 7) * 16u + (uint32_t)(jj & 7) * 2u;
           const __nv_bfloat16 hb = __float2bfloat16_rn(hval[m]);
           asm volatile("st.shared.b16 [%0], %1;" ::"r"(sb + off), "h"(*reinterpret_cast<const unsigned short*>(&hb)) : "memory");
         }
         ptx::fence_proxy_async_smem();  // generic-proxy staging writes -> visible to the bulk-copy (async proxy) reads
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync 1, 256;" ::: "memory");
         if (tid == 0) REC_TRACE(6);
         const int d = warp * dst_per_warp + lane;
         if (lane < dst_per_warp && d < CS) {
@@ -295,7 +293,7 @@ __global__ void __launch_bounds__(REC_THREADS, 1) lstm_recurrence_cluster_kernel
       if (j < p.H) {
 #pragma unroll
         for (int m = 0; m < NB; ++m) {
-          const int b = b_base + 4 * m + g;
+          const int b = b_base + hb * HB + 4 * m + g;
           if (b < p.B) {
             const size_t o = ((size_t)b * Tl + t) * 2 * p.H + (size_t)dir * p.H + j;
             if (p.out_f32) p.out_f32[o] = hval[m];
@@ -309,7 +307,7 @@ __global__ void __launch_bounds__(REC_THREADS, 1) lstm_recurrence_cluster_kernel
   ptx::tc_fence_before();
   __syncthreads();
   ptx::cluster_sync();  // no CTA leaves while a peer could still address its shared memory
-  if (warp == 4) ptx::tmem_dealloc(tmem, tcols);
+  if (warp == REC_MMA_WARP) ptx::tmem_dealloc(tmem, tcols);
 }
 
 // ---- pack kernels ------------------------------------------------------------------------------------------
