@@ -191,7 +191,9 @@ int las_debug_umma_probe(const void* a_bf16, const void* b_bf16, float* d, int N
 
 /* Device buffer of 64*8 int64 that the layer-0 recurrence kernel fills with clock64 stamps (NULL disables). */
 int las_debug_set_trace(void* dev_buf);
-/* Kernel variant switches for A/B tests: key 1 = recurrence keeps W_hh in tensor memory (1, default) or shared memory (0). */
+/* Kernel variant switches for A/B tests.  key 1: recurrence keeps W_hh in tensor memory (1, default) or shared memory (0);
+ * key 2: decoder context through tensor memory (1, default) or CUDA cores (0); key 4: recurrence accumulator chains (0 = default);
+ * key 5: decoder A/B flags (bit 0: W_phi from shared memory instead of registers). */
 int las_debug_set_option(int key, int value);
 
 #ifdef __cplusplus

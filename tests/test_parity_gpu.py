@@ -252,6 +252,26 @@ def test_listener_length_masks(cfgname, precision):
     assert torch.equal(enc_full, las.listener(x.cuda()))
 
 
+def test_bf16_batch_larger_than_one_decoder_launch():
+    """The persistent decoder covers at most 64 utterances per launch (one attention CTA each); larger batches are decoded
+    in chunks.  70 utterances must equal the same utterances decoded as 64 + 6."""
+    if "bf16" not in precisions():
+        pytest.skip("bf16 mode not built")
+    c = tl.CONFIGS["small"]
+    B, T, S = 70, 64, 8
+    las = tl.build_model("small", max_label_len=S, seed=43, gain=3.0, precision="bf16").cuda()
+    x, _ = tl.make_inputs(B, T, c["F"], S, c["V"], seed=43)
+    x = x.cuda()
+    full = torch.stack(las(x, None, 0.0, is_training=False)[0])
+    tok_full = las.speller.last_tokens.clone()
+    a = torch.stack(las(x[:64], None, 0.0, is_training=False)[0])
+    b = torch.stack(las(x[64:], None, 0.0, is_training=False)[0])
+    both = torch.cat([a, b], dim=1)
+    assert full.shape == (S, B, c["V"]) and tok_full.shape == (S, B)
+    assert float((full - both).abs().max()) < 2e-2
+    assert float((full.exp().sum(-1) - 1).abs().max()) < 1e-4
+
+
 def test_forward_step_and_attention_api():
     """Speller.forward_step / Attention.forward (model/las_model.py:178-184, 275-297) against the oracle."""
     c = tl.CONFIGS["tiny"]
