@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define LAS_B200_ABI_VERSION 1
+#define LAS_B200_ABI_VERSION 2
 
 enum {
   LAS_OK = 0,
@@ -115,7 +115,9 @@ typedef struct las_speller_dims {
   int32_t Hs; /* speller hidden size; the reference requires Hs == E */
   int32_t sl; /* stacked LSTM layers */
   int32_t V;  /* vocabulary (label_dim) */
-  int32_t D;  /* attention MLP dim (phi/psi out features) */
+  int32_t D;  /* attention MLP dim per head (phi out features = D * heads, psi out features = D) */
+  int32_t heads;  /* multi_head (model/las_model.py:268-269, 298-314); 0 is read as 1.  heads > 1: LAS_MODE_FP32 only */
+  int32_t no_mlp; /* 1: use_mlp_in_attention=False (:283-285): query = decoder state, keys = enc, D ignored.  LAS_MODE_FP32 only */
 } las_speller_dims;
 
 typedef struct las_speller_weights {
@@ -126,6 +128,8 @@ typedef struct las_speller_weights {
   const float* b_psi; /* [D] */
   const float* w_cd;  /* [V, Hs+E] character_distribution (:174) */
   const float* b_cd;  /* [V] */
+  const float* w_dr;  /* [E, E*heads] attention.dim_reduce (:269), heads > 1 only (else NULL) */
+  const float* b_dr;  /* [E] */
 } las_speller_weights;
 
 size_t las_speller_packed_bytes(const las_speller_dims* d, int mode);
@@ -139,14 +143,17 @@ int las_speller_pack(const las_speller_weights* w, const las_speller_dims* d, in
 int las_psi_precompute(const float* enc, const float* w_psi, const float* b_psi, int B, int U, int E, int D, int relu,
                        float* psi, void* stream);
 
-/* One attention evaluation (Attention.forward, :275-297, single head, 'dot'):
- * state [B,Hs], enc [B,U,E], psi [B,U,D] -> score [B,U], context [B,E].  w_phi [D,Hs] / b_phi [D] are
- * attention.phi; w_phi == NULL means use_mlp_in_attention=False (q = state, needs D == Hs; pass psi = enc).
+/* One attention evaluation (Attention.forward, :275-314, 'dot'):
+ * state [B,Hs], enc [B,U,E], psi [B,U,D] -> score [heads,B,U], context [B,E].  w_phi [D*heads,Hs] / b_phi [D*heads]
+ * are attention.phi; w_phi == NULL means use_mlp_in_attention=False (q = state, needs D == Hs and heads == 1; pass
+ * psi = enc).  heads > 1 (:298-314): every head attends with its own D-wide slice of q over the same keys, the per-head
+ * contexts are concatenated and reduced by w_dr [E, E*heads] / b_dr [E] (attention.dim_reduce).
  * enc_lengths (nullable, int32 [B]) is the length-mask extension; NULL reproduces the reference (softmax
  * over all U). */
 int las_attention_forward(const float* state, const float* enc, const float* psi, const float* w_phi,
-                          const float* b_phi, int B, int U, int E, int Hs, int D, int relu,
-                          const int32_t* enc_lengths, float* score, float* context, void* stream);
+                          const float* b_phi, int B, int U, int E, int Hs, int D, int relu, int heads,
+                          const float* w_dr, const float* b_dr, const int32_t* enc_lengths, float* score,
+                          float* context, void* stream);
 
 typedef struct las_decode_io {
   /* inputs */
@@ -163,7 +170,7 @@ typedef struct las_decode_io {
   float* context;             /* [B,E] current context */
   /* outputs */
   float* logp;                /* [S,B,V] log-probabilities per step (raw_pred_seq, :213) */
-  float* attn;                /* nullable [S,B,U] attention scores per step (attention_record, :214) */
+  float* attn;                /* nullable [S,heads,B,U] attention scores per step (attention_record, :214) */
   int32_t* tokens;            /* nullable [S,B] argmax of logp per step */
 } las_decode_io;
 

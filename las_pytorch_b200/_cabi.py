@@ -12,6 +12,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "liblas_b200.so")
 
+ABI_VERSION = 2
 MODE_FP32 = 0
 MODE_BF16 = 1
 DECODE_RAW = 0
@@ -29,7 +30,7 @@ class LstmWeights(C.Structure):
 class SpellerDims(C.Structure):
     _fields_ = [
         ("B", C.c_int32), ("U", C.c_int32), ("E", C.c_int32), ("Hs", C.c_int32),
-        ("sl", C.c_int32), ("V", C.c_int32), ("D", C.c_int32),
+        ("sl", C.c_int32), ("V", C.c_int32), ("D", C.c_int32), ("heads", C.c_int32), ("no_mlp", C.c_int32),
     ]
 
 
@@ -39,6 +40,7 @@ class SpellerWeights(C.Structure):
         ("w_phi", C.c_void_p), ("b_phi", C.c_void_p),
         ("w_psi", C.c_void_p), ("b_psi", C.c_void_p),
         ("w_cd", C.c_void_p), ("b_cd", C.c_void_p),
+        ("w_dr", C.c_void_p), ("b_dr", C.c_void_p),
     ]
 
 
@@ -70,7 +72,7 @@ PROTOTYPES = {
     "las_speller_packed_bytes": (C.c_size_t, [C.POINTER(SpellerDims), C.c_int]),
     "las_speller_pack": (C.c_int, [C.POINTER(SpellerWeights), C.POINTER(SpellerDims), C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]),
     "las_psi_precompute": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
-    "las_attention_forward": (C.c_int, [C.c_void_p] * 5 + [C.c_int] * 6 + [C.c_void_p] * 4),
+    "las_attention_forward": (C.c_int, [C.c_void_p] * 5 + [C.c_int] * 7 + [C.c_void_p] * 6),
     "las_speller_workspace_bytes": (C.c_size_t, [C.POINTER(SpellerDims), C.c_int, C.c_int]),
     "las_speller_decode": (C.c_int, [C.POINTER(DecodeIO), C.c_void_p, C.POINTER(SpellerDims), C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]),
     "las_debug_gemm_bf16": (C.c_int, [C.c_void_p] * 4 + [C.c_int] * 3 + [C.c_void_p]),
@@ -103,8 +105,8 @@ def load_library(path: str | None = None):
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
-    if lib.las_abi_version() != 1:
-        raise LasB200Error(f"ABI version mismatch: library reports {lib.las_abi_version()}, binding expects 1")
+    if lib.las_abi_version() != ABI_VERSION:
+        raise LasB200Error(f"ABI version mismatch: library reports {lib.las_abi_version()}, binding expects {ABI_VERSION}")
     if path is None:
         _lib = lib
     return lib

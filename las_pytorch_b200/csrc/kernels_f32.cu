@@ -227,23 +227,25 @@ __device__ __forceinline__ float block_reduce_sum(float v, float* red) {
 
 __global__ void __launch_bounds__(256) attend_f32_kernel(AttendArgs a) {
   extern __shared__ float sm[];
+  const int NH = a.heads;
   float* s_state = sm;                 // Hs
-  float* s_q = s_state + a.Hs;         // D
-  float* s_score = s_q + a.D;          // U
+  float* s_q = s_state + a.Hs;         // D * heads
+  float* s_score = s_q + a.D * NH;     // U
   float* s_ctx = s_score + a.U;        // E
   float* s_logit = s_ctx + a.E;        // V
   float* s_red = s_logit + a.V;        // 32
+  float* s_ctxh = s_red + 32;          // E * heads (heads > 1 only)
   const int b = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nw = blockDim.x >> 5;
 
   for (int k = tid; k < a.Hs; k += blockDim.x) s_state[k] = a.state[(size_t)b * a.state_ld + k];
   __syncthreads();
 
-  // q = act(W_phi . state + b_phi)   (:278)
+  // q = act(W_phi . state + b_phi)   (:278); D*heads outputs, split per head below (:303-305)
   if (!a.w_phi) {  // use_mlp_in_attention=False (:283-285): query is the raw decoder state
     for (int d = tid; d < a.D; d += blockDim.x) s_q[d] = s_state[d];
   }
-  for (int d = wid; a.w_phi && d < a.D; d += nw) {
+  for (int d = wid; a.w_phi && d < a.D * NH; d += nw) {
     const float* wr = a.w_phi + (size_t)d * a.Hs;
     float p = 0.f;
     for (int k = lane; k < a.Hs; k += 32) p = fmaf(wr[k], s_state[k], p);
@@ -255,44 +257,66 @@ __global__ void __launch_bounds__(256) attend_f32_kernel(AttendArgs a) {
   }
   __syncthreads();
 
-  // energy[u] = <q, psi[b,u,:]>   (:289-291)
   const int ulen = a.enc_lengths ? min(max(a.enc_lengths[b], 1), a.U) : a.U;
   const float* psib = a.psi + (size_t)b * a.U * a.D;
-  for (int u = wid; u < a.U; u += nw) {
-    const float* pr = psib + (size_t)u * a.D;
-    float p = 0.f;
-    for (int d = lane; d < a.D; d += 32) p = fmaf(s_q[d], pr[d], p);
-    p = warp_sum(p);
-    if (lane == 0) s_score[u] = (u < ulen) ? p : -INFINITY;
-  }
-  __syncthreads();
-
-  // softmax over U   (:292)
-  float m = -INFINITY;
-  for (int u = tid; u < a.U; u += blockDim.x) m = fmaxf(m, s_score[u]);
-  m = block_reduce_max(m, s_red);
-  float ssum = 0.f;
-  for (int u = tid; u < a.U; u += blockDim.x) {
-    const float e = expf(s_score[u] - m);
-    s_score[u] = e;
-    ssum += e;
-  }
-  ssum = block_reduce_sum(ssum, s_red);
-  const float inv = 1.0f / ssum;
-  for (int u = tid; u < a.U; u += blockDim.x) {
-    const float p = s_score[u] * inv;
-    s_score[u] = p;
-    if (a.score_out) a.score_out[(size_t)b * a.U + u] = p;
-  }
-  __syncthreads();
-
-  // context[e] = sum_u score[u] * enc[b,u,e]   (:293-297)
   const float* encb = a.enc + (size_t)b * a.U * a.E;
-  for (int e = tid; e < a.E; e += blockDim.x) {
-    float acc = 0.f;
-    for (int u = 0; u < a.U; ++u) acc = fmaf(s_score[u], encb[(size_t)u * a.E + e], acc);
-    s_ctx[e] = acc;
-    a.ctx_out[(size_t)b * a.ctx_ld + e] = acc;
+  for (int hd = 0; hd < NH; ++hd) {
+    // energy[u] = <q_head, psi[b,u,:]>   (:289-291 / :299-305)
+    const float* qh = s_q + hd * a.D;
+    for (int u = wid; u < a.U; u += nw) {
+      const float* pr = psib + (size_t)u * a.D;
+      float p = 0.f;
+      for (int d = lane; d < a.D; d += 32) p = fmaf(qh[d], pr[d], p);
+      p = warp_sum(p);
+      if (lane == 0) s_score[u] = (u < ulen) ? p : -INFINITY;
+    }
+    __syncthreads();
+
+    // softmax over U   (:292)
+    float m = -INFINITY;
+    for (int u = tid; u < a.U; u += blockDim.x) m = fmaxf(m, s_score[u]);
+    m = block_reduce_max(m, s_red);
+    float ssum = 0.f;
+    for (int u = tid; u < a.U; u += blockDim.x) {
+      const float e = expf(s_score[u] - m);
+      s_score[u] = e;
+      ssum += e;
+    }
+    ssum = block_reduce_sum(ssum, s_red);
+    const float inv = 1.0f / ssum;
+    for (int u = tid; u < a.U; u += blockDim.x) {
+      const float p = s_score[u] * inv;
+      s_score[u] = p;
+      if (a.score_out) a.score_out[((size_t)hd * a.B + b) * a.U + u] = p;
+    }
+    __syncthreads();
+
+    // context[e] = sum_u score[u] * enc[b,u,e]   (:293-297 / :306-312)
+    for (int e = tid; e < a.E; e += blockDim.x) {
+      float acc = 0.f;
+      for (int u = 0; u < a.U; ++u) acc = fmaf(s_score[u], encb[(size_t)u * a.E + e], acc);
+      if (NH == 1) {
+        s_ctx[e] = acc;
+        a.ctx_out[(size_t)b * a.ctx_ld + e] = acc;
+      } else {
+        s_ctxh[hd * a.E + e] = acc;
+      }
+    }
+    __syncthreads();
+  }
+  if (NH > 1) {  // context = dim_reduce(cat(per-head contexts))   (:313)
+    const int KR = a.E * NH;
+    for (int e = wid; e < a.E; e += nw) {
+      const float* wr = a.w_dr + (size_t)e * KR;
+      float p = 0.f;
+      for (int k = lane; k < KR; k += 32) p = fmaf(wr[k], s_ctxh[k], p);
+      p = warp_sum(p);
+      if (lane == 0) {
+        p += a.b_dr[e];
+        s_ctx[e] = p;
+        a.ctx_out[(size_t)b * a.ctx_ld + e] = p;
+      }
+    }
   }
   if (!a.w_cd) return;
   __syncthreads();
@@ -364,7 +388,7 @@ __global__ void __launch_bounds__(256) attend_f32_kernel(AttendArgs a) {
 }
 
 int launch_attend_f32(const AttendArgs& a, cudaStream_t st) {
-  const size_t smem = sizeof(float) * ((size_t)a.Hs + a.D + a.U + a.E + a.V + 32);
+  const size_t smem = sizeof(float) * ((size_t)a.Hs + (size_t)a.D * a.heads + a.U + a.E + a.V + 32 + (a.heads > 1 ? (size_t)a.E * a.heads : 0));
   if (smem > 200 * 1024) return fail(LAS_EINVAL, "attention step needs %zu bytes of shared memory (U=%d too long)", smem, a.U);
   if (smem > 48 * 1024) {
     LAS_CUDA_OK(cudaFuncSetAttribute(attend_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

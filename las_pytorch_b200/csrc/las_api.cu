@@ -184,13 +184,17 @@ static int listener_forward_f32(const float* x, const int32_t* x_lengths, const 
 // ---------------------------------------------------------------------------------------------------------
 struct SpellerPackF32 {
   float *w_ih[8], *w_hh[8], *b_ih[8], *b_hh[8];
-  float *w_phi, *b_phi, *w_psi, *b_psi, *w_cd, *b_cd;
+  float *w_phi, *b_phi, *w_psi, *b_psi, *w_cd, *b_cd, *w_dr, *b_dr;
   size_t bytes;
 };
+static inline int n_heads(const las_speller_dims* d) { return d->heads > 1 ? d->heads : 1; }
+static inline int att_dim(const las_speller_dims* d) { return d->no_mlp ? d->Hs : d->D; }  // width of one head's query / of a key
 static int speller_check(const las_speller_dims* d) {
   LAS_REQUIRE(d != nullptr, "dims is NULL");
-  LAS_REQUIRE(d->B > 0 && d->U > 0 && d->E > 0 && d->Hs > 0 && d->V > 0 && d->D > 0,
+  LAS_REQUIRE(d->B > 0 && d->U > 0 && d->E > 0 && d->Hs > 0 && d->V > 0 && (d->D > 0 || d->no_mlp),
               "speller dims must be positive (B=%d U=%d E=%d Hs=%d V=%d D=%d)", d->B, d->U, d->E, d->Hs, d->V, d->D);
+  LAS_REQUIRE(d->heads >= 0 && d->heads <= 16, "multi_head must be in [1,16] (heads=%d)", d->heads);
+  LAS_REQUIRE(!(d->no_mlp && n_heads(d) > 1), "multi_head > 1 needs use_mlp_in_attention=True (the heads are slices of phi's output)");
   LAS_REQUIRE(d->sl >= 1 && d->sl <= 8, "speller layers must be in [1,8] (sl=%d)", d->sl);
   LAS_REQUIRE(d->Hs == d->E,
               "speller hidden_size (%d) must equal 2*listener_hidden_size (%d): rnn input is [one-hot || encoder feature] "
@@ -208,12 +212,15 @@ static SpellerPackF32 speller_pack_layout_f32(const las_speller_dims* d, void* b
     p.b_ih[l] = cv.take<float>(G);
     p.b_hh[l] = cv.take<float>(G);
   }
-  p.w_phi = cv.take<float>((size_t)d->D * d->Hs);
-  p.b_phi = cv.take<float>(d->D);
-  p.w_psi = cv.take<float>((size_t)d->D * d->E);
-  p.b_psi = cv.take<float>(d->D);
+  const size_t Dm = d->no_mlp ? 0 : (size_t)d->D;  // no MLP: no phi / psi parameters exist
+  p.w_phi = cv.take<float>(Dm * n_heads(d) * d->Hs);
+  p.b_phi = cv.take<float>(Dm * n_heads(d));
+  p.w_psi = cv.take<float>(Dm * d->E);
+  p.b_psi = cv.take<float>(Dm);
   p.w_cd = cv.take<float>((size_t)d->V * (d->Hs + d->E));
   p.b_cd = cv.take<float>(d->V);
+  p.w_dr = cv.take<float>(n_heads(d) > 1 ? (size_t)d->E * d->E * n_heads(d) : 0);
+  p.b_dr = cv.take<float>(n_heads(d) > 1 ? (size_t)d->E : 0);
   p.bytes = cv.total();
   return p;
 }
@@ -228,7 +235,7 @@ struct SpellerWsF32 {
 static SpellerWsF32 speller_ws_layout_f32(const las_speller_dims* d, void* base) {
   SpellerWsF32 w;
   Carver cv(base);
-  w.psi = cv.take<float>((size_t)d->B * d->U * d->D);
+  w.psi = cv.take<float>((size_t)d->B * d->U * (d->no_mlp ? 0 : d->D));
   w.xin = cv.take<float>((size_t)d->B * (d->V + d->E));
   w.h[0] = cv.take<float>((size_t)d->sl * d->B * d->Hs);
   w.h[1] = cv.take<float>((size_t)d->sl * d->B * d->Hs);
@@ -245,8 +252,11 @@ static int speller_decode_f32(const las_decode_io* io, const void* packed, const
   const int xld = V + E;
   const size_t state_n = (size_t)sl * B * Hs;
 
+  const int NH = n_heads(d);
   const float* psi = io->psi;
-  if (!psi) {
+  if (d->no_mlp) {
+    psi = io->enc;  // use_mlp_in_attention=False (model/las_model.py:283-285): the keys are the listener features themselves
+  } else if (!psi) {
     ProfScope ps("speller.psi", st);
     LAS_TRY(launch_sgemm_nt_bias(io->enc, E, pk.w_psi, E, pk.b_psi, w.psi, D, B * U, D, E, relu != 0, st));
     psi = w.psi;
@@ -292,11 +302,12 @@ static int speller_decode_f32(const las_decode_io* io, const void* packed, const
     t.state_ld = Hs;
     t.enc = io->enc;
     t.psi = psi;
-    t.w_phi = pk.w_phi; t.b_phi = pk.b_phi; t.w_cd = pk.w_cd; t.b_cd = pk.b_cd;
+    t.w_phi = d->no_mlp ? nullptr : pk.w_phi; t.b_phi = pk.b_phi; t.w_cd = pk.w_cd; t.b_cd = pk.b_cd;
     t.enc_lengths = io->enc_lengths;
-    t.B = B; t.U = U; t.E = E; t.Hs = Hs; t.V = V; t.D = D;
-    t.relu = relu;
-    t.score_out = io->attn ? io->attn + (size_t)s * B * U : nullptr;
+    t.B = B; t.U = U; t.E = E; t.Hs = Hs; t.V = V; t.D = att_dim(d);
+    t.relu = d->no_mlp ? 0 : relu;
+    t.heads = NH; t.w_dr = pk.w_dr; t.b_dr = pk.b_dr;
+    t.score_out = io->attn ? io->attn + (size_t)s * NH * B * U : nullptr;
     t.ctx_out = w.xin + V;
     t.ctx_ld = xld;
     t.logp_out = io->logp + (size_t)s * B * V;
@@ -436,7 +447,11 @@ int las_speller_pack(const las_speller_weights* w, const las_speller_dims* d, in
   LAS_TRY(speller_check(d));
   LAS_REQUIRE(w && packed && w->rnn_host, "null weights / packed buffer");
   LAS_REQUIRE(mode == LAS_MODE_FP32 || mode == LAS_MODE_BF16, "unknown mode %d", mode);
-  LAS_REQUIRE(w->w_phi && w->b_phi && w->w_psi && w->b_psi && w->w_cd && w->b_cd, "null attention / output weight pointer");
+  LAS_REQUIRE(w->w_cd && w->b_cd, "null output weight pointer");
+  LAS_REQUIRE(d->no_mlp || (w->w_phi && w->b_phi && w->w_psi && w->b_psi), "null attention weight pointer");
+  LAS_REQUIRE(n_heads(d) == 1 || (w->w_dr && w->b_dr), "multi_head > 1 needs attention.dim_reduce weights");
+  LAS_REQUIRE(mode != LAS_MODE_BF16 || (n_heads(d) == 1 && !d->no_mlp),
+              "LAS_MODE_BF16 implements single-head MLP attention only; use LAS_MODE_FP32 for multi_head > 1 / use_mlp_in_attention=False");
   LAS_TRY(device_ok());
   if (packed_bytes < las_speller_packed_bytes(d, mode))
     return fail(LAS_ENOMEM, "packed buffer too small: %zu < %zu", packed_bytes, las_speller_packed_bytes(d, mode));
@@ -453,12 +468,18 @@ int las_speller_pack(const las_speller_weights* w, const las_speller_dims* d, in
     CP(pk.b_ih[l], s.b_ih, G);
     CP(pk.b_hh[l], s.b_hh, G);
   }
-  CP(pk.w_phi, w->w_phi, (size_t)d->D * d->Hs);
-  CP(pk.b_phi, w->b_phi, d->D);
-  CP(pk.w_psi, w->w_psi, (size_t)d->D * d->E);
-  CP(pk.b_psi, w->b_psi, d->D);
+  if (!d->no_mlp) {
+    CP(pk.w_phi, w->w_phi, (size_t)d->D * n_heads(d) * d->Hs);
+    CP(pk.b_phi, w->b_phi, (size_t)d->D * n_heads(d));
+    CP(pk.w_psi, w->w_psi, (size_t)d->D * d->E);
+    CP(pk.b_psi, w->b_psi, d->D);
+  }
   CP(pk.w_cd, w->w_cd, (size_t)d->V * (d->Hs + d->E));
   CP(pk.b_cd, w->b_cd, d->V);
+  if (n_heads(d) > 1) {
+    CP(pk.w_dr, w->w_dr, (size_t)d->E * d->E * n_heads(d));
+    CP(pk.b_dr, w->b_dr, d->E);
+  }
 #undef CP
   if (mode == LAS_MODE_BF16) return fast_speller_pack(w, d, static_cast<char*>(packed) + pk.bytes, st);
   return LAS_OK;
@@ -473,11 +494,13 @@ int las_psi_precompute(const float* enc, const float* w_psi, const float* b_psi,
 }
 
 int las_attention_forward(const float* state, const float* enc, const float* psi, const float* w_phi, const float* b_phi,
-                          int B, int U, int E, int Hs, int D, int relu, const int32_t* enc_lengths, float* score,
-                          float* context, void* stream) {
+                          int B, int U, int E, int Hs, int D, int relu, int heads, const float* w_dr, const float* b_dr,
+                          const int32_t* enc_lengths, float* score, float* context, void* stream) {
   LAS_REQUIRE(state && enc && psi && context, "null pointer argument");
   LAS_REQUIRE(B > 0 && U > 0 && E > 0 && Hs > 0 && D > 0, "bad dims (B=%d U=%d E=%d Hs=%d D=%d)", B, U, E, Hs, D);
   LAS_REQUIRE(w_phi ? (b_phi != nullptr) : (D == Hs), "without phi the query is the decoder state itself: D (%d) must equal Hs (%d)", D, Hs);
+  if (heads < 1) heads = 1;
+  LAS_REQUIRE(heads == 1 || (w_phi && w_dr && b_dr), "multi_head > 1 needs phi and dim_reduce weights");
   LAS_TRY(device_ok());
   AttendArgs t;
   memset(&t, 0, sizeof(t));
@@ -487,6 +510,7 @@ int las_attention_forward(const float* state, const float* enc, const float* psi
   t.enc_lengths = enc_lengths;
   t.B = B; t.U = U; t.E = E; t.Hs = Hs; t.V = 0; t.D = D;
   t.relu = relu;
+  t.heads = heads; t.w_dr = w_dr; t.b_dr = b_dr;
   t.score_out = score;
   t.ctx_out = context; t.ctx_ld = E;
   return launch_attend_f32(t, static_cast<cudaStream_t>(stream));
@@ -516,6 +540,8 @@ int las_speller_decode(const las_decode_io* io, const void* packed, const las_sp
     return fail(LAS_ENOMEM, "workspace too small: %zu < %zu", workspace_bytes, las_speller_workspace_bytes(d, steps, mode));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (steps == 0) return LAS_OK;
+  LAS_REQUIRE(mode != LAS_MODE_BF16 || (n_heads(d) == 1 && !d->no_mlp),
+              "LAS_MODE_BF16 implements single-head MLP attention only; use LAS_MODE_FP32 for multi_head > 1 / use_mlp_in_attention=False");
   if (mode == LAS_MODE_BF16) {
     const size_t f32p = speller_pack_layout_f32(d, nullptr).bytes;
     const size_t f32w = speller_ws_layout_f32(d, nullptr).bytes;

@@ -42,8 +42,11 @@ struct AttendArgs {
   const int32_t* enc_lengths;  // nullable
   int B, U, E, Hs, V, D;
   int relu;
+  int heads;            // >= 1; phi has D*heads outputs, each head attends over the same psi
+  const float* w_dr;    // [E, E*heads] (heads > 1)
+  const float* b_dr;    // [E]
   // outputs
-  float* score_out;     // nullable, [B, U]
+  float* score_out;     // nullable, [heads, B, U]
   float* ctx_out;       // [B, E] row stride ctx_ld
   int ctx_ld;
   float* logp_out;      // [B, V]     (when w_cd)

@@ -8,8 +8,9 @@ torch is used only for device memory, the current stream and parameter storage.
 Extra keyword accepted everywhere the reference swallows **kwargs: `precision` = "fp32" | "bf16"
 (LAS_MODE_FP32 / LAS_MODE_BF16; default from $LAS_B200_PRECISION, else "fp32").
 
-Not on this path (raise NotImplementedError instead of silently running something else): GRU/RNN cells,
-multi_head > 1, decode_mode 2 (sampling), training/backward.
+Variants of the reference classes: multi_head > 1 (with attention.dim_reduce) and use_mlp_in_attention=False run in the
+fp32 mode only (the bf16 mode raises and says so).  Not on this path (raise NotImplementedError instead of silently
+running something else): GRU/RNN cells, decode_mode 2 (sampling), training/backward.
 """
 from __future__ import annotations
 
@@ -242,14 +243,18 @@ class Attention(nn.Module):
         self.mlp_preprocess_input = mlp_preprocess_input
         self.multi_head = multi_head
         self.input_feature_dim = input_feature_dim
-        if multi_head != 1:
-            raise NotImplementedError("multi_head > 1 is not implemented on the B200 path (SURVEY.md section 8 row f4)")
+        if multi_head < 1:
+            raise ValueError(f"multi_head must be >= 1, got {multi_head}")
+        if multi_head > 1 and not mlp_preprocess_input:
+            raise ValueError("multi_head > 1 needs use_mlp_in_attention=True: the heads are slices of phi's output (model/las_model.py:303-305)")
         if self.mode != "dot":
             raise NotImplementedError("only 'dot' attention exists in the reference (model/las_model.py:315-317)")
         if mlp_preprocess_input:
             self.preprocess_mlp_dim = preprocess_mlp_dim
             self.phi = LinearWeights(input_feature_dim, preprocess_mlp_dim * multi_head)
             self.psi = LinearWeights(input_feature_dim, preprocess_mlp_dim)
+            if self.multi_head > 1:  # model/las_model.py:268-269
+                self.dim_reduce = LinearWeights(input_feature_dim * multi_head, input_feature_dim)
             if activate != "None":
                 if activate != "relu":
                     raise NotImplementedError(f"mlp_activate_in_attention={activate!r}: only 'relu' and 'None' are implemented")
@@ -288,16 +293,21 @@ class Attention(nn.Module):
         b, u, e = enc.shape
         hs = state.size(1)
         psi = self.project_listener_feature(enc)
-        score = torch.empty(b, u, dtype=torch.float32, device=enc.device)
+        nh = self.multi_head
+        score = torch.empty(nh, b, u, dtype=torch.float32, device=enc.device)
         context = torch.empty(b, e, dtype=torch.float32, device=enc.device)
         with torch.cuda.device(enc.device):
             if self.mlp_preprocess_input:
                 w, bias = _f32c(self.phi.weight), _f32c(self.phi.bias)
             else:
                 w = bias = None
+            wdr = bdr = None
+            if nh > 1:
+                wdr, bdr = _f32c(self.dim_reduce.weight), _f32c(self.dim_reduce.bias)
             check(lib.las_attention_forward(ptr(state), ptr(enc), ptr(psi), ptr(w), ptr(bias), b, u, e, hs, self.mlp_dim,
-                                            self.relu_flag, None, ptr(score), ptr(context), current_stream_ptr(enc.device)))
-        return [score], context
+                                            self.relu_flag, nh, ptr(wdr), ptr(bdr), None, ptr(score), ptr(context),
+                                            current_stream_ptr(enc.device)))
+        return list(score.unbind(0)), context
 
 
 class Speller(nn.Module):
@@ -319,8 +329,10 @@ class Speller(nn.Module):
         self.precision = kwargs.get("precision") or _default_precision()
         if decode_mode not in (0, 1):
             raise NotImplementedError("decode_mode 2 (sampling, model/las_model.py:229-234) is not implemented on the B200 path")
-        if not use_mlp_in_attention:
-            raise NotImplementedError("use_mlp_in_attention=False is only available through the standalone Attention module")
+        if (not use_mlp_in_attention or multi_head > 1) and self.precision != "fp32":
+            raise NotImplementedError(
+                "the bf16 mode implements single-head MLP attention only; construct the Speller with precision='fp32' for "
+                "multi_head > 1 / use_mlp_in_attention=False (SURVEY.md section 8 row f4)")
         if hidden_size != 2 * listener_hidden_size:
             raise ValueError(
                 f"hidden_size ({hidden_size}) must equal 2*listener_hidden_size ({2 * listener_hidden_size}): the rnn input is "
@@ -339,7 +351,9 @@ class Speller(nn.Module):
 
     # ---- device plumbing -------------------------------------------------------------------------------
     def _dims(self, b, u, e):
-        return SpellerDims(b, u, e, self.hidden_size, self.num_layers, self.label_dim, self.attention.preprocess_mlp_dim)
+        at = self.attention
+        return SpellerDims(b, u, e, self.hidden_size, self.num_layers, self.label_dim,
+                           at.preprocess_mlp_dim if at.mlp_preprocess_input else 0, at.multi_head, 0 if at.mlp_preprocess_input else 1)
 
     def _packed(self, lib, dims, mode, device, st):
         params = list(self.parameters())
@@ -349,10 +363,18 @@ class Speller(nn.Module):
             self._cache.packed.clear()
             arr, keep = _lstm_weight_array(self.rnn_layer, self.num_layers, 1)
             at, cd = self.attention, self.character_distribution
-            ts = [_f32c(t) for t in (at.phi.weight, at.phi.bias, at.psi.weight, at.psi.bias, cd.weight, cd.bias)]
             w = SpellerWeights()
             w.rnn_host = C.cast(arr, C.POINTER(LstmWeights))
-            w.w_phi, w.b_phi, w.w_psi, w.b_psi, w.w_cd, w.b_cd = (t.data_ptr() for t in ts)
+            ts = [_f32c(t) for t in (cd.weight, cd.bias)]
+            w.w_cd, w.b_cd = (t.data_ptr() for t in ts)
+            if at.mlp_preprocess_input:
+                ta = [_f32c(t) for t in (at.phi.weight, at.phi.bias, at.psi.weight, at.psi.bias)]
+                w.w_phi, w.b_phi, w.w_psi, w.b_psi = (t.data_ptr() for t in ta)
+                ts += ta
+            if at.multi_head > 1:
+                td = [_f32c(t) for t in (at.dim_reduce.weight, at.dim_reduce.bias)]
+                w.w_dr, w.b_dr = (t.data_ptr() for t in td)
+                ts += td
             nbytes = lib.las_speller_packed_bytes(C.byref(dims), mode)
             packed = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=device)
             check(lib.las_speller_pack(C.byref(w), C.byref(dims), mode, ptr(packed), packed.numel(), st))
@@ -376,7 +398,7 @@ class Speller(nn.Module):
             ws_bytes = lib.las_speller_workspace_bytes(C.byref(dims), steps, mode)
             ws = self._cache.workspace(("speller", dev, mode), ws_bytes, dev)
             logp = torch.empty(steps, b, self.label_dim, dtype=torch.float32, device=dev)
-            attn = torch.empty(steps, b, u, dtype=torch.float32, device=dev) if want_attn else None
+            attn = torch.empty(steps, self.attention.multi_head, b, u, dtype=torch.float32, device=dev) if want_attn else None
             tokens = torch.empty(steps, b, dtype=torch.int32, device=dev)
             io = DecodeIO()
             io.enc = enc.data_ptr()
@@ -415,7 +437,7 @@ class Speller(nn.Module):
         else:
             h, c = (_f32c(t).clone() for t in last_hidden_state)
         logp, attn, _ = self._decode(listener_feature, 1, state=(h, c), word=word, context=context)
-        return logp[0], (h, c), context, [attn[0]]
+        return logp[0], (h, c), context, list(attn[0].unbind(0))
 
     def forward(self, listener_feature, ground_truth=None, teacher_force_rate=0.9, enc_lengths=None):
         if ground_truth is None:
@@ -440,5 +462,5 @@ class Speller(nn.Module):
         logp, attn, tokens = self._decode(listener_feature, max_step, gt_dense=gt_dense, gt_index=gt_index, enc_lengths=enc_lengths)
         self.last_tokens = tokens  # [S,B] int32 argmax per step (device); not part of the reference API
         raw_pred_seq = list(logp.unbind(0))
-        attention_record = [[a] for a in attn.unbind(0)]
+        attention_record = [list(a.unbind(0)) for a in attn.unbind(0)]  # per step: one [B,U] tensor per head (:214,:292,:299)
         return raw_pred_seq, attention_record

@@ -130,23 +130,44 @@ def psi_project(enc, sd, dtype=np.float32, prefix="speller", activate=True):
     return k.reshape(b, u, -1)
 
 
-def attention(state, enc, psi, sd, dtype=np.float32, prefix="speller", activate=True, enc_lengths=None):
-    """Single-head 'dot' attention with MLP preprocessing -- model/las_model.py:276-297.
-
-    state [B,Hs], enc [B,U,E], psi [B,U,D] -> (score [B,U], context [B,E]).
-    `enc_lengths` (None in the reference) masks encoder steps >= length before the softmax."""
-    q = state @ _w(sd, f"{prefix}.attention.phi.weight", dtype).T + _w(sd, f"{prefix}.attention.phi.bias", dtype)
-    if activate:
-        q = np.maximum(q, 0)
-    energy = np.einsum("bd,bud->bu", q, psi)
+def _attend_one(q, enc, keys, enc_lengths):
+    energy = np.einsum("bd,bud->bu", q, keys)
     if enc_lengths is not None:
         mask = np.arange(enc.shape[1])[None, :] >= np.asarray(enc_lengths)[:, None]
         energy = np.where(mask, -np.inf, energy)
     energy = energy - energy.max(axis=-1, keepdims=True)
     w = np.exp(energy)
     score = w / w.sum(axis=-1, keepdims=True)
-    context = np.einsum("bu,bue->be", score, enc)
-    return score.astype(dtype), context.astype(dtype)
+    return score, np.einsum("bu,bue->be", score, enc)
+
+
+def attention(state, enc, psi, sd, dtype=np.float32, prefix="speller", activate=True, enc_lengths=None):
+    """'dot' attention -- model/las_model.py:275-314.
+
+    state [B,Hs], enc [B,U,E], psi [B,U,D] -> (score [B,U] or list of per-head scores, context [B,E]).
+    Variants, selected by the keys present in `sd` exactly as the reference module is built (:264-273):
+      * no `attention.phi.weight`  -> use_mlp_in_attention=False (:283-285): query = state, keys = enc;
+      * `attention.dim_reduce.weight` present -> multi_head > 1 (:298-314): phi's output is split into heads of D
+        columns, every head attends over the same keys, the contexts are concatenated and reduced.
+    `enc_lengths` (None in the reference) masks encoder steps >= length before the softmax."""
+    if f"{prefix}.attention.phi.weight" not in sd:
+        score, context = _attend_one(state, enc, enc, enc_lengths)
+        return score.astype(dtype), context.astype(dtype)
+    q = state @ _w(sd, f"{prefix}.attention.phi.weight", dtype).T + _w(sd, f"{prefix}.attention.phi.bias", dtype)
+    if activate:
+        q = np.maximum(q, 0)
+    if f"{prefix}.attention.dim_reduce.weight" not in sd:
+        score, context = _attend_one(q, enc, psi, enc_lengths)
+        return score.astype(dtype), context.astype(dtype)
+    d = psi.shape[-1]
+    scores, ctxs = [], []
+    for hd in range(q.shape[1] // d):
+        s_h, c_h = _attend_one(q[:, hd * d:(hd + 1) * d], enc, psi, enc_lengths)
+        scores.append(s_h.astype(dtype))
+        ctxs.append(c_h)
+    context = np.concatenate(ctxs, axis=-1) @ _w(sd, f"{prefix}.attention.dim_reduce.weight", dtype).T
+    context = context + _w(sd, f"{prefix}.attention.dim_reduce.bias", dtype)
+    return scores, context.astype(dtype)
 
 
 def log_softmax(z):
@@ -186,7 +207,7 @@ def speller_forward(
             gt = np.eye(v, dtype=dtype)[gt]
         gt = gt.astype(dtype)
 
-    psi = psi_project(enc, sd, dtype, prefix)
+    psi = psi_project(enc, sd, dtype, prefix) if f"{prefix}.attention.psi.weight" in sd else enc
     h = [np.zeros((b, hs), dtype=dtype) for _ in range(num_layers)]  # hidden_state=None -> zeros
     c = [np.zeros((b, hs), dtype=dtype) for _ in range(num_layers)]
     word = np.zeros((b, v), dtype=dtype)

@@ -52,7 +52,10 @@ def run_reference(las, x, gt_onehot, teacher_forced, dtype):
         else:
             preds, attns = m.speller(enc, ground_truth=None, teacher_force_rate=0)
     logp = torch.stack(preds)
-    attn = torch.stack([a[0] for a in attns])
+    if len(attns[0]) == 1:
+        attn = torch.stack([a[0] for a in attns])                 # [S,B,U]
+    else:
+        attn = torch.stack([torch.stack(list(a)) for a in attns])  # multi_head > 1: [S,heads,B,U]
     return enc.numpy(), logp.numpy(), attn.numpy()
 
 
@@ -75,7 +78,15 @@ def main():
         ("small_tf_g6", "small", 2, 160, 30, "tf", 6.0, False),
         ("paper_tf_g3", "paper", 2, 160, 24, "tf", 3.0, False),
         ("paper_greedy_g3", "paper", 2, 160, 24, "greedy", 3.0, False),
+        # Speller / Attention variants
+        ("tinymh_tf_g3", "tiny_mh", 3, 32, 6, "tf", 3.0, True),
+        ("tinymh_greedy_g3", "tiny_mh", 3, 32, 10, "greedy", 3.0, True),
+        ("tinynomlp_tf_g3", "tiny_nomlp", 3, 32, 6, "tf", 3.0, True),
+        ("tinynomlp_greedy_g3", "tiny_nomlp", 3, 32, 10, "greedy", 3.0, True),
     ]
+    only = [a for a in sys.argv[1:] if not a.startswith("-")]
+    if only:  # regenerate just the named cases (the others stay byte-identical in git)
+        cases = [c for c in cases if c[0] in only]
     for name, cfg, B, T, S, mode, gain, store_w in cases:
         c = tl.CONFIGS[cfg]
         dm = 0 if mode == "raw" else 1

@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), f"{n} is declared in include/las_b200.h but not exported by liblas_b200.so"
     assert sorted(_cabi.PROTOTYPES) == names, "ctypes prototypes and header declarations differ"
-    assert lib.las_abi_version() == 1
+    assert lib.las_abi_version() == _cabi.ABI_VERSION
 
 
 def test_size_queries_run_on_host():

@@ -45,9 +45,11 @@ def test_numpy_oracle_matches_reference(name):
             assert np.array_equal(out["tokens"], g["logp_f64"].argmax(-1))
 
 
-@pytest.mark.parametrize("name", [c for c in CASES if not c.startswith("paper")])
+@pytest.mark.parametrize("name", [c for c in CASES if not c.startswith(("paper", "tinymh", "tinynomlp"))])
 def test_torch_restatement_matches_reference(name):
-    """Same torch ops in the same order as the reference -> expected bit-identical on the same machine."""
+    """Same torch ops in the same order as the reference -> expected bit-identical on the same machine.  (The torch
+    restatement is the timed CPU baseline of the benchmarked single-head configuration; the Attention variants are covered by the
+    numpy oracle above.)"""
     g, cfg, sd = load_case(name)
     mode = str(g["mode"])
     S = g["logp_f32"].shape[0]

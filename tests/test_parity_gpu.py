@@ -51,12 +51,21 @@ def run_ours(las, x, labels, V, mode):
     preds, attns = las(x, gt, 1.1 if mode == "tf" else 0.0, is_training=(mode == "tf"))
     enc = las.listener(x)
     torch.cuda.synchronize()
-    return enc.cpu().numpy(), torch.stack(preds).cpu().numpy(), torch.stack([a[0] for a in attns]).cpu().numpy()
+    if len(attns[0]) == 1:
+        attn = torch.stack([a[0] for a in attns])
+    else:  # multi_head > 1: one [B,U] tensor per head and step (model/las_model.py:299) -> [S,heads,B,U]
+        attn = torch.stack([torch.stack(list(a)) for a in attns])
+    return enc.cpu().numpy(), torch.stack(preds).cpu().numpy(), attn.cpu().numpy()
 
 
 @pytest.mark.parametrize("precision", precisions())
 @pytest.mark.parametrize("name", CASES)
 def test_matches_reference_golden(name, precision):
+    variant = tl.CONFIGS[str(np.load(os.path.join(tl.GOLDEN_DIR, name + ".npz"))["cfg"])]
+    if precision == "bf16" and (variant.get("heads", 1) > 1 or not variant.get("use_mlp", True)):
+        with pytest.raises(NotImplementedError):  # row f4 variants run in the fp32 mode only, and the bf16 mode says so
+            load_case(name, precision)
+        return
     g, cfg, las, mode = load_case(name, precision)
     tol = TOL[precision]
     enc, logp, attn = run_ours(las, torch.from_numpy(g["x"]), torch.from_numpy(g["labels"]).long(), cfg["V"], mode)
