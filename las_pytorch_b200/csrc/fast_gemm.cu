@@ -31,9 +31,25 @@ struct __align__(1024) GemmSmem {
   uint32_t tmem_base;
 };
 
+// Tile schedule / A-operand addressing.  mode 0: A is a plain [M, K] matrix, tiles in natural order.  mode 1 (listener):
+// A is the 3-D view {K, b, t} of the layer input, output row r = t*Bp + b; tile i of the schedule is
+//   (m = i / n_tiles,               n = i % n_tiles)   for the forward direction's column tiles  (n <  nfwd)
+//   (m = m_tiles - 1 - i / n_tiles, n = i % n_tiles)   for the backward direction's             (n >= nfwd)
+// i.e. the recurrence's consumption order: early time steps for the forward LSTM, late ones for the backward LSTM.
+struct GemmSched {
+  int mode, Bp, nfwd;
+  uint32_t* flags;  // nullable: [m_tiles * n_tiles] counters, +1 per epilogue warp that has stored its rows of the tile
+};
+__device__ __forceinline__ void sched_tile(const GemmSched& sc, int i, int m_tiles, int n_tiles, int& m, int& n) {
+  n = i % n_tiles;
+  m = i / n_tiles;
+  if (sc.mode == 1 && n >= sc.nfwd) m = m_tiles - 1 - m;
+}
+
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
-                    const float* __restrict__ bias, float* __restrict__ C, long long ldc, int M, int N, int K, int relu) {
+                    const float* __restrict__ bias, float* __restrict__ C, long long ldc, int M, int N, int K, int relu,
+                    const GemmSched sc) {
   extern __shared__ uint8_t smem_raw[];
   GemmSmem& s = *reinterpret_cast<GemmSmem*>(smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u));  // offset from the __shared__ symbol keeps the address space
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -64,11 +80,14 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m0 = (tile / n_tiles) * BM, n0 = (tile % n_tiles) * BN;
+        int mt, nt;
+        sched_tile(sc, tile, m_tiles, n_tiles, mt, nt);
+        const int m0 = mt * BM, n0 = nt * BN;
         for (int kb = 0; kb < k_blocks; ++kb) {
           ptx::mbar_wait(&s.empty[stage], phase ^ 1);
           ptx::mbar_arrive_expect_tx(&s.full[stage], A_TILE_BYTES + B_TILE_BYTES);
-          ptx::tma_load_2d(s.a[stage], &tm_a, &s.full[stage], kb * BK, m0);
+          if (sc.mode == 1) ptx::tma_load_3d(s.a[stage], &tm_a, &s.full[stage], kb * BK, m0 % sc.Bp, m0 / sc.Bp);  // rows = (t, b) pairs
+          else ptx::tma_load_2d(s.a[stage], &tm_a, &s.full[stage], kb * BK, m0);
           ptx::tma_load_2d(s.b[stage], &tm_b, &s.full[stage], kb * BK, n0);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -107,7 +126,9 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
-      const int m0 = (tile / n_tiles) * BM, n0 = (tile % n_tiles) * BN;
+      int mt, nt;
+      sched_tile(sc, tile, m_tiles, n_tiles, mt, nt);
+      const int m0 = mt * BM, n0 = nt * BN;
       ptx::mbar_wait(&s.tmem_full[acc], acc_phase);
       ptx::tc_fence_after();
       const int row = m0 + q * 32 + lane;
@@ -142,6 +163,10 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
       }
       ptx::tc_fence_before();
       ptx::mbar_arrive(&s.tmem_empty[acc]);
+      if (sc.flags) {  // this warp's 32 rows of the tile are stored: publish (the release is cumulative over the warp barrier)
+        __syncwarp();
+        if (lane == 0) asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(sc.flags + (size_t)mt * n_tiles + nt), "r"(1u) : "memory");
+      }
     }
   }
   ptx::tc_fence_before();
@@ -200,7 +225,56 @@ int launch_gemm_bf16_tc(const __nv_bfloat16* A, long long lda, const __nv_bfloat
     LAS_CUDA_OK(cudaFuncSetAttribute(gemm_bf16_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
   }
-  gemm_bf16_tc_kernel<<<grid, GEMM_THREADS, smem, st>>>(tm_a, tm_b, bias, C, ldc, M, N, K, relu ? 1 : 0);
+  gemm_bf16_tc_kernel<<<grid, GEMM_THREADS, smem, st>>>(tm_a, tm_b, bias, C, ldc, M, N, K, relu ? 1 : 0, GemmSched{0, 0, 0, nullptr});
+  LAS_LAUNCH_OK("gemm_bf16_tc_kernel");
+  return LAS_OK;
+}
+
+int g_gemm_natural_order = 0;  // test hook (las_debug_set_option(8, 1)): ascending tile order
+int listener_padded_batch(int B) {
+  if (B > 128) return (B + 127) / 128 * 128;
+  int bp = 1;
+  while (bp < B) bp <<= 1;
+  return bp;
+}
+
+int launch_gemm_listener(const __nv_bfloat16* A, int B, int Tl, int K, const __nv_bfloat16* W, const float* bias, float* C, int N,
+                         uint32_t* flags, int max_ctas, cudaStream_t st) {
+  LAS_REQUIRE(B > 0 && Tl > 0 && N > 0 && K > 0, "bad listener GEMM shape B=%d Tl=%d N=%d K=%d", B, Tl, N, K);
+  const int Bp = listener_padded_batch(B);
+  const int M = Tl * Bp;
+  EncodeTiledFn enc;
+  LAS_TRY(get_encode_fn(&enc));
+  LAS_REQUIRE((K * 2) % 16 == 0 && (reinterpret_cast<uintptr_t>(A) & 15) == 0, "TMA needs 16-byte aligned rows (K=%d)", K);
+  // A as {k, b, t}: element (k, b, t) at A + (b*Tl + t)*K + k.  One 128-row tile = {64 k, min(Bp,128) b, 128/Bp t}: rows beyond B
+  // (padding) and time steps beyond Tl are out of bounds and read as zeros.
+  CUtensorMap tm_a, tm_b;
+  {
+    cuuint64_t gdim[3] = {(cuuint64_t)K, (cuuint64_t)B, (cuuint64_t)Tl};
+    cuuint64_t gstr[2] = {(cuuint64_t)Tl * K * 2, (cuuint64_t)K * 2};
+    cuuint32_t box[3] = {64, (cuuint32_t)(Bp < 128 ? Bp : 128), (cuuint32_t)(Bp < 128 ? 128 / Bp : 1)};
+    cuuint32_t estr[3] = {1, 1, 1};
+    const CUresult r = enc(&tm_a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<__nv_bfloat16*>(A), gdim, gstr, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(LAS_ECUDA, "cuTensorMapEncodeTiled (3-D listener input) failed with CUresult %d (B=%d Tl=%d K=%d)", (int)r, B, Tl, K);
+  }
+  LAS_TRY(make_tmap_bf16(&tm_b, W, N, K, K, BN));
+  const int n_tiles = (N + BN - 1) / BN;
+  const int tiles = ((M + BM - 1) / BM) * n_tiles;
+  int grid = tiles < sm_count() ? tiles : sm_count();
+  if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
+  const size_t smem = sizeof(GemmSmem) + 1024;
+  static thread_local bool attr_set = false;
+  if (!attr_set) {
+    LAS_CUDA_OK(cudaFuncSetAttribute(gemm_bf16_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  // forward-direction columns are the first half of N; when the halves do not fall on tile boundaries every column tile
+  // serves both directions and the natural (front-first) order is kept
+  int nfwd = ((N / 2) % BN == 0) ? (N / 2) / BN : n_tiles;
+  if (g_gemm_natural_order) nfwd = n_tiles;
+  gemm_bf16_tc_kernel<<<grid, GEMM_THREADS, smem, st>>>(tm_a, tm_b, bias, C, (long long)N, M, N, K, 0, GemmSched{1, Bp, nfwd, flags});
   LAS_LAUNCH_OK("gemm_bf16_tc_kernel");
   return LAS_OK;
 }

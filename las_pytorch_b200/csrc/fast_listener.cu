@@ -21,11 +21,14 @@ namespace las {
 
 namespace {
 
-constexpr int REC_THREADS = 288;  // warps 0-7: epilogue (TMEM lane quadrant = warp % 4, batch half = warp / 4); warp 8: MMA issuer
-constexpr int REC_MMA_WARP = 8, REC_EPI_THREADS = 256;
+constexpr int REC_THREADS = 320;  // warps 0-7: epilogue (TMEM lane quadrant = warp % 4, batch half = warp / 4); warp 8: MMA issuer;
+                                  // warp 9: watches the input-projection GEMM's tile flags (when it runs concurrently)
+constexpr int REC_MMA_WARP = 8, REC_POLL_WARP = 9, REC_EPI_THREADS = 256;
 
 struct RecParams {
-  const float* P;               // [B*Tl, NP] fp32; column = dir*4Hp + r*128 + jj*4 + gate
+  const float* P;               // [Tl*Bp, NP] fp32, time-major: row = t*Bp + b; column = dir*4Hp + r*128 + jj*4 + gate
+  const uint32_t* gemm_flags;   // nullable [m_tiles * n_tiles]: the GEMM's per-tile completion counters (4 = tile stored)
+  int Bp, n_tiles;              // padded batch (rows per time step of P); column tiles of the GEMM
   const uint8_t* whh_img;       // [2][CS] shared-memory images of the W_hh slices (128 x Hp bf16, INTERLEAVE layout)
   float* out_f32;               // nullable [B, Tl, 2H]
   __nv_bfloat16* out_bf16;      // nullable [B, Tl, 2H]
@@ -77,6 +80,7 @@ __global__ void __launch_bounds__(REC_THREADS, 1) lstm_recurrence_cluster_kernel
   uint64_t* h_full = bars;        // [2]
   uint64_t* mma_done = bars + 2;  // [1]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
+  int* s_ready = reinterpret_cast<int*>(bars + 4);  // steps (in processing order) whose P rows are known to be stored
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t r = ptx::cluster_ctarank();
@@ -89,6 +93,7 @@ __global__ void __launch_bounds__(REC_THREADS, 1) lstm_recurrence_cluster_kernel
 
   // ---- one-time setup: barriers, TMEM, resident W_hh slice
   if (threadIdx.x == 0) {
+    *s_ready = p.gemm_flags ? 0 : p.Tl;
     ptx::mbar_init(&h_full[0], 1);  // one local arrive.expect_tx per phase; the peers' bulk copies complete the bytes
     ptx::mbar_init(&h_full[1], 1);
     ptx::mbar_init(mma_done, 1);
@@ -101,7 +106,7 @@ __global__ void __launch_bounds__(REC_THREADS, 1) lstm_recurrence_cluster_kernel
   if (!p.a_tmem) {
     const uint4* src = reinterpret_cast<const uint4*>(w_img);
     uint4* dst = reinterpret_cast<uint4*>(sA);
-    for (uint32_t i = threadIdx.x; i < a_bytes / 16; i += REC_THREADS) dst[i] = src[i];
+    for (uint32_t i = threadIdx.x; i < a_bytes / 16; i += blockDim.x) dst[i] = src[i];
   }
   ptx::fence_proxy_async();
   ptx::tc_fence_before();
@@ -159,6 +164,27 @@ __global__ void __launch_bounds__(REC_THREADS, 1) lstm_recurrence_cluster_kernel
       __syncwarp();
       if (lane == 0) REC_TRACE(1);
     }
+  } else if (warp == REC_POLL_WARP) {
+    // ================================ GEMM progress watcher ================================
+    // One lane follows the tile flags of the column tile this CTA reads, in the order the recurrence consumes time steps, and
+    // publishes how many steps are covered.  Each flag counts the GEMM's four epilogue warps.
+    if (p.gemm_flags && lane == 0) {
+      const int n_tile = (dir * 4 * Hp + (int)r * 128) >> 8;  // 256-column tiles of the GEMM
+      int ready = 0;
+      while (ready < Tl) {
+        const int t = dir ? Tl - 1 - ready : ready;
+        const long long m_tile = ((long long)t * p.Bp + b_base) >> 7;  // the chunk's 16 rows of a time step share one 128-row tile
+        const uint32_t* f = p.gemm_flags + m_tile * p.n_tiles + n_tile;
+        uint32_t v;
+        do {
+          asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+        } while (v < 4u);
+        do {  // every further step whose rows lie in the same tile
+          ++ready;
+        } while (ready < Tl && ((((long long)(dir ? Tl - 1 - ready : ready)) * p.Bp + b_base) >> 7) == m_tile);
+        asm volatile("st.release.cta.shared.s32 [%0], %1;" ::"r"(ptx::smem_u32(s_ready)), "r"(ready) : "memory");
+      }
+    }
   } else {
     // ================================ gate math + h exchange ================================
     const int tid = threadIdx.x;
@@ -178,36 +204,51 @@ __global__ void __launch_bounds__(REC_THREADS, 1) lstm_recurrence_cluster_kernel
       const int b = b_base + hb * HB + 4 * m + g;
       len[m] = (p.lengths && b < p.B) ? p.lengths[b] : Tl;
     }
-    {
-      const int t0 = dir ? Tl - 1 : 0;
+    // P rows may still be in flight from the concurrently running input-projection GEMM: `s_ready` (maintained by the
+    // watcher warp) counts the steps, in processing order, whose rows are stored
+    auto wait_ready = [&](int steps) {
+      if (p.gemm_flags) {
+        int v;
+        do {
+          asm volatile("ld.acquire.cta.shared.s32 %0, [%1];" : "=r"(v) : "r"(ptx::smem_u32(s_ready)) : "memory");
+        } while (v < steps);
+      }
+    };
+    // P rows are loaded into registers two steps ahead and pulled into L2 five steps ahead: with the GEMM writing P at
+    // full rate next to us one step (about a microsecond) of lead does not cover the load latency.  Readiness is checked every
+    // 8 steps for 20 steps ahead, which covers the deepest look-ahead (7 + 5).
+    auto time_of = [&](int step) { return dir ? Tl - 1 - step : step; };
+    auto load_step = [&](int step, float4 (&dst)[NB]) {
+      const int ts = time_of(step);
 #pragma unroll
       for (int m = 0; m < NB; ++m) {
         const int b = b_base + hb * HB + 4 * m + g;
-        pnext[m] = (b < p.B) ? *reinterpret_cast<const float4*>(pcol + ((size_t)b * Tl + t0) * NP) : make_float4(0.f, 0.f, 0.f, 0.f);
+        dst[m] = (b < p.B) ? *reinterpret_cast<const float4*>(pcol + ((size_t)ts * p.Bp + b) * NP) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
-    }
+    };
+    float4 pb[NB];  // pnext = rows of step s+1, pb = rows of step s+2
+    wait_ready(Tl < 20 ? Tl : 20);
+    load_step(0, pnext);
+    if (Tl > 1) load_step(1, pb);
     const uint32_t stage0 = ptx::smem_u32(sStage);
     const uint32_t h0_addr = ptx::smem_u32(sH0);
     const int dst_per_warp = (CS + 7) / 8;  // destination CTAs each warp serves
     for (int s = 0; s < Tl; ++s) {
-      const int t = dir ? Tl - 1 - s : s;
+      const int t = time_of(s);
       float4 pc[NB];
 #pragma unroll
-      for (int m = 0; m < NB; ++m) pc[m] = pnext[m];
-      if (s + 1 < Tl) {
-        const int tn = dir ? t - 1 : t + 1;
+      for (int m = 0; m < NB; ++m) {
+        pc[m] = pnext[m];
+        pnext[m] = pb[m];
+      }
+      if ((s & 7) == 0) wait_ready(s + 20 < Tl ? s + 20 : Tl);
+      if (s + 2 < Tl) load_step(s + 2, pb);
+      if (s + 5 < Tl) {
+        const int tp = time_of(s + 5);
 #pragma unroll
         for (int m = 0; m < NB; ++m) {
           const int b = b_base + hb * HB + 4 * m + g;
-          if (b < p.B) pnext[m] = *reinterpret_cast<const float4*>(pcol + ((size_t)b * Tl + tn) * NP);
-        }
-        if (s + 2 < Tl) {  // pull the step after that into L2 so the register prefetch above never sees DRAM latency
-          const int tnn = dir ? t - 2 : t + 2;
-#pragma unroll
-          for (int m = 0; m < NB; ++m) {
-            const int b = b_base + hb * HB + 4 * m + g;
-            if (b < p.B) asm volatile("prefetch.global.L2 [%0];" ::"l"(pcol + ((size_t)b * Tl + tnn) * NP));
-          }
+          if (b < p.B) asm volatile("prefetch.global.L2 [%0];" ::"l"(pcol + ((size_t)tp * p.Bp + b) * NP));
         }
       }
       ptx::mbar_wait(mma_done, (uint32_t)(s & 1));
@@ -350,6 +391,36 @@ __global__ void pack_whh_kernel(const float* w_fwd, const float* w_rev, uint8_t*
 }
 
 long long* g_rec_trace = nullptr;  // set through las_debug_set_trace (test hook)
+int g_rec_gemm_ctas = 0;           // las_debug_set_option(7, v): persistent CTAs of the overlapped GEMM (0 = all SMs the recurrence leaves free)
+int g_rec_overlap = 1;             // las_debug_set_option(6, v): run each layer's input-projection GEMM concurrently with its recurrence
+
+// Side stream on which a layer's input-projection GEMM runs while the recurrence consumes its tiles on the caller's
+// stream.  One per host thread and device, created on first use and kept (entry points stay re-entrant: nothing here is
+// shared between threads).
+struct SideStream {
+  int dev = -1;
+  cudaStream_t s = nullptr;
+  cudaEvent_t fork = nullptr, join = nullptr;
+};
+thread_local SideStream g_side;
+int side_stream(SideStream** out) {
+  int dev = -1;
+  LAS_CUDA_OK(cudaGetDevice(&dev));
+  if (g_side.s == nullptr || g_side.dev != dev) {
+    if (g_side.s) {
+      cudaStreamDestroy(g_side.s);
+      cudaEventDestroy(g_side.fork);
+      cudaEventDestroy(g_side.join);
+      g_side = SideStream();
+    }
+    LAS_CUDA_OK(cudaStreamCreateWithFlags(&g_side.s, cudaStreamNonBlocking));
+    LAS_CUDA_OK(cudaEventCreateWithFlags(&g_side.fork, cudaEventDisableTiming));
+    LAS_CUDA_OK(cudaEventCreateWithFlags(&g_side.join, cudaEventDisableTiming));
+    g_side.dev = dev;
+  }
+  *out = &g_side;
+  return LAS_OK;
+}
 int g_rec_a_tmem = 1;              // las_debug_set_option(1, v)
 int g_rec_nacc = 0;                // las_debug_set_option(4, v): independent accumulators the K loop is spread over (0 = default)
 
@@ -396,6 +467,8 @@ struct ListenerWsFast {
   float* P;
   __nv_bfloat16* act[2];
   int32_t* len;  // [L][B]
+  uint32_t* flags;  // per-tile completion counters of the layer's input-projection GEMM
+  size_t n_flags;
   size_t bytes;
 };
 ListenerWsFast ws_layout(const las_listener_dims* d, void* base) {
@@ -403,8 +476,11 @@ ListenerWsFast ws_layout(const las_listener_dims* d, void* base) {
   const Geo g = geometry(d->H);
   Carver cv(base);
   const size_t M0 = (size_t)d->B * (d->T / 2);
+  const size_t M0p = (size_t)listener_padded_batch(d->B) * (d->T / 2);  // P is time-major with the batch padded per time step
   w.xb = cv.take<__nv_bfloat16>((size_t)d->B * d->T * d->F);
-  w.P = cv.take<float>(M0 * 8 * g.Hp);
+  w.P = cv.take<float>(M0p * 8 * g.Hp);
+  w.n_flags = (M0p / 128 + 1) * ((size_t)(8 * g.Hp + 255) / 256);
+  w.flags = cv.take<uint32_t>(w.n_flags);
   w.act[0] = cv.take<__nv_bfloat16>(M0 * 2 * d->H);
   w.act[1] = cv.take<__nv_bfloat16>(M0 / 2 * 2 * d->H + 64);
   w.len = cv.take<int32_t>((size_t)d->L * d->B);
@@ -421,13 +497,17 @@ int shape_ok(const las_listener_dims* d) {
 }
 
 template <int BC, int NACC>
-int launch_rec(const RecParams& p, cudaStream_t st) {
-  const size_t smem = 1024 + (p.a_tmem ? 0u : 128u * p.Hp * 2) + 2u * BC * p.Hp * 2 + 2 * 4 * BC * 16 + 64;
+int launch_rec(const RecParams& p, cudaStream_t st, bool exclusive_sm) {
+  size_t smem = 1024 + (p.a_tmem ? 0u : 128u * p.Hp * 2) + 2u * BC * p.Hp * 2 + 2 * 4 * BC * 16 + 64;
+  // While the GEMM runs concurrently, a GEMM CTA (197 KB of shared memory, all 512 TMEM columns) must never land on an SM that
+  // hosts a recurrence CTA (it would wait for tensor memory held by a CTA that waits for the GEMM's tiles): ask for enough
+  // shared memory that the two cannot be co-resident.
+  if (exclusive_sm && smem < 48 * 1024) smem = 48 * 1024;
   LAS_CUDA_OK(cudaFuncSetAttribute(lstm_recurrence_cluster_kernel<BC, NACC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   if (p.CS > 8) LAS_CUDA_OK(cudaFuncSetAttribute(lstm_recurrence_cluster_kernel<BC, NACC>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(p.CS * 2 * p.nchunks);
-  cfg.blockDim = dim3(REC_THREADS);
+  cfg.blockDim = dim3(p.gemm_flags ? REC_THREADS : REC_THREADS - 32);  // the watcher warp exists only next to a concurrent GEMM
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
   cudaLaunchAttribute at[1];
@@ -452,6 +532,9 @@ void fast_set_option_speller(int key, int value);
 void fast_set_option(int key, int value) {
   if (key == 1) g_rec_a_tmem = value;
   if (key == 4) g_rec_nacc = value;
+  if (key == 6) g_rec_overlap = value;
+  if (key == 7) g_rec_gemm_ctas = value;
+  if (key == 8) g_gemm_natural_order = value;
   fast_set_option_speller(key, value);
 }
 
@@ -490,24 +573,18 @@ int fast_listener_forward(const float* x, const int32_t* x_lengths, const void* 
   const __nv_bfloat16* cur = w.xb;
   int Tin = d->T, Fin = d->F;
   for (int l = 0; l < d->L; ++l) {
-    const int Tl = Tin / 2, K = 2 * Fin, M = B * Tl, NP = 8 * g.Hp;
+    const int Tl = Tin / 2, K = 2 * Fin, NP = 8 * g.Hp;
     const int32_t* len_l = nullptr;
     if (x_lengths) {
       LAS_TRY(launch_pyramid_lengths(l == 0 ? x_lengths : w.len + (size_t)(l - 1) * B, w.len + (size_t)l * B, B, Tl, st));
       len_l = w.len + (size_t)l * B;
     }
-    char nm[48];
-    {
-      snprintf(nm, sizeof(nm), "listener.L%d.input_gemm", l);
-      ProfScope ps(nm, st);
-      // pyramid fold = reading [B, Tin, Fin] as [B*Tl, 2*Fin] (model/las_model.py:86-87): only the tensor map changes
-      LAS_TRY(launch_gemm_bf16_tc(cur, K, pk.wih[l], K, pk.bias[l], w.P, NP, M, NP, K, st));
-    }
-    snprintf(nm, sizeof(nm), "listener.L%d.recurrence", l);
-    ProfScope ps(nm, st);
     const bool last = (l == d->L - 1);
     RecParams rp;
     rp.P = w.P;
+    rp.gemm_flags = nullptr;  // set below when the GEMM runs concurrently
+    rp.Bp = listener_padded_batch(B);
+    rp.n_tiles = (NP + 255) / 256;
     rp.whh_img = pk.whh[l];
     rp.out_f32 = last ? enc : nullptr;
     rp.out_bf16 = last ? nullptr : w.act[l & 1];
@@ -517,15 +594,47 @@ int fast_listener_forward(const float* x, const int32_t* x_lengths, const void* 
     rp.a_tmem = g_rec_a_tmem;
     const int bc = pick_bc(B, g.CS);
     rp.nchunks = (B + bc - 1) / bc;
-    if (bc == 16) {
-      const int nacc = g_rec_nacc ? g_rec_nacc : 1;  // measured: one accumulator chain is fastest with the A operand in TMEM
-      if (nacc == 1) LAS_TRY((launch_rec<16, 1>(rp, st)));
-      else if (nacc == 2) LAS_TRY((launch_rec<16, 2>(rp, st)));
-      else LAS_TRY((launch_rec<16, 4>(rp, st)));
-    } else if (bc == 32) {
-      LAS_TRY((launch_rec<32, 2>(rp, st)));
-    } else {
-      LAS_TRY((launch_rec<64, 1>(rp, st)));
+    // The GEMM emits its tiles in the recurrence's consumption order and flags each one, so it can run next to the recurrence
+    // (which occupies 2 * nchunks * CS SMs) on the remaining SMs instead of in front of it.  Needs the two directions' columns
+    // to fall on separate column tiles and enough free SMs to be worth it.
+    const int rec_ctas = 2 * rp.nchunks * g.CS;
+    const int gemm_ctas = g_rec_gemm_ctas > 0 ? g_rec_gemm_ctas : sm_count() - rec_ctas - 4;
+    const bool overlap = g_rec_overlap && ((NP / 2) % 256 == 0) && gemm_ctas >= 32;
+    SideStream* side = nullptr;
+    if (overlap) LAS_TRY(side_stream(&side));
+    if (overlap) rp.gemm_flags = w.flags;
+    char nm[48];
+    if (overlap) LAS_CUDA_OK(cudaMemsetAsync(w.flags, 0, sizeof(uint32_t) * w.n_flags, st));
+    {
+      // pyramid fold = reading [B, Tin, Fin] as [B, Tl, 2*Fin] (model/las_model.py:86-87): only the tensor map changes.
+      // The output is time-major (row = t*Bp + b).
+      cudaStream_t gs = st;
+      if (overlap) {
+        LAS_CUDA_OK(cudaEventRecord(side->fork, st));
+        LAS_CUDA_OK(cudaStreamWaitEvent(side->s, side->fork, 0));
+        gs = side->s;
+      }
+      snprintf(nm, sizeof(nm), overlap ? "listener.L%d.input_gemm.overlapped" : "listener.L%d.input_gemm", l);
+      ProfScope ps(nm, gs);
+      LAS_TRY(launch_gemm_listener(cur, B, Tl, K, pk.wih[l], pk.bias[l], w.P, NP, overlap ? w.flags : nullptr, overlap ? gemm_ctas : 0, gs));
+    }
+    {
+      snprintf(nm, sizeof(nm), "listener.L%d.recurrence", l);
+      ProfScope ps(nm, st);
+      if (bc == 16) {
+        const int nacc = g_rec_nacc ? g_rec_nacc : 1;  // measured: one accumulator chain is fastest with the A operand in TMEM
+        if (nacc == 1) LAS_TRY((launch_rec<16, 1>(rp, st, overlap)));
+        else if (nacc == 2) LAS_TRY((launch_rec<16, 2>(rp, st, overlap)));
+        else LAS_TRY((launch_rec<16, 4>(rp, st, overlap)));
+      } else if (bc == 32) {
+        LAS_TRY((launch_rec<32, 2>(rp, st, overlap)));
+      } else {
+        LAS_TRY((launch_rec<64, 1>(rp, st, overlap)));
+      }
+    }
+    if (overlap) {  // the GEMM kernel has delivered every tile by now; join so that P / flags can be reused by the next layer
+      LAS_CUDA_OK(cudaEventRecord(side->join, side->s));
+      LAS_CUDA_OK(cudaStreamWaitEvent(st, side->join, 0));
     }
     cur = w.act[l & 1];
     Tin = Tl;
