@@ -13,6 +13,6 @@ timeout 600 ncu --set full --clock-control none --import-source on -k regex:spel
   python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_dec_$TAG.log 2>&1; echo "ncu dec rc=$?"
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:lstm_recurrence_cluster -s 9 -c 3 -f -o gpurun_out/prof_rec_$TAG \
   python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_rec_$TAG.log 2>&1; echo "ncu rec rc=$?"
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:gemm_bf16_tc -s 9 -c 3 -f -o gpurun_out/prof_gemm_$TAG \
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:gemm_bf16_tc -s 8 -c 4 -f -o gpurun_out/prof_gemm_$TAG \
   python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_gemm_$TAG.log 2>&1; echo "ncu gemm rc=$?"
 ls -la gpurun_out | tail -12
