@@ -230,7 +230,6 @@ int launch_gemm_bf16_tc(const __nv_bfloat16* A, long long lda, const __nv_bfloat
   return LAS_OK;
 }
 
-int g_gemm_natural_order = 0;  // test hook (las_debug_set_option(8, 1)): ascending tile order
 int listener_padded_batch(int B) {
   if (B > 128) return (B + 127) / 128 * 128;
   int bp = 1;
@@ -272,8 +271,7 @@ int launch_gemm_listener(const __nv_bfloat16* A, int B, int Tl, int K, const __n
   }
   // forward-direction columns are the first half of N; when the halves do not fall on tile boundaries every column tile
   // serves both directions and the natural (front-first) order is kept
-  int nfwd = ((N / 2) % BN == 0) ? (N / 2) / BN : n_tiles;
-  if (g_gemm_natural_order) nfwd = n_tiles;
+  const int nfwd = ((N / 2) % BN == 0) ? (N / 2) / BN : n_tiles;
   gemm_bf16_tc_kernel<<<grid, GEMM_THREADS, smem, st>>>(tm_a, tm_b, bias, C, (long long)N, M, N, K, 0, GemmSched{1, Bp, nfwd, flags});
   LAS_LAUNCH_OK("gemm_bf16_tc_kernel");
   return LAS_OK;

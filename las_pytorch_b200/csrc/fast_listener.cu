@@ -537,7 +537,6 @@ void fast_set_option(int key, int value) {
   if (key == 4) g_rec_nacc = value;
   if (key == 6) g_rec_overlap = value;
   if (key == 7) g_rec_gemm_ctas = value;
-  if (key == 8) g_gemm_natural_order = value;
   fast_set_option_speller(key, value);
 }
 

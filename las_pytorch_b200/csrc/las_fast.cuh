@@ -32,7 +32,6 @@ int launch_gemm_bf16_tc(const __nv_bfloat16* A, long long lda, const __nv_bfloat
 // with the backward direction's); `flags` (nullable, [m_tiles*n_tiles] zeroed counters) get +1 per finished epilogue warp
 // (4 per tile).  max_ctas > 0 limits the persistent grid (the recurrence runs concurrently on the other SMs).
 int listener_padded_batch(int B);
-extern int g_gemm_natural_order;  // test hook: ascending tile order instead of the recurrence's consumption order
 int launch_gemm_listener(const __nv_bfloat16* A, int B, int Tl, int K, const __nv_bfloat16* W, const float* bias, float* C, int N,
                          uint32_t* flags, int max_ctas, cudaStream_t st);
 int launch_umma_probe(const void* A, const void* B, float* D, int N, int K, int a_sw128, int b_sw128, int variant, cudaStream_t st);

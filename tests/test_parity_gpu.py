@@ -261,6 +261,29 @@ def test_listener_length_masks(cfgname, precision):
     assert torch.equal(enc_full, las.listener(x.cuda()))
 
 
+def test_bf16_listener_overlap_is_bit_identical_to_sequential():
+    """The input-projection GEMM running next to the recurrence (tile flags + watcher warp) must give exactly what the
+    GEMM-then-recurrence order gives: same arithmetic, only the schedule differs."""
+    if "bf16" not in precisions():
+        pytest.skip("bf16 mode not built")
+    from las_pytorch_b200 import _cabi
+
+    lib = _cabi.load_library()
+    c = tl.CONFIGS["paper"]
+    lis = tl.build_model("paper", max_label_len=4, seed=47, gain=3.0, precision="bf16").listener.cuda()
+    x, _ = tl.make_inputs(24, 512, c["F"], 4, c["V"], seed=47)
+    x = x.cuda()
+    try:
+        lib.las_debug_set_option(6, 0)
+        seq = lis(x).clone()
+        lib.las_debug_set_option(6, 1)
+        outs = [lis(x).clone() for _ in range(3)]
+    finally:
+        lib.las_debug_set_option(6, 1)
+    for o in outs:
+        assert torch.equal(o, seq)
+
+
 def test_bf16_batch_larger_than_one_decoder_launch():
     """The persistent decoder covers at most 64 utterances per launch (one attention CTA each); larger batches are decoded
     in chunks.  70 utterances must equal the same utterances decoded as 64 + 6."""
