@@ -284,6 +284,61 @@ def test_bf16_listener_overlap_is_bit_identical_to_sequential():
         assert torch.equal(o, seq)
 
 
+@pytest.mark.parametrize("precision", precisions())
+def test_edge_shapes_single_utterance_single_step_single_encoder_frame(precision):
+    """Smallest shapes the path accepts: one utterance, T = 2^L (one encoder step: the softmax is over a single frame),
+    one decode step; and a ragged batch (B = 3) that fills neither a 16-utterance recurrence chunk nor a TMEM quadrant."""
+    c = tl.CONFIGS["small"]
+    for B, T, S in ((1, 4, 1), (1, 8, 3), (3, 12, 2)):
+        las = tl.build_model("small", max_label_len=S, seed=53, gain=3.0, precision=precision)
+        sd = tl.state_dict_numpy(las)
+        x, labels = tl.make_inputs(B, T, c["F"], S, c["V"], seed=53)
+        ref = O.las_forward(x.numpy(), sd, c["L"], c["sl"], S, dtype=np.float64)
+        las = las.cuda()
+        preds, attns = las(x.cuda(), None, 0.0, is_training=False)
+        logp = torch.stack(preds).cpu().numpy()
+        attn = torch.stack([a[0] for a in attns]).cpu().numpy()
+        assert logp.shape == (S, B, c["V"]) and attn.shape == (S, B, T // 4)
+        assert np.abs(logp - ref["logp"]).max() <= TOL[precision]["logp"]
+        assert np.abs(attn.sum(-1) - 1).max() < 1e-5
+        if T // 4 == 1:
+            assert np.array_equal(attn, np.ones_like(attn))  # a single encoder frame gets all the weight, exactly
+
+
+def test_error_paths_raise_instead_of_falling_back():
+    """No CPU fallback and no silent substitution: every unsupported request raises with a message that says what to do."""
+    import las_pytorch_b200 as ours
+    from las_pytorch_b200 import _cabi
+
+    las = tl.build_model("tiny", max_label_len=3, seed=1, gain=1.0)
+    x = torch.randn(2, 16, 40)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        las.listener(x)  # CPU tensor
+    las = las.cuda()
+    with pytest.raises(RuntimeError):  # T not divisible by 2^L: the reference's view() raises too (model/las_model.py:87)
+        las.listener(torch.randn(2, 18, 40, device="cuda"))
+    with pytest.raises(RuntimeError, match="feature dim"):
+        las.listener(torch.randn(2, 16, 39, device="cuda"))
+    with pytest.raises(ValueError, match="2\\*listener_hidden_size"):  # Hs != 2H cannot work in the reference either (SURVEY A.4)
+        ours.Speller(30, 48, "LSTM", 2, 5, True, 16, "relu", 16, 1, 1)
+    with pytest.raises(NotImplementedError):
+        ours.Listener(40, 16, 2, "GRU")
+    with pytest.raises(NotImplementedError):
+        ours.Speller(30, 32, "LSTM", 2, 5, True, 16, "relu", 16, 1, 2)  # decode_mode 2 (sampling)
+    if "bf16" in precisions():
+        with pytest.raises(NotImplementedError, match="fp32"):
+            ours.Speller(30, 32, "LSTM", 2, 5, True, 16, "relu", 16, 2, 1, precision="bf16")  # multi_head in bf16 mode
+        big_v = ours.Speller(80, 32, "LSTM", 2, 3, True, 16, "relu", 16, 1, 1, precision="bf16").cuda()
+        with pytest.raises(_cabi.LasB200Error, match="vocabular"):  # V > 64 is outside the bf16 decoder's word atom
+            big_v(torch.randn(2, 4, 32, device="cuda"), None, 0.0)
+    # the library reports a bad status instead of aborting
+    lib = _cabi.load_library()
+    d = _cabi.ListenerDims(2, 15, 40, 16, 2)
+    import ctypes as C
+    assert lib.las_listener_forward(None, None, C.byref(d), 0, None, None, 0, None) != 0
+    assert b"" != lib.las_last_error()
+
+
 def test_bf16_batch_larger_than_one_decoder_launch():
     """The persistent decoder covers at most 64 utterances per launch (one attention CTA each); larger batches are decoded
     in chunks.  70 utterances must equal the same utterances decoded as 64 + 6."""
