@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define LAS_B200_ABI_VERSION 2
+#define LAS_B200_ABI_VERSION 3
 
 enum {
   LAS_OK = 0,
@@ -41,6 +41,14 @@ enum {
 enum {
   LAS_MODE_FP32 = 0, /* fp32 operands, fp32 FMA accumulate everywhere */
   LAS_MODE_BF16 = 1  /* bf16 GEMM operands on tcgen05 tensor cores, fp32 accumulate, fp32 c/h state, fp32 softmax */
+};
+
+/* Recurrent cell (`rnn_unit`, model/las_model.py:69,156: getattr(nn, rnn_unit.upper())).  Weight rows are torch's:
+ * LSTM [4H, K] gates i,f,g,o; GRU [3H, K] gates r,z,n; RNN [H, K] (tanh).  GRU / RNN: LAS_MODE_FP32 only. */
+enum {
+  LAS_CELL_LSTM = 0,
+  LAS_CELL_GRU = 1,
+  LAS_CELL_RNN = 2
 };
 
 /* decode feedback, model/las_model.py:216-234 */
@@ -73,14 +81,16 @@ typedef struct las_listener_dims {
   int32_t F; /* input feature dim (40) */
   int32_t H; /* hidden size per direction */
   int32_t L; /* pyramid layers; output has U = T / 2^L steps of E = 2H features */
+  int32_t cell; /* LAS_CELL_* */
 } las_listener_dims;
 
-/* One direction of one layer, in the reference's state_dict layout, gate order i,f,g,o. */
+/* One direction of one layer, in the reference's state_dict layout; G = 4 (LSTM: i,f,g,o), 3 (GRU: r,z,n)
+ * or 1 (RNN) gate blocks of H rows. */
 typedef struct las_lstm_weights {
-  const float* w_ih; /* [4H, K_in]  (K_in = 2F for layer 0, 4H for layers >= 1) */
-  const float* w_hh; /* [4H, H] */
-  const float* b_ih; /* [4H] */
-  const float* b_hh; /* [4H] */
+  const float* w_ih; /* [G*H, K_in]  (K_in = 2F for layer 0, 4H for layers >= 1) */
+  const float* w_hh; /* [G*H, H] */
+  const float* b_ih; /* [G*H] */
+  const float* b_hh; /* [G*H] */
 } las_lstm_weights;
 
 /* Packed (kernel-layout) weights.  `w_host` is a HOST array of 2L entries ordered
@@ -118,6 +128,7 @@ typedef struct las_speller_dims {
   int32_t D;  /* attention MLP dim per head (phi out features = D * heads, psi out features = D) */
   int32_t heads;  /* multi_head (model/las_model.py:268-269, 298-314); 0 is read as 1.  heads > 1: LAS_MODE_FP32 only */
   int32_t no_mlp; /* 1: use_mlp_in_attention=False (:283-285): query = decoder state, keys = enc, D ignored.  LAS_MODE_FP32 only */
+  int32_t cell;   /* LAS_CELL_* of rnn_layer; GRU / RNN carry no cell state (c_state is ignored) */
 } las_speller_dims;
 
 typedef struct las_speller_weights {

@@ -12,15 +12,17 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "liblas_b200.so")
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 MODE_FP32 = 0
 MODE_BF16 = 1
 DECODE_RAW = 0
 DECODE_GREEDY = 1
+CELL_LSTM, CELL_GRU, CELL_RNN = 0, 1, 2
+CELLS = {"LSTM": CELL_LSTM, "GRU": CELL_GRU, "RNN": CELL_RNN}
 
 
 class ListenerDims(C.Structure):
-    _fields_ = [("B", C.c_int32), ("T", C.c_int32), ("F", C.c_int32), ("H", C.c_int32), ("L", C.c_int32)]
+    _fields_ = [("B", C.c_int32), ("T", C.c_int32), ("F", C.c_int32), ("H", C.c_int32), ("L", C.c_int32), ("cell", C.c_int32)]
 
 
 class LstmWeights(C.Structure):
@@ -30,7 +32,7 @@ class LstmWeights(C.Structure):
 class SpellerDims(C.Structure):
     _fields_ = [
         ("B", C.c_int32), ("U", C.c_int32), ("E", C.c_int32), ("Hs", C.c_int32),
-        ("sl", C.c_int32), ("V", C.c_int32), ("D", C.c_int32), ("heads", C.c_int32), ("no_mlp", C.c_int32),
+        ("sl", C.c_int32), ("V", C.c_int32), ("D", C.c_int32), ("heads", C.c_int32), ("no_mlp", C.c_int32), ("cell", C.c_int32),
     ]
 
 

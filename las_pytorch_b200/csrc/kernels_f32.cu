@@ -118,7 +118,7 @@ struct CellArgs2 {
 };
 
 __device__ __forceinline__ void cell_accumulate(const float* __restrict__ src, long long src_ld, int K,
-                                                const float* __restrict__ w, int H, int b0, int j0, int B,
+                                                const float* __restrict__ w, int H, int b0, int j0, int B, int G,
                                                 float (&As)[CB][CK + 1], float (&Ws)[4 * CJ][CK + 1], float (&acc)[4]) {
   const int tid = threadIdx.x;
   const int tb = tid / CJ, tj = tid % CJ;
@@ -132,7 +132,7 @@ __device__ __forceinline__ void cell_accumulate(const float* __restrict__ src, l
       As[r][cc] = (gb < B && gk < K) ? src[(long long)gb * src_ld + gk] : 0.f;
       const int g = r / CJ, jj = r % CJ;
       const int gj = j0 + jj;
-      Ws[r][cc] = (gj < H && gk < K) ? w[(size_t)(g * H + gj) * K + gk] : 0.f;
+      Ws[r][cc] = (g < G && gj < H && gk < K) ? w[(size_t)(g * H + gj) * K + gk] : 0.f;
     }
     __syncthreads();
 #pragma unroll
@@ -145,14 +145,15 @@ __device__ __forceinline__ void cell_accumulate(const float* __restrict__ src, l
   }
 }
 
-__global__ void __launch_bounds__(256) lstm_cell_f32_kernel(CellArgs2 args, int B, int H) {
+__global__ void __launch_bounds__(256) lstm_cell_f32_kernel(CellArgs2 args, int B, int H, int cell) {
   const CellArgs& a = args.d[blockIdx.z];
   __shared__ float As[CB][CK + 1];
   __shared__ float Ws[4 * CJ][CK + 1];
   const int j0 = blockIdx.x * CJ, b0 = blockIdx.y * CB;
-  float acc[4] = {0.f, 0.f, 0.f, 0.f};
-  if (a.x) cell_accumulate(a.x, a.x_ld, a.Kx, a.w_ih, H, b0, j0, B, As, Ws, acc);
-  if (a.h_prev) cell_accumulate(a.h_prev, a.h_ld, H, a.w_hh, H, b0, j0, B, As, Ws, acc);
+  const int G = cell == LAS_CELL_LSTM ? 4 : (cell == LAS_CELL_GRU ? 3 : 1);
+  float ax[4] = {0.f, 0.f, 0.f, 0.f}, ah[4] = {0.f, 0.f, 0.f, 0.f};  // x part / h part of the gate pre-activations
+  if (a.x) cell_accumulate(a.x, a.x_ld, a.Kx, a.w_ih, H, b0, j0, B, G, As, Ws, ax);
+  if (a.h_prev) cell_accumulate(a.h_prev, a.h_ld, H, a.w_hh, H, b0, j0, B, G, As, Ws, ah);
 
   const int tb = threadIdx.x / CJ, tj = threadIdx.x % CJ;
   const int b = b0 + tb, j = j0 + tj;
@@ -161,21 +162,33 @@ __global__ void __launch_bounds__(256) lstm_cell_f32_kernel(CellArgs2 args, int 
     a.h_out[(long long)b * a.hout_ld + j] = 0.f;
     return;
   }
-  float pre[4];
+  const int GH = G * H;
 #pragma unroll
   for (int g = 0; g < 4; ++g) {
-    float v = acc[g];
-    if (a.pre_add) v += a.pre_add[(long long)b * a.pre_ld + g * H + j];
-    if (a.b_ih) v += a.b_ih[g * H + j] + a.b_hh[g * H + j];
-    pre[g] = v;
+    if (g < G) {
+      if (a.pre_add) ax[g] += a.pre_add[(long long)b * a.pre_ld + g * H + j];
+      if (a.b_ih) ax[g] += a.b_ih[g * H + j];
+      if (a.b_hh) ah[g] += a.b_hh[g * H + j];
+    }
   }
-  const float ig = sigmoid_precise(pre[0]);
-  const float fg = sigmoid_precise(pre[1]);
-  const float gg = tanhf(pre[2]);
-  const float og = sigmoid_precise(pre[3]);
-  const float c_new = fg * a.c[(size_t)b * H + j] + ig * gg;
-  a.c[(size_t)b * H + j] = c_new;
-  a.h_out[(long long)b * a.hout_ld + j] = og * tanhf(c_new);
+  (void)GH;
+  if (cell == LAS_CELL_LSTM) {
+    const float ig = sigmoid_precise(ax[0] + ah[0]);
+    const float fg = sigmoid_precise(ax[1] + ah[1]);
+    const float gg = tanhf(ax[2] + ah[2]);
+    const float og = sigmoid_precise(ax[3] + ah[3]);
+    const float c_new = fg * a.c[(size_t)b * H + j] + ig * gg;
+    a.c[(size_t)b * H + j] = c_new;
+    a.h_out[(long long)b * a.hout_ld + j] = og * tanhf(c_new);
+  } else if (cell == LAS_CELL_GRU) {
+    const float hp = a.h_prev ? a.h_prev[(long long)b * a.h_ld + j] : 0.f;
+    const float rg = sigmoid_precise(ax[0] + ah[0]);
+    const float zg = sigmoid_precise(ax[1] + ah[1]);
+    const float ng = tanhf(ax[2] + rg * ah[2]);
+    a.h_out[(long long)b * a.hout_ld + j] = (1.0f - zg) * ng + zg * hp;
+  } else {
+    a.h_out[(long long)b * a.hout_ld + j] = tanhf(ax[0] + ah[0]);
+  }
 }
 
 __global__ void pyramid_lengths_kernel(const int32_t* in, int32_t* out, int B, int cap) {
@@ -188,12 +201,12 @@ int launch_pyramid_lengths(const int32_t* in, int32_t* out, int B, int cap, cuda
   return LAS_OK;
 }
 
-int launch_lstm_cell_f32(const CellArgs* args, int ndir, int B, int H, cudaStream_t st) {
+int launch_lstm_cell_f32(const CellArgs* args, int ndir, int B, int H, cudaStream_t st, int cell) {
   CellArgs2 a2;
   a2.d[0] = args[0];
   a2.d[1] = args[ndir > 1 ? 1 : 0];
   dim3 grid((H + CJ - 1) / CJ, (B + CB - 1) / CB, ndir);
-  lstm_cell_f32_kernel<<<grid, 256, 0, st>>>(a2, B, H);
+  lstm_cell_f32_kernel<<<grid, 256, 0, st>>>(a2, B, H, cell);
   LAS_LAUNCH_OK("lstm_cell_f32_kernel");
   return LAS_OK;
 }

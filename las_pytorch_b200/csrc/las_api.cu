@@ -74,10 +74,13 @@ struct ListenerPackF32 {
   float* wcat[16];
   float* bias[16];
   float* whh[16];
+  float* bhh[16];  // GRU / RNN: b_hh kept apart from the input projection's bias (the GRU's n gate needs it inside r * (...))
   size_t bytes;
 };
+static inline int n_gates(int cell) { return cell == LAS_CELL_LSTM ? 4 : (cell == LAS_CELL_GRU ? 3 : 1); }
 static int listener_check(const las_listener_dims* d) {
   LAS_REQUIRE(d != nullptr, "dims is NULL");
+  LAS_REQUIRE(d->cell >= LAS_CELL_LSTM && d->cell <= LAS_CELL_RNN, "unknown recurrent cell %d", d->cell);
   LAS_REQUIRE(d->B > 0 && d->T > 0 && d->F > 0 && d->H > 0, "listener dims must be positive (B=%d T=%d F=%d H=%d)", d->B, d->T, d->F, d->H);
   LAS_REQUIRE(d->L >= 1 && d->L <= 16, "Listener should have at least 1 layer (L=%d)", d->L);
   LAS_REQUIRE(d->T % (1 << d->L) == 0,
@@ -90,9 +93,11 @@ static ListenerPackF32 listener_pack_layout_f32(const las_listener_dims* d, void
   Carver cv(base);
   for (int l = 0; l < d->L; ++l) {
     const size_t K = (l == 0) ? 2 * (size_t)d->F : 4 * (size_t)d->H;
-    p.wcat[l] = cv.take<float>(8 * (size_t)d->H * K);
-    p.bias[l] = cv.take<float>(8 * (size_t)d->H);
-    p.whh[l] = cv.take<float>(8 * (size_t)d->H * d->H);
+    const size_t GH2 = 2 * (size_t)n_gates(d->cell) * d->H;  // both directions' gate rows
+    p.wcat[l] = cv.take<float>(GH2 * K);
+    p.bias[l] = cv.take<float>(GH2);
+    p.whh[l] = cv.take<float>(GH2 * d->H);
+    p.bhh[l] = cv.take<float>(GH2);
   }
   p.bytes = cv.total();
   return p;
@@ -109,7 +114,7 @@ static ListenerWsF32 listener_ws_layout_f32(const las_listener_dims* d, void* ba
   ListenerWsF32 w;
   Carver cv(base);
   const size_t M0 = (size_t)d->B * (d->T / 2);
-  w.P = cv.take<float>(M0 * 8 * d->H);
+  w.P = cv.take<float>(M0 * 2 * n_gates(d->cell) * d->H);
   w.act[0] = cv.take<float>(M0 * 2 * d->H);
   w.act[1] = cv.take<float>(M0 / 2 * 2 * d->H + 16);
   w.c = cv.take<float>(2 * (size_t)d->B * d->H);
@@ -123,6 +128,8 @@ static int listener_forward_f32(const float* x, const int32_t* x_lengths, const 
   const ListenerPackF32 pk = listener_pack_layout_f32(d, const_cast<void*>(packed));
   const ListenerWsF32 w = listener_ws_layout_f32(d, ws);
   const int B = d->B, H = d->H;
+  const int GH = n_gates(d->cell) * H;
+  const bool lstm = d->cell == LAS_CELL_LSTM;
   const float* cur = x;
   int Tin = d->T, Fin = d->F;
   for (int l = 0; l < d->L; ++l) {
@@ -137,7 +144,7 @@ static int listener_forward_f32(const float* x, const int32_t* x_lengths, const 
     {
       snprintf(nm, sizeof(nm), "listener.L%d.input_gemm", l);
       ProfScope ps(nm, st);
-      LAS_TRY(launch_sgemm_nt_bias(cur, K, pk.wcat[l], K, pk.bias[l], w.P, 8 * H, M, 8 * H, K, false, st));
+      LAS_TRY(launch_sgemm_nt_bias(cur, K, pk.wcat[l], K, pk.bias[l], w.P, 2 * GH, M, 2 * GH, K, false, st));
     }
     snprintf(nm, sizeof(nm), "listener.L%d.recurrence", l);
     ProfScope ps(nm, st);
@@ -151,8 +158,9 @@ static int listener_forward_f32(const float* x, const int32_t* x_lengths, const 
       a[0].h_prev = step ? out + (size_t)(tf - 1) * 2 * H : nullptr;
       a[0].h_ld = row_ld;
       a[0].w_hh = pk.whh[l];
-      a[0].pre_add = w.P + (size_t)tf * 8 * H;
-      a[0].pre_ld = (long long)Tl * 8 * H;
+      a[0].pre_add = w.P + (size_t)tf * 2 * GH;
+      a[0].pre_ld = (long long)Tl * 2 * GH;
+      a[0].b_hh = lstm ? nullptr : pk.bhh[l];
       a[0].c = w.c;
       a[0].h_out = out + (size_t)tf * 2 * H;
       a[0].hout_ld = row_ld;
@@ -162,13 +170,14 @@ static int listener_forward_f32(const float* x, const int32_t* x_lengths, const 
       a[1].t = tb;
       a[1].h_prev = step ? out + (size_t)(tb + 1) * 2 * H + H : nullptr;
       a[1].h_ld = row_ld;
-      a[1].w_hh = pk.whh[l] + 4 * (size_t)H * H;
-      a[1].pre_add = w.P + (size_t)tb * 8 * H + 4 * H;
-      a[1].pre_ld = (long long)Tl * 8 * H;
+      a[1].w_hh = pk.whh[l] + (size_t)GH * H;
+      a[1].pre_add = w.P + (size_t)tb * 2 * GH + GH;
+      a[1].pre_ld = (long long)Tl * 2 * GH;
+      a[1].b_hh = lstm ? nullptr : pk.bhh[l] + GH;
       a[1].c = w.c + (size_t)B * H;
       a[1].h_out = out + (size_t)tb * 2 * H + H;
       a[1].hout_ld = row_ld;
-      LAS_TRY(launch_lstm_cell_f32(a, 2, B, H, st));
+      LAS_TRY(launch_lstm_cell_f32(a, 2, B, H, st, d->cell));
     }
     cur = out;
     Tin = Tl;
@@ -194,6 +203,7 @@ static int speller_check(const las_speller_dims* d) {
   LAS_REQUIRE(d->B > 0 && d->U > 0 && d->E > 0 && d->Hs > 0 && d->V > 0 && (d->D > 0 || d->no_mlp),
               "speller dims must be positive (B=%d U=%d E=%d Hs=%d V=%d D=%d)", d->B, d->U, d->E, d->Hs, d->V, d->D);
   LAS_REQUIRE(d->heads >= 0 && d->heads <= 16, "multi_head must be in [1,16] (heads=%d)", d->heads);
+  LAS_REQUIRE(d->cell >= LAS_CELL_LSTM && d->cell <= LAS_CELL_RNN, "unknown recurrent cell %d", d->cell);
   LAS_REQUIRE(!(d->no_mlp && n_heads(d) > 1), "multi_head > 1 needs use_mlp_in_attention=True (the heads are slices of phi's output)");
   LAS_REQUIRE(d->sl >= 1 && d->sl <= 8, "speller layers must be in [1,8] (sl=%d)", d->sl);
   LAS_REQUIRE(d->Hs == d->E,
@@ -204,7 +214,7 @@ static int speller_check(const las_speller_dims* d) {
 static SpellerPackF32 speller_pack_layout_f32(const las_speller_dims* d, void* base) {
   SpellerPackF32 p;
   Carver cv(base);
-  const size_t G = 4 * (size_t)d->Hs;
+  const size_t G = (size_t)n_gates(d->cell) * d->Hs;
   for (int l = 0; l < d->sl; ++l) {
     const size_t Kx = (l == 0) ? (size_t)d->V + d->E : (size_t)d->Hs;
     p.w_ih[l] = cv.take<float>(G * Kx);
@@ -267,9 +277,10 @@ static int speller_decode_f32(const las_decode_io* io, const void* packed, const
   } else {
     LAS_TRY(launch_speller_init(w.xin, xld, io->enc, B, U, E, V, st));
   }
-  if (io->h_state && io->c_state) {
+  if (io->h_state && (io->c_state || d->cell != LAS_CELL_LSTM)) {
     LAS_CUDA_OK(cudaMemcpyAsync(w.h[0], io->h_state, sizeof(float) * state_n, cudaMemcpyDeviceToDevice, st));
-    LAS_CUDA_OK(cudaMemcpyAsync(w.c, io->c_state, sizeof(float) * state_n, cudaMemcpyDeviceToDevice, st));
+    if (io->c_state) LAS_CUDA_OK(cudaMemcpyAsync(w.c, io->c_state, sizeof(float) * state_n, cudaMemcpyDeviceToDevice, st));
+    else LAS_CUDA_OK(cudaMemsetAsync(w.c, 0, sizeof(float) * state_n, st));
   } else {
     LAS_CUDA_OK(cudaMemsetAsync(w.h[0], 0, sizeof(float) * state_n, st));
     LAS_CUDA_OK(cudaMemsetAsync(w.c, 0, sizeof(float) * state_n, st));
@@ -294,7 +305,7 @@ static int speller_decode_f32(const las_decode_io* io, const void* packed, const
       a.c = w.c + (size_t)l * B * Hs;
       a.h_out = hn + (size_t)l * B * Hs;
       a.hout_ld = Hs;
-      LAS_TRY(launch_lstm_cell_f32(&a, 1, B, Hs, st));
+      LAS_TRY(launch_lstm_cell_f32(&a, 1, B, Hs, st, d->cell));
     }
     AttendArgs t;
     memset(&t, 0, sizeof(t));
@@ -324,9 +335,9 @@ static int speller_decode_f32(const las_decode_io* io, const void* packed, const
     t.decode_mode = decode_mode;
     LAS_TRY(launch_attend_f32(t, st));
   }
-  if (io->h_state && io->c_state) {
+  if (io->h_state && (io->c_state || d->cell != LAS_CELL_LSTM)) {
     LAS_CUDA_OK(cudaMemcpyAsync(io->h_state, w.h[steps & 1], sizeof(float) * state_n, cudaMemcpyDeviceToDevice, st));
-    LAS_CUDA_OK(cudaMemcpyAsync(io->c_state, w.c, sizeof(float) * state_n, cudaMemcpyDeviceToDevice, st));
+    if (io->c_state) LAS_CUDA_OK(cudaMemcpyAsync(io->c_state, w.c, sizeof(float) * state_n, cudaMemcpyDeviceToDevice, st));
   }
   if (io->word && io->context) {
     LAS_TRY(launch_copy2d(io->word, V, w.xin, xld, B, V, st));
@@ -391,18 +402,24 @@ int las_listener_pack(const las_lstm_weights* w, const las_listener_dims* d, int
   if (packed_bytes < las_listener_packed_bytes(d, mode))
     return fail(LAS_ENOMEM, "packed buffer too small: %zu < %zu", packed_bytes, las_listener_packed_bytes(d, mode));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  LAS_REQUIRE(mode != LAS_MODE_BF16 || d->cell == LAS_CELL_LSTM, "LAS_MODE_BF16 implements LSTM cells only; use LAS_MODE_FP32 for GRU / RNN");
   if (mode == LAS_MODE_BF16) return fast_listener_pack(w, d, packed, st);
   const ListenerPackF32 pk = listener_pack_layout_f32(d, packed);
-  const size_t H = d->H;
+  const size_t H = d->H, GH = (size_t)n_gates(d->cell) * H;
   for (int l = 0; l < d->L; ++l) {
     const size_t K = (l == 0) ? 2 * (size_t)d->F : 4 * H;
     for (int dir = 0; dir < 2; ++dir) {
       const las_lstm_weights& s = w[2 * l + dir];
       LAS_REQUIRE(s.w_ih && s.w_hh && s.b_ih && s.b_hh, "null weight pointer in layer %d dir %d", l, dir);
-      LAS_CUDA_OK(cudaMemcpyAsync(pk.wcat[l] + dir * 4 * H * K, s.w_ih, sizeof(float) * 4 * H * K, cudaMemcpyDeviceToDevice, st));
-      LAS_CUDA_OK(cudaMemcpyAsync(pk.whh[l] + dir * 4 * H * H, s.w_hh, sizeof(float) * 4 * H * H, cudaMemcpyDeviceToDevice, st));
-      bias_sum_kernel<<<(unsigned)((4 * H + 255) / 256), 256, 0, st>>>(pk.bias[l] + dir * 4 * H, s.b_ih, s.b_hh, (int)(4 * H));
-      LAS_LAUNCH_OK("bias_sum_kernel");
+      LAS_CUDA_OK(cudaMemcpyAsync(pk.wcat[l] + dir * GH * K, s.w_ih, sizeof(float) * GH * K, cudaMemcpyDeviceToDevice, st));
+      LAS_CUDA_OK(cudaMemcpyAsync(pk.whh[l] + dir * GH * H, s.w_hh, sizeof(float) * GH * H, cudaMemcpyDeviceToDevice, st));
+      LAS_CUDA_OK(cudaMemcpyAsync(pk.bhh[l] + dir * GH, s.b_hh, sizeof(float) * GH, cudaMemcpyDeviceToDevice, st));
+      if (d->cell == LAS_CELL_LSTM) {  // both biases fold into the input projection
+        bias_sum_kernel<<<(unsigned)((GH + 255) / 256), 256, 0, st>>>(pk.bias[l] + dir * GH, s.b_ih, s.b_hh, (int)GH);
+        LAS_LAUNCH_OK("bias_sum_kernel");
+      } else {  // GRU / RNN: the projection carries b_ih only, the cell kernel adds b_hh on the recurrent side
+        LAS_CUDA_OK(cudaMemcpyAsync(pk.bias[l] + dir * GH, s.b_ih, sizeof(float) * GH, cudaMemcpyDeviceToDevice, st));
+      }
     }
   }
   return LAS_OK;
@@ -429,6 +446,7 @@ int las_listener_forward_masked(const float* x, const int32_t* x_lengths, const 
   if (workspace_bytes < las_listener_workspace_bytes(d, mode))
     return fail(LAS_ENOMEM, "workspace too small: %zu < %zu", workspace_bytes, las_listener_workspace_bytes(d, mode));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  LAS_REQUIRE(mode != LAS_MODE_BF16 || d->cell == LAS_CELL_LSTM, "LAS_MODE_BF16 implements LSTM cells only; use LAS_MODE_FP32 for GRU / RNN");
   if (mode == LAS_MODE_BF16) return fast_listener_forward(x, x_lengths, packed, d, enc, enc_lengths, workspace, st);
   return listener_forward_f32(x, x_lengths, packed, d, enc, enc_lengths, workspace, st);
 }
@@ -450,14 +468,15 @@ int las_speller_pack(const las_speller_weights* w, const las_speller_dims* d, in
   LAS_REQUIRE(w->w_cd && w->b_cd, "null output weight pointer");
   LAS_REQUIRE(d->no_mlp || (w->w_phi && w->b_phi && w->w_psi && w->b_psi), "null attention weight pointer");
   LAS_REQUIRE(n_heads(d) == 1 || (w->w_dr && w->b_dr), "multi_head > 1 needs attention.dim_reduce weights");
-  LAS_REQUIRE(mode != LAS_MODE_BF16 || (n_heads(d) == 1 && !d->no_mlp),
-              "LAS_MODE_BF16 implements single-head MLP attention only; use LAS_MODE_FP32 for multi_head > 1 / use_mlp_in_attention=False");
+  LAS_REQUIRE(mode != LAS_MODE_BF16 || (n_heads(d) == 1 && !d->no_mlp && d->cell == LAS_CELL_LSTM),
+              "LAS_MODE_BF16 implements single-head MLP attention with LSTM cells only; use LAS_MODE_FP32 for multi_head > 1 / "
+              "use_mlp_in_attention=False / GRU / RNN");
   LAS_TRY(device_ok());
   if (packed_bytes < las_speller_packed_bytes(d, mode))
     return fail(LAS_ENOMEM, "packed buffer too small: %zu < %zu", packed_bytes, las_speller_packed_bytes(d, mode));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const SpellerPackF32 pk = speller_pack_layout_f32(d, packed);
-  const size_t G = 4 * (size_t)d->Hs;
+  const size_t G = (size_t)n_gates(d->cell) * d->Hs;
 #define CP(dst, src, n) LAS_CUDA_OK(cudaMemcpyAsync(dst, src, sizeof(float) * (n), cudaMemcpyDeviceToDevice, st))
   for (int l = 0; l < d->sl; ++l) {
     const las_lstm_weights& s = w->rnn_host[l];
@@ -533,15 +552,16 @@ int las_speller_decode(const las_decode_io* io, const void* packed, const las_sp
   LAS_REQUIRE(decode_mode == LAS_DECODE_RAW || decode_mode == LAS_DECODE_GREEDY,
               "decode_mode %d is not supported on the device path (0 = raw, 1 = greedy)", decode_mode);
   LAS_REQUIRE(!(io->gt_dense || io->gt_index) || io->gt_steps >= steps, "ground truth has %d steps, %d requested", io->gt_steps, steps);
-  LAS_REQUIRE((io->h_state == nullptr) == (io->c_state == nullptr), "h_state and c_state must be given together");
+  LAS_REQUIRE(d->cell != LAS_CELL_LSTM || (io->h_state == nullptr) == (io->c_state == nullptr), "h_state and c_state must be given together");
   LAS_REQUIRE((io->word == nullptr) == (io->context == nullptr), "word and context must be given together");
   LAS_TRY(device_ok());
   if (workspace_bytes < las_speller_workspace_bytes(d, steps, mode))
     return fail(LAS_ENOMEM, "workspace too small: %zu < %zu", workspace_bytes, las_speller_workspace_bytes(d, steps, mode));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (steps == 0) return LAS_OK;
-  LAS_REQUIRE(mode != LAS_MODE_BF16 || (n_heads(d) == 1 && !d->no_mlp),
-              "LAS_MODE_BF16 implements single-head MLP attention only; use LAS_MODE_FP32 for multi_head > 1 / use_mlp_in_attention=False");
+  LAS_REQUIRE(mode != LAS_MODE_BF16 || (n_heads(d) == 1 && !d->no_mlp && d->cell == LAS_CELL_LSTM),
+              "LAS_MODE_BF16 implements single-head MLP attention with LSTM cells only; use LAS_MODE_FP32 for multi_head > 1 / "
+              "use_mlp_in_attention=False / GRU / RNN");
   if (mode == LAS_MODE_BF16) {
     const size_t f32p = speller_pack_layout_f32(d, nullptr).bytes;
     const size_t f32w = speller_ws_layout_f32(d, nullptr).bytes;

@@ -10,7 +10,9 @@ namespace las {
 int launch_sgemm_nt_bias(const float* A, int lda, const float* W, int ldw, const float* bias, float* C, int ldc,
                          int M, int N, int K, bool relu, cudaStream_t st);
 
-// One LSTM cell update for a batch: pre = [x . W_ih^T] + [h_prev . W_hh^T] + [pre_add] + [b_ih + b_hh].
+// One recurrent cell update for a batch.  x part: [x . W_ih^T] + [pre_add] + [b_ih]; h part: [h_prev . W_hh^T] + [b_hh].
+// LSTM (4 gates i,f,g,o) and RNN (1 gate, tanh) use x part + h part; GRU (r,z,n) keeps them apart for the n gate:
+// n = tanh(x_n + r * h_n), h' = (1 - z) * n + z * h_prev (torch nn.GRU).
 struct CellArgs {
   const float* x;       // nullable, [B, Kx] row stride x_ld
   int x_ld, Kx;
@@ -28,7 +30,7 @@ struct CellArgs {
   const int32_t* lengths;  // nullable [B]: rows with t >= lengths[b] keep c and write h = 0 (length-mask extension)
   int t;
 };
-int launch_lstm_cell_f32(const CellArgs* args, int ndir, int B, int H, cudaStream_t st);
+int launch_lstm_cell_f32(const CellArgs* args, int ndir, int B, int H, cudaStream_t st, int cell = 0);
 
 struct AttendArgs {
   const float* state;   // [B, Hs] row stride state_ld : top-layer decoder state

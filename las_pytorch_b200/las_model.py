@@ -9,8 +9,9 @@ Extra keyword accepted everywhere the reference swallows **kwargs: `precision` =
 (LAS_MODE_FP32 / LAS_MODE_BF16; default from $LAS_B200_PRECISION, else "fp32").
 
 Variants of the reference classes: multi_head > 1 (with attention.dim_reduce) and use_mlp_in_attention=False run in the
-fp32 mode only (the bf16 mode raises and says so).  Not on this path (raise NotImplementedError instead of silently
-running something else): GRU/RNN cells, decode_mode 2 (sampling), training/backward.
+fp32 mode only, and so do the GRU / RNN cells (`rnn_unit`; the reference does getattr(nn, rnn_unit.upper()), :69,156) -- the bf16
+mode raises and says so.  Not on this path (raise NotImplementedError instead of silently running something else):
+decode_mode 2 (sampling), training/backward.
 """
 from __future__ import annotations
 
@@ -82,7 +83,7 @@ def _lstm_weight_array(holder, layers, directions):
     return arr, keep
 
 
-def _run_listener(x, holders, input_feature_dim, hidden_size, mode, cache, lengths=None):
+def _run_listener(x, holders, input_feature_dim, hidden_size, mode, cache, lengths=None, cell="LSTM"):
     """x [B,T,F] -> [B, T/2^L, 2H] through `len(holders)` pyramid layers.  With `lengths` ([B] valid frames; extension)
     returns (enc, enc_lengths [B] int32)."""
     _require_cuda(x, "input_x")
@@ -92,7 +93,7 @@ def _run_listener(x, holders, input_feature_dim, hidden_size, mode, cache, lengt
     if f != input_feature_dim:
         raise RuntimeError(f"input feature dim {f} != {input_feature_dim}")
     nl = len(holders)
-    dims = ListenerDims(b, t, f, hidden_size, nl)
+    dims = ListenerDims(b, t, f, hidden_size, nl, _cabi.CELLS[cell])
     if t % (1 << nl) != 0:
         # the reference fails inside `view` (model/las_model.py:87) with a RuntimeError; so do we
         raise RuntimeError(
@@ -180,11 +181,14 @@ class LAS(nn.Module):
         return package
 
 
-def _check_unit(rnn_unit):
-    if str(rnn_unit).upper() != "LSTM":
-        raise NotImplementedError(
-            f"rnn_unit={rnn_unit!r}: only LSTM cells are implemented on the B200 path (SURVEY.md section 8 row f4)"
-        )
+def _check_unit(rnn_unit, precision="fp32"):
+    """-> "LSTM" | "GRU" | "RNN" (the reference resolves the string with getattr(nn, rnn_unit.upper()))."""
+    unit = str(rnn_unit).upper()
+    if unit not in _cabi.CELLS:
+        raise NotImplementedError(f"rnn_unit={rnn_unit!r}: LSTM, GRU and RNN cells are implemented (SURVEY.md section 8 row f4)")
+    if unit != "LSTM" and precision != "fp32":
+        raise NotImplementedError(f"rnn_unit={rnn_unit!r} runs in the fp32 mode only; construct the module with precision='fp32'")
+    return unit
 
 
 class pBLSTMLayer(nn.Module):
@@ -192,17 +196,18 @@ class pBLSTMLayer(nn.Module):
 
     def __init__(self, input_feature_dim, hidden_dim, rnn_unit="LSTM", dropout_rate=0.0, precision=None):
         super().__init__()
-        _check_unit(rnn_unit)
-        self.rnn_unit = nn.LSTM  # the reference stores the class here (:69)
+        self.precision = precision or _default_precision()
+        self.cell = _check_unit(rnn_unit, self.precision)
+        self.rnn_unit = getattr(nn, self.cell)  # the reference stores the class here (:69)
         self.input_feature_dim = input_feature_dim
         self.hidden_dim = hidden_dim
-        self.precision = precision or _default_precision()
         # same parameter names as nn.LSTM(input_feature_dim*2, hidden_dim, 1, bidirectional=True) (:72-79)
-        self.BLSTM = LSTMWeights(input_feature_dim * 2, hidden_dim, 1, bidirectional=True)
+        self.BLSTM = LSTMWeights(input_feature_dim * 2, hidden_dim, 1, bidirectional=True, cell=self.cell)
         self._cache = _Cache()
 
     def forward(self, input_x):
-        out = _run_listener(input_x, [self.BLSTM], self.input_feature_dim, self.hidden_dim, _mode_of(self.precision), self._cache)
+        out = _run_listener(input_x, [self.BLSTM], self.input_feature_dim, self.hidden_dim, _mode_of(self.precision), self._cache,
+                            cell=self.cell)
         h = self.hidden_dim
         h_n = torch.stack([out[:, -1, :h], out[:, 0, h:]])  # final hidden of each direction
         return out, (h_n, None)
@@ -213,17 +218,19 @@ class Listener(nn.Module):
 
     def __init__(self, input_feature_dim, hidden_size, num_layers, rnn_unit, use_gpu=True, dropout_rate=0.0, **kwargs):
         super().__init__()
-        _check_unit(rnn_unit)
+        self.precision = kwargs.get("precision") or _default_precision()
+        self.cell = _check_unit(rnn_unit, self.precision)
         self.input_feature_dim = input_feature_dim
         self.hidden_size = hidden_size
         self.num_layers = num_layers
         self.rnn_unit = rnn_unit
         self.dropout_rate = dropout_rate
-        self.precision = kwargs.get("precision") or _default_precision()
         assert self.num_layers >= 1, "Listener should have at least 1 layer"
-        self.pLSTM_layer0 = pBLSTMLayer(input_feature_dim, hidden_size, rnn_unit=rnn_unit, dropout_rate=dropout_rate)
+        self.pLSTM_layer0 = pBLSTMLayer(input_feature_dim, hidden_size, rnn_unit=rnn_unit, dropout_rate=dropout_rate,
+                                        precision=self.precision)
         for i in range(1, self.num_layers):
-            setattr(self, "pLSTM_layer" + str(i), pBLSTMLayer(hidden_size * 2, hidden_size, rnn_unit=rnn_unit, dropout_rate=dropout_rate))
+            setattr(self, "pLSTM_layer" + str(i), pBLSTMLayer(hidden_size * 2, hidden_size, rnn_unit=rnn_unit, dropout_rate=dropout_rate,
+                                                              precision=self.precision))
         self._cache = _Cache()
 
     def forward(self, input_x, input_lengths=None):
@@ -231,7 +238,7 @@ class Listener(nn.Module):
         (listener_feature, enc_lengths)."""
         holders = [getattr(self, "pLSTM_layer" + str(i)).BLSTM for i in range(self.num_layers)]
         return _run_listener(input_x, holders, self.input_feature_dim, self.hidden_size, _mode_of(self.precision), self._cache,
-                             lengths=input_lengths)
+                             lengths=input_lengths, cell=self.cell)
 
 
 class Attention(nn.Module):
@@ -317,8 +324,9 @@ class Speller(nn.Module):
                  mlp_dim_in_attention, mlp_activate_in_attention, listener_hidden_size, multi_head, decode_mode,
                  use_gpu=True, **kwargs):
         super().__init__()
-        _check_unit(rnn_unit)
-        self.rnn_unit = nn.LSTM  # the reference stores the class (:156); serialize() writes it under "etype"
+        self.precision = kwargs.get("precision") or _default_precision()
+        self.cell = _check_unit(rnn_unit, self.precision)
+        self.rnn_unit = getattr(nn, self.cell)  # the reference stores the class (:156); serialize() writes it under "etype"
         self.hidden_size = hidden_size
         self.num_layers = num_layers
         self.max_label_len = max_label_len
@@ -326,7 +334,6 @@ class Speller(nn.Module):
         self.use_gpu = use_gpu
         self.float_type = torch.cuda.FloatTensor if use_gpu else torch.FloatTensor
         self.label_dim = vocab_size
-        self.precision = kwargs.get("precision") or _default_precision()
         if decode_mode not in (0, 1):
             raise NotImplementedError("decode_mode 2 (sampling, model/las_model.py:229-234) is not implemented on the B200 path")
         if (not use_mlp_in_attention or multi_head > 1) and self.precision != "fp32":
@@ -338,7 +345,7 @@ class Speller(nn.Module):
                 f"hidden_size ({hidden_size}) must equal 2*listener_hidden_size ({2 * listener_hidden_size}): the rnn input is "
                 "[one-hot || encoder feature] (model/las_model.py:165,198)"
             )
-        self.rnn_layer = LSTMWeights(vocab_size + hidden_size, hidden_size, num_layers=num_layers)
+        self.rnn_layer = LSTMWeights(vocab_size + hidden_size, hidden_size, num_layers=num_layers, cell=self.cell)
         self.attention = Attention(
             mlp_preprocess_input=use_mlp_in_attention,
             preprocess_mlp_dim=mlp_dim_in_attention,
@@ -353,7 +360,8 @@ class Speller(nn.Module):
     def _dims(self, b, u, e):
         at = self.attention
         return SpellerDims(b, u, e, self.hidden_size, self.num_layers, self.label_dim,
-                           at.preprocess_mlp_dim if at.mlp_preprocess_input else 0, at.multi_head, 0 if at.mlp_preprocess_input else 1)
+                           at.preprocess_mlp_dim if at.mlp_preprocess_input else 0, at.multi_head, 0 if at.mlp_preprocess_input else 1,
+                           _cabi.CELLS[self.cell])
 
     def _packed(self, lib, dims, mode, device, st):
         params = list(self.parameters())
@@ -413,7 +421,8 @@ class Speller(nn.Module):
             if enc_lengths is not None:
                 io.enc_lengths = enc_lengths.data_ptr()
             if state is not None:
-                io.h_state, io.c_state = state[0].data_ptr(), state[1].data_ptr()
+                io.h_state = state[0].data_ptr()
+                io.c_state = state[1].data_ptr() if state[1] is not None else None
             if word is not None:
                 io.word, io.context = word.data_ptr(), context.data_ptr()
             io.logp = logp.data_ptr()
@@ -431,13 +440,16 @@ class Speller(nn.Module):
         flat = _f32c(input_word).reshape(b, -1)
         word = flat[:, :v].contiguous()
         context = flat[:, v:].contiguous()
+        lstm = self.cell == "LSTM"
         if last_hidden_state is None:
             h = torch.zeros(self.num_layers, b, self.hidden_size, dtype=torch.float32, device=flat.device)
-            c = torch.zeros_like(h)
-        else:
+            c = torch.zeros_like(h) if lstm else None
+        elif lstm:
             h, c = (_f32c(t).clone() for t in last_hidden_state)
+        else:  # nn.GRU / nn.RNN carry a single hidden-state tensor
+            h, c = _f32c(last_hidden_state).clone(), None
         logp, attn, _ = self._decode(listener_feature, 1, state=(h, c), word=word, context=context)
-        return logp[0], (h, c), context, list(attn[0].unbind(0))
+        return logp[0], ((h, c) if lstm else h), context, list(attn[0].unbind(0))
 
     def forward(self, listener_feature, ground_truth=None, teacher_force_rate=0.9, enc_lengths=None):
         if ground_truth is None:

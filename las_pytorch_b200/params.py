@@ -19,14 +19,19 @@ import torch.nn as nn
 
 
 class LSTMWeights(nn.Module):
-    """Parameter layout of torch.nn.LSTM(input_size, hidden_size, num_layers, bidirectional).
+    """Parameter layout of torch.nn.LSTM / nn.GRU / nn.RNN(input_size, hidden_size, num_layers, bidirectional).
 
-    Names: weight_ih_l{k}[_reverse] [4H,in], weight_hh_l{k}[_reverse] [4H,H], bias_ih_l{k}[_reverse],
-    bias_hh_l{k}[_reverse]; gate order i,f,g,o; all U(-1/sqrt(H), 1/sqrt(H)) drawn in registration order.
+    Names: weight_ih_l{k}[_reverse] [G*H,in], weight_hh_l{k}[_reverse] [G*H,H], bias_ih_l{k}[_reverse],
+    bias_hh_l{k}[_reverse]; G = 4 (LSTM, gates i,f,g,o), 3 (GRU, gates r,z,n) or 1 (RNN, tanh); all
+    U(-1/sqrt(H), 1/sqrt(H)) drawn in registration order, exactly as torch's RNNBase does.
     """
 
-    def __init__(self, input_size, hidden_size, num_layers=1, bidirectional=False):
+    GATES = {"LSTM": 4, "GRU": 3, "RNN": 1}
+
+    def __init__(self, input_size, hidden_size, num_layers=1, bidirectional=False, cell="LSTM"):
         super().__init__()
+        self.cell = cell
+        gates = self.GATES[cell]
         self.input_size = input_size
         self.hidden_size = hidden_size
         self.num_layers = num_layers
@@ -36,10 +41,10 @@ class LSTMWeights(nn.Module):
             in_dim = input_size if layer == 0 else hidden_size * dirs
             for d in range(dirs):
                 sfx = "_reverse" if d == 1 else ""
-                self.register_parameter(f"weight_ih_l{layer}{sfx}", nn.Parameter(torch.empty(4 * hidden_size, in_dim)))
-                self.register_parameter(f"weight_hh_l{layer}{sfx}", nn.Parameter(torch.empty(4 * hidden_size, hidden_size)))
-                self.register_parameter(f"bias_ih_l{layer}{sfx}", nn.Parameter(torch.empty(4 * hidden_size)))
-                self.register_parameter(f"bias_hh_l{layer}{sfx}", nn.Parameter(torch.empty(4 * hidden_size)))
+                self.register_parameter(f"weight_ih_l{layer}{sfx}", nn.Parameter(torch.empty(gates * hidden_size, in_dim)))
+                self.register_parameter(f"weight_hh_l{layer}{sfx}", nn.Parameter(torch.empty(gates * hidden_size, hidden_size)))
+                self.register_parameter(f"bias_ih_l{layer}{sfx}", nn.Parameter(torch.empty(gates * hidden_size)))
+                self.register_parameter(f"bias_hh_l{layer}{sfx}", nn.Parameter(torch.empty(gates * hidden_size)))
         self.reset_parameters()
 
     def reset_parameters(self):

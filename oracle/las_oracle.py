@@ -55,19 +55,35 @@ def lstm_cell(pre, c):
     return h_new, c_new
 
 
+def rnn_cell_step(px, ph, h, c):
+    """One step of the cell the weights describe -- torch nn.LSTM / nn.GRU / nn.RNN equations.  px = x . W_ih^T + b_ih,
+    ph = h . W_hh^T + b_hh, both [B, G*H]; G = 4: LSTM (i,f,g,o), 3: GRU (r,z,n), 1: RNN (tanh).  The reference builds the
+    module with getattr(nn, rnn_unit.upper()) (model/las_model.py:69,156)."""
+    hdim = h.shape[1]
+    gates = px.shape[1] // hdim
+    if gates == 4:
+        return lstm_cell(px + ph, c)
+    if gates == 3:
+        r = _sigmoid(px[:, :hdim] + ph[:, :hdim])
+        z = _sigmoid(px[:, hdim:2 * hdim] + ph[:, hdim:2 * hdim])
+        n = np.tanh(px[:, 2 * hdim:] + r * ph[:, 2 * hdim:])
+        return (1 - z) * n + z * h, c
+    return np.tanh(px + ph), c
+
+
 def lstm_direction(xr, w_ih, w_hh, b_ih, b_hh, reverse):
-    """One direction of a 1-layer nn.LSTM(batch_first=True) over xr [B,Tl,K] -> [B,Tl,H]."""
+    """One direction of a 1-layer nn.LSTM / nn.GRU / nn.RNN(batch_first=True) over xr [B,Tl,K] -> [B,Tl,H]."""
     b, tl, _ = xr.shape
     hdim = w_hh.shape[1]
     # input projection for all timesteps at once (SURVEY.md row a3)
-    p = xr.reshape(b * tl, -1) @ w_ih.T + (b_ih + b_hh)
-    p = p.reshape(b, tl, 4 * hdim)
+    p = xr.reshape(b * tl, -1) @ w_ih.T + b_ih
+    p = p.reshape(b, tl, -1)
     h = np.zeros((b, hdim), dtype=xr.dtype)
     c = np.zeros((b, hdim), dtype=xr.dtype)
     out = np.empty((b, tl, hdim), dtype=xr.dtype)
     steps = range(tl - 1, -1, -1) if reverse else range(tl)
     for t in steps:  # recurrence (row a4)
-        h, c = lstm_cell(p[:, t] + h @ w_hh.T, c)
+        h, c = rnn_cell_step(p[:, t], h @ w_hh.T + b_hh, h, c)
         out[:, t] = h
     return out
 
@@ -218,13 +234,9 @@ def speller_forward(
     for s in range(steps):
         inp = np.concatenate([word, ctx], axis=-1)  # [B, V+E] (:198,:236)
         for l in range(num_layers):  # stacked cells, seq-len 1 (:179)
-            pre = (
-                inp @ _w(sd, f"{prefix}.rnn_layer.weight_ih_l{l}", dtype).T
-                + _w(sd, f"{prefix}.rnn_layer.bias_ih_l{l}", dtype)
-                + h[l] @ _w(sd, f"{prefix}.rnn_layer.weight_hh_l{l}", dtype).T
-                + _w(sd, f"{prefix}.rnn_layer.bias_hh_l{l}", dtype)
-            )
-            h[l], c[l] = lstm_cell(pre, c[l])
+            px = inp @ _w(sd, f"{prefix}.rnn_layer.weight_ih_l{l}", dtype).T + _w(sd, f"{prefix}.rnn_layer.bias_ih_l{l}", dtype)
+            ph = h[l] @ _w(sd, f"{prefix}.rnn_layer.weight_hh_l{l}", dtype).T + _w(sd, f"{prefix}.rnn_layer.bias_hh_l{l}", dtype)
+            h[l], c[l] = rnn_cell_step(px, ph, h[l], c[l])
             inp = h[l]
         score, ctx = attention(h[-1], enc, psi, sd, dtype, prefix, enc_lengths=enc_lengths)  # (:180)
         logp = log_softmax(np.concatenate([h[-1], ctx], axis=-1) @ w_cd.T + b_cd)  # (:181-182)

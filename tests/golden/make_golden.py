@@ -83,6 +83,10 @@ def main():
         ("tinymh_greedy_g3", "tiny_mh", 3, 32, 10, "greedy", 3.0, True),
         ("tinynomlp_tf_g3", "tiny_nomlp", 3, 32, 6, "tf", 3.0, True),
         ("tinynomlp_greedy_g3", "tiny_nomlp", 3, 32, 10, "greedy", 3.0, True),
+        ("tinygru_tf_g3", "tiny_gru", 3, 32, 6, "tf", 3.0, True),
+        ("tinygru_greedy_g3", "tiny_gru", 3, 32, 10, "greedy", 3.0, True),
+        ("tinyrnn_tf_g3", "tiny_rnn", 3, 32, 6, "tf", 3.0, True),
+        ("tinyrnn_greedy_g3", "tiny_rnn", 3, 32, 10, "greedy", 3.0, True),
     ]
     only = [a for a in sys.argv[1:] if not a.startswith("-")]
     if only:  # regenerate just the named cases (the others stay byte-identical in git)

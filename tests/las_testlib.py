@@ -21,6 +21,9 @@ CONFIGS = {
     # Speller / Attention variants of SURVEY.md section 8 row f4 (fp32 mode): two heads + dim_reduce; no MLP in the attention
     "tiny_mh": dict(F=40, H=16, L=2, sl=2, V=30, D=16, heads=2),
     "tiny_nomlp": dict(F=40, H=16, L=2, sl=2, V=30, D=16, use_mlp=False),
+    # rnn_unit variants (the reference resolves the string with getattr(nn, rnn_unit.upper()), model/las_model.py:69,156)
+    "tiny_gru": dict(F=40, H=16, L=2, sl=2, V=30, D=16, unit="GRU"),
+    "tiny_rnn": dict(F=40, H=16, L=2, sl=2, V=30, D=16, unit="RNN"),
     # README small LAS (listener 128x2, speller 256x2) and the paper-size model
     "small": dict(F=40, H=128, L=2, sl=2, V=30, D=64),
     "paper": dict(F=40, H=256, L=3, sl=2, V=30, D=64),
@@ -35,9 +38,10 @@ def build_model(cfg, max_label_len, decode_mode=1, seed=17, gain=1.0, precision=
     c = CONFIGS[cfg] if isinstance(cfg, str) else cfg
     torch.manual_seed(seed)
     extra = {} if module.__name__.startswith("model") else {"precision": precision}
-    listener = module.Listener(input_feature_dim=c["F"], hidden_size=c["H"], num_layers=c["L"], rnn_unit="LSTM",
+    unit = c.get("unit", "LSTM")
+    listener = module.Listener(input_feature_dim=c["F"], hidden_size=c["H"], num_layers=c["L"], rnn_unit=unit,
                                use_gpu=False, **extra)
-    speller = module.Speller(vocab_size=c["V"], hidden_size=2 * c["H"], rnn_unit="LSTM", num_layers=c["sl"],
+    speller = module.Speller(vocab_size=c["V"], hidden_size=2 * c["H"], rnn_unit=unit, num_layers=c["sl"],
                              max_label_len=max_label_len, use_mlp_in_attention=c.get("use_mlp", True), mlp_dim_in_attention=c["D"],
                              mlp_activate_in_attention="relu", listener_hidden_size=c["H"], multi_head=c.get("heads", 1),
                              decode_mode=decode_mode, use_gpu=False, **extra)

@@ -89,8 +89,14 @@ def test_constructor_contract():
         lp.Listener(40, 16, 0, "LSTM", True)
     with pytest.raises(ValueError):
         lp.Speller(30, 48, "LSTM", 2, 7, True, 16, "relu", 16, 1, 1)  # Hs != 2H
+    gru = lp.Listener(40, 16, 2, "GRU", True)  # rnn_unit as the reference resolves it: getattr(nn, rnn_unit.upper())
+    assert gru.pLSTM_layer0.BLSTM.weight_ih_l0.shape == (3 * 16, 80) and gru.pLSTM_layer1.BLSTM.weight_hh_l0_reverse.shape == (48, 16)
+    assert list(gru.state_dict()) == list(torch.nn.GRU(80, 16, 1, bidirectional=True).state_dict().__class__(
+        (f"pLSTM_layer{i}.BLSTM.{k}", None) for i in range(2) for k in torch.nn.GRU(80, 16, 1, bidirectional=True).state_dict()))
     with pytest.raises(NotImplementedError):
-        lp.Listener(40, 16, 2, "GRU", True)
+        lp.Listener(40, 16, 2, "GRU", True, precision="bf16")  # GRU / RNN cells run in the fp32 mode only
+    with pytest.raises(NotImplementedError):
+        lp.Listener(40, 16, 2, "QRNN", True)
 
 
 def test_no_cpu_fallback_and_single_rng_draw():

@@ -38,6 +38,8 @@ def test_numpy_oracle_matches_reference(name):
         out = O.las_forward(g["x"], sd, cfg["L"], cfg["sl"], S, ground_truth=g["labels"] if mode == "tf" else None,
                             teacher_forced=(mode == "tf"), decode_mode=0 if mode == "raw" else 1, dtype=dtype)
         scale = 100.0 if float(g["gain"]) >= 6 and tag == "f32" else 1.0  # gain-6 is chaotic even fp32-vs-fp64
+        if tag == "f32":  # no fp32 restatement can be closer to the reference's fp32 run than that run is to its own fp64 run
+            scale = max(scale, 20.0 * float(np.abs(g["logp_f32"] - g["logp_f64"]).max()) / tol_lp)
         assert np.abs(out["enc"] - g[f"enc_{tag}"]).max() <= tol_enc * scale
         assert np.abs(out["logp"] - g[f"logp_{tag}"]).max() <= tol_lp * scale
         assert np.abs(out["attn"] - g[f"attn_{tag}"]).max() <= tol_lp * scale
@@ -45,11 +47,11 @@ def test_numpy_oracle_matches_reference(name):
             assert np.array_equal(out["tokens"], g["logp_f64"].argmax(-1))
 
 
-@pytest.mark.parametrize("name", [c for c in CASES if not c.startswith(("paper", "tinymh", "tinynomlp"))])
+@pytest.mark.parametrize("name", [c for c in CASES if not c.startswith(("paper", "tinymh", "tinynomlp", "tinygru", "tinyrnn"))])
 def test_torch_restatement_matches_reference(name):
     """Same torch ops in the same order as the reference -> expected bit-identical on the same machine.  (The torch
-    restatement is the timed CPU baseline of the benchmarked single-head configuration; the Attention variants are covered by the
-    numpy oracle above.)"""
+    restatement is the timed CPU baseline of the benchmarked single-head LSTM configuration; the Attention / rnn_unit variants are
+    covered by the numpy oracle above.)"""
     g, cfg, sd = load_case(name)
     mode = str(g["mode"])
     S = g["logp_f32"].shape[0]

@@ -20,7 +20,7 @@ def main():
         c = tl.CONFIGS[cfg]
         S = g["logp_f64"].shape[0]
         for prec in ("fp32", "bf16"):
-            if prec == "bf16" and (c.get("heads", 1) > 1 or not c.get("use_mlp", True)):
+            if prec == "bf16" and (c.get("heads", 1) > 1 or not c.get("use_mlp", True) or c.get("unit", "LSTM") != "LSTM"):
                 continue  # attention variants run in the fp32 mode only
             las = tl.build_model(cfg, max_label_len=S, decode_mode=0 if mode == "raw" else 1, seed=int(g["seed"]), gain=float(g["gain"]), precision=prec)
             sd = {k[2:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("w:")}
