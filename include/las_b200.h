@@ -54,7 +54,12 @@ enum {
 /* decode feedback, model/las_model.py:216-234 */
 enum {
   LAS_DECODE_RAW = 0,    /* decode_mode 0: feed the log-prob vector back */
-  LAS_DECODE_GREEDY = 1  /* decode_mode 1: feed one-hot(argmax) back (ties -> lowest index) */
+  LAS_DECODE_GREEDY = 1, /* decode_mode 1: feed one-hot(argmax) back (ties -> lowest index) */
+  LAS_DECODE_SAMPLE = 2  /* decode_mode 2 (:229-234): feed one-hot(sample) back.  The reference draws from Categorical(raw_pred),
+                            i.e. it hands the LOG-probabilities to `probs`, which torch renormalises: p_i = logp_i / sum_j logp_j
+                             -- reproduced.  Its draws come from torch's global generator; here they come from
+                            a counter-based generator keyed on (io->sample_seed, step, utterance), so a run is reproducible from
+                            its seed but not draw-for-draw equal to the reference's.  `tokens` then holds the sampled tokens. */
 };
 
 int las_abi_version(void);
@@ -174,6 +179,7 @@ typedef struct las_decode_io {
   const int32_t* gt_index;    /* nullable [B,S] int32: same, as label indices (one-hot implied) */
   int32_t gt_steps;           /* S dimension of gt_dense / gt_index (>= steps) */
   const int32_t* enc_lengths; /* nullable [B]: attention length mask extension */
+  uint64_t sample_seed;       /* LAS_DECODE_SAMPLE: seed of the counter-based generator */
   /* recurrent state, in/out, nullable: NULL = start from zeros / <sos> / enc[:,0,:] (:193-200) */
   float* h_state;             /* [sl,B,Hs] */
   float* c_state;             /* [sl,B,Hs] */

@@ -17,6 +17,7 @@ MODE_FP32 = 0
 MODE_BF16 = 1
 DECODE_RAW = 0
 DECODE_GREEDY = 1
+DECODE_SAMPLE = 2
 CELL_LSTM, CELL_GRU, CELL_RNN = 0, 1, 2
 CELLS = {"LSTM": CELL_LSTM, "GRU": CELL_GRU, "RNN": CELL_RNN}
 
@@ -50,7 +51,7 @@ class DecodeIO(C.Structure):
     _fields_ = [
         ("enc", C.c_void_p), ("psi", C.c_void_p),
         ("gt_dense", C.c_void_p), ("gt_index", C.c_void_p), ("gt_steps", C.c_int32),
-        ("enc_lengths", C.c_void_p),
+        ("enc_lengths", C.c_void_p), ("sample_seed", C.c_uint64),
         ("h_state", C.c_void_p), ("c_state", C.c_void_p), ("word", C.c_void_p), ("context", C.c_void_p),
         ("logp", C.c_void_p), ("attn", C.c_void_p), ("tokens", C.c_void_p),
     ]

@@ -79,6 +79,7 @@ struct DecParams {
   int b0;
   int U, E, Hs, sl, V, D, steps, decode_mode, relu, gt_steps, ncl, k_in_smem;
   int ab_flags;     // test hook (las_debug_set_option(5, v)): bit 0 = W_phi from shared memory instead of registers
+  unsigned long long sample_seed;  // LAS_DECODE_SAMPLE
   int word_gather;  // 1: the fed-back word is an index (greedy argmax / gt_index); 0: a dense vector (part 1b)
   int ctx_tmem;     // 1: enc[b]^T is resident in the attention CTA's tensor memory and the context is a UMMA
   int nstages, stage_bytes;  // activation slots: [64 batch rows x 64 bf16], 128-byte swizzled; last slot = word atom
@@ -846,6 +847,16 @@ __device__ void attention_role(const DecParams& p, uint8_t* smem, int b) {
         const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
         if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
       }
+      if (p.decode_mode == LAS_DECODE_SAMPLE && !p.gt_index && !p.gt_dense) {
+        // decode_mode 2 (:229-234): feed back (and report) a draw from Categorical(probs = log-probs); s_logit -> log-probs first
+        __syncwarp();
+        for (int v = lane; v < V; v += 32) s_logit[v] -= lse;
+        __syncwarp();
+        if (lane == 0) bi = las_sample_logp_as_probs(s_logit, V, las_uniform(p.sample_seed, (uint32_t)s, (uint32_t)gb));
+        bi = __shfl_sync(0xffffffffu, bi, 0);
+        for (int v = lane; v < V; v += 32) s_logit[v] += lse;  // the raw-feedback branch below expects logits
+        __syncwarp();
+      }
       if (lane == 0 && p.tokens) p.tokens[(size_t)s * p.Bfull + gb] = bi;
       if (p.word_gather) {
         // the word is an index: layer 0's epilogue adds the matching column of W_word itself
@@ -1152,7 +1163,8 @@ int fast_speller_decode(const las_decode_io* io, const void* packed_f32, const v
     p.tok_ll = w.tok_ll;
     // the fed-back word is an index (greedy argmax / index teacher forcing) unless a dense vector is asked for
     p.ab_flags = g_dec_ab_flags;
-    p.word_gather = io->gt_dense ? 0 : (io->gt_index ? 1 : (decode_mode == LAS_DECODE_GREEDY ? 1 : 0));
+    p.word_gather = io->gt_dense ? 0 : (io->gt_index ? 1 : (decode_mode != LAS_DECODE_RAW ? 1 : 0));
+    p.sample_seed = io->sample_seed;
     p.trace = fast_get_trace() ? fast_get_trace() + 512 : nullptr;  // needs 5 roles x 32 steps x 8 stamps behind the recurrence trace
 
     {

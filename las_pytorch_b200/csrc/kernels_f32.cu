@@ -376,6 +376,9 @@ __global__ void __launch_bounds__(256) attend_f32_kernel(AttendArgs a) {
     }
     best = bi;
     if (lane == 0) {
+      // decode_mode 2 (:229-234): the word fed back (and reported) is a draw from Categorical(probs = log-probs)
+      if (a.decode_mode == LAS_DECODE_SAMPLE && !a.gt_dense_step && !a.gt_index_step)
+        best = las_sample_logp_as_probs(s_logit, a.V, las_uniform(a.sample_seed, (uint32_t)a.step, (uint32_t)b));
       s_red[0] = __int_as_float(best);
       if (a.token_out) a.token_out[b] = best;
     }

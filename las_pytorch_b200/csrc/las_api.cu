@@ -333,6 +333,8 @@ static int speller_decode_f32(const las_decode_io* io, const void* packed, const
       t.gt_index_ld = io->gt_steps;
     }
     t.decode_mode = decode_mode;
+    t.sample_seed = io->sample_seed;
+    t.step = s;
     LAS_TRY(launch_attend_f32(t, st));
   }
   if (io->h_state && (io->c_state || d->cell != LAS_CELL_LSTM)) {
@@ -549,8 +551,8 @@ int las_speller_decode(const las_decode_io* io, const void* packed, const las_sp
   LAS_REQUIRE(io->enc && io->logp, "io->enc and io->logp are required");
   LAS_REQUIRE(steps >= 0, "steps must be >= 0");
   LAS_REQUIRE(mode == LAS_MODE_FP32 || mode == LAS_MODE_BF16, "unknown mode %d", mode);
-  LAS_REQUIRE(decode_mode == LAS_DECODE_RAW || decode_mode == LAS_DECODE_GREEDY,
-              "decode_mode %d is not supported on the device path (0 = raw, 1 = greedy)", decode_mode);
+  LAS_REQUIRE(decode_mode == LAS_DECODE_RAW || decode_mode == LAS_DECODE_GREEDY || decode_mode == LAS_DECODE_SAMPLE,
+              "decode_mode %d is not supported (0 = raw, 1 = greedy, 2 = sample)", decode_mode);
   LAS_REQUIRE(!(io->gt_dense || io->gt_index) || io->gt_steps >= steps, "ground truth has %d steps, %d requested", io->gt_steps, steps);
   LAS_REQUIRE(d->cell != LAS_CELL_LSTM || (io->h_state == nullptr) == (io->c_state == nullptr), "h_state and c_state must be given together");
   LAS_REQUIRE((io->word == nullptr) == (io->context == nullptr), "word and context must be given together");

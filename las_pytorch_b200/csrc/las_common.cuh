@@ -71,6 +71,27 @@ struct ProfScope {
   ~ProfScope();
 };
 
+// ---- counter-based uniform generator for LAS_DECODE_SAMPLE: splitmix64 of (seed, step, utterance) -> [0, 1) ----------
+__host__ __device__ __forceinline__ float las_uniform(uint64_t seed, uint32_t step, uint32_t b) {
+  uint64_t z = seed + 0x9E3779B97F4A7C15ull * ((uint64_t)step + 1) + 0xD1B54A32D192ED03ull * ((uint64_t)b + 1);
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z ^= z >> 31;
+  return (float)(z >> 40) * (1.0f / 16777216.0f);
+}
+// index drawn from p_i = lp_i / sum_j lp_j (what Categorical(probs=log-probs) samples from), inverse-CDF over V entries
+__host__ __device__ __forceinline__ int las_sample_logp_as_probs(const float* lp, int V, float u) {
+  float tot = 0.f;
+  for (int v = 0; v < V; ++v) tot += lp[v];
+  const float target = u * tot;  // tot < 0: the cumulative sum decreases towards tot
+  float acc = 0.f;
+  for (int v = 0; v < V; ++v) {
+    acc += lp[v];
+    if (acc <= target) return v;
+  }
+  return V - 1;
+}
+
 // ---- device math ---------------------------------------------------------------------------------------
 __device__ __forceinline__ float sigmoid_precise(float x) { return 1.0f / (1.0f + expf(-x)); }
 

@@ -61,6 +61,8 @@ struct AttendArgs {
   const int32_t* gt_index_step; // nullable [B] stride gt_index_ld
   int gt_index_ld;
   int decode_mode;
+  unsigned long long sample_seed;  // LAS_DECODE_SAMPLE
+  int step;
 };
 int launch_attend_f32(const AttendArgs& a, cudaStream_t st);
 

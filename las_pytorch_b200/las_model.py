@@ -10,8 +10,9 @@ Extra keyword accepted everywhere the reference swallows **kwargs: `precision` =
 
 Variants of the reference classes: multi_head > 1 (with attention.dim_reduce) and use_mlp_in_attention=False run in the
 fp32 mode only, and so do the GRU / RNN cells (`rnn_unit`; the reference does getattr(nn, rnn_unit.upper()), :69,156) -- the bf16
-mode raises and says so.  Not on this path (raise NotImplementedError instead of silently running something else):
-decode_mode 2 (sampling), training/backward.
+mode raises and says so.  decode_mode 2 samples the fed-back word on the device from the reference's distribution
+(Categorical(probs=log-probs)) with a counter-based generator seeded from torch's global generator, so runs are
+reproducible under torch.manual_seed but not draw-for-draw equal to the reference.  Not on this path: training/backward.
 """
 from __future__ import annotations
 
@@ -334,8 +335,8 @@ class Speller(nn.Module):
         self.use_gpu = use_gpu
         self.float_type = torch.cuda.FloatTensor if use_gpu else torch.FloatTensor
         self.label_dim = vocab_size
-        if decode_mode not in (0, 1):
-            raise NotImplementedError("decode_mode 2 (sampling, model/las_model.py:229-234) is not implemented on the B200 path")
+        if decode_mode not in (0, 1, 2):
+            raise ValueError(f"decode_mode must be 0 (raw), 1 (greedy) or 2 (sample), got {decode_mode}")
         if (not use_mlp_in_attention or multi_head > 1) and self.precision != "fp32":
             raise NotImplementedError(
                 "the bf16 mode implements single-head MLP attention only; construct the Speller with precision='fp32' for "
@@ -420,6 +421,9 @@ class Speller(nn.Module):
                 io.gt_steps = gt_index.size(1)
             if enc_lengths is not None:
                 io.enc_lengths = enc_lengths.data_ptr()
+            if int(self.decode_mode) == 2 and gt_dense is None and gt_index is None:
+                # one draw from torch's global generator seeds the device-side generator (reproducible under torch.manual_seed)
+                io.sample_seed = int(torch.randint(0, 2 ** 62, (1,)).item())
             if state is not None:
                 io.h_state = state[0].data_ptr()
                 io.c_state = state[1].data_ptr() if state[1] is not None else None

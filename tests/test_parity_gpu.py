@@ -323,8 +323,8 @@ def test_error_paths_raise_instead_of_falling_back():
         ours.Speller(30, 48, "LSTM", 2, 5, True, 16, "relu", 16, 1, 1)
     with pytest.raises(NotImplementedError):
         ours.Listener(40, 16, 2, "QRNN")  # only what getattr(nn, ...) would give the reference: LSTM, GRU, RNN
-    with pytest.raises(NotImplementedError):
-        ours.Speller(30, 32, "LSTM", 2, 5, True, 16, "relu", 16, 1, 2)  # decode_mode 2 (sampling)
+    with pytest.raises(ValueError):
+        ours.Speller(30, 32, "LSTM", 2, 5, True, 16, "relu", 16, 1, 3)  # decode_mode is 0, 1 or 2 in the reference
     if "bf16" in precisions():
         with pytest.raises(NotImplementedError, match="fp32"):
             ours.Speller(30, 32, "LSTM", 2, 5, True, 16, "relu", 16, 2, 1, precision="bf16")  # multi_head in bf16 mode
@@ -337,6 +337,45 @@ def test_error_paths_raise_instead_of_falling_back():
     import ctypes as C
     assert lib.las_listener_forward(None, None, C.byref(d), 0, None, None, 0, None) != 0
     assert b"" != lib.las_last_error()
+
+
+@pytest.mark.parametrize("precision", precisions())
+def test_decode_mode_2_sampling(precision):
+    """decode_mode 2 (model/las_model.py:229-234): the fed-back word is a draw from Categorical(probs = log-probs), i.e.
+    p_i = logp_i / sum_j logp_j.  The draws cannot equal torch's generator stream, so the check is:
+    (1) re-scoring the sampled tokens through the oracle in teacher-forced mode reproduces every log-prob (the sampled word really
+    is what was fed back); (2) runs are reproducible under torch.manual_seed and differ across seeds; (3) first-step draws over
+    many identical utterances follow the reference's (inverted) distribution."""
+    c = tl.CONFIGS["small"]
+    B, T, S = 6, 64, 10
+    las = tl.build_model("small", max_label_len=S, decode_mode=2, seed=59, gain=3.0, precision=precision)
+    sd = tl.state_dict_numpy(las)
+    x, _ = tl.make_inputs(B, T, c["F"], S, c["V"], seed=59)
+    las = las.cuda()
+    torch.manual_seed(1234)
+    preds, _ = las(x.cuda(), None, 0.0, is_training=False)
+    toks = las.speller.last_tokens.cpu().numpy().T  # [B,S] sampled tokens
+    ref = O.las_forward(x.numpy(), sd, c["L"], c["sl"], S, ground_truth=toks, teacher_forced=True, dtype=np.float64)
+    assert np.abs(torch.stack(preds).cpu().numpy() - ref["logp"]).max() <= TOL[precision]["logp"]
+    assert not np.array_equal(toks, ref["tokens"].T)  # sampling from the inverted distribution is not the argmax path
+    torch.manual_seed(1234)
+    las(x.cuda(), None, 0.0, is_training=False)
+    assert np.array_equal(las.speller.last_tokens.cpu().numpy().T, toks)
+    torch.manual_seed(4321)
+    las(x.cuda(), None, 0.0, is_training=False)
+    assert not np.array_equal(las.speller.last_tokens.cpu().numpy().T, toks)
+    # distribution of the first draw: 64 copies of one utterance x 40 seeds = 2560 draws
+    xr = x[:1].repeat(64, 1, 1).cuda()
+    counts = np.zeros(c["V"])
+    for seed in range(40):
+        torch.manual_seed(seed)
+        las(xr, None, 0.0, is_training=False)
+        counts += np.bincount(las.speller.last_tokens[0].cpu().numpy(), minlength=c["V"])
+    lp0 = ref["logp"][0, 0]
+    p = lp0 / lp0.sum()
+    n = counts.sum()
+    z = (counts - n * p) / np.sqrt(n * p * (1 - p))
+    assert np.abs(z).max() < 5.0, (counts, n * p)
 
 
 def test_bf16_batch_larger_than_one_decoder_launch():
