@@ -172,7 +172,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default=None, choices=["bf16", "fp32"])
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
-    ap.add_argument("--cpu-sample", type=int, default=8, help="utterances in the bounded CPU-baseline sample")
+    ap.add_argument("--cpu-sample", type=int, default=0, help="utterances in the CPU-baseline sample (0 = the workload's whole batch)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
@@ -188,7 +188,8 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        val, info = cpu_reference_arm(wl, args.cpu_sample, args.steps, args.warmup)
+        # one step = the whole workload batch on the host cores (1-20 s depending on the host): at most 10 timed steps, 1 warm-up
+        val, info = cpu_reference_arm(wl, args.cpu_sample or wl["B"], min(args.steps, 10), min(args.warmup, 1))
         out = dict(base, impl="reference", value=val, ms_per_step=info["ms_per_step"], dtype="f32",
                    config={"workload": f"{args.workload}: {wl['desc']}", "per_step_sample": info["sample"], "device": "host CPU"},
                    cpu_baseline={"value": val, "unit": "audio-s/s", "cores": info["cores"], "kind": "port", "sample": info["sample"],
@@ -409,7 +410,7 @@ def main():
                     "pipeline": "double-buffered: H2D of step i+1 on a copy stream during step i, D2H read event-synchronised one step later; wall clock"},
                roofline=roofline, rooflines=rooflines, token_checksum=float(chk))
     if world == 1 and not args.no_cpu_baseline:
-        v, info = cpu_reference_arm(wl, args.cpu_sample, 1, 1)
+        v, info = cpu_reference_arm(wl, args.cpu_sample or wl["B"], 5, 1)  # the whole batch: one warm-up + five timed passes (~10 s)
         out["cpu_baseline"] = {"value": v, "unit": "audio-s/s", "cores": info["cores"], "kind": "port", "sample": info["sample"],
                                "us_per_decoder_step": info["us_per_decoder_step"], "listener_ms": info["listener_ms"]}
     sys.stdout.flush()
