@@ -378,6 +378,40 @@ def test_decode_mode_2_sampling(precision):
     assert np.abs(z).max() < 5.0, (counts, n * p)
 
 
+@pytest.mark.parametrize("precision", precisions())
+def test_single_layer_speller_and_padded_index_targets(precision):
+    """A one-layer speller (the same LSTM CTA is both the layer that takes [word | context] and the one that feeds the attention)
+    and index targets with padding: index -1 feeds the zero vector, exactly like an all-zero row of the reference's one-hot tensor
+    (what collate_fn pads with, utils/data.py:133-136)."""
+    cfg = dict(F=40, H=32, L=2, sl=1, V=30, D=16)
+    B, T, S = 5, 32, 7
+    las = tl.build_model(cfg, max_label_len=S, seed=61, gain=3.0, precision=precision)
+    sd = tl.state_dict_numpy(las)
+    x, labels = tl.make_inputs(B, T, cfg["F"], S, cfg["V"], seed=61)
+    dense = tl.onehot(labels, cfg["V"]).clone()
+    padded = labels.clone()
+    dense[:, -2:, :] = 0   # padded steps: all-zero rows
+    padded[:, -2:] = -1
+    ref = O.las_forward(x.numpy(), sd, cfg["L"], cfg["sl"], S, ground_truth=dense.numpy().astype(np.float64), teacher_forced=True, dtype=np.float64)
+    las = las.cuda()
+    tol = TOL[precision]["logp"]
+    for gt in (dense.cuda(), padded.cuda()):
+        np.random.seed(0)
+        preds, _ = las(x.cuda(), gt, 1.1, is_training=True)
+        assert np.abs(torch.stack(preds).cpu().numpy() - ref["logp"]).max() <= tol
+    greedy_ref = O.las_forward(x.numpy(), sd, cfg["L"], cfg["sl"], S, dtype=np.float64)
+    preds, _ = las(x.cuda(), None, 0.0, is_training=False)
+    lg = torch.stack(preds).cpu().numpy()
+    if precision == "fp32":
+        assert np.abs(lg - greedy_ref["logp"]).max() <= tol
+    else:
+        # a 32-unit net flips near-tied tokens under bf16 rounding and then follows another trajectory; what must hold is that every
+        # step's log-probs are the oracle's for the tokens that were actually fed back
+        toks = las.speller.last_tokens.cpu().numpy().T
+        rescored = O.las_forward(x.numpy(), sd, cfg["L"], cfg["sl"], S, ground_truth=toks, teacher_forced=True, dtype=np.float64)
+        assert np.abs(lg - rescored["logp"]).max() <= tol
+
+
 def test_bf16_batch_larger_than_one_decoder_launch():
     """The persistent decoder covers at most 64 utterances per launch (one attention CTA each); larger batches are decoded
     in chunks.  70 utterances must equal the same utterances decoded as 64 + 6."""
