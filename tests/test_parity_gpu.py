@@ -93,6 +93,12 @@ def test_matches_reference_golden(name, precision):
         assert np.array_equal(tok[safe], ref_tok[safe])  # argmax bit-exact wherever the oracle's margin is meaningful
     elif precision == "fp32":
         assert (tok == ref_tok).mean() >= 0.99
+    elif mode == "greedy":
+        # bf16, free running: whatever trajectory the decoder follows, each step's log-probs must be the oracle's for the tokens that
+        # were fed back (teacher-forced re-scoring of our own output)
+        rescored = O.las_forward(g["x"], tl.state_dict_numpy(las), cfg["L"], cfg["sl"], logp.shape[0], ground_truth=tok.T,
+                                 teacher_forced=True, dtype=np.float64)
+        assert np.abs(logp - rescored["logp"]).max() <= tol["logp"] * slack
     assert np.abs(np.exp(logp).sum(-1) - 1).max() < 1e-4
     assert np.abs(attn.sum(-1) - 1).max() < 1e-4
 
