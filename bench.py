@@ -322,6 +322,7 @@ def main():
                 xd[nxt].copy_(x_host, non_blocking=True)
                 in_ready[nxt].record(copy_stream)
         main.wait_event(in_ready[cur])
+        flush.zero_()  # cold L2 for every step here too; the 256 MiB write (~0.07 ms) is inside this wall-clock region
         las(xd[cur], None, 0.0, is_training=False)
         in_free[cur].record(main)
         tok_host[cur].copy_(las.speller.last_tokens, non_blocking=True)
@@ -407,7 +408,7 @@ def main():
                us_per_decoder_step=1e3 * spl_ms / S, listener_ms=lis_ms, speller_ms=spl_ms, phase_ms=per_step,
                clocks=clocks, gpu_launches=launches,
                e2e={"value": e2e_value, "unit": "audio-s/s", "h2d_bytes_per_step": x_host.numel() * 4, "d2h_bytes_per_step": tok_host[0].numel() * 4,
-                    "pipeline": "double-buffered: H2D of step i+1 on a copy stream during step i, D2H read event-synchronised one step later; wall clock"},
+                    "pipeline": "double-buffered: H2D of step i+1 on a copy stream during step i, D2H read event-synchronised one step later; wall clock, L2 flush write included"},
                roofline=roofline, rooflines=rooflines, token_checksum=float(chk))
     if world == 1 and not args.no_cpu_baseline:
         v, info = cpu_reference_arm(wl, args.cpu_sample or wl["B"], 5, 1)  # the whole batch: one warm-up + five timed passes (~10 s)
