@@ -220,11 +220,8 @@ int launch_gemm_bf16_tc(const __nv_bfloat16* A, long long lda, const __nv_bfloat
   const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
   const int grid = tiles < sm_count() ? tiles : sm_count();
   const size_t smem = sizeof(GemmSmem) + 1024;
-  static thread_local bool attr_set = false;
-  if (!attr_set) {
-    LAS_CUDA_OK(cudaFuncSetAttribute(gemm_bf16_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
-  }
+  // per launch, not cached: the attribute belongs to the current device's context and a host thread may serve several devices
+  LAS_CUDA_OK(cudaFuncSetAttribute(gemm_bf16_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   gemm_bf16_tc_kernel<<<grid, GEMM_THREADS, smem, st>>>(tm_a, tm_b, bias, C, ldc, M, N, K, relu ? 1 : 0, GemmSched{0, 0, 0, nullptr});
   LAS_LAUNCH_OK("gemm_bf16_tc_kernel");
   return LAS_OK;
@@ -264,11 +261,8 @@ int launch_gemm_listener(const __nv_bfloat16* A, int B, int Tl, int K, const __n
   int grid = tiles < sm_count() ? tiles : sm_count();
   if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
   const size_t smem = sizeof(GemmSmem) + 1024;
-  static thread_local bool attr_set = false;
-  if (!attr_set) {
-    LAS_CUDA_OK(cudaFuncSetAttribute(gemm_bf16_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
-  }
+  // per launch, not cached: the attribute belongs to the current device's context and a host thread may serve several devices
+  LAS_CUDA_OK(cudaFuncSetAttribute(gemm_bf16_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   // forward-direction columns are the first half of N; when the halves do not fall on tile boundaries every column tile
   // serves both directions and the natural (front-first) order is kept
   const int nfwd = ((N / 2) % BN == 0) ? (N / 2) / BN : n_tiles;

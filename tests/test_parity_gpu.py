@@ -418,6 +418,39 @@ def test_single_layer_speller_and_padded_index_targets(precision):
         assert np.abs(lg - rescored["logp"]).max() <= tol
 
 
+def test_two_devices_from_two_host_threads():
+    """The boundary's threading contract (nn.DataParallel runs forward on one thread per GPU replica, train.py:76-78):
+    two host threads drive two devices concurrently through the same library and each gets what a lone run gets."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    import copy
+    import threading
+
+    c = tl.CONFIGS["small"]
+    B, T, S = 8, 128, 12
+    x, _ = tl.make_inputs(B, T, c["F"], S, c["V"], seed=67)
+    for precision in precisions():
+        base = tl.build_model("small", max_label_len=S, seed=67, gain=3.0, precision=precision)
+        lone = torch.stack(copy.deepcopy(base).cuda(0)(x.cuda(0), None, 0.0, is_training=False)[0]).cpu()
+        out, err = {}, []
+
+        def work(dev):
+            try:
+                with torch.cuda.device(dev):
+                    m = copy.deepcopy(base).cuda(dev)
+                    for _ in range(3):
+                        r = torch.stack(m(x.cuda(dev), None, 0.0, is_training=False)[0])
+                    out[dev] = r.cpu()
+            except Exception as e:  # noqa: BLE001
+                err.append(e)
+
+        ts = [threading.Thread(target=work, args=(d,)) for d in (0, 1)]
+        [t.start() for t in ts]
+        [t.join() for t in ts]
+        assert not err, err
+        assert torch.equal(out[0], lone) and torch.equal(out[1], lone)
+
+
 def test_bf16_batch_larger_than_one_decoder_launch():
     """The persistent decoder covers at most 64 utterances per launch (one attention CTA each); larger batches are decoded
     in chunks.  70 utterances must equal the same utterances decoded as 64 + 6."""
