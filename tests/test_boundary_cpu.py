@@ -140,3 +140,20 @@ def test_checkpoint_package_roundtrip(tmp_path):
     pkg["state_dict"] = {"module." + k: v for k, v in pkg["state_dict"].items()}
     las3, _ = checkpoint.load_package(pkg, las=tl.build_model("tiny", max_label_len=9, seed=1))
     assert torch.equal(las3.listener.pLSTM_layer1.BLSTM.weight_hh_l0_reverse, las.listener.pLSTM_layer1.BLSTM.weight_hh_l0_reverse)
+
+
+def test_models_build_from_the_shipped_yaml_sections():
+    """train.py:73-74 builds the models with Listener(**params["model"]["listener"]) / Speller(**params["model"]["speller"]); the
+    shipped config (config/librispeech-config.yaml:13-34) carries keys the classes swallow (dropout, bidirectional)."""
+    import las_pytorch_b200 as lp
+
+    listener_cfg = dict(input_feature_dim=40, hidden_size=512, num_layers=3, dropout=0.0, bidirectional=True, rnn_unit="LSTM", use_gpu=True)
+    speller_cfg = dict(hidden_size=1024, num_layers=2, bidirectional=True, rnn_unit="LSTM", vocab_size=30, multi_head=1, decode_mode=1,
+                       use_mlp_in_attention=True, mlp_dim_in_attention=64, mlp_activate_in_attention="relu", listener_hidden_size=512,
+                       max_label_len=576)
+    las = lp.LAS(lp.Listener(**listener_cfg), lp.Speller(**speller_cfg))
+    sd = las.state_dict()
+    assert sd["listener.pLSTM_layer2.BLSTM.weight_ih_l0_reverse"].shape == (2048, 2048)
+    assert sd["speller.rnn_layer.weight_ih_l0"].shape == (4096, 30 + 1024)
+    assert sd["speller.character_distribution.weight"].shape == (30, 2048)
+    assert sum(v.numel() for v in sd.values()) == sum(p.numel() for p in las.parameters())

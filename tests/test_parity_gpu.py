@@ -451,6 +451,29 @@ def test_two_devices_from_two_host_threads():
         assert torch.equal(out[0], lone) and torch.equal(out[1], lone)
 
 
+def test_shipped_config_size_runs_in_fp32_and_bf16_says_what_it_cannot_do():
+    """config/librispeech-config.yaml:13-34 ships listener 512x3 / speller 1024x2.  The fp32 path takes any size; the bf16 listener
+    takes H = 512 (16-CTA clusters); the bf16 persistent decoder keeps every LSTM weight on chip, which 1024-wide cells exceed --
+    it must say so instead of running something else."""
+    from las_pytorch_b200 import _cabi
+
+    cfg = dict(F=40, H=512, L=3, sl=2, V=30, D=64)
+    B, T, S = 2, 32, 3
+    las = tl.build_model(cfg, max_label_len=S, seed=71, gain=2.0, precision="fp32")
+    sd = tl.state_dict_numpy(las)
+    x, _ = tl.make_inputs(B, T, cfg["F"], S, cfg["V"], seed=71)
+    ref = O.las_forward(x.numpy(), sd, cfg["L"], cfg["sl"], S, dtype=np.float64)
+    las = las.cuda()
+    preds, _ = las(x.cuda(), None, 0.0, is_training=False)
+    assert np.abs(torch.stack(preds).cpu().numpy() - ref["logp"]).max() <= 1e-4
+    if "bf16" in precisions():
+        lasb = tl.build_model(cfg, max_label_len=S, seed=71, gain=2.0, precision="bf16").cuda()
+        enc = lasb.listener(x.cuda())  # H = 512 is within the bf16 listener's range
+        assert np.abs(enc.cpu().numpy() - ref["enc"]).max() <= 3e-2
+        with pytest.raises(_cabi.LasB200Error, match="LAS_MODE_FP32"):
+            lasb.speller(enc, None, 0.0)
+
+
 def test_bf16_batch_larger_than_one_decoder_launch():
     """The persistent decoder covers at most 64 utterances per launch (one attention CTA each); larger batches are decoded
     in chunks.  70 utterances must equal the same utterances decoded as 64 + 6."""
