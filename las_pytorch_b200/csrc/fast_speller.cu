@@ -78,6 +78,7 @@ struct DecParams {
   int Bfull;  // batch pitch of the caller's tensors; this launch covers utterances [b0, b0 + B)
   int b0;
   int U, E, Hs, sl, V, D, steps, decode_mode, relu, gt_steps, ncl, k_in_smem;
+  int wreg;  // 1: every attention thread keeps its chunks of W_phi in registers (D <= 64, Hs <= 512); no shared-memory copy
   int ab_flags;     // test hook (las_debug_set_option(5, v)): bit 0 = W_phi from shared memory instead of registers
   unsigned long long sample_seed;  // LAS_DECODE_SAMPLE
   int word_gather;  // 1: the fed-back word is an index (greedy argmax / gt_index); 0: a dense vector (part 1b)
@@ -429,7 +430,7 @@ struct AttLayout {
   int WPS, WCS, KS, Up;
   size_t o_wcd, o_h, o_q, o_score, o_logit, o_bphi, o_bcd, o_red, o_part, o_k, total;
 };
-__host__ __device__ inline AttLayout att_layout(int Hs, int E, int U, int D, int V, bool k_in) {
+__host__ __device__ inline AttLayout att_layout(int Hs, int E, int U, int D, int V, bool k_in, bool wreg) {
   AttLayout a;
   a.WPS = Hs + 8;          // bf16 row strides: multiples of 8 keep every 16-byte chunk aligned
   a.WCS = Hs + E + 8;
@@ -437,7 +438,7 @@ __host__ __device__ inline AttLayout att_layout(int Hs, int E, int U, int D, int
   a.Up = (U + 3) & ~3;
   size_t o = 0;
   auto take = [&](size_t bytes) { const size_t at = o; o = (o + bytes + 15) & ~(size_t)15; return at; };
-  take((size_t)D * a.WPS * 2);                         // W_phi at offset 0
+  take(wreg ? 0 : (size_t)D * a.WPS * 2);              // W_phi at offset 0 (not staged when the threads hold it in registers)
   a.o_wcd = take((size_t)V * a.WCS * 2);
   a.o_h = take((size_t)(((Hs + 63) & ~63) + ((E + 63) & ~63)) * 4);  // h, then ctx, each permuted (xpos) and padded to 64 floats
   a.o_q = take((size_t)a.KS * 4);
@@ -457,7 +458,7 @@ __device__ void attention_role(const DecParams& p, uint8_t* smem, int b) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr int NWARP = DEC_THREADS / 32;
   const int Hs = p.Hs, E = p.E, U = p.U, D = p.D, V = p.V, KC = p.Hs + p.E;
-  const AttLayout L = att_layout(Hs, E, U, D, V, p.k_in_smem != 0);
+  const AttLayout L = att_layout(Hs, E, U, D, V, p.k_in_smem != 0, p.wreg != 0);
   const int KS = L.KS, WPS = L.WPS, WCS = L.WCS;
   const int gb = p.b0 + b;  // utterance index in the caller's tensors
   __nv_bfloat16* s_wphi = reinterpret_cast<__nv_bfloat16*>(smem);               // [D][WPS]
@@ -482,7 +483,8 @@ __device__ void attention_role(const DecParams& p, uint8_t* smem, int b) {
   const int CU = nks * 8;                                     // TMEM columns of one 128-feature tile of enc^T
   const int NT = E / 128;                                     // feature tiles
 
-  for (int i = tid; i < D * Hs; i += DEC_THREADS) s_wphi[(size_t)(i / Hs) * WPS + (i % Hs)] = p.w_phi[i];
+  if (!p.wreg)
+    for (int i = tid; i < D * Hs; i += DEC_THREADS) s_wphi[(size_t)(i / Hs) * WPS + (i % Hs)] = p.w_phi[i];
   for (int i = tid; i < V * KC; i += DEC_THREADS) s_wcd[(size_t)(i / KC) * WCS + (i % KC)] = p.w_cd[i];
   for (int i = tid; i < KS; i += DEC_THREADS) s_q[i] = 0.f;
   for (int i = tid; i < D; i += DEC_THREADS) s_bphi[i] = p.b_phi[i];
@@ -537,12 +539,12 @@ __device__ void attention_role(const DecParams& p, uint8_t* smem, int b) {
   // W_phi in registers: thread (d = tid / 8, part = tid % 8) keeps the chunks part, part + 8, ... of row d (32 registers)
   // for all S steps, so the query GEMV reads only h from shared memory (the 64 KB of W_phi would otherwise be half of
   // the step's shared-memory wavefronts).  Falls back to the shared-memory copy for D > 64 or Hs > 512.
-  const bool wreg = (D <= DEC_THREADS / 8) && (hchunks <= 64) && !(p.ab_flags & 1);
+  const bool wreg = p.wreg != 0;
   uint4 wq[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const int d = tid >> 3, c = (tid & 7) + 8 * j;
-    wq[j] = (wreg && d < D && c < hchunks) ? *reinterpret_cast<const uint4*>(s_wphi + (size_t)d * WPS + 8 * c) : make_uint4(0, 0, 0, 0);
+    wq[j] = (wreg && d < D && c < hchunks) ? *reinterpret_cast<const uint4*>(p.w_phi + (size_t)d * Hs + 8 * c) : make_uint4(0, 0, 0, 0);
   }
   const int Dp = (D + 3) & ~3, Vp = (V + 1) & ~1;
   const int nd4 = (D + 3) >> 2;                    // float4 chunks of a psi row
@@ -996,7 +998,8 @@ RingCfg ring_cfg(const las_speller_dims* d, int rows) {
   r.smem = fixed + (size_t)r.nstages * r.stage_bytes + (r.box_rows == 64 ? 0 : 0);
   return r;
 }
-size_t att_smem(const las_speller_dims* d, bool k_in) { return att_layout(d->Hs, d->E, d->U, d->D, d->V, k_in).total + 64; }
+bool att_wreg(const las_speller_dims* d) { return d->D <= DEC_THREADS / 8 && d->Hs <= 512 && !(g_dec_ab_flags & 1); }
+size_t att_smem(const las_speller_dims* d, bool k_in) { return att_layout(d->Hs, d->E, d->U, d->D, d->V, k_in, att_wreg(d)).total + 64; }
 int supported(const las_speller_dims* d) {
   LAS_REQUIRE(d->sl <= MAX_SL, "LAS_MODE_BF16 speller supports at most %d layers (sl=%d)", MAX_SL, d->sl);
   LAS_REQUIRE(d->Hs % 16 == 0 && d->Hs <= 512, "LAS_MODE_BF16 speller needs hidden_size %% 16 == 0 and <= 512 (Hs=%d); use LAS_MODE_FP32", d->Hs);
@@ -1124,6 +1127,7 @@ int fast_speller_decode(const las_decode_io* io, const void* packed_f32, const v
     memset(&p, 0, sizeof(p));
     p.B = Bc; p.U = d->U; p.E = d->E; p.Hs = d->Hs; p.sl = d->sl; p.V = d->V; p.D = d->D;
     p.steps = steps; p.decode_mode = decode_mode; p.relu = relu; p.gt_steps = io->gt_steps; p.ncl = s.ncl;
+    p.wreg = att_wreg(d) ? 1 : 0;
     p.k_in_smem = att_smem(d, true) <= 220 * 1024;
     {
       const int nks = (d->U + 15) / 16, NT = d->E / 128;
