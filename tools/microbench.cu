@@ -73,6 +73,58 @@ __global__ void __launch_bounds__(128, 1) mma_chain_kernel(long long* out, int c
   if (threadIdx.x < 32) ptx::tmem_dealloc(tmem, 512);
 }
 
+
+// ------------------------------------------------------------------------------------------------ 1b. two issuing warps
+// Does the ~57-cycle SS issue interval belong to the issuing thread or to the tensor pipe?  Two warps issue half of the chain
+// each (own accumulator, own commit barrier); time until both halves have completed.
+template <int N>
+__global__ void __launch_bounds__(128, 1) mma_two_issuers_kernel(long long* out, int chain, int reps, int issuers) {
+  extern __shared__ uint8_t raw[];
+  uint8_t* base = raw + ((1024u - (ptx::smem_u32(raw) & 1023u)) & 1023u);
+  uint8_t* sa = base;
+  uint8_t* sb = base + 4 * 16384;
+  __shared__ uint64_t bar[2];
+  __shared__ uint32_t slot;
+  __shared__ long long t_done[2];
+  for (int i = threadIdx.x; i < (4 * 16384 + 4 * N * 128) / 16; i += blockDim.x) reinterpret_cast<uint4*>(base)[i] = make_uint4(0, 0, 0, 0);
+  if (threadIdx.x == 0) { ptx::mbar_init(&bar[0], 1); ptx::mbar_init(&bar[1], 1); ptx::fence_mbar_init(); }
+  if (threadIdx.x < 32) ptx::tmem_alloc(&slot, 512);
+  ptx::fence_proxy_async();
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem = slot;
+  const int w = threadIdx.x >> 5;
+  const UmmaLayout la{1, 0, 1024, 16384}, lb{1, 0, 1024, (uint32_t)N * 128u};
+  const uint32_t idesc = umma_idesc_bf16(128, N);
+  const uint32_t a0 = ptx::smem_u32(sa), b0 = ptx::smem_u32(sb);
+  for (int r = 0; r < reps; ++r) {
+    __syncthreads();
+    const long long t0 = clock64();
+    if (w < issuers) {
+      const int per = chain / issuers / 4;  // atoms per issuer
+      for (int at = 0; at < per; ++at) {
+        if (ptx::elect_one()) {
+          const uint32_t a_addr = a0 + ((at + w) & 3) * 16384, b_addr = b0 + ((at + w) & 3) * N * 128;
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            ptx::umma_bf16(tmem + w * N, umma_smem_desc(la, a_addr, k * 16), umma_smem_desc(lb, b_addr, k * 16), idesc, (at | k) != 0);
+        }
+        __syncwarp();
+      }
+      if (ptx::elect_one()) ptx::umma_commit(&bar[w]);
+      __syncwarp();
+      ptx::mbar_wait(&bar[w], (uint32_t)(r & 1));
+      if ((threadIdx.x & 31) == 0) t_done[w] = clock64() - t0;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) out[0] = issuers == 2 ? (t_done[0] > t_done[1] ? t_done[0] : t_done[1]) : t_done[0];
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (threadIdx.x < 32) ptx::tmem_dealloc(tmem, 512);
+}
+
 // ------------------------------------------------------------------------------------------------ 2. hop
 constexpr int HOP_ROWS = 64, HOP_K = 512, HOP_NCTA = 32, HOP_THREADS = 512;
 struct HopParams {
@@ -260,6 +312,15 @@ int main() {
   run(mma_chain_kernel<64, 1, 1>, 64, 1, 1);
   run(mma_chain_kernel<64, 4, 1>, 64, 4, 1);
 
+  printf("== two issuers: cycles until a chain of 32 SS tcgen05.mma (M=128, N=64, K=16) has completed\n");
+  for (int issuers = 1; issuers <= 2; ++issuers) {
+    const size_t smem2 = 4 * 16384 + 4 * 64 * 128 + 2048;
+    CK(cudaFuncSetAttribute(mma_two_issuers_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+    mma_two_issuers_kernel<64><<<1, 128, smem2>>>(out, 32, 5, issuers);
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(h, out, 8, cudaMemcpyDeviceToHost));
+    printf("issuing warps=%d : %lld cycles\n", issuers, h[0]);
+  }
   printf("== hop: ns per hand-off (32 producer CTAs -> 32 consumer CTAs, [64 x 512] bf16)\n");
   void* fn = nullptr;
   cudaDriverEntryPointQueryResult qres;
