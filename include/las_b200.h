@@ -188,7 +188,13 @@ typedef struct las_decode_io {
   /* outputs */
   float* logp;                /* [S,B,V] log-probabilities per step (raw_pred_seq, :213) */
   float* attn;                /* nullable [S,heads,B,U] attention scores per step (attention_record, :214) */
-  int32_t* tokens;            /* nullable [S,B] argmax of logp per step */
+  int32_t* tokens;            /* nullable [S,B] argmax of logp per step (LAS_DECODE_SAMPLE: the sampled tokens) */
+  /* Fused loss terms ("next" row f1: NLLLoss(ignore_index=0), solver/solver.py:62,70-77).  nll_labels (nullable, int32
+   * [B, nll_steps], independent of teacher forcing) -> nll_terms [S,B] = -logp[s,b,label] where label != 0 and s < nll_steps, else
+   * 0.  loss = sum(nll_terms) / count(labels != 0): the caller never has to read the [S,B,V] log-probabilities back. */
+  const int32_t* nll_labels;
+  int32_t nll_steps;
+  float* nll_terms;
 } las_decode_io;
 
 size_t las_speller_workspace_bytes(const las_speller_dims* d, int steps, int mode);

@@ -54,6 +54,7 @@ class DecodeIO(C.Structure):
         ("enc_lengths", C.c_void_p), ("sample_seed", C.c_uint64),
         ("h_state", C.c_void_p), ("c_state", C.c_void_p), ("word", C.c_void_p), ("context", C.c_void_p),
         ("logp", C.c_void_p), ("attn", C.c_void_p), ("tokens", C.c_void_p),
+        ("nll_labels", C.c_void_p), ("nll_steps", C.c_int32), ("nll_terms", C.c_void_p),
     ]
 
 

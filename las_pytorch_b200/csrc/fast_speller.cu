@@ -71,6 +71,9 @@ struct DecParams {
   float* logp;                  // [S, B, V]
   float* attn;                  // nullable [S, B, U]
   int32_t* tokens;              // nullable [S, B]
+  const int32_t* nll_labels;    // nullable [B, nll_steps]
+  float* nll_terms;             // nullable [S, B]
+  int nll_steps;
   float* word_out;              // nullable [B, V]
   float* ctx_out;               // nullable [B, E]
   uint32_t* sync;               // counters, 32 uint32 apart: [l] = h_ready[l], [CTR_CTX], [CTR_WORD]
@@ -843,6 +846,10 @@ __device__ void attention_role(const DecParams& p, uint8_t* smem, int b) {
         p.logp[((size_t)s * p.Bfull + gb) * V + v] = lp;
         if (lp > bv) { bv = lp; bi = v; }
       }
+      if (p.nll_terms && lane == 0) {  // NLLLoss(ignore_index=0) term of this (step, utterance)
+        const int lab = (p.nll_labels && s < p.nll_steps) ? p.nll_labels[(size_t)gb * p.nll_steps + s] : 0;
+        p.nll_terms[(size_t)s * p.Bfull + gb] = (lab > 0 && lab < V) ? -(s_logit[lab] - lse) : 0.f;
+      }
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) {
         const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
@@ -1161,6 +1168,7 @@ int fast_speller_decode(const las_decode_io* io, const void* packed_f32, const v
     p.gt_index = io->gt_index;
     p.enc_lengths = io->enc_lengths;
     p.logp = io->logp; p.attn = io->attn; p.tokens = io->tokens;
+    p.nll_labels = io->nll_labels; p.nll_terms = io->nll_terms; p.nll_steps = io->nll_steps;
     p.word_out = io->word; p.ctx_out = io->context;
     p.sync = w.sync;
     p.h_ll = w.h_ll;

@@ -358,6 +358,10 @@ __global__ void __launch_bounds__(256) attend_f32_kernel(AttendArgs a) {
     a.logp_out[(size_t)b * a.V + v] = lp;
   }
   __syncthreads();
+  if (a.nll_term_out && tid == 0) {  // NLLLoss(ignore_index=0) term of this (step, utterance)
+    const int lab = a.nll_label_step ? a.nll_label_step[(size_t)b * a.nll_label_ld] : 0;
+    a.nll_term_out[b] = (lab > 0 && lab < a.V) ? -s_logit[lab] : 0.f;
+  }
 
   // argmax (lowest index wins ties, as torch.topk / argmax do on a row)   (:225)
   int best = 0;

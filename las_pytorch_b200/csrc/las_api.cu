@@ -335,6 +335,11 @@ static int speller_decode_f32(const las_decode_io* io, const void* packed, const
     t.decode_mode = decode_mode;
     t.sample_seed = io->sample_seed;
     t.step = s;
+    if (io->nll_terms) {
+      t.nll_term_out = io->nll_terms + (size_t)s * B;
+      t.nll_label_step = (io->nll_labels && s < io->nll_steps) ? io->nll_labels + s : nullptr;
+      t.nll_label_ld = io->nll_steps;
+    }
     LAS_TRY(launch_attend_f32(t, st));
   }
   if (io->h_state && (io->c_state || d->cell != LAS_CELL_LSTM)) {

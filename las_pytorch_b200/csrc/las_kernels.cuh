@@ -63,6 +63,9 @@ struct AttendArgs {
   int decode_mode;
   unsigned long long sample_seed;  // LAS_DECODE_SAMPLE
   int step;
+  const int32_t* nll_label_step;  // nullable [B] stride nll_label_ld: label of this step for the fused NLL term
+  int nll_label_ld;
+  float* nll_term_out;            // nullable [B]
 };
 int launch_attend_f32(const AttendArgs& a, cudaStream_t st);
 

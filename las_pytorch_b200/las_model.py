@@ -143,9 +143,10 @@ class LAS(nn.Module):
         self.listener = listener
         self.speller = speller
 
-    def forward(self, batch_data, batch_label, teacher_force_rate, is_training=True, input_lengths=None):
+    def forward(self, batch_data, batch_label, teacher_force_rate, is_training=True, input_lengths=None, nll_labels=None):
         """`input_lengths` ([B] valid frames per utterance) is an extension: the reference's collate_fn computes it
-        (utils/data.py:146) and train.py:117 drops it.  When given, the BLSTMs and the attention skip the padding."""
+        (utils/data.py:146) and train.py:117 drops it.  When given, the BLSTMs and the attention skip the padding.
+        `nll_labels` ([B,S'] label indices; extension) -> `self.speller.last_nll_terms` (see Speller.forward)."""
         enc_lengths = None
         if input_lengths is None:
             listener_feature = self.listener(batch_data)
@@ -153,11 +154,12 @@ class LAS(nn.Module):
             listener_feature, enc_lengths = self.listener(batch_data, input_lengths=input_lengths)
         if is_training:
             raw_pred_seq, attention_record = self.speller(
-                listener_feature, ground_truth=batch_label, teacher_force_rate=teacher_force_rate, enc_lengths=enc_lengths
+                listener_feature, ground_truth=batch_label, teacher_force_rate=teacher_force_rate, enc_lengths=enc_lengths,
+                nll_labels=nll_labels
             )
         else:
             raw_pred_seq, attention_record = self.speller(listener_feature, ground_truth=None, teacher_force_rate=0,
-                                                          enc_lengths=enc_lengths)
+                                                          enc_lengths=enc_lengths, nll_labels=nll_labels)
         return raw_pred_seq, attention_record
 
     def serialize(self, optimizer, epoch, tr_loss, val_loss):
@@ -392,7 +394,7 @@ class Speller(nn.Module):
         return packed
 
     def _decode(self, enc, steps, gt_dense=None, gt_index=None, state=None, word=None, context=None, enc_lengths=None,
-                want_attn=True):
+                want_attn=True, nll_labels=None):
         """Runs `steps` decoder steps.  Returns (logp [S,B,V], attn [S,B,U] | None, tokens [S,B])."""
         _require_cuda(enc, "listener_feature")
         lib = _cabi.load_library()
@@ -429,6 +431,12 @@ class Speller(nn.Module):
                 io.c_state = state[1].data_ptr() if state[1] is not None else None
             if word is not None:
                 io.word, io.context = word.data_ptr(), context.data_ptr()
+            self.last_nll_terms = None
+            if nll_labels is not None:
+                # fused NLLLoss(ignore_index=0) terms (solver/solver.py:62,70-77): [S,B], zero where the label is 0 / past the labels
+                nll_labels = nll_labels.to(device=dev, dtype=torch.int32).contiguous()
+                self.last_nll_terms = torch.empty(steps, b, dtype=torch.float32, device=dev)
+                io.nll_labels, io.nll_steps, io.nll_terms = nll_labels.data_ptr(), nll_labels.size(1), self.last_nll_terms.data_ptr()
             io.logp = logp.data_ptr()
             io.attn = attn.data_ptr() if attn is not None else None
             io.tokens = tokens.data_ptr()
@@ -455,7 +463,9 @@ class Speller(nn.Module):
         logp, attn, _ = self._decode(listener_feature, 1, state=(h, c), word=word, context=context)
         return logp[0], ((h, c) if lstm else h), context, list(attn[0].unbind(0))
 
-    def forward(self, listener_feature, ground_truth=None, teacher_force_rate=0.9, enc_lengths=None):
+    def forward(self, listener_feature, ground_truth=None, teacher_force_rate=0.9, enc_lengths=None, nll_labels=None):
+        """`nll_labels` ([B,S'] label indices; extension) makes the decoder also emit the NLLLoss(ignore_index=0) terms of
+        solver/solver.py:62,70-77 as `self.last_nll_terms` [S,B], so the loss needs no pass over the log-probabilities."""
         if ground_truth is None:
             teacher_force_rate = 0
         # one draw from numpy's global RNG per call, exactly like the reference (:189)
@@ -475,7 +485,8 @@ class Speller(nn.Module):
                 gt_dense = ground_truth.to(device=listener_feature.device, dtype=torch.float32).contiguous()
         if enc_lengths is not None:
             enc_lengths = enc_lengths.to(device=listener_feature.device, dtype=torch.int32).contiguous()
-        logp, attn, tokens = self._decode(listener_feature, max_step, gt_dense=gt_dense, gt_index=gt_index, enc_lengths=enc_lengths)
+        logp, attn, tokens = self._decode(listener_feature, max_step, gt_dense=gt_dense, gt_index=gt_index, enc_lengths=enc_lengths,
+                                          nll_labels=nll_labels)
         self.last_tokens = tokens  # [S,B] int32 argmax per step (device); not part of the reference API
         raw_pred_seq = list(logp.unbind(0))
         attention_record = [list(a.unbind(0)) for a in attn.unbind(0)]  # per step: one [B,U] tensor per head (:214,:292,:299)

@@ -70,12 +70,13 @@ def batch_iterator(batch_data, batch_label, las_model, optimizer, tf_rate, is_tr
     if is_training:
         raise NotImplementedError("the B200 path is forward-only; training (backward / optimizer step, solver/solver.py:94-97) is out of scope")
     max_label_len = min([batch_label.size()[1], max_label_len])
-    raw_pred_seq, _ = las_model(batch_data=batch_data, batch_label=batch_label, teacher_force_rate=tf_rate, is_training=is_training)
-    pred_y = torch.stack(raw_pred_seq, dim=1)[:, :max_label_len, :].contiguous()  # [B,S,V], as solver.py:68
     true_idx = torch.max(batch_label, dim=2)[1][:, :max_label_len].contiguous()
-    # is_training is False here, so the reference takes the NLLLoss(ignore_index=0) branch (solver.py:70-77)
-    logp_sbv = pred_y.permute(1, 0, 2).contiguous()
-    sums = nll_sums(logp_sbv, true_idx.to(torch.int32), max_label_len)
-    loss = sums[0] / sums[1]
+    # is_training is False here, so the reference takes the NLLLoss(ignore_index=0) branch (solver.py:70-77); the decoder emits its
+    # terms -logp[s,b,label] itself (fused epilogue), so the loss needs no pass over the [B,S,V] log-probabilities
+    raw_pred_seq, _ = las_model(batch_data=batch_data, batch_label=batch_label, teacher_force_rate=tf_rate, is_training=is_training,
+                                nll_labels=true_idx)
+    pred_y = torch.stack(raw_pred_seq, dim=1)[:, :max_label_len, :].contiguous()  # [B,S,V], as solver.py:68 (for the LER below)
+    terms = las_model.speller.last_nll_terms
+    loss = terms.sum() / (true_idx != 0).sum().to(terms.device)
     batch_ler = LetterErrorRate(torch.max(pred_y, dim=2)[1].cpu().numpy(), true_idx.cpu().numpy())
     return loss.cpu().numpy(), batch_ler

@@ -576,6 +576,16 @@ def test_solver_batch_iterator_matches_oracle():
     ref_ler = O.letter_error_rate(ref["tokens"].T, labels.numpy())
     loss, ler = batch_iterator(x.cuda(), tl.onehot(labels, c["V"]).cuda(), las.cuda(), None, 0.0, False, S, 0.1)
     assert abs(float(loss) - ref_loss) < 1e-4
+    # the fused NLL terms equal the stand-alone reduction kernel over the returned log-probabilities
+    from las_pytorch_b200.solver import nll_sums
+    preds, _ = las(x.cuda(), None, 0.0, is_training=False, nll_labels=labels.cuda())
+    sums = nll_sums(torch.stack(preds).contiguous(), labels.to(torch.int32).cuda(), S)
+    terms = las.speller.last_nll_terms
+    assert abs(float(terms.sum()) - float(sums[0])) < 1e-3 and int((terms != 0).sum()) == int(sums[1])
+    if "bf16" in precisions():
+        lasb = tl.build_model("small", max_label_len=S, seed=11, gain=3.0, precision="bf16").cuda()
+        loss_b, _ = batch_iterator(x.cuda(), tl.onehot(labels, c["V"]).cuda(), lasb, None, 0.0, False, S, 0.1)
+        assert abs(float(loss_b) - ref_loss) < 5e-2
     assert np.allclose(ler, ref_ler, atol=1e-12)
     with pytest.raises(NotImplementedError):
         batch_iterator(x.cuda(), tl.onehot(labels, c["V"]).cuda(), las, None, 0.9, True, S, 0.1)
