@@ -46,7 +46,8 @@ def build(force=False, verbose=False):
         o = os.path.join(OBJ, os.path.basename(s)[:-3] + ".o")
         objs.append(o)
         if force or _stale(o, [s] + hdrs):
-            cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]
+            extra = os.environ.get("LAS_NVCC_EXTRA", "").split()  # e.g. -DLAS_GUARD_LL=0 for an A/B tree
+            cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]
             jobs.append(cmd)
 
     def run(cmd):

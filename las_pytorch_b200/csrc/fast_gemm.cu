@@ -211,6 +211,24 @@ int make_tmap_bf16_box(CUtensorMap* tm, const void* base, long long rows, long l
   return make_tmap_bf16(tm, base, rows, cols, ld, box_rows);
 }
 
+// The same row-major bf16 matrix [rows, 64*atoms] seen as {64 k, rows, atoms}: one copy of box {64, box_rows, box_atoms}
+// lands as box_atoms consecutive 128-byte-swizzled [box_rows x 64] atoms, i.e. what box_atoms 2-D copies would write.
+int make_tmap_bf16_atoms(CUtensorMap* tm, const void* base, long long rows, int atoms, long long ld, int box_rows, int box_atoms) {
+  EncodeTiledFn enc;
+  LAS_TRY(get_encode_fn(&enc));
+  LAS_REQUIRE((ld * 2) % 16 == 0 && (reinterpret_cast<uintptr_t>(base) & 15) == 0 && (long long)atoms * 64 <= ld,
+              "TMA atom view needs 16-byte aligned rows of at least %d elements (ld=%lld)", atoms * 64, ld);
+  cuuint64_t gdim[3] = {64, (cuuint64_t)rows, (cuuint64_t)atoms};
+  cuuint64_t gstr[2] = {(cuuint64_t)ld * 2, 128};
+  cuuint32_t box[3] = {64, (cuuint32_t)box_rows, (cuuint32_t)box_atoms};
+  cuuint32_t estr[3] = {1, 1, 1};
+  const CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), gdim, gstr, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(LAS_ECUDA, "cuTensorMapEncodeTiled (atom view) failed with CUresult %d (rows=%lld atoms=%d ld=%lld)", (int)r, rows, atoms, ld);
+  return LAS_OK;
+}
+
 int launch_gemm_bf16_tc(const __nv_bfloat16* A, long long lda, const __nv_bfloat16* W, long long ldw, const float* bias, float* C,
                         long long ldc, int M, int N, int K, cudaStream_t st, bool relu) {
   LAS_REQUIRE(M > 0 && N > 0 && K > 0, "bad GEMM shape %dx%dx%d", M, N, K);

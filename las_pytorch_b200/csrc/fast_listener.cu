@@ -176,9 +176,12 @@ __global__ void __launch_bounds__(REC_THREADS, 1) lstm_recurrence_cluster_kernel
         const long long m_tile = ((long long)t * p.Bp + b_base) >> 7;  // the chunk's 16 rows of a time step share one 128-row tile
         const uint32_t* f = p.gemm_flags + m_tile * p.n_tiles + n_tile;
         uint32_t v;
-        do {
+        ptx::SpinGuard guard;
+        for (;;) {
           asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
-        } while (v < 4u);
+          if (v >= 4u) break;
+          guard.tick();
+        }
         do {  // every further step whose rows lie in the same tile
           ++ready;
         } while (ready < Tl && ((((long long)(dir ? Tl - 1 - ready : ready)) * p.Bp + b_base) >> 7) == m_tile);

@@ -33,6 +33,7 @@
 namespace las {
 
 int make_tmap_bf16_box(CUtensorMap* tm, const void* base, long long rows, long long cols, long long ld, int box_rows);  // fast_gemm.cu
+int make_tmap_bf16_atoms(CUtensorMap* tm, const void* base, long long rows, int atoms, long long ld, int box_rows, int box_atoms);
 
 namespace {
 
@@ -50,6 +51,9 @@ typedef unsigned long long u64;
 struct DecParams {
   CUtensorMap tm_h[MAX_SL][2];  // hbuf[l][parity]  bf16 [B, Hs]
   CUtensorMap tm_x[2];          // xbuf[parity]     bf16 [B, VP + E]  (word atom first, then the context)
+  CUtensorMap tm_h3[MAX_SL][2]; // the same buffers as {64 k, B, atoms}: one copy brings a whole activation part (tma3d)
+  CUtensorMap tm_x3[2];
+  int tma3d;                    // 1: Hs and E are multiples of 64, every part is ONE 3-D copy completing on full[0]
   const uint8_t* w_img[MAX_SL]; // [ncl][atoms_l] swizzled 64x64 bf16 atoms: h part, (layer 0: word atom), input part
   const float* bias[MAX_SL];    // [ncl*64] b_ih + b_hh in CTA column order
   __nv_bfloat16* hbuf[MAX_SL][2];
@@ -82,7 +86,7 @@ struct DecParams {
   int b0;
   int U, E, Hs, sl, V, D, steps, decode_mode, relu, gt_steps, ncl, k_in_smem;
   int wreg;  // 1: every attention thread keeps its chunks of W_phi in registers (D <= 64, Hs <= 512); no shared-memory copy
-  int ab_flags;     // test hook (las_debug_set_option(5, v)): bit 0 = W_phi from shared memory instead of registers
+  int ab_flags;     // test hook (las_debug_set_option(5, v)): bit 0 = W_phi from shared memory instead of registers; bit 2 (value 4) = eight 2-D copies per activation part instead of one 3-D copy
   unsigned long long sample_seed;  // LAS_DECODE_SAMPLE
   int word_gather;  // 1: the fed-back word is an index (greedy argmax / gt_index); 0: a dense vector (part 1b)
   int ctx_tmem;     // 1: enc[b]^T is resident in the attention CTA's tensor memory and the context is a UMMA
@@ -122,8 +126,8 @@ __device__ __forceinline__ uint32_t ld_relaxed(const uint32_t* p) {
 // spin with relaxed loads, then one acquire load to synchronise (tools/microbench.cu: the cheapest correct pairing
 // with red.release on this part)
 __device__ __forceinline__ void wait_counter(const uint32_t* ctr, uint32_t target) {
-  while (ld_relaxed(ctr) < target) {
-  }
+  ptx::SpinGuard g;
+  while (ld_relaxed(ctr) < target) g.tick();
   (void)ld_acquire(ctr);
 }
 __device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
@@ -141,10 +145,16 @@ __device__ __forceinline__ void ll_store2(u64* p, u64 a, u64 b) {
   asm volatile("st.relaxed.gpu.global.v2.b64 [%0], {%1, %2};" ::"l"(p), "l"(a), "l"(b) : "memory");
 }
 __device__ __forceinline__ uint32_t ll_wait(const u64* p, uint32_t tag) {
-  u64 v;
-  do {
+#if LAS_GUARD_LL
+  ptx::SpinGuard g;
+#endif
+  u64 v = ll_load(p);
+  while ((uint32_t)(v >> 32) != tag) {
+#if LAS_GUARD_LL
+    g.tick();
+#endif
     v = ll_load(p);
-  } while ((uint32_t)(v >> 32) != tag);
+  }
   return (uint32_t)v;
 }
 
@@ -236,17 +246,25 @@ __device__ void lstm_role(const DecParams& p, uint8_t* smem, int l, int nb) {
       __syncwarp();
       fence_proxy_async_global();  // other SMs' generic-proxy stores (acquired above) -> this warp's TMA reads
       if (ptx::elect_one()) {
-        for (int i = 0; i < nh; ++i) {
-          ptx::mbar_arrive_expect_tx(&full[i], STAGE_BYTES);
-          ptx::tma_load_2d(abuf + (size_t)i * STAGE_BYTES, &p.tm_h[l][par], &full[i], i * 64, 0);
+        if (p.tma3d) {
+          ptx::mbar_arrive_expect_tx(&full[0], nh * STAGE_BYTES);
+          ptx::tma_load_3d(abuf, &p.tm_h3[l][par], &full[0], 0, 0, 0);
+        } else {
+          for (int i = 0; i < nh; ++i) {
+            ptx::mbar_arrive_expect_tx(&full[i], STAGE_BYTES);
+            ptx::tma_load_2d(abuf + (size_t)i * STAGE_BYTES, &p.tm_h[l][par], &full[i], i * 64, 0);
+          }
         }
       }
       __syncwarp();
       // ---- part 1a: context of step s-1 (layer 0) / the lower layer's h of THIS step
       ptx::mbar_wait(part_empty, (uint32_t)((n - 1) & 1));
       ++n;
-      if (ptx::elect_one())  // slots are free: arm their barriers now, so that only the copies are left to issue once the input is there
-        for (int i = 0; i < nc; ++i) ptx::mbar_arrive_expect_tx(&full[i], STAGE_BYTES);
+      if (ptx::elect_one()) {  // slots are free: arm their barriers now, so that only the copies are left to issue once the input is there
+        if (p.tma3d) ptx::mbar_arrive_expect_tx(&full[0], nc * STAGE_BYTES);
+        else
+          for (int i = 0; i < nc; ++i) ptx::mbar_arrive_expect_tx(&full[i], STAGE_BYTES);
+      }
       __syncwarp();
       if (lane == 0) {
         wait_counter(in_ctr, first ? (uint32_t)s * p.B : (uint32_t)(s + 1) * p.ncl);
@@ -255,11 +273,16 @@ __device__ void lstm_role(const DecParams& p, uint8_t* smem, int l, int nb) {
       }
       __syncwarp();
       fence_proxy_async_global();
+      if (lane == 0 && trole >= 0) DEC_TRACE(4, 6 + trole);
       {
         const CUtensorMap* tm = first ? &p.tm_x[par] : &p.tm_h[l - 1][par ^ 1];
+        const CUtensorMap* tm3 = first ? &p.tm_x3[par] : &p.tm_h3[l - 1][par ^ 1];
         const int col0 = first ? DEC_VP : 0;
         if (ptx::elect_one()) {
-          for (int i = 0; i < nc; ++i) ptx::tma_load_2d(abuf + (size_t)i * STAGE_BYTES, tm, &full[i], col0 + i * 64, 0);
+          // one instruction for the whole part: issuing eight 2-D copies took ~0.55 us (~68 ns each), all of it on the critical path
+          if (p.tma3d) ptx::tma_load_3d(abuf, tm3, &full[0], 0, 0, col0 / 64);
+          else
+            for (int i = 0; i < nc; ++i) ptx::tma_load_2d(abuf + (size_t)i * STAGE_BYTES, tm, &full[i], col0 + i * 64, 0);
         }
         __syncwarp();
       }
@@ -289,22 +312,28 @@ __device__ void lstm_role(const DecParams& p, uint8_t* smem, int l, int nb) {
       for (int part = 0; part < 2; ++part) {
         const int na = part == 0 ? nh : nc;
         const uint32_t d = tmem + (part == 0 ? 0u : (uint32_t)DEC_NW);  // separate accumulators for the two parts
-        for (int i = 0; i < na; ++i) {
-          ptx::mbar_wait(&full[i], (phase_bits >> i) & 1u);
-          phase_bits ^= 1u << i;
-          ptx::tc_fence_after();
-          if (ptx::elect_one()) {
+        // All boxes of the part landed, then one elected thread issues the part's MMAs back to back (~57 cycles apart, the
+        // rate the tensor pipe accepts).  Issuing box by box as they land is slower: MMAs issued while later boxes are
+        // still being written into shared memory slow both down (measured per group size 1 / 2 / 4 / all boxes:
+        // 15.3 / 14.8 / 14.3 / 14.2 us per step, profiles/r01_decoder_issue_groups.log).
+        const int nwait = p.tma3d ? 1 : na;
+        for (int i = 0; i < nwait; ++i) ptx::mbar_wait(&full[i], (phase_bits >> i) & 1u);
+        phase_bits ^= (1u << nwait) - 1u;
+        ptx::tc_fence_after();
+        if (part == 1 && lane == 0 && trole >= 0) DEC_TRACE(4, 3 + 2 * trole);  // critical part landed
+        if (ptx::elect_one()) {
+          for (int i = 0; i < na; ++i) {
             const uint32_t a_addr = a0 + i * STAGE_BYTES, b_addr = w_addr + (part == 0 ? i : nh + nwd + i) * WATOM_BYTES;
 #pragma unroll
             for (int k = 0; k < 4; ++k)
               ptx::umma_bf16(d, umma_smem_desc(la, a_addr, k * 16), umma_smem_desc(lb, b_addr, k * 16), idesc, !(i == 0 && k == 0));
-            if (i == na - 1 && (part == 0 || !wd)) {
-              ptx::umma_commit(part_empty);
-              if (part == 1) ptx::umma_commit(tmem_full);
-            }
           }
-          __syncwarp();
+          if (part == 0 || !wd) {
+            ptx::umma_commit(part_empty);
+            if (part == 1) ptx::umma_commit(tmem_full);
+          }
         }
+        __syncwarp();
         if (part == 0 && lane == 0 && trole >= 0) DEC_TRACE(trole, 6);
       }
       if (wd) {
@@ -1154,6 +1183,13 @@ int fast_speller_decode(const las_decode_io* io, const void* packed_f32, const v
     for (int k = 0; k < 2; ++k) {
       p.xbuf[k] = w.xbuf[k];
       LAS_TRY(make_tmap_bf16_box(&p.tm_x[k], w.xbuf[k], Bc, DEC_VP + d->E, DEC_VP + d->E, rc.box_rows));
+    }
+    p.tma3d = (d->Hs % 64 == 0 && d->E % 64 == 0 && !(g_dec_ab_flags & 4)) ? 1 : 0;
+    if (p.tma3d) {
+      for (int l = 0; l < d->sl; ++l)
+        for (int k = 0; k < 2; ++k) LAS_TRY(make_tmap_bf16_atoms(&p.tm_h3[l][k], w.hbuf[l][k], Bc, d->Hs / 64, d->Hs, rc.box_rows, d->Hs / 64));
+      for (int k = 0; k < 2; ++k)
+        LAS_TRY(make_tmap_bf16_atoms(&p.tm_x3[k], w.xbuf[k], Bc, (DEC_VP + d->E) / 64, DEC_VP + d->E, rc.box_rows, d->E / 64));
     }
     const size_t so = (size_t)b0;  // batch offset into caller tensors
     p.Bfull = d->B;

@@ -10,6 +10,34 @@ namespace ptx {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
 
+// Watchdog for the unbounded CROSS-CTA waits of the persistent kernels (release/acquire counters, flag-in-data slots, GEMM
+// tile flags): a wait that has not been satisfied after LAS_SPIN_LIMIT_NS traps, so a protocol bug or a lost peer surfaces
+// as a CUDA launch failure (-> RuntimeError in the host mirror) instead of hanging the device.  The trap kills the whole
+// grid, so the CTA-local mbarrier waits (which only ever wait for this CTA's own TMA / MMA completions or for a peer that
+// is itself behind a guarded wait) need no guard of their own -- measured: guarding them as well costs 4 % per decoder step.
+// The clock is only read once every 2^14 failed polls.
+#ifndef LAS_SPIN_LIMIT_NS
+#define LAS_SPIN_LIMIT_NS 20000000000ll
+#endif
+#ifndef LAS_GUARD_MBAR
+#define LAS_GUARD_MBAR 0
+#endif
+#ifndef LAS_GUARD_LL
+#define LAS_GUARD_LL 1
+#endif
+struct SpinGuard {
+  uint32_t n = 0;
+  long long t0 = 0;
+  __device__ __forceinline__ void tick() {
+    if ((++n & 0x3FFFu) == 0) {
+      long long t;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      if (t0 == 0) t0 = t;
+      else if (t - t0 > LAS_SPIN_LIMIT_NS) __trap();
+    }
+  }
+};
+
 // ---------------------------------------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
@@ -33,8 +61,13 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   return ok != 0;
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+#if LAS_GUARD_MBAR
+  SpinGuard g;
+  while (!mbar_try_wait(bar, parity)) g.tick();
+#else
   while (!mbar_try_wait(bar, parity)) {
   }
+#endif
 }
 // cluster-scope acquire: pairs with remote arrives / complete_tx from other CTAs of the cluster
 __device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
@@ -49,8 +82,13 @@ __device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t pa
   return ok != 0;
 }
 __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+#if LAS_GUARD_MBAR
+  SpinGuard g;
+  while (!mbar_try_wait_cluster(bar, parity)) g.tick();
+#else
   while (!mbar_try_wait_cluster(bar, parity)) {
   }
+#endif
 }
 // arrive on the barrier at shared::cluster address `remote_bar` (from mapa), release at cluster scope
 __device__ __forceinline__ void mbar_arrive_remote(uint32_t remote_bar) {

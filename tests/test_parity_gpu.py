@@ -290,6 +290,35 @@ def test_bf16_listener_overlap_is_bit_identical_to_sequential():
         assert torch.equal(o, seq)
 
 
+def test_bf16_decoder_single_3d_copy_matches_per_atom_copies():
+    """The decoder's activation parts arrive as ONE 3-D TMA copy when Hs and E are multiples of 64, and as one 2-D copy per
+    64-column atom otherwise (las_debug_set_option(5, 4) forces the latter): same bytes in shared memory, so greedy tokens,
+    log-probs and attention must be bit-identical."""
+    if "bf16" not in precisions():
+        pytest.skip("bf16 path not built")
+    from las_pytorch_b200 import _cabi
+
+    lib = _cabi.load_library()
+    c = tl.CONFIGS["paper"]
+    S = 24
+    las = tl.build_model("paper", max_label_len=S, seed=61, gain=3.0, precision="bf16").cuda()
+    x, _ = tl.make_inputs(10, 256, c["F"], S, c["V"], seed=61)
+    enc = las.listener(x.cuda())
+
+    def run():
+        pred, att = las.speller(enc, None, 0.0)
+        return torch.stack(pred).clone(), torch.stack([a[0] for a in att]).clone()
+
+    try:
+        lib.las_debug_set_option(5, 4)
+        p2, a2 = run()
+    finally:
+        lib.las_debug_set_option(5, 0)
+    p3, a3 = run()
+    assert torch.equal(p2, p3) and torch.equal(a2, a3)
+    assert torch.isfinite(p3).all()
+
+
 @pytest.mark.parametrize("precision", precisions())
 def test_edge_shapes_single_utterance_single_step_single_encoder_frame(precision):
     """Smallest shapes the path accepts: one utterance, T = 2^L (one encoder step: the softmax is over a single frame),

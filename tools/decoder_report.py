@@ -31,8 +31,10 @@ def main():
     print(f"speller c3 bf16: {e0.elapsed_time(e1) / 3:.3f} ms  ({e0.elapsed_time(e1) / 3 / S * 1e3:.2f} us/step)")
     buf = torch.zeros(512 + 5 * 32 * 8 + 148 * 8, dtype=torch.int64, device="cuda")
     lib.las_debug_set_trace(_cabi.ptr(buf))
+    lib.las_debug_set_option(5, int(os.environ.get("LAS_AB_FLAGS", "0")))
     las.speller(enc, None, 0.0)
     torch.cuda.synchronize()
+    lib.las_debug_set_option(5, 0)
     lib.las_debug_set_trace(None)
     raw = buf.cpu().numpy()
     t = raw[512:512 + 5 * 32 * 8].reshape(5, 32, 8)
@@ -49,6 +51,8 @@ def main():
         print("   att fine (rel. h arrived): " + "  ".join(f"{n}={int(t[3, s, i] - t[3, s, 0])}" for i, n in enumerate(
             ["h", "dot", "shfl", "q sync", "energy", "max sync", "sum sync"])))
         print(f"   L0 epilogue: word column gathered at +{int(t[4, s, 1] - base)} ns")
+        print(f"   critical activation part (ns): L0 fenced={int(t[4, s, 6] - base)} landed={int(t[4, s, 3] - base)}  "
+              f"L1 fenced={int(t[4, s, 7] - base)} landed={int(t[4, s, 5] - base)}")
         if s == 8:
             spread(allc, base)
         print(f"   attention CTA 0: {int(t[2, s + 1, 7] - t[2, s, 7])} SM cycles in {int(t[2, s + 1, 0] - t[2, s, 0])} ns "
