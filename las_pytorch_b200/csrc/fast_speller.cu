@@ -50,7 +50,8 @@ typedef unsigned long long u64;
 
 struct DecParams {
   CUtensorMap tm_h[MAX_SL][2];  // hbuf[l][parity]  bf16 [B, Hs]
-  CUtensorMap tm_x[2];          // xbuf[parity]     bf16 [B, VP + E]  (word atom first, then the context)
+  CUtensorMap tm_x[2];          // xbuf[parity]     bf16 [B, E]   the context fed to layer 0 (same pitch as an h buffer)
+  CUtensorMap tm_w[2];          // wbuf[parity]     bf16 [B, VP]  the dense word fed to layer 0 (one atom)
   CUtensorMap tm_h3[MAX_SL][2]; // the same buffers as {64 k, B, atoms}: one copy brings a whole activation part (tma3d)
   CUtensorMap tm_x3[2];
   int tma3d;                    // 1: Hs and E are multiples of 64, every part is ONE 3-D copy completing on full[0]
@@ -58,6 +59,7 @@ struct DecParams {
   const float* bias[MAX_SL];    // [ncl*64] b_ih + b_hh in CTA column order
   __nv_bfloat16* hbuf[MAX_SL][2];
   __nv_bfloat16* xbuf[2];
+  __nv_bfloat16* wbuf[2];
   u64* h_ll;                    // [B, Hs] {fp32 h of the top layer, step tag}
   u64* tok_ll;                  // [ncl, B] {token fed back, step tag}: one private copy per layer-0 CTA (no polling hot spot)
   const float* c_init;          // nullable [sl, B, Hs]
@@ -277,12 +279,11 @@ __device__ void lstm_role(const DecParams& p, uint8_t* smem, int l, int nb) {
       {
         const CUtensorMap* tm = first ? &p.tm_x[par] : &p.tm_h[l - 1][par ^ 1];
         const CUtensorMap* tm3 = first ? &p.tm_x3[par] : &p.tm_h3[l - 1][par ^ 1];
-        const int col0 = first ? DEC_VP : 0;
         if (ptx::elect_one()) {
           // one instruction for the whole part: issuing eight 2-D copies took ~0.55 us (~68 ns each), all of it on the critical path
-          if (p.tma3d) ptx::tma_load_3d(abuf, tm3, &full[0], 0, 0, col0 / 64);
+          if (p.tma3d) ptx::tma_load_3d(abuf, tm3, &full[0], 0, 0, 0);
           else
-            for (int i = 0; i < nc; ++i) ptx::tma_load_2d(abuf + (size_t)i * STAGE_BYTES, tm, &full[i], col0 + i * 64, 0);
+            for (int i = 0; i < nc; ++i) ptx::tma_load_2d(abuf + (size_t)i * STAGE_BYTES, tm, &full[i], i * 64, 0);
         }
         __syncwarp();
       }
@@ -294,7 +295,7 @@ __device__ void lstm_role(const DecParams& p, uint8_t* smem, int l, int nb) {
         fence_proxy_async_global();
         if (ptx::elect_one()) {
           ptx::mbar_arrive_expect_tx(&full[wslot], STAGE_BYTES);
-          ptx::tma_load_2d(abuf + (size_t)wslot * STAGE_BYTES, &p.tm_x[par], &full[wslot], 0, 0);
+          ptx::tma_load_2d(abuf + (size_t)wslot * STAGE_BYTES, &p.tm_w[par], &full[wslot], 0, 0);
         }
         __syncwarp();
       }
@@ -750,7 +751,8 @@ __device__ void attention_role(const DecParams& p, uint8_t* smem, int b) {
         if (part == 0 && v < V) s_logit[v] = acc + s_bcd[v];
       }
     }
-    __nv_bfloat16* xr = p.xbuf[np] + (size_t)b * (DEC_VP + E);  // next LSTM input row: [word (padded to 64) | context]
+    __nv_bfloat16* xr = p.xbuf[np] + (size_t)b * E;        // next LSTM input: context row
+    __nv_bfloat16* wr_next = p.wbuf[np] + (size_t)b * DEC_VP;  // ... and dense word row (padded to 64)
     if (p.ctx_tmem) {
       ptx::mbar_wait(ctx_bar, (uint32_t)(s & 1));
       ptx::tc_fence_after();
@@ -821,7 +823,7 @@ __device__ void attention_role(const DecParams& p, uint8_t* smem, int b) {
           const float4 lo = xv[0], hi = xv[8];
           const __nv_bfloat162 p0 = __floats2bfloat162_rn(lo.x, lo.y), p1 = __floats2bfloat162_rn(lo.z, lo.w);
           const __nv_bfloat162 p2 = __floats2bfloat162_rn(hi.x, hi.y), p3 = __floats2bfloat162_rn(hi.z, hi.w);
-          *reinterpret_cast<uint4*>(xr + DEC_VP + 8 * tid) =
+          *reinterpret_cast<uint4*>(xr + 8 * tid) =
               make_uint4(*reinterpret_cast<const uint32_t*>(&p0), *reinterpret_cast<const uint32_t*>(&p1),
                          *reinterpret_cast<const uint32_t*>(&p2), *reinterpret_cast<const uint32_t*>(&p3));
         }
@@ -861,29 +863,34 @@ __device__ void attention_role(const DecParams& p, uint8_t* smem, int b) {
     // ---- F: warp 0: log_softmax (:182), argmax / teacher forcing (:216-227), the word fed back (:236).  The other
     //         warps go straight on to poll for the next step's h.
     if (warp == 0) {
+      // Greedy feedback first: argmax(log_softmax(z)) = argmax(z), so the token leaves for layer 0 (whose epilogue needs it
+      // ~2.5 us after the context was published) before the log-sum-exp, the log-prob stores and the loss term are done.
+      const bool early_tok = p.word_gather && !p.gt_index && !p.gt_dense && p.decode_mode != LAS_DECODE_SAMPLE;
       float lm = -INFINITY;
-      for (int v = lane; v < V; v += 32) lm = fmaxf(lm, s_logit[v]);
-      lm = warp_max(lm);
+      int li = 0x7fffffff;
+      for (int v = lane; v < V; v += 32) {
+        const float z = s_logit[v];
+        if (z > lm) { lm = z; li = v; }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, lm, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, li, o);
+        if (ov > lm || (ov == lm && oi < li)) { lm = ov; li = oi; }
+      }
+      if (early_tok) {
+        for (int i = lane; i < p.ncl; i += 32) ll_store(p.tok_ll + (size_t)i * p.B + b, ll_pack((uint32_t)li, (uint32_t)(s + 1)));
+        if (lane == 0 && b == 0) DEC_TRACE(2, 6);
+      }
       float ls = 0.f;
       for (int v = lane; v < V; v += 32) ls += __expf(s_logit[v] - lm);
       ls = warp_sum(ls);
       const float lse = lm + __logf(ls);
-      float bv = -INFINITY;
-      int bi = 0x7fffffff;
-      for (int v = lane; v < V; v += 32) {
-        const float lp = s_logit[v] - lse;
-        p.logp[((size_t)s * p.Bfull + gb) * V + v] = lp;
-        if (lp > bv) { bv = lp; bi = v; }
-      }
+      for (int v = lane; v < V; v += 32) p.logp[((size_t)s * p.Bfull + gb) * V + v] = s_logit[v] - lse;
+      int bi = li;  // ties -> lowest index, as torch.topk / argmax on the host
       if (p.nll_terms && lane == 0) {  // NLLLoss(ignore_index=0) term of this (step, utterance)
         const int lab = (p.nll_labels && s < p.nll_steps) ? p.nll_labels[(size_t)gb * p.nll_steps + s] : 0;
         p.nll_terms[(size_t)s * p.Bfull + gb] = (lab > 0 && lab < V) ? -(s_logit[lab] - lse) : 0.f;
-      }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
-        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-        if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
       }
       if (p.decode_mode == LAS_DECODE_SAMPLE && !p.gt_index && !p.gt_dense) {
         // decode_mode 2 (:229-234): feed back (and report) a draw from Categorical(probs = log-probs); s_logit -> log-probs first
@@ -899,7 +906,7 @@ __device__ void attention_role(const DecParams& p, uint8_t* smem, int b) {
       if (p.word_gather) {
         // the word is an index: layer 0's epilogue adds the matching column of W_word itself
         const int fed = p.gt_index ? p.gt_index[(size_t)gb * p.gt_steps + s] : bi;
-        if (!p.gt_index)
+        if (!p.gt_index && !early_tok)
           for (int i = lane; i < p.ncl; i += 32) ll_store(p.tok_ll + (size_t)i * p.B + b, ll_pack((uint32_t)fed, (uint32_t)(s + 1)));
         if (last && p.word_out)
           for (int i = lane; i < V; i += 32) p.word_out[(size_t)gb * V + i] = (i == fed) ? 1.f : 0.f;
@@ -912,12 +919,12 @@ __device__ void attention_role(const DecParams& p, uint8_t* smem, int b) {
             else val = (i == bi) ? 1.f : 0.f;
             if (last && p.word_out) p.word_out[(size_t)gb * V + i] = val;
           }
-          xr[i] = __float2bfloat16_rn(val);
+          wr_next[i] = __float2bfloat16_rn(val);
         }
         __syncwarp();
         if (lane == 0) red_release_add(word_ctr, 1u);
       }
-      if (lane == 0 && b == 0) DEC_TRACE(2, 6);
+      if (!early_tok && lane == 0 && b == 0) DEC_TRACE(2, 6);
     }
   }
   if (p.ctx_tmem) {
@@ -981,12 +988,11 @@ __global__ void pack_dec_bias_kernel(const float* b_ih, const float* b_hh, float
 // initial decoder input / state in the kernel's operand formats
 __global__ void dec_init_kernel(DecParams p, const float* enc_f32, const float* word_in, const float* ctx_in, const float* h_in) {
   const int b = blockIdx.x, gb = p.b0 + blockIdx.x;
-  __nv_bfloat16* xr = p.xbuf[0] + (size_t)b * (DEC_VP + p.E);
+  __nv_bfloat16* xr = p.xbuf[0] + (size_t)b * p.E;
+  __nv_bfloat16* wr = p.wbuf[0] + (size_t)b * DEC_VP;
   for (int i = threadIdx.x; i < DEC_VP + p.E; i += blockDim.x) {
-    float v;
-    if (i < DEC_VP) v = (i < p.V) ? (word_in ? word_in[(size_t)gb * p.V + i] : (i == 0 ? 1.f : 0.f)) : 0.f;  // <sos> = index 0
-    else v = ctx_in ? ctx_in[(size_t)gb * p.E + (i - DEC_VP)] : enc_f32[(size_t)gb * p.U * p.E + (i - DEC_VP)];  // enc[:,0,:]
-    xr[i] = __float2bfloat16_rn(v);
+    if (i < DEC_VP) wr[i] = __float2bfloat16_rn((i < p.V) ? (word_in ? word_in[(size_t)gb * p.V + i] : (i == 0 ? 1.f : 0.f)) : 0.f);  // <sos> = index 0
+    else xr[i - DEC_VP] = __float2bfloat16_rn(ctx_in ? ctx_in[(size_t)gb * p.E + (i - DEC_VP)] : enc_f32[(size_t)gb * p.U * p.E + (i - DEC_VP)]);  // enc[:,0,:]
   }
   for (int l = 0; l < p.sl; ++l)
     for (int i = threadIdx.x; i < p.Hs; i += blockDim.x)
@@ -1073,6 +1079,7 @@ struct SpellerWsFast {
   __nv_bfloat16* enc_bf16;
   __nv_bfloat16* hbuf[MAX_SL][2];
   __nv_bfloat16* xbuf[2];
+  __nv_bfloat16* wbuf[2];
   uint8_t* flags;      // one block cleared per launch: counters, token slots, h slots
   size_t flag_bytes;
   uint32_t* sync;
@@ -1086,7 +1093,8 @@ SpellerWsFast ws_layout(const las_speller_dims* d, void* base) {
   w.enc_bf16 = cv.take<__nv_bfloat16>((size_t)d->B * d->U * d->E);
   for (int l = 0; l < MAX_SL; ++l)
     for (int k = 0; k < 2; ++k) w.hbuf[l][k] = cv.take<__nv_bfloat16>((size_t)d->B * d->Hs);
-  for (int k = 0; k < 2; ++k) w.xbuf[k] = cv.take<__nv_bfloat16>((size_t)d->B * (DEC_VP + d->E));
+  for (int k = 0; k < 2; ++k) w.xbuf[k] = cv.take<__nv_bfloat16>((size_t)d->B * d->E);
+  for (int k = 0; k < 2; ++k) w.wbuf[k] = cv.take<__nv_bfloat16>((size_t)d->B * DEC_VP);
   const size_t sync_bytes = sizeof(uint32_t) * 32 * N_CTR, tok_bytes = align_up(sizeof(u64) * (size_t)d->B * (d->Hs / DEC_UNITS), 256);
   w.flag_bytes = sync_bytes + tok_bytes + sizeof(u64) * (size_t)d->B * d->Hs;
   w.flags = cv.take<uint8_t>(w.flag_bytes);
@@ -1182,14 +1190,16 @@ int fast_speller_decode(const las_decode_io* io, const void* packed_f32, const v
     }
     for (int k = 0; k < 2; ++k) {
       p.xbuf[k] = w.xbuf[k];
-      LAS_TRY(make_tmap_bf16_box(&p.tm_x[k], w.xbuf[k], Bc, DEC_VP + d->E, DEC_VP + d->E, rc.box_rows));
+      p.wbuf[k] = w.wbuf[k];
+      LAS_TRY(make_tmap_bf16_box(&p.tm_x[k], w.xbuf[k], Bc, d->E, d->E, rc.box_rows));
+      LAS_TRY(make_tmap_bf16_box(&p.tm_w[k], w.wbuf[k], Bc, DEC_VP, DEC_VP, rc.box_rows));
     }
     p.tma3d = (d->Hs % 64 == 0 && d->E % 64 == 0 && !(g_dec_ab_flags & 4)) ? 1 : 0;
     if (p.tma3d) {
       for (int l = 0; l < d->sl; ++l)
         for (int k = 0; k < 2; ++k) LAS_TRY(make_tmap_bf16_atoms(&p.tm_h3[l][k], w.hbuf[l][k], Bc, d->Hs / 64, d->Hs, rc.box_rows, d->Hs / 64));
       for (int k = 0; k < 2; ++k)
-        LAS_TRY(make_tmap_bf16_atoms(&p.tm_x3[k], w.xbuf[k], Bc, (DEC_VP + d->E) / 64, DEC_VP + d->E, rc.box_rows, d->E / 64));
+        LAS_TRY(make_tmap_bf16_atoms(&p.tm_x3[k], w.xbuf[k], Bc, d->E / 64, d->E, rc.box_rows, d->E / 64));
     }
     const size_t so = (size_t)b0;  // batch offset into caller tensors
     p.Bfull = d->B;
