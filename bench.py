@@ -269,24 +269,29 @@ def main():
         name, t, n = line.rsplit(" ", 2)
         g = groups.setdefault(name, [0.0, 0])
         g[0] += float(t); g[1] += int(n)
-    # untimed extra pass with the listener's GEMM / recurrence overlap switched off (las_debug_set_option(6, 0)): the duration
-    # of each input-projection GEMM running ALONE on the whole chip, which is what its roofline line is quoted on
-    alone = {}
+    # untimed extra passes with the listener's GEMM / recurrence overlap switched off (las_debug_set_option(6, 0)): the duration
+    # of each input-projection GEMM running ALONE on the whole chip, which is what its roofline line is quoted on.  Pass 1 uses
+    # the epilogue the pipeline runs (row-per-thread stores, option 8 = 1: the variant that runs next to the recurrence); pass 2
+    # the shared-memory-staged TMA-store epilogue a stand-alone launch would pick (reported alongside, not as the roofline).
+    alone, alone_tma = {}, {}
     if rank == 0:
-        lib.las_debug_set_option(6, 0)
-        one_step(x_dev)
-        torch.cuda.synchronize()
-        lib.las_prof_enable(1)
-        for _ in range(3):
-            flush.zero_()
+        for store_opt, dst in ((1, alone), (0, alone_tma)):
+            lib.las_debug_set_option(6, 0)
+            lib.las_debug_set_option(8, store_opt)
             one_step(x_dev)
-        torch.cuda.synchronize()
-        _cabi.check(lib.las_prof_report(ctypes_buf, len(ctypes_buf)))
-        lib.las_prof_enable(0)
-        lib.las_debug_set_option(6, 1)
-        for line in ctypes_buf.value.decode().splitlines():
-            name, t, n = line.rsplit(" ", 2)
-            alone[name] = alone.get(name, 0.0) + float(t) / 3
+            torch.cuda.synchronize()
+            lib.las_prof_enable(1)
+            for _ in range(3):
+                flush.zero_()
+                one_step(x_dev)
+            torch.cuda.synchronize()
+            _cabi.check(lib.las_prof_report(ctypes_buf, len(ctypes_buf)))
+            lib.las_prof_enable(0)
+            lib.las_debug_set_option(6, 1)
+            lib.las_debug_set_option(8, 0)
+            for line in ctypes_buf.value.decode().splitlines():
+                name, t, n = line.rsplit(" ", 2)
+                dst[name] = dst.get(name, 0.0) + float(t) / 3
     t_ms = torch.tensor([ms], dtype=torch.float64, device=dev)
     chk = torch.tensor([float(tokens.sum())], dtype=torch.float64, device=dev)
     if dist is not None:
@@ -362,11 +367,14 @@ def main():
         extra = {}
         if name.endswith(".overlapped"):
             # quoted on the kernel running alone on the whole chip (untimed extra pass); the in-pipeline duration is kept alongside
-            extra = {"ms_in_pipeline_overlapped_with_recurrence": per_step[name]}
+            extra = {"ms_in_pipeline_overlapped_with_recurrence": per_step[name],
+                     "epilogue": "row-per-thread stores (the variant that runs next to the recurrence)"}
             name = name[: -len(".overlapped")]
             if name not in alone:
                 return None
             dt = alone[name] / 1e3
+            if name in alone_tma:
+                extra["ms_alone_with_tma_store_epilogue"] = alone_tma[name]
         if dt <= 0:
             return None
         if name.endswith("input_gemm"):

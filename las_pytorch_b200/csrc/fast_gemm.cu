@@ -9,9 +9,15 @@
 //              4-stage mbarrier ring; K / M / N tails are TMA out-of-bounds zero fill
 //   warp 1     TMEM allocator + single-thread tcgen05.mma issuer (M=128, N=256, K=16 per instruction),
 //              tcgen05.commit releases smem stages and publishes finished accumulators
-//   warps 2-5  epilogue: tcgen05.ld accumulator rows -> +bias -> 128-byte row segments to global;
-//              two 256-column accumulators in TMEM so the epilogue of tile i overlaps the MMAs of tile i+1
+//   warps 2-5  epilogue: tcgen05.ld accumulator rows -> +bias -> a 32x32 fp32 block per warp in shared memory (128-byte rows,
+//              chunk-swizzled: conflict-free) -> one TMA store per block (full 128-byte lines; M / N tails clipped by the
+//              tensor map); two 256-column accumulators in TMEM so the epilogue of tile i overlaps the MMAs of tile i+1.
+//              Row-per-thread st.global.v4 stores (32 partial lines per instruction) are the other epilogue: slower when the
+//              GEMM has the chip to itself (K=80: 172 vs 148 us, K=1024: 129 vs 104 us), but the one used when the GEMM runs next to
+//              the listener's recurrence with tile flags: there the bulk stores slow the recurrence by ~5 % (1.70 vs 1.66 ms per
+//              listener pass, profiles/r01_gemm_epilogue_ab.log), and the GEMM is hidden behind the recurrence anyway.
 #include <cuda.h>
+#include <string.h>
 
 #include "las_fast.cuh"
 #include "umma.cuh"
@@ -24,9 +30,11 @@ constexpr int BM = 128, BN = 256, BK = 64, STAGES = 4;
 constexpr int A_TILE_BYTES = BM * BK * 2, B_TILE_BYTES = BN * BK * 2;
 constexpr int GEMM_THREADS = 192;
 
+constexpr int EPI_BLOCK_BYTES = 32 * 32 * 4;  // one epilogue warp's staging block: 32 rows x 32 fp32
 struct __align__(1024) GemmSmem {
   uint8_t a[STAGES][A_TILE_BYTES];
   uint8_t b[STAGES][B_TILE_BYTES];
+  uint8_t epi[4][2][EPI_BLOCK_BYTES];  // [epilogue warp][double buffer]: source of the TMA stores (1024-byte aligned blocks)
   uint64_t full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2];
   uint32_t tmem_base;
 };
@@ -36,6 +44,8 @@ struct __align__(1024) GemmSmem {
 //   (m = i / n_tiles,               n = i % n_tiles)   for the forward direction's column tiles  (n <  nfwd)
 //   (m = m_tiles - 1 - i / n_tiles, n = i % n_tiles)   for the backward direction's             (n >= nfwd)
 // i.e. the recurrence's consumption order: early time steps for the forward LSTM, late ones for the backward LSTM.
+int g_gemm_direct_store = 0;  // las_debug_set_option(8, 1): row-per-thread global stores instead of the TMA-store epilogue (A/B, tests)
+
 struct GemmSched {
   int mode, Bp, nfwd;
   uint32_t* flags;  // nullable: [m_tiles * n_tiles] counters, +1 per epilogue warp that has stored its rows of the tile
@@ -48,8 +58,8 @@ __device__ __forceinline__ void sched_tile(const GemmSched& sc, int i, int m_til
 
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
-                    const float* __restrict__ bias, float* __restrict__ C, long long ldc, int M, int N, int K, int relu,
-                    const GemmSched sc) {
+                    const __grid_constant__ CUtensorMap tm_c, const float* __restrict__ bias, float* __restrict__ C, long long ldc,
+                    int M, int N, int K, int relu, int tma_store, const GemmSched sc) {
   extern __shared__ uint8_t smem_raw[];
   GemmSmem& s = *reinterpret_cast<GemmSmem*>(smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u));  // offset from the __shared__ symbol keeps the address space
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -59,6 +69,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
   if (threadIdx.x == 0) {
     ptx::prefetch_tensormap(&tm_a);
     ptx::prefetch_tensormap(&tm_b);
+    if (tma_store) ptx::prefetch_tensormap(&tm_c);
     for (int i = 0; i < STAGES; ++i) {
       ptx::mbar_init(&s.full[i], 1);
       ptx::mbar_init(&s.empty[i], 1);
@@ -123,6 +134,64 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
     const int q = warp & 3;  // TMEM lane quadrant this warp may access
     const bool vec_ok = (ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0);
     int it = 0;
+    if (tma_store) {
+      // ---- TMA-store epilogue.  Bulk groups: one per 32-column block, 8 per tile.
+      uint8_t* const blk0 = s.epi[q][0];
+      const uint32_t sw = (uint32_t)(lane & 7);
+      uint32_t nblk = 0;                 // blocks issued so far by this warp (buffer = nblk & 1)
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        int mt, nt;
+        sched_tile(sc, tile, m_tiles, n_tiles, mt, nt);
+        const int m0 = mt * BM, n0 = nt * BN;
+        ptx::mbar_wait(&s.tmem_full[acc], acc_phase);
+        ptx::tc_fence_after();
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+          const int col0 = n0 + c0;
+          if (col0 >= N) break;  // warp-uniform: this and the following blocks lie beyond the last column
+          uint32_t v[32];
+          ptx::tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + c0, v);
+          ptx::tmem_ld_wait();
+          uint8_t* dst = blk0 + (nblk & 1) * EPI_BLOCK_BYTES;
+          if (nblk >= 2) {  // the store issued from this buffer two blocks ago must have read it
+            if (lane == 0) ptx::tma_store_wait_read<1>();
+            __syncwarp();
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float4 bv;
+            if (col0 + 4 * j + 3 < N) bv = *reinterpret_cast<const float4*>(bias + col0 + 4 * j);
+            else {
+              bv.x = col0 + 4 * j < N ? bias[col0 + 4 * j] : 0.f;
+              bv.y = col0 + 4 * j + 1 < N ? bias[col0 + 4 * j + 1] : 0.f;
+              bv.z = col0 + 4 * j + 2 < N ? bias[col0 + 4 * j + 2] : 0.f;
+              bv.w = 0.f;
+            }
+            float4 o;
+            o.x = __uint_as_float(v[4 * j]) + bv.x;
+            o.y = __uint_as_float(v[4 * j + 1]) + bv.y;
+            o.z = __uint_as_float(v[4 * j + 2]) + bv.z;
+            o.w = __uint_as_float(v[4 * j + 3]) + bv.w;
+            if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+            // row `lane`, 16-byte chunk j at the SWIZZLE_128B position: the 8 lanes of a quarter warp fill all 32 banks
+            *reinterpret_cast<float4*>(dst + lane * 128 + (((uint32_t)j ^ sw) << 4)) = o;
+          }
+          ptx::fence_proxy_async_smem();  // generic-proxy writes above -> the bulk store's async-proxy reads
+          __syncwarp();
+          if (lane == 0) {
+            if (m0 + q * 32 < M) ptx::tma_store_2d(&tm_c, dst, col0, m0 + q * 32);  // rows >= M / columns >= N are clipped
+            ptx::tma_store_commit();
+          }
+          ++nblk;
+        }
+        ptx::tc_fence_before();
+        ptx::mbar_arrive(&s.tmem_empty[acc]);
+      }
+      if (lane == 0) ptx::tma_store_wait<0>();  // every store has read its buffer and landed before the CTA retires
+      __syncwarp();
+    } else
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
@@ -205,7 +274,31 @@ int make_tmap_bf16(CUtensorMap* tm, const void* base, long long rows, long long 
   return LAS_OK;
 }
 
+// row-major fp32 matrix [rows, cols] with row pitch `ld` elements; box = {32 cols, 32 rows}, 128-byte swizzle (TMA store target)
+int make_tmap_f32_store(CUtensorMap* tm, const void* base, long long rows, long long cols, long long ld) {
+  EncodeTiledFn enc;
+  LAS_TRY(get_encode_fn(&enc));
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t gstr[1] = {(cuuint64_t)ld * 4};
+  cuuint32_t box[2] = {32, 32};
+  cuuint32_t estr[2] = {1, 1};
+  const CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), gdim, gstr, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(LAS_ECUDA, "cuTensorMapEncodeTiled (fp32 output) failed with CUresult %d (rows=%lld cols=%lld ld=%lld)", (int)r, rows, cols, ld);
+  return LAS_OK;
+}
+// TMA can address the output when the base and the row pitch are 16-byte aligned; otherwise the kernel stores rows directly.
+// Narrow outputs (psi: N = 64, two blocks per tile) are a little faster with direct stores (14.3 vs 16.4 us), so they keep them.
+bool tma_store_ok(const float* C, long long ldc, int N, const uint32_t* flags) {
+  return (reinterpret_cast<uintptr_t>(C) & 15) == 0 && (ldc * 4) % 16 == 0 && N >= 128 && !flags && !g_gemm_direct_store;
+}
+
 }  // namespace
+
+void fast_set_option_gemm(int key, int value) {
+  if (key == 8) g_gemm_direct_store = value;
+}
 
 int make_tmap_bf16_box(CUtensorMap* tm, const void* base, long long rows, long long cols, long long ld, int box_rows) {
   return make_tmap_bf16(tm, base, rows, cols, ld, box_rows);
@@ -235,12 +328,16 @@ int launch_gemm_bf16_tc(const __nv_bfloat16* A, long long lda, const __nv_bfloat
   CUtensorMap tm_a, tm_b;
   LAS_TRY(make_tmap_bf16(&tm_a, A, M, K, lda, BM));
   LAS_TRY(make_tmap_bf16(&tm_b, W, N, K, ldw, BN));
+  CUtensorMap tm_c;
+  memset(&tm_c, 0, sizeof(tm_c));
+  const bool ts = tma_store_ok(C, ldc, N, nullptr);
+  if (ts) LAS_TRY(make_tmap_f32_store(&tm_c, C, M, N, ldc));
   const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
   const int grid = tiles < sm_count() ? tiles : sm_count();
   const size_t smem = sizeof(GemmSmem) + 1024;
   // per launch, not cached: the attribute belongs to the current device's context and a host thread may serve several devices
   LAS_CUDA_OK(cudaFuncSetAttribute(gemm_bf16_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  gemm_bf16_tc_kernel<<<grid, GEMM_THREADS, smem, st>>>(tm_a, tm_b, bias, C, ldc, M, N, K, relu ? 1 : 0, GemmSched{0, 0, 0, nullptr});
+  gemm_bf16_tc_kernel<<<grid, GEMM_THREADS, smem, st>>>(tm_a, tm_b, tm_c, bias, C, ldc, M, N, K, relu ? 1 : 0, ts ? 1 : 0, GemmSched{0, 0, 0, nullptr});
   LAS_LAUNCH_OK("gemm_bf16_tc_kernel");
   return LAS_OK;
 }
@@ -274,6 +371,10 @@ int launch_gemm_listener(const __nv_bfloat16* A, int B, int Tl, int K, const __n
     if (r != CUDA_SUCCESS) return fail(LAS_ECUDA, "cuTensorMapEncodeTiled (3-D listener input) failed with CUresult %d (B=%d Tl=%d K=%d)", (int)r, B, Tl, K);
   }
   LAS_TRY(make_tmap_bf16(&tm_b, W, N, K, K, BN));
+  CUtensorMap tm_c;
+  memset(&tm_c, 0, sizeof(tm_c));
+  const bool ts = tma_store_ok(C, N, N, flags);
+  if (ts) LAS_TRY(make_tmap_f32_store(&tm_c, C, M, N, N));
   const int n_tiles = (N + BN - 1) / BN;
   const int tiles = ((M + BM - 1) / BM) * n_tiles;
   int grid = tiles < sm_count() ? tiles : sm_count();
@@ -284,7 +385,7 @@ int launch_gemm_listener(const __nv_bfloat16* A, int B, int Tl, int K, const __n
   // forward-direction columns are the first half of N; when the halves do not fall on tile boundaries every column tile
   // serves both directions and the natural (front-first) order is kept
   const int nfwd = ((N / 2) % BN == 0) ? (N / 2) / BN : n_tiles;
-  gemm_bf16_tc_kernel<<<grid, GEMM_THREADS, smem, st>>>(tm_a, tm_b, bias, C, (long long)N, M, N, K, 0, GemmSched{1, Bp, nfwd, flags});
+  gemm_bf16_tc_kernel<<<grid, GEMM_THREADS, smem, st>>>(tm_a, tm_b, tm_c, bias, C, (long long)N, M, N, K, 0, ts ? 1 : 0, GemmSched{1, Bp, nfwd, flags});
   LAS_LAUNCH_OK("gemm_bf16_tc_kernel");
   return LAS_OK;
 }

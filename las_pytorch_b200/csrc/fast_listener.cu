@@ -535,12 +535,14 @@ int launch_rec(const RecParams& p, cudaStream_t st, bool exclusive_sm) {
 void fast_set_trace(long long* p) { g_rec_trace = p; }
 long long* fast_get_trace() { return g_rec_trace; }
 void fast_set_option_speller(int key, int value);
+void fast_set_option_gemm(int key, int value);  // fast_gemm.cu: 8 = direct-store epilogue
 void fast_set_option(int key, int value) {
   if (key == 1) g_rec_a_tmem = value;
   if (key == 4) g_rec_nacc = value;
   if (key == 6) g_rec_overlap = value;
   if (key == 7) g_rec_gemm_ctas = value;
   fast_set_option_speller(key, value);
+  fast_set_option_gemm(key, value);
 }
 
 size_t fast_listener_packed_bytes(const las_listener_dims* d) { return pack_layout(d, nullptr).bytes; }

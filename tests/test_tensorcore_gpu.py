@@ -33,3 +33,29 @@ def test_input_projection_gemm(M, N, K):
     torch.cuda.synchronize()
     ref = a.float() @ w.float().t() + bias
     assert float((c - ref).abs().max()) <= 2e-3
+
+
+@pytest.mark.parametrize("M,N,K", [(300, 128, 80), (389, 280, 96), (4096, 2048, 256), (1000, 136, 512)])
+def test_gemm_tma_store_epilogue_matches_direct_stores(M, N, K):
+    """The epilogue stages 32x32 blocks in shared memory and writes them with TMA stores (M / N tails clipped by the tensor map);
+    las_debug_set_option(8, 1) selects the row-per-thread global stores that remain as the fallback: bit-identical outputs, and
+    nothing is written outside [M, N]."""
+    lib = _cabi.load_library()
+    g = torch.Generator().manual_seed(7 * M + N + K)
+    a = torch.randn(M, K, generator=g).cuda().to(torch.bfloat16)
+    w = (torch.randn(N, K, generator=g) / K ** 0.5).cuda().to(torch.bfloat16)
+    bias = torch.randn(N, generator=g).cuda()
+    outs = []
+    for direct in (1, 0):
+        buf = torch.full((M + 64, N), float("nan"), device="cuda")  # guard rows behind the output
+        try:
+            lib.las_debug_set_option(8, direct)
+            _cabi.check(lib.las_debug_gemm_bf16(_cabi.ptr(a), _cabi.ptr(w), _cabi.ptr(bias), _cabi.ptr(buf), M, N, K, _cabi.current_stream_ptr()))
+            torch.cuda.synchronize()
+        finally:
+            lib.las_debug_set_option(8, 0)
+        assert torch.isnan(buf[M:]).all()
+        outs.append(buf[:M].clone())
+    assert torch.equal(outs[0], outs[1])
+    ref = a.float() @ w.float().t() + bias
+    assert float((outs[1] - ref).abs().max()) <= 2e-3
