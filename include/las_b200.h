@@ -222,7 +222,8 @@ int las_debug_umma_probe(const void* a_bf16, const void* b_bf16, float* d, int N
 /* Device buffer of 64*8 int64 that the layer-0 recurrence kernel fills with clock64 stamps (NULL disables). */
 int las_debug_set_trace(void* dev_buf);
 /* Kernel variant switches for A/B tests.  key 1: recurrence keeps W_hh in tensor memory (1, default) or shared memory (0);
- * key 2: decoder context through tensor memory (1, default) or CUDA cores (0); key 4: recurrence accumulator chains (0 = default);
+ * key 2: decoder context through tensor memory (1, default: all feature tiles when they fit, otherwise as many as fit + the rest on the
+ * CUDA cores), CUDA cores only (0), tensor memory only when everything fits (2); key 4: recurrence accumulator chains (0 = default);
  * key 5: decoder A/B flags (bit 0: W_phi from shared memory instead of registers; bit 2: one 2-D TMA copy per 64-column atom of an
  * activation part instead of one 3-D copy); key 6: listener input-projection GEMM concurrent with the recurrence (1, default) or in
  * front of it (0); key 7: persistent CTAs of that concurrent GEMM (0 = auto); key 8: tcgen05 GEMM epilogue with row-per-thread

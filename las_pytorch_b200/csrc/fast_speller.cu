@@ -91,7 +91,9 @@ struct DecParams {
   int ab_flags;     // test hook (las_debug_set_option(5, v)): bit 0 = W_phi from shared memory instead of registers; bit 2 (value 4) = eight 2-D copies per activation part instead of one 3-D copy
   unsigned long long sample_seed;  // LAS_DECODE_SAMPLE
   int word_gather;  // 1: the fed-back word is an index (greedy argmax / gt_index); 0: a dense vector (part 1b)
-  int ctx_tmem;     // 1: enc[b]^T is resident in the attention CTA's tensor memory and the context is a UMMA
+  int ctx_tmem;     // > 0: enc[b]^T is resident in the attention CTA's tensor memory and the context is a UMMA
+  int ctx_ntm;      // 128-feature tiles of enc[b]^T held in tensor memory: E/128 = all of them; fewer (long encoders, e.g. U = 375:
+                    // 2 of 4) = hybrid, the remaining features are reduced on the CUDA cores from the L2-resident bf16 copy
   int nstages, stage_bytes;  // activation slots: [64 batch rows x 64 bf16], 128-byte swizzled; last slot = word atom
   long long* trace;  // nullable test hook: [3 roles][32 steps][8] globaltimer stamps (layer-0 CTA 0, top-layer CTA 0, attention CTA 0)
 };
@@ -461,9 +463,10 @@ __host__ __device__ inline int att_kstride(int D) {
 }
 struct AttLayout {
   int WPS, WCS, KS, Up;
-  size_t o_wcd, o_h, o_q, o_score, o_logit, o_bphi, o_bcd, o_red, o_part, o_k, total;
+  size_t o_wcd, o_h, o_q, o_score, o_logit, o_bphi, o_bcd, o_red, o_part, o_bop, o_k, total;
 };
-__host__ __device__ inline AttLayout att_layout(int Hs, int E, int U, int D, int V, bool k_in, bool wreg) {
+__host__ __device__ inline size_t att_bop_bytes(int U) { return (size_t)((U + 15) / 16) * 512 + 16; }
+__host__ __device__ inline AttLayout att_layout(int Hs, int E, int U, int D, int V, bool k_in, bool wreg, bool hybrid = false) {
   AttLayout a;
   a.WPS = Hs + 8;          // bf16 row strides: multiples of 8 keep every 16-byte chunk aligned
   a.WCS = Hs + E + 8;
@@ -481,6 +484,7 @@ __host__ __device__ inline AttLayout att_layout(int Hs, int E, int U, int D, int
   a.o_bcd = take(64 * 4);
   a.o_red = take(64 * 4);
   a.o_part = take(4096 * 4);                           // context partial sums, or {mbarrier, TMEM slot, score operand}
+  a.o_bop = hybrid ? take(att_bop_bytes(U)) : a.o_part; // hybrid context path: both at once
   a.o_k = o;
   if (k_in) take((size_t)U * a.KS * 4);
   a.total = o;
@@ -491,7 +495,10 @@ __device__ void attention_role(const DecParams& p, uint8_t* smem, int b) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr int NWARP = DEC_THREADS / 32;
   const int Hs = p.Hs, E = p.E, U = p.U, D = p.D, V = p.V, KC = p.Hs + p.E;
-  const AttLayout L = att_layout(Hs, E, U, D, V, p.k_in_smem != 0, p.wreg != 0);
+  const int NT = E / 128;                                     // feature tiles
+  const int ntm = p.ctx_tmem ? p.ctx_ntm : 0;                 // ... of which in tensor memory
+  const bool hybrid = ntm > 0 && ntm * 128 < E;               // (E need not be a multiple of 128 when ntm = 0)
+  const AttLayout L = att_layout(Hs, E, U, D, V, p.k_in_smem != 0, p.wreg != 0, hybrid);
   const int KS = L.KS, WPS = L.WPS, WCS = L.WCS;
   const int gb = p.b0 + b;  // utterance index in the caller's tensors
   __nv_bfloat16* s_wphi = reinterpret_cast<__nv_bfloat16*>(smem);               // [D][WPS]
@@ -506,15 +513,18 @@ __device__ void attention_role(const DecParams& p, uint8_t* smem, int b) {
   float* s_red = reinterpret_cast<float*>(smem + L.o_red);      // [0,16): warp maxima, [16,32): warp sums
   float* s_part = reinterpret_cast<float*>(smem + L.o_part);
   float* s_k = reinterpret_cast<float*>(smem + L.o_k);          // [U][KS] when k_in_smem
-  const int ncg = E / 8;              // 8-column groups of enc (non-TMEM context path)
+  const int e_cc = ntm * 128;         // first feature of the CUDA-core context path (0: all of them; E: none)
+  const int Ec = E - e_cc;
+  const int ncg = Ec > 0 ? Ec / 8 : 1;  // 8-column groups of enc (CUDA-core context path)
   const int nrg = DEC_THREADS / ncg;  // row groups working in parallel
-  // tensor-memory context path: s_part's space holds the mbarrier, the TMEM slot and the score operand instead
-  uint64_t* ctx_bar = reinterpret_cast<uint64_t*>(s_part);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_part + 2);
-  uint8_t* s_bop = reinterpret_cast<uint8_t*>(s_part + 4);   // [2*nks core-K][2][8 rows][16 B]: row 0 = scores (bf16)
+  // tensor-memory context path: the mbarrier, the TMEM slot and the score operand live in s_part's space (all features in
+  // tensor memory: no partial sums needed) or in their own region (hybrid)
+  float* s_tm = reinterpret_cast<float*>(smem + L.o_bop);
+  uint64_t* ctx_bar = reinterpret_cast<uint64_t*>(s_tm);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_tm + 2);
+  uint8_t* s_bop = reinterpret_cast<uint8_t*>(s_tm + 4);     // [2*nks core-K][2][8 rows][16 B]: row 0 = scores (bf16)
   const int nks = (U + 15) / 16;                              // UMMA K steps over the encoder axis
   const int CU = nks * 8;                                     // TMEM columns of one 128-feature tile of enc^T
-  const int NT = E / 128;                                     // feature tiles
 
   if (!p.wreg)
     for (int i = tid; i < D * Hs; i += DEC_THREADS) s_wphi[(size_t)(i / Hs) * WPS + (i % Hs)] = p.w_phi[i];
@@ -548,7 +558,7 @@ __device__ void attention_role(const DecParams& p, uint8_t* smem, int b) {
     ptx::tc_fence_after();
     tmem = *tmem_slot;
     const int qd = warp & 3;
-    for (int t = warp >> 2; t < NT; t += NWARP / 4) {
+    for (int t = warp >> 2; t < ntm; t += NWARP / 4) {
       const __nv_bfloat16* col = encb + t * 128 + qd * 32 + lane;
       for (int ks = 0; ks < nks; ++ks) {
         uint32_t v[8];
@@ -687,8 +697,8 @@ __device__ void attention_role(const DecParams& p, uint8_t* smem, int b) {
           lsum += ev[ps];
           const int u = ps * 256 + (tid >> 1);
           if (u < U) {
-            if (p.ctx_tmem) *reinterpret_cast<__nv_bfloat16*>(s_bop + (u >> 3) * 256 + (u & 7) * 2) = __float2bfloat16_rn(ev[ps]);
-            else s_score[u] = ev[ps];
+            if (ntm > 0) *reinterpret_cast<__nv_bfloat16*>(s_bop + (u >> 3) * 256 + (u & 7) * 2) = __float2bfloat16_rn(ev[ps]);
+            if (Ec > 0) s_score[u] = ev[ps];
           }
         }
       }
@@ -717,9 +727,9 @@ __device__ void attention_role(const DecParams& p, uint8_t* smem, int b) {
           const UmmaLayout lb{0, 256, 128, 0};
           const uint32_t idesc = umma_idesc_bf16(128, 16);
           const uint32_t bop = ptx::smem_u32(s_bop);
-          for (int t = 0; t < NT; ++t)
+          for (int t = 0; t < ntm; ++t)
             for (int ks = 0; ks < nks; ++ks)
-              ptx::umma_bf16_ts(tmem + NT * CU + t * 16, tmem + t * CU + ks * 8, umma_smem_desc(lb, bop, ks * 16), idesc, ks != 0);
+              ptx::umma_bf16_ts(tmem + ntm * CU + t * 16, tmem + t * CU + ks * 8, umma_smem_desc(lb, bop, ks * 16), idesc, ks != 0);
           ptx::umma_commit(ctx_bar);
         }
         __syncwarp();
@@ -732,7 +742,7 @@ __device__ void attention_role(const DecParams& p, uint8_t* smem, int b) {
         if (u < U) p.attn[((size_t)s * p.Bfull + gb) * U + u] = ev[ps] * inv;
       }
     }
-    if (warp != 0) {
+    if (warp != 0 && !hybrid) {
       const int part = tid & 15;
       for (int v = (tid - 32) >> 4; v < Vp; v += (DEC_THREADS - 32) / 16) {
         float acc = 0.f;
@@ -753,13 +763,48 @@ __device__ void attention_role(const DecParams& p, uint8_t* smem, int b) {
     }
     __nv_bfloat16* xr = p.xbuf[np] + (size_t)b * E;        // next LSTM input: context row
     __nv_bfloat16* wr_next = p.wbuf[np] + (size_t)b * DEC_VP;  // ... and dense word row (padded to 64)
-    if (p.ctx_tmem) {
+    if (Ec > 0) {
+      // CUDA-core part, features [e_cc, E): 16-byte bf16 loads of enc[b] (L2 resident), nrg row groups in parallel, 8 loads in
+      // flight.  In the hybrid case this runs while the tensor pipe reduces the features below e_cc.
+      const int rg = tid / ncg, cg = tid % ncg;
+      float acc[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+      if (rg < nrg) {
+        const uint4* col = reinterpret_cast<const uint4*>(encb + e_cc + cg * 8);
+        const int rstride = E / 8;  // uint4 per row
+        for (int u = rg; u < ulen; u += 8 * nrg) {
+          uint4 v[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int uu = u + j * nrg;
+            v[j] = (uu < ulen) ? __ldg(col + (size_t)uu * rstride) : make_uint4(0, 0, 0, 0);
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int uu = u + j * nrg;
+            const float a = (uu < ulen) ? s_score[uu] : 0.f;  // unnormalised exp(e - max)
+            const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&v[j]);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float2 f = __bfloat1622float2(h2[i]);
+              acc[2 * i] = fmaf(a, f.x, acc[2 * i]);
+              acc[2 * i + 1] = fmaf(a, f.y, acc[2 * i + 1]);
+            }
+          }
+        }
+        float4* dst = reinterpret_cast<float4*>(s_part + (size_t)rg * Ec + cg * 8);
+        dst[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+        dst[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+      }
+    }
+    if (ntm > 0) {
       ptx::mbar_wait(ctx_bar, (uint32_t)(s & 1));
       ptx::tc_fence_after();
-      if (tid == 0 && b == 0) DEC_TRACE(2, 3);
+      if (tid == 0 && b == 0 && !hybrid) DEC_TRACE(2, 3);
       const int qd = warp & 3;
-      for (int t = warp >> 2; t < NT; t += NWARP / 4) {
-        const uint32_t r = ptx::tmem_ld_32x32b_x1(tmem + ((uint32_t)(qd * 32) << 16) + NT * CU + t * 16);
+      for (int t = warp >> 2; t < ntm; t += NWARP / 4) {
+        const uint32_t r = ptx::tmem_ld_32x32b_x1(tmem + ((uint32_t)(qd * 32) << 16) + ntm * CU + t * 16);
         ptx::tmem_ld_wait();
         const int e = t * 128 + qd * 32 + lane;
         const float cv = __uint_as_float(r) * inv;
@@ -767,49 +812,16 @@ __device__ void attention_role(const DecParams& p, uint8_t* smem, int b) {
         if (last && p.ctx_out) p.ctx_out[(size_t)gb * E + e] = cv;
       }
       ptx::tc_fence_before();
-    } else {
-      // 16-byte bf16 loads of enc[b] (L2 resident), nrg row groups in parallel, 8 loads in flight
-      {
-        const int rg = tid / ncg, cg = tid % ncg;
-        float acc[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-        if (rg < nrg) {
-          const uint4* col = reinterpret_cast<const uint4*>(encb + cg * 8);
-          const int rstride = E / 8;  // uint4 per row
-          for (int u = rg; u < ulen; u += 8 * nrg) {
-            uint4 v[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const int uu = u + j * nrg;
-              v[j] = (uu < ulen) ? __ldg(col + (size_t)uu * rstride) : make_uint4(0, 0, 0, 0);
-            }
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const int uu = u + j * nrg;
-              const float a = (uu < ulen) ? s_score[uu] : 0.f;  // unnormalised exp(e - max)
-              const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&v[j]);
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const float2 f = __bfloat1622float2(h2[i]);
-                acc[2 * i] = fmaf(a, f.x, acc[2 * i]);
-                acc[2 * i + 1] = fmaf(a, f.y, acc[2 * i + 1]);
-              }
-            }
-          }
-          float4* dst = reinterpret_cast<float4*>(s_part + (size_t)rg * E + cg * 8);
-          dst[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
-          dst[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
-        }
-      }
+    }
+    if (Ec > 0) {
       __syncthreads();
       if (tid == 0 && b == 0) DEC_TRACE(2, 3);
-      for (int e = tid; e < E; e += DEC_THREADS) {
+      for (int ee = tid; ee < Ec; ee += DEC_THREADS) {
         float acc = 0.f;
-        for (int rg = 0; rg < nrg; ++rg) acc += s_part[(size_t)rg * E + e];
+        for (int rg = 0; rg < nrg; ++rg) acc += s_part[(size_t)rg * Ec + ee];
         acc *= inv;
-        s_ctx[xpos(e)] = acc;
-        if (last && p.ctx_out) p.ctx_out[(size_t)gb * E + e] = acc;
+        s_ctx[xpos(e_cc + ee)] = acc;
+        if (last && p.ctx_out) p.ctx_out[(size_t)gb * E + e_cc + ee] = acc;
       }
     }
     __syncthreads();
@@ -849,12 +861,19 @@ __device__ void attention_role(const DecParams& p, uint8_t* smem, int b) {
             const float4* xv = xchunk(s_ctx, c);
             acc = dot8(lds128(wr + hchunks + c), xv[0], xv[8], acc);
           }
+          if (hybrid) {  // the h half was not evaluated during the context reduction (every warp was busy with it)
+#pragma unroll 4
+            for (int c = part; c < hchunks; c += 16) {
+              const float4* xv = xchunk(s_h, c);
+              acc = dot8(lds128(wr + c), xv[0], xv[8], acc);
+            }
+          }
         }
         acc += __shfl_xor_sync(0xffffffffu, acc, 1);
         acc += __shfl_xor_sync(0xffffffffu, acc, 2);
         acc += __shfl_xor_sync(0xffffffffu, acc, 4);
         acc += __shfl_xor_sync(0xffffffffu, acc, 8);
-        if (part == 0 && v < V) s_logit[v] += acc;
+        if (part == 0 && v < V) s_logit[v] = hybrid ? acc + s_bcd[v] : s_logit[v] + acc;
       }
     }
     __syncthreads();
@@ -1041,7 +1060,7 @@ RingCfg ring_cfg(const las_speller_dims* d, int rows) {
   return r;
 }
 bool att_wreg(const las_speller_dims* d) { return d->D <= DEC_THREADS / 8 && d->Hs <= 512 && !(g_dec_ab_flags & 1); }
-size_t att_smem(const las_speller_dims* d, bool k_in) { return att_layout(d->Hs, d->E, d->U, d->D, d->V, k_in, att_wreg(d)).total + 64; }
+size_t att_smem(const las_speller_dims* d, bool k_in, bool hybrid = false) { return att_layout(d->Hs, d->E, d->U, d->D, d->V, k_in, att_wreg(d), hybrid).total + 64; }
 int supported(const las_speller_dims* d) {
   LAS_REQUIRE(d->sl <= MAX_SL, "LAS_MODE_BF16 speller supports at most %d layers (sl=%d)", MAX_SL, d->sl);
   LAS_REQUIRE(d->Hs % 16 == 0 && d->Hs <= 512, "LAS_MODE_BF16 speller needs hidden_size %% 16 == 0 and <= 512 (Hs=%d); use LAS_MODE_FP32", d->Hs);
@@ -1175,7 +1194,20 @@ int fast_speller_decode(const las_decode_io* io, const void* packed_f32, const v
     p.k_in_smem = att_smem(d, true) <= 220 * 1024;
     {
       const int nks = (d->U + 15) / 16, NT = d->E / 128;
-      p.ctx_tmem = (d->E % 128 == 0) && (NT * (nks * 8 + 16) <= 512) && (nks * 512 + 16 <= 4096 * 4) && g_dec_ctx_tmem;
+      // all feature tiles of enc[b]^T in tensor memory when they fit its 512 columns (U <= 224 at E = 512); otherwise as many
+      // as fit, the rest on the CUDA cores (hybrid; needs the score operand in its own shared-memory region)
+      int ntm = 0;
+      if (d->E % 128 == 0 && g_dec_ctx_tmem > 0) {
+        ntm = 512 / (nks * 8 + 16);
+        if (ntm > NT) ntm = NT;
+        if (ntm == NT && att_bop_bytes(d->U) > 4096 * 4) ntm = 0;
+        if (ntm < NT && (g_dec_ctx_tmem == 2 || (512 % ((d->E - ntm * 128) / 8)) != 0)) ntm = 0;  // option 2: value 2 = no hybrid
+      }
+      p.ctx_ntm = ntm;
+      p.ctx_tmem = ntm > 0;
+      const bool hyb = ntm > 0 && ntm < NT;
+      p.k_in_smem = att_smem(d, true, hyb) <= 220 * 1024;
+      if (hyb && att_smem(d, p.k_in_smem != 0, true) > 220 * 1024) { p.ctx_ntm = 0; p.ctx_tmem = 0; p.k_in_smem = att_smem(d, true, false) <= 220 * 1024; }
     }
     const RingCfg rc = ring_cfg(d, Bc);
     p.nstages = rc.nstages;
@@ -1240,7 +1272,7 @@ int fast_speller_decode(const las_decode_io* io, const void* packed_f32, const v
                                   relu != 0));
     }
     ProfScope ps("speller.steps", st);
-    const size_t smem_l = rc.smem, smem_a = att_smem(d, p.k_in_smem != 0);
+    const size_t smem_l = rc.smem, smem_a = att_smem(d, p.k_in_smem != 0, p.ctx_ntm > 0 && p.ctx_ntm < d->E / 128);
     const size_t smem = (smem_l > smem_a ? smem_l : smem_a) + 1024;
     LAS_CUDA_OK(cudaFuncSetAttribute(speller_decode_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cudaLaunchConfig_t cfg = {};

@@ -319,6 +319,39 @@ def test_bf16_decoder_single_3d_copy_matches_per_atom_copies():
     assert torch.isfinite(p3).all()
 
 
+def test_bf16_long_encoder_hybrid_context_path():
+    """Long encoders (BASELINE config 4: 3000 frames -> U = 375): enc[b]^T no longer fits the attention CTA's tensor memory, so
+    two of the four 128-feature tiles are reduced by the UMMA and the other two on the CUDA cores (hybrid).  Teacher-forced
+    log-probs / attention against the fp64 oracle, and against the CUDA-core-only path (las_debug_set_option(2, 0))."""
+    if "bf16" not in precisions():
+        pytest.skip("bf16 path not built")
+    from las_pytorch_b200 import _cabi
+
+    lib = _cabi.load_library()
+    c = tl.CONFIGS["paper"]
+    B, T, S = 3, 3000, 12
+    las = tl.build_model("paper", max_label_len=S, seed=71, gain=3.0, precision="bf16")
+    sd = tl.state_dict_numpy(las)
+    x, labels = tl.make_inputs(B, T, c["F"], S, c["V"], seed=71)
+    ref = O.las_forward(x.numpy(), sd, c["L"], c["sl"], S, ground_truth=labels.numpy(), teacher_forced=True, dtype=np.float64)
+    las = las.cuda()
+    out = {}
+    for opt in (0, 1):
+        try:
+            lib.las_debug_set_option(2, opt)
+            out[opt] = run_ours(las, x, labels, c["V"], "tf")
+        finally:
+            lib.las_debug_set_option(2, 1)
+    for opt in (0, 1):
+        _, logp, attn = out[opt]
+        assert np.abs(logp - ref["logp"]).max() <= TOL["bf16"]["logp"]
+        assert np.abs(attn - ref["attn"]).max() <= TOL["bf16"]["attn"]
+    assert np.abs(out[0][1] - out[1][1]).max() <= 5e-3       # the two context paths differ only by the bf16 rounding of the scores
+    assert not np.array_equal(out[0][1], out[1][1])          # ... and are indeed different code paths
+    _, logp_g, _ = run_ours(las, x, labels, c["V"], "greedy")
+    assert np.isfinite(logp_g).all() and np.abs(np.exp(logp_g).sum(-1) - 1).max() < 1e-4
+
+
 @pytest.mark.parametrize("precision", precisions())
 def test_edge_shapes_single_utterance_single_step_single_encoder_frame(precision):
     """Smallest shapes the path accepts: one utterance, T = 2^L (one encoder step: the softmax is over a single frame),
