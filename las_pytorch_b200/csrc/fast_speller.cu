@@ -88,7 +88,7 @@ struct DecParams {
   int b0;
   int U, E, Hs, sl, V, D, steps, decode_mode, relu, gt_steps, ncl, k_in_smem;
   int wreg;  // 1: every attention thread keeps its chunks of W_phi in registers (D <= 64, Hs <= 512); no shared-memory copy
-  int ab_flags;     // test hook (las_debug_set_option(5, v)): bit 0 = W_phi from shared memory instead of registers; bit 2 (value 4) = eight 2-D copies per activation part instead of one 3-D copy
+  int ab_flags;     // test hook (las_debug_set_option(5, v)): bit 0 = W_phi from shared memory instead of registers; bit 2 (value 4) = eight 2-D copies per activation part instead of one 3-D copy; bit 5 (value 32) = query GEMV after a CTA-wide barrier (8 lanes per output) instead of per-warp partials
   unsigned long long sample_seed;  // LAS_DECODE_SAMPLE
   int word_gather;  // 1: the fed-back word is an index (greedy argmax / gt_index); 0: a dense vector (part 1b)
   int ctx_tmem;     // > 0: enc[b]^T is resident in the attention CTA's tensor memory and the context is a UMMA
@@ -463,7 +463,7 @@ __host__ __device__ inline int att_kstride(int D) {
 }
 struct AttLayout {
   int WPS, WCS, KS, Up;
-  size_t o_wcd, o_h, o_q, o_score, o_logit, o_bphi, o_bcd, o_red, o_part, o_bop, o_k, total;
+  size_t o_wcd, o_h, o_hw, o_qp, o_q, o_score, o_logit, o_bphi, o_bcd, o_red, o_part, o_bop, o_k, total;
 };
 __host__ __device__ inline size_t att_bop_bytes(int U) { return (size_t)((U + 15) / 16) * 512 + 16; }
 __host__ __device__ inline AttLayout att_layout(int Hs, int E, int U, int D, int V, bool k_in, bool wreg, bool hybrid = false) {
@@ -477,6 +477,8 @@ __host__ __device__ inline AttLayout att_layout(int Hs, int E, int U, int D, int
   take(wreg ? 0 : (size_t)D * a.WPS * 2);              // W_phi at offset 0 (not staged when the threads hold it in registers)
   a.o_wcd = take((size_t)V * a.WCS * 2);
   a.o_h = take((size_t)(((Hs + 63) & ~63) + ((E + 63) & ~63)) * 4);  // h, then ctx, each permuted (xpos) and padded to 64 floats
+  a.o_hw = take((size_t)DEC_THREADS * 4);              // h in plain order, one 32-value segment per warp (per-warp query partials)
+  a.o_qp = take((size_t)(DEC_THREADS / 32) * 64 * 4);  // [warp][64] partial sums of q
   a.o_q = take((size_t)a.KS * 4);
   a.o_score = take((size_t)a.Up * 4);
   a.o_logit = take(64 * 4);
@@ -505,6 +507,8 @@ __device__ void attention_role(const DecParams& p, uint8_t* smem, int b) {
   __nv_bfloat16* s_wcd = reinterpret_cast<__nv_bfloat16*>(smem + L.o_wcd);      // [V][WCS]
   float* s_h = reinterpret_cast<float*>(smem + L.o_h);      // [Hs]
   float* s_ctx = s_h + ((Hs + 63) & ~63);                   // [E]
+  float* s_hw = reinterpret_cast<float*>(smem + L.o_hw);    // [DEC_THREADS]
+  float* s_qp = reinterpret_cast<float*>(smem + L.o_qp);    // [NWARP][64]
   float* s_q = reinterpret_cast<float*>(smem + L.o_q);      // [KS] (zero padded)
   float* s_score = reinterpret_cast<float*>(smem + L.o_score);  // [U]
   float* s_logit = reinterpret_cast<float*>(smem + L.o_logit);  // [V]
@@ -583,11 +587,20 @@ __device__ void attention_role(const DecParams& p, uint8_t* smem, int b) {
   // for all S steps, so the query GEMV reads only h from shared memory (the 64 KB of W_phi would otherwise be half of
   // the step's shared-memory wavefronts).  Falls back to the shared-memory copy for D > 64 or Hs > 512.
   const bool wreg = p.wreg != 0;
+  // Per-warp query partials (default with W_phi in registers): warp w owns h[32w, 32w+32) -- the values it polls itself -- and lane
+  // l the outputs d = l and l + 32, so a warp starts its share of the GEMV the moment ITS OWN 32 values have arrived (the layer-1
+  // CTAs finish up to ~0.5 us apart) instead of after a CTA-wide barrier; the 16 partial sums per output are added after one barrier.
+  const bool qwarp = wreg && !(p.ab_flags & 32);
   uint4 wq[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    const int d = tid >> 3, c = (tid & 7) + 8 * j;
-    wq[j] = (wreg && d < D && c < hchunks) ? *reinterpret_cast<const uint4*>(p.w_phi + (size_t)d * Hs + 8 * c) : make_uint4(0, 0, 0, 0);
+    if (qwarp) {
+      const int d = lane + 32 * (j >> 2), k = 32 * warp + 8 * (j & 3);
+      wq[j] = (d < D && k < Hs) ? *reinterpret_cast<const uint4*>(p.w_phi + (size_t)d * Hs + k) : make_uint4(0, 0, 0, 0);
+    } else {
+      const int d = tid >> 3, c = (tid & 7) + 8 * j;
+      wq[j] = (wreg && d < D && c < hchunks) ? *reinterpret_cast<const uint4*>(p.w_phi + (size_t)d * Hs + 8 * c) : make_uint4(0, 0, 0, 0);
+    }
   }
   const int Dp = (D + 3) & ~3, Vp = (V + 1) & ~1;
   const int nd4 = (D + 3) >> 2;                    // float4 chunks of a psi row
@@ -596,6 +609,39 @@ __device__ void attention_role(const DecParams& p, uint8_t* smem, int b) {
     const int np = (s + 1) & 1;
     const bool last = (s == p.steps - 1);
     // ---- A: this step's top-layer h, polled straight out of the LSTM epilogue's flag-in-data slots
+    if (qwarp) {
+      float hv = 0.f;
+      if (tid < Hs) {
+        hv = __uint_as_float(ll_wait(p.h_ll + (size_t)b * Hs + tid, (uint32_t)(s + 1)));
+        s_h[xpos(tid)] = hv;  // permuted copy for the character distribution
+      }
+      s_hw[tid] = hv;
+      __syncwarp();
+      if (tid == 0) DEC_TRACE_ALL(0);
+      if (tid == 0 && b == 0) { DEC_TRACE(2, 0); DEC_TRACE(3, 0); if (p.trace && s < 32) p.trace[(2 * 32 + s) * 8 + 7] = clock64(); }
+      // ---- B: q = act(W_phi . h + b_phi)   (model/las_model.py:278): this warp's 32 columns of W_phi x its 32 values of h
+      float a0 = 0.f, a1 = 0.f;
+      const float4* hx = reinterpret_cast<const float4*>(s_hw + 32 * warp);  // same address in every lane: broadcast loads
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float4 x0 = hx[2 * j], x1 = hx[2 * j + 1];
+        a0 = dot8(wq[j], x0, x1, a0);
+        a1 = dot8(wq[4 + j], x0, x1, a1);
+      }
+      s_qp[warp * 64 + lane] = a0;
+      s_qp[warp * 64 + 32 + lane] = a1;
+      if (tid == 0 && b == 0) { DEC_TRACE(3, 1); DEC_TRACE(3, 2); }
+      __syncthreads();
+      if (tid < Dp) {
+        float acc = 0.f;
+#pragma unroll
+        for (int w = 0; w < NWARP; ++w) acc += s_qp[w * 64 + tid];
+        if (tid < D) {
+          acc += s_bphi[tid];
+          s_q[tid] = p.relu ? fmaxf(acc, 0.f) : acc;
+        }
+      }
+    } else {
     if (tid < Hs) s_h[xpos(tid)] = __uint_as_float(ll_wait(p.h_ll + (size_t)b * Hs + tid, (uint32_t)(s + 1)));
     __syncthreads();
     if (tid == 0) DEC_TRACE_ALL(0);
@@ -638,6 +684,7 @@ __device__ void attention_role(const DecParams& p, uint8_t* smem, int b) {
           s_q[d] = p.relu ? fmaxf(acc, 0.f) : acc;
         }
       }
+    }
     }
     __syncthreads();
     if (tid == 0 && b == 0) { DEC_TRACE(2, 1); DEC_TRACE(3, 3); }
