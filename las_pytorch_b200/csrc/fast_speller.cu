@@ -88,7 +88,7 @@ struct DecParams {
   int b0;
   int U, E, Hs, sl, V, D, steps, decode_mode, relu, gt_steps, ncl, k_in_smem;
   int wreg;  // 1: every attention thread keeps its chunks of W_phi in registers (D <= 64, Hs <= 512); no shared-memory copy
-  int ab_flags;     // test hook (las_debug_set_option(5, v)): bit 0 = W_phi from shared memory instead of registers; bit 2 (value 4) = eight 2-D copies per activation part instead of one 3-D copy; bit 5 (value 32) = query GEMV after a CTA-wide barrier (8 lanes per output) instead of per-warp partials
+  int ab_flags;     // test hook (las_debug_set_option(5, v)): bit 0 = W_phi from shared memory instead of registers; bit 2 (value 4) = eight 2-D copies per activation part instead of one 3-D copy; bit 5 (value 32) = query GEMV after a CTA-wide barrier (8 lanes per output) instead of per-warp partials; bit 6 (value 64) = LSTM epilogue stores one row per thread from the registers instead of staging + coalesced rows
   unsigned long long sample_seed;  // LAS_DECODE_SAMPLE
   int word_gather;  // 1: the fed-back word is an index (greedy argmax / gt_index); 0: a dense vector (part 1b)
   int ctx_tmem;     // > 0: enc[b]^T is resident in the attention CTA's tensor memory and the context is a UMMA
@@ -207,6 +207,7 @@ __device__ void lstm_role(const DecParams& p, uint8_t* smem, int l, int nb) {
   uint64_t* tmem_full = part_empty + 1;
   uint64_t* tmem_empty = tmem_full + 1;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 1);
+  float* s_st = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_slot + 2) + 15) & ~uintptr_t(15));  // [64 rows][20] epilogue staging
   // Warp roles.  A launch covers at most 64 utterances, so only TMEM lane quadrants 0 and 1 (batch rows 0..63) carry
   // data; the eight warps that can read them (warp % 4 < 2) form the epilogue, four per quadrant with four hidden
   // units each.  The producer and the MMA issuer sit on the two idle quadrants.
@@ -414,8 +415,41 @@ __device__ void lstm_role(const DecParams& p, uint8_t* smem, int l, int nb) {
       }
       ptx::tc_fence_before();
       ptx::mbar_arrive(tmem_empty);
+      const int np = (s + 1) & 1;
+      if (!(p.ab_flags & 64)) {
+        // Coalesced hand-off stores.  A thread owns one batch row, so a warp-wide store of its values touches 32 different
+        // rows of the row-major hand-off buffers (32 partial sectors per instruction; the top layer's flag-in-data slots took
+        // up to ~1.4 us to become visible).  The 64 x 16 block goes through shared memory instead (rows padded to 20 floats:
+        // conflict-free 16-byte writes) and every warp writes 8 whole rows: full 128-byte lines of {h, tag} slots for the
+        // attention CTAs, full 32-byte sectors of the bf16 operand copy.
+        if (warp_live) *reinterpret_cast<float4*>(s_st + b * 20 + cs * 4) = make_float4(h[0], h[1], h[2], h[3]);
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        const int r0 = (cs * 2 + q) * 8;  // this warp's 8 rows
+        if (top) {
+          const uint32_t tag = (uint32_t)(s + 1);
+#pragma unroll
+          for (int hf = 0; hf < 2; ++hf) {
+            const int row = r0 + hf * 4 + (lane >> 3), piece = lane & 7;
+            if (row < p.B) {
+              const float2 v = *reinterpret_cast<const float2*>(s_st + row * 20 + piece * 2);
+              ll_store2(p.h_ll + (size_t)row * p.Hs + nb * DEC_UNITS + piece * 2, ll_pack(__float_as_uint(v.x), tag), ll_pack(__float_as_uint(v.y), tag));
+            }
+          }
+        }
+        if (lane < 16) {
+          const int row = r0 + (lane >> 1), hf = lane & 1;
+          if (row < p.B) {
+            const float4 x0 = *reinterpret_cast<const float4*>(s_st + row * 20 + hf * 8), x1 = *reinterpret_cast<const float4*>(s_st + row * 20 + hf * 8 + 4);
+            const __nv_bfloat162 t0 = __floats2bfloat162_rn(x0.x, x0.y), t1 = __floats2bfloat162_rn(x0.z, x0.w);
+            const __nv_bfloat162 t2 = __floats2bfloat162_rn(x1.x, x1.y), t3 = __floats2bfloat162_rn(x1.z, x1.w);
+            *reinterpret_cast<uint4*>(p.hbuf[l][np] + (size_t)row * p.Hs + nb * DEC_UNITS + hf * 8) =
+                make_uint4(*reinterpret_cast<const uint32_t*>(&t0), *reinterpret_cast<const uint32_t*>(&t1),
+                           *reinterpret_cast<const uint32_t*>(&t2), *reinterpret_cast<const uint32_t*>(&t3));
+          }
+        }
+      }
       if (live) {
-        const int np = (s + 1) & 1;
+        if (p.ab_flags & 64) {  // A/B: one row per thread, straight from the registers
         if (top) {  // attention CTA b polls these slots directly
           const uint32_t tag = (uint32_t)(s + 1);
           u64* dst = p.h_ll + (size_t)b * p.Hs + u0;
@@ -425,6 +459,7 @@ __device__ void lstm_role(const DecParams& p, uint8_t* smem, int l, int nb) {
         const __nv_bfloat162 t0 = __floats2bfloat162_rn(h[0], h[1]), t1 = __floats2bfloat162_rn(h[2], h[3]);
         *reinterpret_cast<uint2*>(p.hbuf[l][np] + (size_t)b * p.Hs + u0) =
             make_uint2(*reinterpret_cast<const uint32_t*>(&t0), *reinterpret_cast<const uint32_t*>(&t1));
+        }
         if (s == S - 1) {
           if (p.h_out) {
 #pragma unroll
@@ -1097,7 +1132,7 @@ RingCfg ring_cfg(const las_speller_dims* d, int rows) {
   (void)rows;
   r.box_rows = 64;
   r.stage_bytes = r.box_rows * 128;
-  const size_t fixed = (size_t)mx * WATOM_BYTES + DEC_NW * 4 + (DEC_MAX_STAGES + 4) * 8 + 64;
+  const size_t fixed = (size_t)mx * WATOM_BYTES + DEC_NW * 4 + (DEC_MAX_STAGES + 4) * 8 + 64 + 64 * 20 * 4;  // + the epilogue's staging block
   // one slot per atom of the larger shared part (own h: ceil(Hs/64); context / lower h: ceil(E/64)) + the word slot
   int need = (d->Hs + 63) / 64;
   const int nc0 = (d->E + 63) / 64;
