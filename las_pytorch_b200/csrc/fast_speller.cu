@@ -824,7 +824,10 @@ __device__ void attention_role(const DecParams& p, uint8_t* smem, int b) {
         if (u < U) p.attn[((size_t)s * p.Bfull + gb) * U + u] = ev[ps] * inv;
       }
     }
-    if (warp != 0 && !hybrid) {
+    const bool late_h = hybrid;  // h half of the logits together with the context half, after the publish (measured for the pure
+                                 // tensor-memory path too: -0.07 us/step, but the fed-back token then reaches layer 0 only ~0.4 us
+                                 // before its MMAs finish)
+    if (warp != 0 && !late_h) {
       const int part = tid & 15;
       for (int v = (tid - 32) >> 4; v < Vp; v += (DEC_THREADS - 32) / 16) {
         float acc = 0.f;
@@ -943,7 +946,7 @@ __device__ void attention_role(const DecParams& p, uint8_t* smem, int b) {
             const float4* xv = xchunk(s_ctx, c);
             acc = dot8(lds128(wr + hchunks + c), xv[0], xv[8], acc);
           }
-          if (hybrid) {  // the h half was not evaluated during the context reduction (every warp was busy with it)
+          if (late_h) {  // the h half was not evaluated during the context reduction
 #pragma unroll 4
             for (int c = part; c < hchunks; c += 16) {
               const float4* xv = xchunk(s_h, c);
@@ -955,7 +958,7 @@ __device__ void attention_role(const DecParams& p, uint8_t* smem, int b) {
         acc += __shfl_xor_sync(0xffffffffu, acc, 2);
         acc += __shfl_xor_sync(0xffffffffu, acc, 4);
         acc += __shfl_xor_sync(0xffffffffu, acc, 8);
-        if (part == 0 && v < V) s_logit[v] = hybrid ? acc + s_bcd[v] : s_logit[v] + acc;
+        if (part == 0 && v < V) s_logit[v] = late_h ? acc + s_bcd[v] : s_logit[v] + acc;
       }
     }
     __syncthreads();
