@@ -88,7 +88,7 @@ struct DecParams {
   int b0;
   int U, E, Hs, sl, V, D, steps, decode_mode, relu, gt_steps, ncl, k_in_smem;
   int wreg;  // 1: every attention thread keeps its chunks of W_phi in registers (D <= 64, Hs <= 512); no shared-memory copy
-  int ab_flags;     // test hook (las_debug_set_option(5, v)): bit 0 = W_phi from shared memory instead of registers; bit 2 (value 4) = eight 2-D copies per activation part instead of one 3-D copy; bit 5 (value 32) = query GEMV after a CTA-wide barrier (8 lanes per output) instead of per-warp partials; bit 6 (value 64) = LSTM epilogue stores one row per thread from the registers instead of staging + coalesced rows
+  int ab_flags;     // test hook (las_debug_set_option(5, v)): bit 0 = W_phi from shared memory instead of registers; bit 2 (value 4) = eight 2-D copies per activation part instead of one 3-D copy; bit 5 (value 32) = query GEMV after a CTA-wide barrier (8 lanes per output) instead of per-warp partials; bit 6 (value 64) = LSTM epilogue stores one row per thread from the registers instead of staging + coalesced rows; bit 9 (value 512) = context UMMA descriptors rebuilt per instruction instead of advanced by constants
   unsigned long long sample_seed;  // LAS_DECODE_SAMPLE
   int word_gather;  // 1: the fed-back word is an index (greedy argmax / gt_index); 0: a dense vector (part 1b)
   int ctx_tmem;     // > 0: enc[b]^T is resident in the attention CTA's tensor memory and the context is a UMMA
@@ -809,9 +809,29 @@ __device__ void attention_role(const DecParams& p, uint8_t* smem, int b) {
           const UmmaLayout lb{0, 256, 128, 0};
           const uint32_t idesc = umma_idesc_bf16(128, 16);
           const uint32_t bop = ptx::smem_u32(s_bop);
-          for (int t = 0; t < ntm; ++t)
-            for (int ks = 0; ks < nks; ++ks)
-              ptx::umma_bf16_ts(tmem + ntm * CU + t * 16, tmem + t * CU + ks * 8, umma_smem_desc(lb, bop, ks * 16), idesc, ks != 0);
+          if (p.ab_flags & 512) {  // A/B: descriptors rebuilt per instruction
+            for (int t = 0; t < ntm; ++t)
+              for (int ks = 0; ks < nks; ++ks)
+                ptx::umma_bf16_ts(tmem + ntm * CU + t * 16, tmem + t * CU + ks * 8, umma_smem_desc(lb, bop, ks * 16), idesc, ks != 0);
+          } else {
+            // The issuing thread's own instructions between two tcgen05.mma set the pace of this chain (N = 16: the pipe needs
+            // ~8 cycles per instruction; tools/microbench_mma_insitu.cu reaches ~27 with a lean loop, the per-instruction
+            // descriptor arithmetic cost ~58).  Consecutive K steps are 512 bytes apart in the score operand and 8 columns apart
+            // in tensor memory, so both operands advance by constants: 32 in the descriptor's 16-byte address field (which
+            // cannot carry out of its 14 bits: shared memory ends below 256 KB) and 8 in the tensor-memory address.
+            const uint64_t bd0 = umma_smem_desc(lb, bop, 0);
+            for (int t = 0; t < ntm; ++t) {
+              uint64_t bd = bd0;
+              uint32_t a = tmem + t * CU;
+              const uint32_t dcol = tmem + ntm * CU + t * 16;
+#pragma unroll 4
+              for (int ks = 0; ks < nks; ++ks) {
+                ptx::umma_bf16_ts(dcol, a, bd, idesc, ks != 0);
+                a += 8;
+                bd += 32;
+              }
+            }
+          }
           ptx::umma_commit(ctx_bar);
         }
         __syncwarp();
