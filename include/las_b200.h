@@ -209,6 +209,13 @@ int las_speller_decode(const las_decode_io* io, const void* packed, const las_sp
 int las_nll_sums(const float* logp /*[S,B,V]*/, const int32_t* labels /*[B,S_lab]*/, int S, int S_lab, int B, int V,
                  int max_label_len, float* out2, void* stream);
 
+/* label_smoothing_loss, solver/solver.py:33-45 (the training-branch loss, :79-84), reduced on the device per utterance:
+ * per_utt[b] = sum_{s < min(S, S_lab, max_label_len), labels[b,s] >= 0} [ (1-ls) logp[s,b,labels[b,s]] + (ls/V) sum_v logp[s,b,v] ]
+ *              / #{s: labels[b,s] >= 0};   the reference's scalar is  -mean_b per_utt[b].
+ * labels int32 [B,S_lab]: the index of the 1 in the reference's one-hot target row, or -1 for an all-zero (padding) row. */
+int las_label_smoothing_terms(const float* logp /*[S,B,V]*/, const int32_t* labels /*[B,S_lab]*/, int S, int S_lab, int B, int V,
+                              int max_label_len, float label_smoothing, float* per_utt /*[B]*/, void* stream);
+
 /* --------------------------------------------------------------------------------------------------------
  * Test hooks (used by tests/ only): exercise single kernels through the same ABI.
  * ------------------------------------------------------------------------------------------------------ */

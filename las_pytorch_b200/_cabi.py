@@ -84,6 +84,7 @@ PROTOTYPES = {
     "las_debug_set_trace": (C.c_int, [C.c_void_p]),
     "las_debug_set_option": (C.c_int, [C.c_int, C.c_int]),
     "las_nll_sums": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "las_label_smoothing_terms": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_void_p]),
 }
 
 _lib = None

@@ -476,4 +476,37 @@ int launch_nll_sums(const float* logp, const int32_t* labels, int S, int S_lab, 
   return LAS_OK;
 }
 
+// solver/solver.py:33-45 label_smoothing_loss, per utterance: sum_s [ (1-ls) logp[s,b,lab] + (ls/V) sum_v logp[s,b,v] ] / #labelled steps.
+// labels < 0 mark the all-zero rows of the reference's one-hot target (no contribution); the caller takes -mean over b.
+__global__ void __launch_bounds__(256) label_smoothing_kernel(const float* logp, const int32_t* labels, int S_lab, int B, int V, int L, float ls,
+                                                              float* per_utt) {
+  __shared__ float red[32];
+  const int b = blockIdx.x;
+  float acc = 0.f, cnt = 0.f;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
+  for (int s = warp; s < L; s += nwarp) {  // one warp per step: coalesced read of the V log-probs
+    const int lab = labels[(size_t)b * S_lab + s];
+    if (lab < 0 || lab >= V) continue;
+    const float* row = logp + ((size_t)s * B + b) * V;
+    float sum = 0.f;
+    for (int v = lane; v < V; v += 32) sum += row[v];
+    sum = warp_sum(sum);
+    if (lane == 0) {
+      acc += (1.0f - ls) * row[lab] + (ls / (float)V) * sum;
+      cnt += 1.f;
+    }
+  }
+  acc = block_reduce_sum(acc, red);
+  cnt = block_reduce_sum(cnt, red);
+  if (threadIdx.x == 0) per_utt[b] = acc / cnt;  // cnt == 0 -> nan, as the reference's division by seq_len == 0
+}
+int launch_label_smoothing(const float* logp, const int32_t* labels, int S, int S_lab, int B, int V, int max_label_len, float ls,
+                           float* per_utt, cudaStream_t st) {
+  int L = max_label_len < S ? max_label_len : S;
+  if (S_lab < L) L = S_lab;
+  label_smoothing_kernel<<<B, 256, 0, st>>>(logp, labels, S_lab, B, V, L, ls, per_utt);
+  LAS_LAUNCH_OK("label_smoothing_kernel");
+  return LAS_OK;
+}
+
 }  // namespace las

@@ -586,6 +586,14 @@ int las_nll_sums(const float* logp, const int32_t* labels, int S, int S_lab, int
   return launch_nll_sums(logp, labels, S, S_lab, B, V, max_label_len, out2, static_cast<cudaStream_t>(stream));
 }
 
+int las_label_smoothing_terms(const float* logp, const int32_t* labels, int S, int S_lab, int B, int V, int max_label_len,
+                              float label_smoothing, float* per_utt, void* stream) {
+  LAS_REQUIRE(logp && labels && per_utt, "null pointer argument");
+  LAS_REQUIRE(S > 0 && S_lab > 0 && B > 0 && V > 0, "bad dims");
+  LAS_TRY(device_ok());
+  return launch_label_smoothing(logp, labels, S, S_lab, B, V, max_label_len, label_smoothing, per_utt, static_cast<cudaStream_t>(stream));
+}
+
 int las_debug_gemm_bf16(const void* a, const void* w, const float* bias, float* c, int M, int N, int K, void* stream) {
   LAS_REQUIRE(a && w && bias && c, "null pointer argument");
   LAS_TRY(device_ok());

@@ -80,4 +80,7 @@ int launch_pyramid_lengths(const int32_t* in, int32_t* out, int B, int cap, cuda
 int launch_nll_sums(const float* logp, const int32_t* labels, int S, int S_lab, int B, int V, int max_label_len,
                     float* out2, cudaStream_t st);
 
+int launch_label_smoothing(const float* logp, const int32_t* labels, int S, int S_lab, int B, int V, int max_label_len, float ls,
+                           float* per_utt, cudaStream_t st);
+
 }  // namespace las

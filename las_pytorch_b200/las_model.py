@@ -18,6 +18,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import threading
 
 import numpy as np
 import torch
@@ -51,22 +52,58 @@ def _f32c(t):
     return t.detach().to(torch.float32).contiguous()
 
 
+def _weight_tensors(*holders):
+    """The tensors a pack call will read, in registration order.  `_parameters` (not `.parameters()`) on purpose: an
+    nn.DataParallel replica (train.py:76-78) keeps its per-device broadcast copies there as plain tensors, and
+    `.parameters()` yields nothing on a replica."""
+    out = []
+    for h in holders:
+        for m in h.modules():
+            out.extend(t for t in m._parameters.values() if t is not None)
+    return out
+
+
 class _Cache:
-    """Packed-weight / workspace cache keyed on (device, mode, parameter versions and storage)."""
+    """Packed-weight / workspace cache.  One packed image per (device, mode), valid while the tensors that were packed are still
+    the module's tensors: the key is (data_ptr, version counter, device) of every weight actually handed to the pack call.
+
+    nn.DataParallel shallow-copies a module's __dict__ into every replica, so replicas on all devices share THIS object with
+    the original: entries are per device, a device only ever replaces its own entry, and mutation is locked.  A replica's
+    weights are fresh broadcast copies each forward (same addresses can come back from the caching allocator with new contents,
+    version 0), so replicas never reuse a packed image: they repack on every call (a few pack kernels, ~30 MB at paper size).
+    In-place writes through `.data` (nn.init.*_(p.data), p.data.copy_()) do not bump the version counter: call
+    `invalidate()` (LAS.invalidate_packed_weights) after such an update."""
 
     def __init__(self):
         self.packed = {}
         self.work = {}
+        self.lock = threading.Lock()
 
     @staticmethod
-    def params_key(params, mode):
-        return (mode,) + tuple((p.data_ptr(), p._version, str(p.device)) for p in params)
+    def tensors_key(tensors, mode):
+        return (mode,) + tuple((t.data_ptr(), t._version, t.device.index) for t in tensors)
+
+    def lookup(self, device, mode, key, is_replica):
+        if is_replica:
+            return None
+        with self.lock:
+            hit = self.packed.get((device.index, mode))
+        return hit[1] if hit is not None and hit[0] == key else None
+
+    def store(self, device, mode, key, packed):
+        with self.lock:
+            self.packed[(device.index, mode)] = (key, packed)
+
+    def invalidate(self):
+        with self.lock:
+            self.packed.clear()
 
     def workspace(self, key, nbytes, device):
-        buf = self.work.get(key)
-        if buf is None or buf.numel() < nbytes:
-            buf = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
-            self.work[key] = buf
+        with self.lock:
+            buf = self.work.get(key)
+            if buf is None or buf.numel() < nbytes:
+                buf = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+                self.work[key] = buf
         return buf
 
 
@@ -84,7 +121,7 @@ def _lstm_weight_array(holder, layers, directions):
     return arr, keep
 
 
-def _run_listener(x, holders, input_feature_dim, hidden_size, mode, cache, lengths=None, cell="LSTM"):
+def _run_listener(x, holders, input_feature_dim, hidden_size, mode, cache, lengths=None, cell="LSTM", is_replica=False):
     """x [B,T,F] -> [B, T/2^L, 2H] through `len(holders)` pyramid layers.  With `lengths` ([B] valid frames; extension)
     returns (enc, enc_lengths [B] int32)."""
     _require_cuda(x, "input_x")
@@ -103,11 +140,14 @@ def _run_listener(x, holders, input_feature_dim, hidden_size, mode, cache, lengt
         )
     with torch.cuda.device(x.device):
         st = current_stream_ptr(x.device)
-        params = [p for h in holders for p in h.parameters()]
-        key = _Cache.params_key(params, mode)
-        packed = cache.packed.get(key)
+        tensors = _weight_tensors(*holders)
+        for t in tensors:
+            _require_cuda(t, "listener weight")
+            if t.device != x.device:
+                raise RuntimeError(f"listener weights are on {t.device}, input_x on {x.device}")
+        key = _Cache.tensors_key(tensors, mode)
+        packed = cache.lookup(x.device, mode, key, is_replica)
         if packed is None:
-            cache.packed.clear()
             arr = (LstmWeights * (2 * nl))()
             keep = []
             for l, h in enumerate(holders):
@@ -118,7 +158,7 @@ def _run_listener(x, holders, input_feature_dim, hidden_size, mode, cache, lengt
             nbytes = lib.las_listener_packed_bytes(C.byref(dims), mode)
             packed = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=x.device)
             check(lib.las_listener_pack(arr, C.byref(dims), mode, ptr(packed), packed.numel(), st))
-            cache.packed[key] = packed
+            cache.store(x.device, mode, key, packed)
             del keep
         ws_bytes = lib.las_listener_workspace_bytes(C.byref(dims), mode)
         ws = cache.workspace(("listener", x.device, mode), ws_bytes, x.device)
@@ -161,6 +201,14 @@ class LAS(nn.Module):
             raw_pred_seq, attention_record = self.speller(listener_feature, ground_truth=None, teacher_force_rate=0,
                                                           enc_lengths=enc_lengths, nll_labels=nll_labels)
         return raw_pred_seq, attention_record
+
+    def invalidate_packed_weights(self):
+        """Drops every cached kernel-layout weight image.  The caches follow parameter identity and version counters, which
+        `load_state_dict`, optimizer steps and `.to()` change; an in-place write through `.data` does not -- call this after one."""
+        for m in self.modules():
+            c = getattr(m, "_cache", None)
+            if isinstance(c, _Cache):
+                c.invalidate()
 
     def serialize(self, optimizer, epoch, tr_loss, val_loss):
         """Checkpoint package with the reference's keys (model/las_model.py:42-63; "etype" is written twice
@@ -210,7 +258,7 @@ class pBLSTMLayer(nn.Module):
 
     def forward(self, input_x):
         out = _run_listener(input_x, [self.BLSTM], self.input_feature_dim, self.hidden_dim, _mode_of(self.precision), self._cache,
-                            cell=self.cell)
+                            cell=self.cell, is_replica=getattr(self, "_is_replica", False))
         h = self.hidden_dim
         h_n = torch.stack([out[:, -1, :h], out[:, 0, h:]])  # final hidden of each direction
         return out, (h_n, None)
@@ -241,7 +289,7 @@ class Listener(nn.Module):
         (listener_feature, enc_lengths)."""
         holders = [getattr(self, "pLSTM_layer" + str(i)).BLSTM for i in range(self.num_layers)]
         return _run_listener(input_x, holders, self.input_feature_dim, self.hidden_size, _mode_of(self.precision), self._cache,
-                             lengths=input_lengths, cell=self.cell)
+                             lengths=input_lengths, cell=self.cell, is_replica=getattr(self, "_is_replica", False))
 
 
 class Attention(nn.Module):
@@ -367,11 +415,14 @@ class Speller(nn.Module):
                            _cabi.CELLS[self.cell])
 
     def _packed(self, lib, dims, mode, device, st):
-        params = list(self.parameters())
-        key = _Cache.params_key(params, mode)
-        packed = self._cache.packed.get(key)
+        tensors = _weight_tensors(self)
+        for t in tensors:
+            _require_cuda(t, "speller weight")
+            if t.device != device:
+                raise RuntimeError(f"speller weights are on {t.device}, listener_feature on {device}")
+        key = _Cache.tensors_key(tensors, mode)
+        packed = self._cache.lookup(device, mode, key, getattr(self, "_is_replica", False))
         if packed is None:
-            self._cache.packed.clear()
             arr, keep = _lstm_weight_array(self.rnn_layer, self.num_layers, 1)
             at, cd = self.attention, self.character_distribution
             w = SpellerWeights()
@@ -389,7 +440,7 @@ class Speller(nn.Module):
             nbytes = lib.las_speller_packed_bytes(C.byref(dims), mode)
             packed = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=device)
             check(lib.las_speller_pack(C.byref(w), C.byref(dims), mode, ptr(packed), packed.numel(), st))
-            self._cache.packed[key] = packed
+            self._cache.store(device, mode, key, packed)
             del keep, ts
         return packed
 
@@ -403,6 +454,23 @@ class Speller(nn.Module):
         mode = _mode_of(self.precision)
         dims = self._dims(b, u, e)
         dev = enc.device
+        # the kernels index these with strides derived from (B, label_dim): a mismatching tensor must raise here, as the
+        # reference does at torch.cat (model/las_model.py:236), not read out of bounds
+        if e != self.hidden_size:
+            raise RuntimeError(f"listener_feature has {e} features; the speller was built for {self.hidden_size} (model/las_model.py:165,198)")
+        if gt_dense is not None and (gt_dense.dim() != 3 or gt_dense.size(0) != b or gt_dense.size(2) != self.label_dim or gt_dense.size(1) < steps):
+            raise RuntimeError(f"ground_truth has shape {tuple(gt_dense.shape)}; expected [{b}, >={steps}, {self.label_dim}]")
+        if gt_index is not None:
+            if gt_index.dim() != 2 or gt_index.size(0) != b or gt_index.size(1) < steps:
+                raise RuntimeError(f"ground_truth indices have shape {tuple(gt_index.shape)}; expected [{b}, >={steps}]")
+        if enc_lengths is not None and enc_lengths.numel() != b:
+            raise RuntimeError(f"enc_lengths has {enc_lengths.numel()} entries for a batch of {b}")
+        if nll_labels is not None and (nll_labels.dim() != 2 or nll_labels.size(0) != b):
+            raise RuntimeError(f"nll_labels has shape {tuple(nll_labels.shape)}; expected [{b}, S']")
+        for name, t, shape in (("state h", state[0] if state is not None else None, (self.num_layers, b, self.hidden_size)),
+                               ("word", word, (b, self.label_dim)), ("context", context, (b, e))):
+            if t is not None and tuple(t.shape) != shape:
+                raise RuntimeError(f"{name} has shape {tuple(t.shape)}; expected {shape}")
         with torch.cuda.device(dev):
             st = current_stream_ptr(dev)
             packed = self._packed(lib, dims, mode, dev, st)
@@ -479,6 +547,9 @@ class Speller(nn.Module):
             if ground_truth.dim() == 2:
                 # extension: [B,S] label indices instead of the reference's [B,S,V] one-hot
                 # tensor -- V times less host-to-device traffic; index v feeds one_hot(v), a negative index the zero vector
+                if not ground_truth.is_cuda and ground_truth.numel() and int(ground_truth.max()) >= self.label_dim:
+                    # (checked on host tensors only: a device tensor would cost a sync per call; there an index >= V feeds the zero vector)
+                    raise RuntimeError(f"ground_truth index {int(ground_truth.max())} is out of range for a vocabulary of {self.label_dim}")
                 gt_index = ground_truth.to(device=listener_feature.device, dtype=torch.int32).contiguous()
             else:
                 # `.type(self.float_type)` in the reference (:217): the label tensor is consumed as dense floats
@@ -488,6 +559,7 @@ class Speller(nn.Module):
         logp, attn, tokens = self._decode(listener_feature, max_step, gt_dense=gt_dense, gt_index=gt_index, enc_lengths=enc_lengths,
                                           nll_labels=nll_labels)
         self.last_tokens = tokens  # [S,B] int32 argmax per step (device); not part of the reference API
+        self.last_logp = logp      # [S,B,V] the buffer raw_pred_seq's entries are views of
         raw_pred_seq = list(logp.unbind(0))
         attention_record = [list(a.unbind(0)) for a in attn.unbind(0)]  # per step: one [B,U] tensor per head (:214,:292,:299)
         return raw_pred_seq, attention_record

@@ -44,12 +44,27 @@ def LetterErrorRate(pred_y, true_y):
 
 
 def label_smoothing_loss(pred_y, true_y, label_smoothing=0.1):
-    """solver/solver.py:33-45 (pred_y log-probs [B,S,V], true_y one-hot floats padded with all-zero rows)."""
+    """solver/solver.py:33-45 on the device: pred_y log-probs [B,S,V] (or the decoder's own [S,B,V] buffer, see `layout`), true_y
+    one-hot [B,S,V] whose padding rows are all zero.  Per labelled step the smoothed target ((1-ls) one-hot + ls/V) dotted with
+    the log-probs is (1-ls) logp[label] + (ls/V) sum_v logp[v]; `las_label_smoothing_terms` reduces that per utterance and
+    divides by the utterance's label count, the scalar is minus the batch mean."""
     assert pred_y.size() == true_y.size()
-    seq_len = torch.sum(torch.sum(true_y, dim=-1), dim=-1, keepdim=True)
-    class_dim = true_y.size()[-1]
-    smooth_y = ((1.0 - label_smoothing) * true_y + (label_smoothing / class_dim)) * torch.sum(true_y, dim=-1, keepdim=True)
-    return -torch.mean(torch.sum((torch.sum(smooth_y * pred_y, dim=-1) / seq_len), dim=-1))
+    if not pred_y.is_cuda:
+        raise RuntimeError("label_smoothing_loss runs on the device (las_label_smoothing_terms); there is no CPU fallback")
+    rows = true_y.sum(dim=-1)
+    labels = torch.where(rows > 0, true_y.argmax(dim=-1), torch.full_like(rows, -1, dtype=torch.long)).to(torch.int32).contiguous()
+    return label_smoothing_loss_from_indices(pred_y.permute(1, 0, 2).contiguous(), labels, label_smoothing, pred_y.size(1))
+
+
+def label_smoothing_loss_from_indices(logp_sbv, labels, label_smoothing, max_label_len):
+    """Same loss straight from the decoder's [S,B,V] log-prob buffer (Speller.last_logp) and int32 labels [B,S'] (-1 = padding row)."""
+    lib = _cabi.load_library()
+    S, B, V = logp_sbv.shape
+    per_utt = torch.empty(B, dtype=torch.float32, device=logp_sbv.device)
+    with torch.cuda.device(logp_sbv.device):
+        _cabi.check(lib.las_label_smoothing_terms(_cabi.ptr(logp_sbv), _cabi.ptr(labels), S, labels.size(1), B, V, int(max_label_len),
+                                                  float(label_smoothing), _cabi.ptr(per_utt), _cabi.current_stream_ptr(logp_sbv.device)))
+    return -per_utt.mean()
 
 
 def nll_sums(logp_sbv, label_idx, max_label_len):
@@ -66,17 +81,31 @@ def nll_sums(logp_sbv, label_idx, max_label_len):
 
 def batch_iterator(batch_data, batch_label, las_model, optimizer, tf_rate, is_training, max_label_len, label_smoothing,
                    use_gpu=True, vocab_dict=None):
-    """Forward + loss + LER for one batch; same return value as the reference: (loss ndarray, [LER per utterance])."""
+    """Forward + loss + LER for one batch; same return value as the reference: (loss ndarray, [LER per utterance]).
+    `las_model` may be wrapped in nn.DataParallel as train.py:76-78 does: the wrapper's replicas cannot hand back attributes, so
+    the loss is then reduced from the gathered log-probabilities (`las_nll_sums`) instead of the decoder's fused terms."""
     if is_training:
         raise NotImplementedError("the B200 path is forward-only; training (backward / optimizer step, solver/solver.py:94-97) is out of scope")
     max_label_len = min([batch_label.size()[1], max_label_len])
     true_idx = torch.max(batch_label, dim=2)[1][:, :max_label_len].contiguous()
+    wrapped = hasattr(las_model, "module") and not hasattr(las_model, "speller")
     # is_training is False here, so the reference takes the NLLLoss(ignore_index=0) branch (solver.py:70-77); the decoder emits its
     # terms -logp[s,b,label] itself (fused epilogue), so the loss needs no pass over the [B,S,V] log-probabilities
-    raw_pred_seq, _ = las_model(batch_data=batch_data, batch_label=batch_label, teacher_force_rate=tf_rate, is_training=is_training,
-                                nll_labels=true_idx)
+    if wrapped:
+        raw_pred_seq, _ = las_model(batch_data=batch_data, batch_label=batch_label, teacher_force_rate=tf_rate, is_training=is_training)
+    else:
+        raw_pred_seq, _ = las_model(batch_data=batch_data, batch_label=batch_label, teacher_force_rate=tf_rate, is_training=is_training,
+                                    nll_labels=true_idx)
+    if len(raw_pred_seq) < max_label_len:
+        # the reference fails here too (NLLLoss gets [B,V,steps] against [B,max_label_len] targets, solver.py:68-72)
+        raise RuntimeError(f"the decoder ran {len(raw_pred_seq)} steps but the loss covers {max_label_len} labels: "
+                           "speller.max_label_len is smaller than the label length")
     pred_y = torch.stack(raw_pred_seq, dim=1)[:, :max_label_len, :].contiguous()  # [B,S,V], as solver.py:68 (for the LER below)
-    terms = las_model.speller.last_nll_terms
-    loss = terms.sum() / (true_idx != 0).sum().to(terms.device)
+    if wrapped:
+        sums = nll_sums(pred_y.permute(1, 0, 2).contiguous(), true_idx.to(device=pred_y.device, dtype=torch.int32).contiguous(), max_label_len)
+        loss = sums[0] / sums[1]
+    else:
+        terms = las_model.speller.last_nll_terms[:max_label_len]
+        loss = terms.sum() / (true_idx != 0).sum().to(terms.device)
     batch_ler = LetterErrorRate(torch.max(pred_y, dim=2)[1].cpu().numpy(), true_idx.cpu().numpy())
     return loss.cpu().numpy(), batch_ler

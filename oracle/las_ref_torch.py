@@ -26,28 +26,33 @@ import torch.nn.functional as F
 class RefTorchLAS:
     """Holds torch modules shaped like the reference's and replays its forward op sequence on CPU."""
 
-    def __init__(self, sd, listener_layers, speller_layers, dtype=torch.float32):
+    def __init__(self, sd, listener_layers, speller_layers, dtype=torch.float32, device="cpu"):
+        """device="cuda" replays the same op sequence the reference runs with use_gpu=True (torch -> cuDNN RNN / cuBLAS; the
+        <sos> one-hot is still built on the host and copied, utils/functions.py:60-63; the greedy loop still does one int(i) host
+        sync per sample and step, model/las_model.py:225-226): bench.py's `gpu_baseline`, SURVEY.md 2.1's "kernel to beat on the
+        same box"."""
         sd = {k: torch.as_tensor(v).to(dtype) for k, v in sd.items()}
         self.dtype = dtype
+        self.device = torch.device(device)
         self.blstm = []
         for l in range(listener_layers):
             pre = f"listener.pLSTM_layer{l}.BLSTM."
             w_ih = sd[pre + "weight_ih_l0"]
             m = nn.LSTM(w_ih.shape[1], w_ih.shape[0] // 4, 1, bidirectional=True, batch_first=True).to(dtype)
             m.load_state_dict({k[len(pre):]: v for k, v in sd.items() if k.startswith(pre)})
-            self.blstm.append(m.eval())
+            self.blstm.append(m.eval().to(self.device))
         pre = "speller.rnn_layer."
         w_ih = sd[pre + "weight_ih_l0"]
         self.hs = w_ih.shape[0] // 4
         self.rnn = nn.LSTM(w_ih.shape[1], self.hs, num_layers=speller_layers, batch_first=True).to(dtype)
         self.rnn.load_state_dict({k[len(pre):]: v for k, v in sd.items() if k.startswith(pre)})
-        self.rnn.eval()
+        self.rnn.eval().to(self.device)
 
         def lin(name):
             w, b = sd[name + ".weight"], sd[name + ".bias"]
             m = nn.Linear(w.shape[1], w.shape[0]).to(dtype)
             m.load_state_dict({"weight": w, "bias": b})
-            return m.eval()
+            return m.eval().to(self.device)
 
         self.phi = lin("speller.attention.phi")
         self.psi = lin("speller.attention.psi")
@@ -56,7 +61,7 @@ class RefTorchLAS:
 
     @torch.no_grad()
     def listener(self, x):
-        out = x.to(self.dtype)
+        out = x.to(self.dtype).to(self.device)
         for m in self.blstm:
             b, t, f = out.shape
             out, _ = m(out.contiguous().view(b, int(t / 2), f * 2))
@@ -76,7 +81,7 @@ class RefTorchLAS:
         """ground_truth: one-hot int64 [B,S,V] (teacher forcing) or None (free running)."""
         b = enc.size(0)
         idx = torch.zeros(b, 1).unsqueeze(2).type(torch.LongTensor)
-        word = torch.LongTensor(b, 1, self.vocab).zero_().scatter_(-1, idx, 1).to(self.dtype)
+        word = torch.LongTensor(b, 1, self.vocab).zero_().scatter_(-1, idx, 1).to(self.dtype).to(self.device)
         rnn_in = torch.cat([word, enc[:, 0:1, :]], dim=-1)
         hidden = None
         logps, attns = [], []

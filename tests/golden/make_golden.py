@@ -59,11 +59,72 @@ def run_reference(las, x, gt_onehot, teacher_forced, dtype):
     return enc.numpy(), logp.numpy(), attn.numpy()
 
 
+def make_extras(ref, tl):
+    """Fixtures for the "next" rows: (f3) a checkpoint package written by the REFERENCE's own LAS.serialize + torch.save
+    (model/las_model.py:42-63, train.py:181-192) together with the reference's outputs for it; (f1) the reference's
+    label_smoothing_loss / NLLLoss / LetterErrorRate values (solver/solver.py:11-24,33-45,62,70-92) on seeded inputs."""
+    import solver.solver as ref_solver  # the reference's solver (editdistance stubbed: give it a Levenshtein)
+
+    def lev(a, b):
+        prev = list(range(len(b) + 1))
+        for i, ca in enumerate(a, 1):
+            cur = [i]
+            for j, cb in enumerate(b, 1):
+                cur.append(min(prev[j] + 1, cur[j - 1] + 1, prev[j - 1] + (ca != cb)))
+            prev = cur
+        return prev[-1]
+
+    sys.modules["editdistance"].eval = lev
+    ref_solver.ed.eval = lev
+    # ---- f3: package from the reference
+    cfg, B, T, S = "tiny", 3, 32, 8
+    c = tl.CONFIGS[cfg]
+    ref_las = tl.build_model(cfg, max_label_len=S, decode_mode=1, seed=41, gain=3.0, module=ref)
+    opt = torch.optim.Adam(ref_las.parameters(), lr=1e-3)
+    pkg = ref_las.serialize(opt, epoch=7, tr_loss=1.25, val_loss=1.5)
+    # as nn.DataParallel-wrapped training would have saved it (train.py:76-78): keys carry a "module." prefix in one of the two files
+    torch.save(pkg, os.path.join(HERE, "ref_package_tiny.pth.tar"))
+    pkg_dp = dict(pkg, state_dict={"module." + k: v for k, v in pkg["state_dict"].items()})
+    torch.save(pkg_dp, os.path.join(HERE, "ref_package_tiny_dataparallel.pth.tar"))
+    x, labels = tl.make_inputs(B, T, c["F"], S, c["V"], seed=41)
+    gt = tl.onehot(labels, c["V"])
+    out = {"x": x.numpy(), "labels": labels.numpy().astype(np.int32)}
+    for mode in ("tf", "greedy"):
+        enc, logp, attn = run_reference(ref_las, x, gt, mode == "tf", torch.float64)
+        out["enc_f64"], out[f"logp_{mode}_f64"], out[f"attn_{mode}_f64"] = enc, logp, attn
+    np.savez_compressed(os.path.join(HERE, "ref_package_tiny_outputs.npz"), **out)
+    print("ref_package_tiny.pth.tar:", sorted(pkg), "etype =", pkg["etype"])
+
+    # ---- f1: solver losses from the reference's own functions
+    g = torch.Generator().manual_seed(43)
+    Bs, Ss, V = 5, 12, 30
+    logp = torch.log_softmax(3.0 * torch.randn(Bs, Ss, V, generator=g), dim=-1)
+    lab = torch.randint(2, V, (Bs, Ss), generator=g)
+    lens = torch.tensor([12, 9, 5, 12, 1])
+    onehot_zero_pad = tl.onehot(lab, V).float()     # padding rows all zero (what label_smoothing_loss documents)
+    lab_pad0 = lab.clone()                           # padding rows = one-hot(0) (what utils/data.py:133-136 produces)
+    for b in range(Bs):
+        onehot_zero_pad[b, lens[b]:, :] = 0
+        lab_pad0[b, lens[b]:] = 0
+    onehot_pad0 = tl.onehot(lab_pad0, V).float()
+    res = {"logp": logp.numpy(), "labels": lab.numpy().astype(np.int32), "lens": lens.numpy().astype(np.int32)}
+    for ls in (0.1, 0.3):
+        res[f"ls_zero_pad_{ls}"] = float(ref_solver.label_smoothing_loss(logp, onehot_zero_pad, label_smoothing=ls))
+        res[f"ls_pad0_{ls}"] = float(ref_solver.label_smoothing_loss(logp, onehot_pad0, label_smoothing=ls))
+    res["nll_ignore0"] = float(torch.nn.NLLLoss(ignore_index=0)(logp.permute(0, 2, 1), lab_pad0))
+    res["ler"] = np.asarray(ref_solver.LetterErrorRate(logp.argmax(-1).numpy(), lab_pad0.numpy()), dtype=np.float64)
+    np.savez_compressed(os.path.join(HERE, "ref_solver_losses.npz"), **res)
+    print("ref_solver_losses.npz:", {k: v for k, v in res.items() if k.startswith(("ls_", "nll"))}, "ler", res["ler"])
+
+
 def main():
     import las_testlib as tl
     import las_pytorch_b200 as ours
 
     ref = import_reference()
+    if "extras" in sys.argv[1:]:
+        make_extras(ref, tl)
+        return
     cases = [
         # name, cfg, B, T, S, mode ("tf" | "greedy" | "raw"), gain, store_weights
         ("tiny_tf_g3", "tiny", 3, 32, 6, "tf", 3.0, True),

@@ -13,6 +13,13 @@ if ROOT not in sys.path:
 
 GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
 
+
+def golden_cases():
+    """Names of the model-forward golden cases (tests/golden/<name>.npz); the `ref_*` files are the solver / checkpoint fixtures."""
+    import glob
+
+    return sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")) if not os.path.basename(p).startswith("ref_"))
+
 # name -> (listener kwargs, speller kwargs).  V=30, D=64 from config/librispeech-config.yaml:12,31.
 CONFIGS = {
     # tiny shapes whose weights are stored inside the golden files

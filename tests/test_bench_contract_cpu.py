@@ -27,6 +27,16 @@ def test_reference_arm_prints_one_contract_line():
     assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "utterances" in cb["sample"]
     assert d["e2e"] == {"value": d["value"], "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["config"]["workload"].startswith("c2:")
+    # the line reports the steps it RAN (the arm is bounded to 10 timed steps) and keeps the request alongside
+    assert d["steps"] == 1 and d["steps_requested"] == 1 and "1 timed runs" in cb["sample"]
+    # both arms print the same `config` dict (the driver compares them)
+    sys.path.insert(0, ROOT)
+    import argparse
+
+    import bench
+
+    ours = bench.shared_config(argparse.Namespace(workload="c2"), bench.WORKLOADS["c2"], 1)
+    assert d["config"] == ours
 
 
 def test_reference_arm_is_silent_on_other_ranks():

@@ -157,3 +157,86 @@ def test_models_build_from_the_shipped_yaml_sections():
     assert sd["speller.rnn_layer.weight_ih_l0"].shape == (4096, 30 + 1024)
     assert sd["speller.character_distribution.weight"].shape == (30, 2048)
     assert sum(v.numel() for v in sd.values()) == sum(p.numel() for p in las.parameters())
+
+
+def test_reference_written_package_loads():
+    """Row f3 against the real thing: tests/golden/ref_package_tiny*.pth.tar were written by the REFERENCE's LAS.serialize +
+    torch.save (model/las_model.py:42-63, train.py:181-192; tests/golden/make_golden.py extras).  `etype` is the pickled class
+    nn.LSTM (the :49/:54 duplicate-key quirk); the second file carries nn.DataParallel's `module.` key prefix."""
+    from las_pytorch_b200 import checkpoint
+
+    las, pkg = checkpoint.load_package(os.path.join(tl.GOLDEN_DIR, "ref_package_tiny.pth.tar"), max_label_len=8)
+    assert pkg["etype"] is torch.nn.LSTM and pkg["epoch"] == 7 and pkg["tr_loss"] == 1.25 and pkg["val_loss"] == 1.5
+    assert pkg["optim_dict"]["param_groups"][0]["lr"] == 1e-3
+    c = tl.CONFIGS["tiny"]
+    assert (las.listener.hidden_size, las.listener.num_layers, las.speller.hidden_size, las.speller.num_layers, las.speller.label_dim) == \
+        (c["H"], c["L"], 2 * c["H"], c["sl"], c["V"])
+    assert las.speller.attention.preprocess_mlp_dim == c["D"] and las.speller.attention.multi_head == 1
+    for k, v in pkg["state_dict"].items():
+        assert torch.equal(las.state_dict()[k], v)
+    # our serialize() writes the same key set, with the same `etype` value, as the reference's
+    ours = las.serialize(None, 7, 1.25, 1.5)
+    assert sorted(ours) == sorted(pkg) and ours["etype"] is pkg["etype"]
+    assert list(ours["state_dict"]) == list(pkg["state_dict"])
+    las_dp, _ = checkpoint.load_package(os.path.join(tl.GOLDEN_DIR, "ref_package_tiny_dataparallel.pth.tar"), max_label_len=8)
+    for a, b in zip(las.state_dict().values(), las_dp.state_dict().values()):
+        assert torch.equal(a, b)
+    # the variants' hyper-parameters the package does not record are read off the state_dict
+    mh = tl.build_model("tiny_mh", max_label_len=4, seed=3)
+    las_mh, _ = checkpoint.load_package(mh.serialize(None, 0, None, None), max_label_len=4)
+    assert las_mh.speller.attention.multi_head == 2 and las_mh.speller.attention.preprocess_mlp_dim == 16
+    gru = tl.build_model("tiny_gru", max_label_len=4, seed=3)
+    las_gru, _ = checkpoint.load_package(gru.serialize(None, 0, None, None), max_label_len=4)
+    assert las_gru.speller.cell == "GRU" and las_gru.listener.cell == "GRU"
+
+
+def test_oracle_solver_losses_match_the_reference_values():
+    """Row f1: the oracle's restatement of label_smoothing_loss / NLLLoss(ignore_index=0) / LetterErrorRate
+    (solver/solver.py:11-24,33-45,62) against values the reference's own functions produced (ref_solver_losses.npz)."""
+    from las_pytorch_b200 import solver as our_solver
+    from oracle import las_oracle as O
+
+    g = np.load(os.path.join(tl.GOLDEN_DIR, "ref_solver_losses.npz"))
+    logp, lab, lens = g["logp"], g["labels"], g["lens"]
+    V = logp.shape[-1]
+    zero_pad = np.eye(V)[lab]
+    lab0 = lab.copy()
+    for b, n in enumerate(lens):
+        zero_pad[b, n:] = 0
+        lab0[b, n:] = 0
+    pad0 = np.eye(V)[lab0]
+    for ls in (0.1, 0.3):
+        assert abs(O.label_smoothing_loss(logp, zero_pad, ls) - float(g[f"ls_zero_pad_{ls}"])) < 1e-5
+        assert abs(O.label_smoothing_loss(logp, pad0, ls) - float(g[f"ls_pad0_{ls}"])) < 1e-5
+    assert abs(O.nll_ignore0(logp, lab0) - float(g["nll_ignore0"])) < 1e-5
+    assert np.allclose(our_solver.LetterErrorRate(logp.argmax(-1), lab0), g["ler"])
+
+
+def test_packed_weight_cache_keys_follow_the_tensors_handed_to_the_pack_call():
+    """under nn.DataParallel replicas share the original's cache object and `.parameters()` is empty on a
+    replica, so the key must come from the tensors themselves, entries must be per device, and replicas must never reuse one."""
+    from las_pytorch_b200.las_model import _Cache, _weight_tensors
+
+    las = tl.build_model("tiny", max_label_len=4, seed=3)
+    ts = _weight_tensors(las.speller)
+    assert len(ts) == len(list(las.speller.parameters())) > 0
+    assert las.speller._replicate_for_data_parallel()._cache is las.speller._cache  # shallow __dict__ copy: ONE cache object
+    replica = las.speller.rnn_layer._replicate_for_data_parallel()
+    assert list(replica.parameters()) == [] and getattr(replica, "_is_replica", False)
+    for name, p in las.speller.rnn_layer._parameters.items():  # what nn.parallel.replicate does: plain tensors in _parameters
+        replica._parameters[name] = p.detach().clone()
+    assert len(_weight_tensors(replica)) == len(las.speller.rnn_layer._parameters)
+    k1 = _Cache.tensors_key(ts, 0)
+    with torch.no_grad():
+        ts[0].add_(1.0)
+    assert _Cache.tensors_key(ts, 0) != k1  # an in-place update (optimizer step, load_state_dict) changes the key
+    cache = _Cache()
+    dev = torch.device("cuda", 0)
+    cache.store(dev, 0, k1, "image")
+    assert cache.lookup(dev, 0, k1, is_replica=False) == "image"
+    assert cache.lookup(dev, 0, k1, is_replica=True) is None           # replicas always repack
+    assert cache.lookup(torch.device("cuda", 1), 0, k1, False) is None  # entries are per device
+    cache.store(torch.device("cuda", 1), 0, k1, "image1")
+    assert cache.lookup(dev, 0, k1, False) == "image"                   # ... and a device replaces only its own
+    cache.invalidate()
+    assert cache.lookup(dev, 0, k1, False) is None

@@ -10,7 +10,7 @@ import las_testlib as tl
 from oracle import las_oracle as O
 from oracle.las_ref_torch import RefTorchLAS
 
-CASES = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(tl.GOLDEN_DIR, "*.npz")))
+CASES = tl.golden_cases()
 
 
 def load_case(name):

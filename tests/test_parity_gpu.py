@@ -15,7 +15,7 @@ from oracle import las_oracle as O
 
 pytestmark = pytest.mark.gpu
 
-CASES = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(tl.GOLDEN_DIR, "*.npz")))
+CASES = tl.golden_cases()
 TOL = {"fp32": dict(enc=2e-5, logp=1e-4, attn=2e-5), "bf16": dict(enc=3e-2, logp=2e-2, attn=1e-2)}
 
 
@@ -651,3 +651,134 @@ def test_solver_batch_iterator_matches_oracle():
     assert np.allclose(ler, ref_ler, atol=1e-12)
     with pytest.raises(NotImplementedError):
         batch_iterator(x.cuda(), tl.onehot(labels, c["V"]).cuda(), las, None, 0.9, True, S, 0.1)
+
+
+@pytest.mark.parametrize("precision", precisions())
+def test_reference_written_package_loads_and_decodes(precision):
+    """Row f3 end to end: a package written by the REFERENCE (LAS.serialize + torch.save, model/las_model.py:42-63,
+    train.py:181-192; generated by tests/golden/make_golden.py extras) is loaded with checkpoint.load_package -- plain and with
+    nn.DataParallel's `module.` prefix -- moved to the GPU and decoded; outputs against what the reference computed from the very
+    same module before saving it."""
+    from las_pytorch_b200 import checkpoint
+
+    g = np.load(os.path.join(tl.GOLDEN_DIR, "ref_package_tiny_outputs.npz"))
+    tol = TOL[precision]
+    for fname in ("ref_package_tiny.pth.tar", "ref_package_tiny_dataparallel.pth.tar"):
+        las, pkg = checkpoint.load_package(os.path.join(tl.GOLDEN_DIR, fname), precision=precision, max_label_len=g["logp_greedy_f64"].shape[0])
+        assert pkg["etype"] is torch.nn.LSTM and pkg["epoch"] == 7
+        las = las.cuda()
+        x, labels = torch.from_numpy(g["x"]), torch.from_numpy(g["labels"]).long()
+        enc, logp, attn = run_ours(las, x, labels, las.speller.label_dim, "tf")
+        assert np.abs(enc - g["enc_f64"]).max() <= tol["enc"]
+        assert np.abs(logp - g["logp_tf_f64"]).max() <= tol["logp"]
+        assert np.abs(attn - g["attn_tf_f64"]).max() <= tol["attn"]
+        _, logp_g, _ = run_ours(las, x, labels, las.speller.label_dim, "greedy")
+        if precision == "fp32":
+            assert np.abs(logp_g - g["logp_greedy_f64"]).max() <= tol["logp"]
+            assert np.array_equal(logp_g.argmax(-1), g["logp_greedy_f64"].argmax(-1))
+
+
+def test_label_smoothing_and_nll_kernels_match_the_reference_values():
+    """Row f1: las_label_smoothing_terms / las_nll_sums against numbers produced by the reference's own label_smoothing_loss and
+    NLLLoss(ignore_index=0) (solver/solver.py:33-45,62; tests/golden/ref_solver_losses.npz)."""
+    from las_pytorch_b200 import solver
+
+    g = np.load(os.path.join(tl.GOLDEN_DIR, "ref_solver_losses.npz"))
+    logp = torch.from_numpy(g["logp"]).cuda()          # [B,S,V]
+    lab, lens = torch.from_numpy(g["labels"]).long(), g["lens"]
+    V = logp.shape[-1]
+    zero_pad = tl.onehot(lab, V).float()
+    lab0 = lab.clone()
+    for b, n in enumerate(lens):
+        zero_pad[b, n:] = 0
+        lab0[b, n:] = 0
+    pad0 = tl.onehot(lab0, V).float()
+    for ls in (0.1, 0.3):
+        assert abs(float(solver.label_smoothing_loss(logp, zero_pad.cuda(), ls)) - float(g[f"ls_zero_pad_{ls}"])) < 2e-5
+        assert abs(float(solver.label_smoothing_loss(logp, pad0.cuda(), ls)) - float(g[f"ls_pad0_{ls}"])) < 2e-5
+    sums = solver.nll_sums(logp.permute(1, 0, 2).contiguous(), lab0.cuda().to(torch.int32).contiguous(), lab0.size(1))
+    assert abs(float(sums[0] / sums[1]) - float(g["nll_ignore0"])) < 2e-5
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        solver.label_smoothing_loss(logp.cpu(), zero_pad, 0.1)
+
+
+@pytest.mark.parametrize("precision", precisions())
+def test_data_parallel_replicas_and_weight_updates(precision):
+    """the reference wraps the model in nn.DataParallel when device_count() > 1 (train.py:76-78).  Replicas share
+    the original module's cache object and hold broadcast copies of the weights, so a cached kernel-layout image must never be
+    reused across devices or across a weight update.  With two GPUs this runs the real nn.DataParallel; with one, replicate() +
+    parallel_apply() place both replicas on cuda:0 (two host threads, same sharing of the cache)."""
+    from torch.nn.parallel import parallel_apply, replicate
+
+    c = tl.CONFIGS["small"]
+    B, T, S = 6, 64, 8
+    x, _ = tl.make_inputs(B, T, c["F"], S, c["V"], seed=83)
+    las = tl.build_model("small", max_label_len=S, seed=83, gain=3.0, precision=precision).cuda(0)
+    ndev = min(torch.cuda.device_count(), 2)
+
+    def lone(model):
+        return torch.stack(model(x.cuda(0), None, 0.0, False)[0]).cpu()
+
+    def replicated(model):
+        if ndev >= 2:
+            out, _ = torch.nn.DataParallel(model, device_ids=[0, 1])(x.cuda(0), None, 0.0, False)
+            return torch.stack(list(out)).cpu()
+        reps = replicate(model, [0, 0])
+        halves = parallel_apply(reps, [(x[:3].cuda(0), None, 0.0, False), (x[3:].cuda(0), None, 0.0, False)], devices=[0, 0])
+        return torch.cat([torch.stack(list(h[0])) for h in halves], dim=1).cpu()
+
+    for round_ in range(2):
+        want = lone(las)
+        for _ in range(2):
+            got = replicated(las)
+            if precision == "fp32":
+                assert torch.equal(got, want)
+            else:
+                assert float((got - want).abs().max()) < 2e-2
+        with torch.no_grad():  # an optimizer-style in-place update between calls: stale packed weights would reproduce `want`
+            for p in las.parameters():
+                p.mul_(1.5 if p.dim() == 2 else 1.0)
+        assert float((lone(las) - want).abs().max()) > 1e-3
+    # in-place writes through .data bypass the version counter: documented, with an explicit hook
+    before = lone(las)
+    for p in las.parameters():
+        p.data.mul_(0.5)
+    las.invalidate_packed_weights()
+    assert float((lone(las) - before).abs().max()) > 1e-3
+
+
+def test_mismatched_teacher_forcing_shapes_raise():
+    """the kernels stride ground truth / labels by (B, label_dim); a mismatching tensor must raise like the
+    reference's torch.cat (model/las_model.py:236) instead of reading out of bounds."""
+    c = tl.CONFIGS["tiny"]
+    las = tl.build_model("tiny", max_label_len=4, seed=3).cuda()
+    enc = las.listener(torch.randn(3, 16, c["F"]).cuda())
+    good = tl.onehot(torch.randint(2, c["V"], (3, 4)), c["V"]).cuda()
+    np.random.seed(0)
+    las.speller(enc, good, 1.1)
+    for bad in (good[:2], torch.zeros(3, 4, c["V"] + 1, dtype=torch.int64).cuda()):
+        np.random.seed(0)
+        with pytest.raises(RuntimeError, match="ground_truth"):
+            las.speller(enc, bad, 1.1)
+    np.random.seed(0)
+    with pytest.raises(RuntimeError, match="ground_truth"):
+        las.speller(enc, torch.randint(2, c["V"], (2, 4)).cuda(), 1.1)
+    with pytest.raises(RuntimeError, match="out of range"):
+        np.random.seed(0)
+        las.speller(enc, torch.full((3, 4), c["V"]), 1.1)
+    with pytest.raises(RuntimeError, match="nll_labels"):
+        las.speller(enc, None, 0.0, nll_labels=torch.zeros(2, 4, dtype=torch.int32).cuda())
+    with pytest.raises(RuntimeError, match="enc_lengths"):
+        las.speller(enc, None, 0.0, enc_lengths=torch.ones(2, dtype=torch.int32).cuda())
+
+
+def test_solver_raises_when_the_decoder_is_shorter_than_the_labels():
+    """speller.max_label_len < label length made the fused loss silently too small; the reference fails with a
+    shape error there (solver/solver.py:68-72)."""
+    from las_pytorch_b200 import solver
+
+    c = tl.CONFIGS["tiny"]
+    las = tl.build_model("tiny", max_label_len=3, seed=3).cuda()
+    x, labels = tl.make_inputs(2, 16, c["F"], 6, c["V"], seed=3)
+    with pytest.raises(RuntimeError, match="max_label_len"):
+        solver.batch_iterator(x.cuda(), tl.onehot(labels, c["V"]).cuda(), las, None, 0.0, False, 6, 0.0)

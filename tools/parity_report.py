@@ -14,7 +14,7 @@ import las_testlib as tl  # noqa: E402
 
 def main():
     print(f"{'case':18s} {'prec':5s} {'enc':>10s} {'logp':>10s} {'attn':>10s} {'argmax agree':>13s}  (vs the reference's fp64 run)")
-    for path in sorted(glob.glob(os.path.join(tl.GOLDEN_DIR, "*.npz"))):
+    for path in (os.path.join(tl.GOLDEN_DIR, n + ".npz") for n in tl.golden_cases()):
         g = np.load(path)
         cfg, mode = str(g["cfg"]), str(g["mode"])
         c = tl.CONFIGS[cfg]
