@@ -586,12 +586,22 @@ def main():
         onehot = tl.onehot(torch.from_numpy(ours_tok.T.astype(np.int64)), c["V"])
         rescored, _ = info["model"].speller(info["enc"], S, onehot, 1)  # the reference, teacher-forced on OUR tokens
         same = (ours_tok == ref_tok)
+        # calibration for the bf16 mode: the reference's own op sequence with only its 2-D weights rounded to bf16 vs itself
+        # (free-running greedy decoding at these weights is chaotic: one near-tie flip changes the rest of an utterance)
+        from oracle.las_ref_torch import RefTorchLAS
+
+        sd_b = {k: (v.detach().cpu().to(torch.bfloat16).float().numpy() if v.dim() == 2 else v.detach().cpu().numpy()) for k, v in las.state_dict().items()}
+        mb = RefTorchLAS(sd_b, c["L"], c["sl"])
+        xs = (x_host if not strong else x_global)[:cpu_sample]
+        lb, _ = mb.speller(mb.listener(xs), S, None, 1)
+        cal = float((lb.argmax(-1).numpy() == ref_tok).mean())
         out["parity"] = {"against": "cpu_baseline (oracle/las_ref_torch.py, fp32) on the same utterances and weights",
                          "utterances": cpu_sample, "token_agreement": float(same.mean()),
                          "utterances_identical": int(same.all(0).sum()),
                          "logp_max_abs": float(np.abs(ours_logp - rescored.numpy()).max()),
                          "logp_max_abs_is": "our greedy log-probs vs the reference teacher-forced on the tokens we fed back (every step)",
-                         "logp_max_abs_free_running": float(np.abs(ours_logp - info["logp"].numpy()).max())}
+                         "logp_max_abs_free_running": float(np.abs(ours_logp - info["logp"].numpy()).max()),
+                         "reference_with_bf16_rounded_weights_token_agreement": cal}
     if world == 1 and not args.no_gpu_baseline:
         try:  # the reference's own op sequence with use_gpu=True on this B200 (torch -> cuDNN / cuBLAS), bounded
             v, info = reference_arm(wl, cpu_sample, 2, 1, device=str(dev), x=x_host if not strong else x_global)

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define LAS_B200_ABI_VERSION 3
+#define LAS_B200_ABI_VERSION 4
 
 enum {
   LAS_OK = 0,
@@ -195,12 +195,55 @@ typedef struct las_decode_io {
   const int32_t* nll_labels;
   int32_t nll_steps;
   float* nll_terms;
+  /* Segmented decode.  segment_steps > 0 (rounded up to even): the step loop runs as ceil(steps / segment_steps) persistent launches
+   * instead of one, the recurrent state carried between them on the device -- outputs are bit-identical to a single launch
+   * (LAS_MODE_BF16; LAS_MODE_FP32 is launch-per-step anyway and ignores it).
+   * early_exit != 0 ("next" row f4, <eos> early-exit batching; an extension -- the reference always runs max_label_len steps,
+   * model/las_model.py:205-209): after each segment (default 32 steps) the library checks on the device whether every utterance of the
+   * launch group (<= 64 consecutive utterances) has emitted `eos_token` (1 in the reference's vocabulary, utils/functions.py:124-125);
+   * if so the group's remaining segments return immediately, and its outputs for the steps it did not decode are filled with
+   * tokens = eos_token, logp = attn = nll_terms = 0.  Needs `tokens`.  steps_done (nullable, device int32[1]) receives the number of
+   * steps decoded (max over the groups).  No host synchronisation is involved. */
+  int32_t segment_steps;
+  int32_t early_exit;
+  int32_t eos_token;
+  int32_t* steps_done;
 } las_decode_io;
 
 size_t las_speller_workspace_bytes(const las_speller_dims* d, int steps, int mode);
 /* Runs `steps` decoder steps (Speller.forward loop, :209-236).  relu: attention activation flag. */
 int las_speller_decode(const las_decode_io* io, const void* packed, const las_speller_dims* d, int steps,
                        int decode_mode, int mode, int relu, void* workspace, size_t workspace_bytes, void* stream);
+
+/* --------------------------------------------------------------------------------------------------------
+ * Cross-batch serving pipeline.  One call stands for `las_speller_decode` of batch i AND `las_listener_forward[_masked]` of batch
+ * i+1 (the two calls LAS.forward makes, model/las_model.py:31-39, for two consecutive batches) and produces exactly their
+ * results.  In LAS_MODE_BF16, when the listener's recurrence fits on the SMs the persistent decoder leaves free, the two run
+ * CONCURRENTLY: the decoder's step loop is cut into L segments, each layer's recurrence of the next batch runs next to one segment
+ * and its input-projection GEMM alone on the chip between two segments (csrc/fast_pipeline.cu).  Otherwise (fp32 mode, variants,
+ * no free SMs, early_exit) the two are simply enqueued one after the other.  dec_io == NULL: encode only; x == NULL: decode only.
+ * `las_pipeline_overlaps` tells whether the concurrent schedule applies to a pair of shapes.
+ * ------------------------------------------------------------------------------------------------------ */
+typedef struct las_pipeline_args {
+  /* batch i: what las_speller_decode takes */
+  const las_decode_io* dec_io;
+  const void* speller_packed;
+  const las_speller_dims* speller_dims;
+  int32_t steps, decode_mode, relu;
+  void* speller_ws;
+  size_t speller_ws_bytes;
+  /* batch i+1: what las_listener_forward_masked takes */
+  const float* x;
+  const int32_t* x_lengths;  /* nullable */
+  const void* listener_packed;
+  const las_listener_dims* listener_dims;
+  float* enc;
+  int32_t* enc_lengths;      /* nullable */
+  void* listener_ws;
+  size_t listener_ws_bytes;
+} las_pipeline_args;
+int las_pipeline_step(const las_pipeline_args* a, int mode, void* stream);
+int las_pipeline_overlaps(const las_listener_dims* ld, const las_speller_dims* sd, int steps, int mode);
 
 /* --------------------------------------------------------------------------------------------------------
  * Solver epilogue ("next" row f1, solver/solver.py:62-92): NLL(ignore_index=0) sums on device.
@@ -234,7 +277,8 @@ int las_debug_set_trace(void* dev_buf);
  * key 5: decoder A/B flags (bit 0: W_phi from shared memory instead of registers; bit 2: one 2-D TMA copy per 64-column atom of an
  * activation part instead of one 3-D copy); key 6: listener input-projection GEMM concurrent with the recurrence (1, default) or in
  * front of it (0); key 7: persistent CTAs of that concurrent GEMM (0 = auto); key 8: tcgen05 GEMM epilogue with row-per-thread
- * global stores (1) instead of shared-memory staging + TMA stores (0, default). */
+ * global stores (1) instead of shared-memory staging + TMA stores (0, default); key 9: batch chunk per recurrence cluster (16 / 32 /
+ * 64; 0 = automatic); keys 20 + l: decoder steps of the serving pipeline's segment l (0 = proportional to the layer's time steps). */
 int las_debug_set_option(int key, int value);
 
 #ifdef __cplusplus

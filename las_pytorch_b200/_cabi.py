@@ -12,7 +12,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "liblas_b200.so")
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 MODE_FP32 = 0
 MODE_BF16 = 1
 DECODE_RAW = 0
@@ -55,6 +55,16 @@ class DecodeIO(C.Structure):
         ("h_state", C.c_void_p), ("c_state", C.c_void_p), ("word", C.c_void_p), ("context", C.c_void_p),
         ("logp", C.c_void_p), ("attn", C.c_void_p), ("tokens", C.c_void_p),
         ("nll_labels", C.c_void_p), ("nll_steps", C.c_int32), ("nll_terms", C.c_void_p),
+        ("segment_steps", C.c_int32), ("early_exit", C.c_int32), ("eos_token", C.c_int32), ("steps_done", C.c_void_p),
+    ]
+
+
+class PipelineArgs(C.Structure):
+    _fields_ = [
+        ("dec_io", C.POINTER(DecodeIO)), ("speller_packed", C.c_void_p), ("speller_dims", C.POINTER(SpellerDims)),
+        ("steps", C.c_int32), ("decode_mode", C.c_int32), ("relu", C.c_int32), ("speller_ws", C.c_void_p), ("speller_ws_bytes", C.c_size_t),
+        ("x", C.c_void_p), ("x_lengths", C.c_void_p), ("listener_packed", C.c_void_p), ("listener_dims", C.POINTER(ListenerDims)),
+        ("enc", C.c_void_p), ("enc_lengths", C.c_void_p), ("listener_ws", C.c_void_p), ("listener_ws_bytes", C.c_size_t),
     ]
 
 
@@ -79,6 +89,8 @@ PROTOTYPES = {
     "las_attention_forward": (C.c_int, [C.c_void_p] * 5 + [C.c_int] * 7 + [C.c_void_p] * 6),
     "las_speller_workspace_bytes": (C.c_size_t, [C.POINTER(SpellerDims), C.c_int, C.c_int]),
     "las_speller_decode": (C.c_int, [C.POINTER(DecodeIO), C.c_void_p, C.POINTER(SpellerDims), C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "las_pipeline_step": (C.c_int, [C.POINTER(PipelineArgs), C.c_int, C.c_void_p]),
+    "las_pipeline_overlaps": (C.c_int, [C.POINTER(ListenerDims), C.POINTER(SpellerDims), C.c_int, C.c_int]),
     "las_debug_gemm_bf16": (C.c_int, [C.c_void_p] * 4 + [C.c_int] * 3 + [C.c_void_p]),
     "las_debug_umma_probe": (C.c_int, [C.c_void_p] * 3 + [C.c_int] * 5 + [C.c_void_p]),
     "las_debug_set_trace": (C.c_int, [C.c_void_p]),

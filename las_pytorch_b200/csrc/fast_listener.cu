@@ -36,6 +36,8 @@ struct RecParams {
   int B, Tl, H, Hp, CS, nchunks;
   int a_tmem;                   // 1: W_hh slice lives in tensor memory (UMMA .ts form); 0: in shared memory
   long long* trace;             // nullable test hook: [64 steps][8] clock64 stamps from CTA 0
+  int* resident;                // nullable: every CTA adds 1 once it is running (the serving pipeline launches the decoder, which takes
+                                // all but a few SMs, only after this kernel's clusters have been placed)
 };
 
 #define REC_TRACE(slot) do { if (p.trace && blockIdx.x == 0 && s < 64) p.trace[s * 8 + (slot)] = clock64(); } while (0)
@@ -93,6 +95,7 @@ __global__ void __launch_bounds__(REC_THREADS, 1) lstm_recurrence_cluster_kernel
 
   // ---- one-time setup: barriers, TMEM, resident W_hh slice
   if (threadIdx.x == 0) {
+    if (p.resident) atomicAdd(p.resident, 1);
     *s_ready = p.gemm_flags ? 0 : p.Tl;
     ptx::mbar_init(&h_full[0], 1);  // one local arrive.expect_tx per phase; the peers' bulk copies complete the bytes
     ptx::mbar_init(&h_full[1], 1);
@@ -428,6 +431,7 @@ int side_stream(SideStream** out) {
   return LAS_OK;
 }
 int g_rec_a_tmem = 1;              // las_debug_set_option(1, v)
+int g_rec_force_bc = 0;            // las_debug_set_option(9, v): batch chunk per recurrence cluster (0 = pick_bc)
 int g_rec_nacc = 0;                // las_debug_set_option(4, v): independent accumulators the K loop is spread over (0 = default)
 
 struct Geo {
@@ -541,8 +545,10 @@ void fast_set_option(int key, int value) {
   if (key == 4) g_rec_nacc = value;
   if (key == 6) g_rec_overlap = value;
   if (key == 7) g_rec_gemm_ctas = value;
+  if (key == 9) g_rec_force_bc = value;
   fast_set_option_speller(key, value);
   fast_set_option_gemm(key, value);
+  fast_set_option_pipeline(key, value);
 }
 
 size_t fast_listener_packed_bytes(const las_listener_dims* d) { return pack_layout(d, nullptr).bytes; }
@@ -566,47 +572,120 @@ int fast_listener_pack(const las_lstm_weights* w, const las_listener_dims* d, vo
   return LAS_OK;
 }
 
+// One stage of the listener: stage 0 = input cast, 1 + 2l = layer l's input-projection GEMM, 2 + 2l = layer l's recurrence.
+// fast_listener_forward chains them (GEMM concurrent with the recurrence where possible); the serving pipeline (fast_pipeline.cu)
+// issues them one by one between / next to the decoder's segments.
+struct LayerGeom {
+  const __nv_bfloat16* in;
+  int Tl, K, NP;
+};
+static LayerGeom layer_geom(const las_listener_dims* d, const Geo& g, const ListenerWsFast& w, int l) {
+  LayerGeom q;
+  q.in = (l == 0) ? w.xb : w.act[(l - 1) & 1];
+  q.Tl = d->T >> (l + 1);
+  q.K = (l == 0) ? 2 * d->F : 4 * d->H;
+  q.NP = 8 * g.Hp;
+  return q;
+}
+static RecParams rec_params(const las_listener_dims* d, const Geo& g, const ListenerPackFast& pk, const ListenerWsFast& w, int l, float* enc,
+                            const int32_t* len_l, int bc) {
+  const LayerGeom q = layer_geom(d, g, w, l);
+  const bool last = (l == d->L - 1);
+  RecParams rp;
+  rp.P = w.P;
+  rp.gemm_flags = nullptr;
+  rp.Bp = listener_padded_batch(d->B);
+  rp.n_tiles = (q.NP + 255) / 256;
+  rp.whh_img = pk.whh[l];
+  rp.out_f32 = last ? enc : nullptr;
+  rp.out_bf16 = last ? nullptr : w.act[l & 1];
+  rp.lengths = len_l;
+  rp.B = d->B; rp.Tl = q.Tl; rp.H = d->H; rp.Hp = g.Hp; rp.CS = g.CS;
+  rp.trace = (l == 0) ? g_rec_trace : nullptr;
+  rp.a_tmem = g_rec_a_tmem;
+  rp.nchunks = (d->B + bc - 1) / bc;
+  rp.resident = nullptr;
+  return rp;
+}
+static int launch_rec_bc(const RecParams& rp, int bc, cudaStream_t st, bool exclusive) {
+  if (bc == 16) {
+    const int nacc = g_rec_nacc ? g_rec_nacc : 1;  // measured: one accumulator chain is fastest with the A operand in TMEM
+    if (nacc == 1) return launch_rec<16, 1>(rp, st, exclusive);
+    if (nacc == 2) return launch_rec<16, 2>(rp, st, exclusive);
+    return launch_rec<16, 4>(rp, st, exclusive);
+  }
+  if (bc == 32) return launch_rec<32, 2>(rp, st, exclusive);
+  return launch_rec<64, 1>(rp, st, exclusive);
+}
+
+// CTAs the recurrence of this model occupies with batch chunk `bc`
+int fast_listener_rec_ctas(const las_listener_dims* d, int bc) {
+  const Geo g = geometry(d->H);
+  return 2 * ((d->B + bc - 1) / bc) * g.CS;
+}
+
+int fast_listener_stage(const float* x, const int32_t* x_lengths, const void* packed, const las_listener_dims* d, float* enc,
+                        int32_t* enc_lengths, void* ws, int stage, int bc, int* resident, cudaStream_t st) {
+  LAS_TRY(shape_ok(d));
+  const Geo g = geometry(d->H);
+  const ListenerPackFast pk = pack_layout(d, const_cast<void*>(packed));
+  const ListenerWsFast w = ws_layout(d, ws);
+  char nm[48];
+  if (stage == 0) {
+    ProfScope ps("listener.cast_bf16", st);
+    return launch_f32_to_bf16(x, w.xb, (size_t)d->B * d->T * d->F, st);
+  }
+  const int l = (stage - 1) / 2;
+  const LayerGeom q = layer_geom(d, g, w, l);
+  if ((stage - 1) % 2 == 0) {
+    if (x_lengths) LAS_TRY(launch_pyramid_lengths(l == 0 ? x_lengths : w.len + (size_t)(l - 1) * d->B, w.len + (size_t)l * d->B, d->B, q.Tl, st));
+    snprintf(nm, sizeof(nm), "listener.L%d.input_gemm", l);
+    ProfScope ps(nm, st);
+    return launch_gemm_listener(q.in, d->B, q.Tl, q.K, pk.wih[l], pk.bias[l], w.P, q.NP, nullptr, 0, st);
+  }
+  RecParams rp = rec_params(d, g, pk, w, l, enc, x_lengths ? w.len + (size_t)l * d->B : nullptr, bc);
+  rp.resident = resident;
+  snprintf(nm, sizeof(nm), "listener.L%d.recurrence", l);
+  {
+    ProfScope ps(nm, st);
+    LAS_TRY(launch_rec_bc(rp, bc, st, true));
+  }
+  if (l == d->L - 1 && x_lengths && enc_lengths)
+    LAS_CUDA_OK(cudaMemcpyAsync(enc_lengths, w.len + (size_t)(d->L - 1) * d->B, sizeof(int32_t) * d->B, cudaMemcpyDeviceToDevice, st));
+  return LAS_OK;
+}
+
+// events / side stream of the calling thread (fast_pipeline.cu)
+int fast_side_stream(cudaStream_t* s) {
+  SideStream* side = nullptr;
+  LAS_TRY(side_stream(&side));
+  *s = side->s;
+  return LAS_OK;
+}
+
 int fast_listener_forward(const float* x, const int32_t* x_lengths, const void* packed, const las_listener_dims* d, float* enc,
                           int32_t* enc_lengths, void* ws, cudaStream_t st) {
   LAS_TRY(shape_ok(d));
   const Geo g = geometry(d->H);
   const ListenerPackFast pk = pack_layout(d, const_cast<void*>(packed));
   const ListenerWsFast w = ws_layout(d, ws);
-  const int B = d->B, H = d->H;
-  {
-    ProfScope ps("listener.cast_bf16", st);
-    LAS_TRY(launch_f32_to_bf16(x, w.xb, (size_t)B * d->T * d->F, st));
-  }
-  const __nv_bfloat16* cur = w.xb;
-  int Tin = d->T, Fin = d->F;
+  const int B = d->B;
+  LAS_TRY(fast_listener_stage(x, x_lengths, packed, d, enc, enc_lengths, ws, 0, 0, nullptr, st));
   for (int l = 0; l < d->L; ++l) {
-    const int Tl = Tin / 2, K = 2 * Fin, NP = 8 * g.Hp;
+    const LayerGeom q = layer_geom(d, g, w, l);
     const int32_t* len_l = nullptr;
     if (x_lengths) {
-      LAS_TRY(launch_pyramid_lengths(l == 0 ? x_lengths : w.len + (size_t)(l - 1) * B, w.len + (size_t)l * B, B, Tl, st));
+      LAS_TRY(launch_pyramid_lengths(l == 0 ? x_lengths : w.len + (size_t)(l - 1) * B, w.len + (size_t)l * B, B, q.Tl, st));
       len_l = w.len + (size_t)l * B;
     }
-    const bool last = (l == d->L - 1);
-    RecParams rp;
-    rp.P = w.P;
-    rp.gemm_flags = nullptr;  // set below when the GEMM runs concurrently
-    rp.Bp = listener_padded_batch(B);
-    rp.n_tiles = (NP + 255) / 256;
-    rp.whh_img = pk.whh[l];
-    rp.out_f32 = last ? enc : nullptr;
-    rp.out_bf16 = last ? nullptr : w.act[l & 1];
-    rp.lengths = len_l;
-    rp.B = B; rp.Tl = Tl; rp.H = H; rp.Hp = g.Hp; rp.CS = g.CS;
-    rp.trace = (l == 0) ? g_rec_trace : nullptr;
-    rp.a_tmem = g_rec_a_tmem;
-    const int bc = pick_bc(B, g.CS);
-    rp.nchunks = (B + bc - 1) / bc;
+    const int bc = g_rec_force_bc ? g_rec_force_bc : pick_bc(B, g.CS);
+    RecParams rp = rec_params(d, g, pk, w, l, enc, len_l, bc);
     // The GEMM emits its tiles in the recurrence's consumption order and flags each one, so it can run next to the recurrence
     // (which occupies 2 * nchunks * CS SMs) on the remaining SMs instead of in front of it.  Needs the two directions' columns
     // to fall on separate column tiles and enough free SMs to be worth it.
     const int rec_ctas = 2 * rp.nchunks * g.CS;
     const int gemm_ctas = g_rec_gemm_ctas > 0 ? g_rec_gemm_ctas : sm_count() - rec_ctas - 4;
-    const bool overlap = g_rec_overlap && ((NP / 2) % 256 == 0) && gemm_ctas >= 32;
+    const bool overlap = g_rec_overlap && ((q.NP / 2) % 256 == 0) && gemm_ctas >= 32;
     SideStream* side = nullptr;
     if (overlap) LAS_TRY(side_stream(&side));
     if (overlap) rp.gemm_flags = w.flags;
@@ -623,29 +702,17 @@ int fast_listener_forward(const float* x, const int32_t* x_lengths, const void* 
       }
       snprintf(nm, sizeof(nm), overlap ? "listener.L%d.input_gemm.overlapped" : "listener.L%d.input_gemm", l);
       ProfScope ps(nm, gs);
-      LAS_TRY(launch_gemm_listener(cur, B, Tl, K, pk.wih[l], pk.bias[l], w.P, NP, overlap ? w.flags : nullptr, overlap ? gemm_ctas : 0, gs));
+      LAS_TRY(launch_gemm_listener(q.in, B, q.Tl, q.K, pk.wih[l], pk.bias[l], w.P, q.NP, overlap ? w.flags : nullptr, overlap ? gemm_ctas : 0, gs));
     }
     {
       snprintf(nm, sizeof(nm), "listener.L%d.recurrence", l);
       ProfScope ps(nm, st);
-      if (bc == 16) {
-        const int nacc = g_rec_nacc ? g_rec_nacc : 1;  // measured: one accumulator chain is fastest with the A operand in TMEM
-        if (nacc == 1) LAS_TRY((launch_rec<16, 1>(rp, st, overlap)));
-        else if (nacc == 2) LAS_TRY((launch_rec<16, 2>(rp, st, overlap)));
-        else LAS_TRY((launch_rec<16, 4>(rp, st, overlap)));
-      } else if (bc == 32) {
-        LAS_TRY((launch_rec<32, 2>(rp, st, overlap)));
-      } else {
-        LAS_TRY((launch_rec<64, 1>(rp, st, overlap)));
-      }
+      LAS_TRY(launch_rec_bc(rp, bc, st, overlap));
     }
     if (overlap) {  // the GEMM kernel has delivered every tile by now; join so that P / flags can be reused by the next layer
       LAS_CUDA_OK(cudaEventRecord(side->join, side->s));
       LAS_CUDA_OK(cudaStreamWaitEvent(st, side->join, 0));
     }
-    cur = w.act[l & 1];
-    Tin = Tl;
-    Fin = 2 * H;
   }
   if (x_lengths && enc_lengths)
     LAS_CUDA_OK(cudaMemcpyAsync(enc_lengths, w.len + (size_t)(d->L - 1) * B, sizeof(int32_t) * B, cudaMemcpyDeviceToDevice, st));

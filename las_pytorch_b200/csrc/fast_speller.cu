@@ -62,9 +62,16 @@ struct DecParams {
   __nv_bfloat16* wbuf[2];
   u64* h_ll;                    // [B, Hs] {fp32 h of the top layer, step tag}
   u64* tok_ll;                  // [ncl, B] {token fed back, step tag}: one private copy per layer-0 CTA (no polling hot spot)
-  const float* c_init;          // nullable [sl, B, Hs]
-  float* h_out;                 // nullable [sl, B, Hs]
-  float* c_out;                 // nullable [sl, B, Hs]
+  const float* c_init;          // nullable [sl, c_init_rows, Hs], row of utterance b: c_init_b0 + b
+  float* h_out;                 // nullable [sl, Bfull, Hs]
+  float* c_out;                 // nullable [sl, c_out_rows, Hs], row c_out_b0 + b
+  int c_init_rows, c_init_b0, c_out_rows, c_out_b0;  // the caller's [sl,Bfull,Hs] tensors or the workspace's per-launch carry buffer
+  // Segmented decode (cross-batch pipeline, <eos> early exit): this launch covers the global steps [s0, s0 + steps).  Counters, tags
+  // and buffer parities are launch-local (s0 is even, so parities line up); outputs, labels and the sampling counter use s0 + s.
+  int s0;
+  const int32_t* tok_init;      // nullable [B]: the token fed back by global step s0 - 1 (index-word modes, s0 > 0)
+  int32_t* tok_carry;           // nullable [B]: receives the token fed back by this launch's last step
+  const int32_t* stop;          // nullable: *stop != 0 -> every CTA returns at once (all utterances have emitted <eos>)
   const __nv_bfloat16* enc;     // [B, U, E] bf16
   const float* psi;             // [B, U, D] fp32
   const __nv_bfloat16* w_phi;   // [D, Hs] bf16
@@ -292,7 +299,7 @@ __device__ void lstm_role(const DecParams& p, uint8_t* smem, int l, int nb) {
       }
       if (lane == 0 && trole >= 0) DEC_TRACE(trole, 1);
       // ---- part 1b: dense word vector of step s-1
-      if (first && (s == 0 || !p.word_gather)) {
+      if (first && (p.s0 + s == 0 || !p.word_gather)) {
         if (lane == 0) wait_counter(word_ctr, (uint32_t)s * p.B);
         __syncwarp();
         fence_proxy_async_global();
@@ -310,7 +317,7 @@ __device__ void lstm_role(const DecParams& p, uint8_t* smem, int l, int nb) {
     const uint32_t a0 = ptx::smem_u32(abuf), w_addr = ptx::smem_u32(wsm);
     uint32_t phase_bits = 0;  // per-slot phase parity
     for (int s = 0; s < S; ++s) {
-      const bool wd = first && (s == 0 || !p.word_gather);
+      const bool wd = first && (p.s0 + s == 0 || !p.word_gather);
       ptx::mbar_wait(tmem_empty, (uint32_t)((s & 1) ^ 1));
       ptx::tc_fence_after();
       for (int part = 0; part < 2; ++part) {
@@ -368,7 +375,7 @@ __device__ void lstm_role(const DecParams& p, uint8_t* smem, int l, int nb) {
     const int gb = p.b0 + b;
     float c[4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) c[i] = (live && p.c_init) ? p.c_init[((size_t)l * p.Bfull + gb) * p.Hs + u0 + i] : 0.f;
+    for (int i = 0; i < 4; ++i) c[i] = (live && p.c_init) ? p.c_init[((size_t)l * p.c_init_rows + p.c_init_b0 + b) * p.Hs + u0 + i] : 0.f;
     float bias_r[16];
 #pragma unroll
     for (int i = 0; i < 16; ++i) bias_r[i] = bias_s[c0 + i];
@@ -379,8 +386,9 @@ __device__ void lstm_role(const DecParams& p, uint8_t* smem, int l, int nb) {
       float pb[16];
 #pragma unroll
       for (int i = 0; i < 16; ++i) pb[i] = bias_r[i];
-      if (first && s > 0 && p.word_gather && live) {
-        int tok = p.gt_index ? p.gt_index[(size_t)gb * p.gt_steps + (s - 1)] : (int)ll_wait(p.tok_ll + (size_t)nb * p.B + b, (uint32_t)s);
+      if (first && p.s0 + s > 0 && p.word_gather && live) {
+        int tok = p.gt_index ? p.gt_index[(size_t)gb * p.gt_steps + (p.s0 + s - 1)]
+                             : (s > 0 ? (int)ll_wait(p.tok_ll + (size_t)nb * p.B + b, (uint32_t)s) : p.tok_init[b]);
         if (tok >= 0 && tok < p.V) {
           const uint32_t tok_off = (uint32_t)(tok & 7) * 2u, tok_chunk = (uint32_t)(tok >> 3);
 #pragma unroll
@@ -467,7 +475,7 @@ __device__ void lstm_role(const DecParams& p, uint8_t* smem, int l, int nb) {
           }
           if (p.c_out) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) p.c_out[((size_t)l * p.Bfull + gb) * p.Hs + u0 + i] = c[i];
+            for (int i = 0; i < 4; ++i) p.c_out[((size_t)l * p.c_out_rows + p.c_out_b0 + b) * p.Hs + u0 + i] = c[i];
           }
         }
       }
@@ -841,7 +849,7 @@ __device__ void attention_role(const DecParams& p, uint8_t* smem, int b) {
 #pragma unroll
       for (int ps = 0; ps < ATT_MAXP; ++ps) {
         const int u = ps * 256 + (tid >> 1);
-        if (u < U) p.attn[((size_t)s * p.Bfull + gb) * U + u] = ev[ps] * inv;
+        if (u < U) p.attn[((size_t)(p.s0 + s) * p.Bfull + gb) * U + u] = ev[ps] * inv;
       }
     }
     const bool late_h = hybrid;  // h half of the logits together with the context half, after the publish (measured for the pure
@@ -1010,26 +1018,28 @@ __device__ void attention_role(const DecParams& p, uint8_t* smem, int b) {
       for (int v = lane; v < V; v += 32) ls += __expf(s_logit[v] - lm);
       ls = warp_sum(ls);
       const float lse = lm + __logf(ls);
-      for (int v = lane; v < V; v += 32) p.logp[((size_t)s * p.Bfull + gb) * V + v] = s_logit[v] - lse;
+      for (int v = lane; v < V; v += 32) p.logp[((size_t)(p.s0 + s) * p.Bfull + gb) * V + v] = s_logit[v] - lse;
       int bi = li;  // ties -> lowest index, as torch.topk / argmax on the host
       if (p.nll_terms && lane == 0) {  // NLLLoss(ignore_index=0) term of this (step, utterance)
-        const int lab = (p.nll_labels && s < p.nll_steps) ? p.nll_labels[(size_t)gb * p.nll_steps + s] : 0;
-        p.nll_terms[(size_t)s * p.Bfull + gb] = (lab > 0 && lab < V) ? -(s_logit[lab] - lse) : 0.f;
+        const int sg = p.s0 + s;
+        const int lab = (p.nll_labels && sg < p.nll_steps) ? p.nll_labels[(size_t)gb * p.nll_steps + sg] : 0;
+        p.nll_terms[(size_t)sg * p.Bfull + gb] = (lab > 0 && lab < V) ? -(s_logit[lab] - lse) : 0.f;
       }
       if (p.decode_mode == LAS_DECODE_SAMPLE && !p.gt_index && !p.gt_dense) {
         // decode_mode 2 (:229-234): feed back (and report) a draw from Categorical(probs = log-probs); s_logit -> log-probs first
         __syncwarp();
         for (int v = lane; v < V; v += 32) s_logit[v] -= lse;
         __syncwarp();
-        if (lane == 0) bi = las_sample_logp_as_probs(s_logit, V, las_uniform(p.sample_seed, (uint32_t)s, (uint32_t)gb));
+        if (lane == 0) bi = las_sample_logp_as_probs(s_logit, V, las_uniform(p.sample_seed, (uint32_t)(p.s0 + s), (uint32_t)gb));
         bi = __shfl_sync(0xffffffffu, bi, 0);
         for (int v = lane; v < V; v += 32) s_logit[v] += lse;  // the raw-feedback branch below expects logits
         __syncwarp();
       }
-      if (lane == 0 && p.tokens) p.tokens[(size_t)s * p.Bfull + gb] = bi;
+      if (lane == 0 && p.tokens) p.tokens[(size_t)(p.s0 + s) * p.Bfull + gb] = bi;
       if (p.word_gather) {
         // the word is an index: layer 0's epilogue adds the matching column of W_word itself
-        const int fed = p.gt_index ? p.gt_index[(size_t)gb * p.gt_steps + s] : bi;
+        const int fed = p.gt_index ? p.gt_index[(size_t)gb * p.gt_steps + p.s0 + s] : bi;
+        if (last && lane == 0 && p.tok_carry) p.tok_carry[b] = fed;
         if (!p.gt_index && !early_tok)
           for (int i = lane; i < p.ncl; i += 32) ll_store(p.tok_ll + (size_t)i * p.B + b, ll_pack((uint32_t)fed, (uint32_t)(s + 1)));
         if (last && p.word_out)
@@ -1038,7 +1048,7 @@ __device__ void attention_role(const DecParams& p, uint8_t* smem, int b) {
         for (int i = lane; i < DEC_VP; i += 32) {
           float val = 0.f;
           if (i < V) {
-            if (p.gt_dense) val = p.gt_dense[((size_t)gb * p.gt_steps + s) * V + i];
+            if (p.gt_dense) val = p.gt_dense[((size_t)gb * p.gt_steps + p.s0 + s) * V + i];
             else if (p.decode_mode == LAS_DECODE_RAW) val = s_logit[i] - lse;
             else val = (i == bi) ? 1.f : 0.f;
             if (last && p.word_out) p.word_out[(size_t)gb * V + i] = val;
@@ -1064,6 +1074,7 @@ __global__ void __launch_bounds__(DEC_THREADS, 1) speller_decode_persistent_kern
   // address space and emits LDS/STS instead of generic loads
   uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
   const int n_lstm = p.sl * p.ncl;
+  if (p.stop && *reinterpret_cast<const volatile int32_t*>(p.stop) != 0) return;  // written before this launch: every CTA sees the same value
   if ((int)blockIdx.x < n_lstm) lstm_role(p, smem, blockIdx.x / p.ncl, blockIdx.x % p.ncl);
   else attention_role(p, smem, blockIdx.x - n_lstm);
 }
@@ -1209,6 +1220,9 @@ struct SpellerWsFast {
   uint32_t* sync;
   u64* tok_ll;
   u64* h_ll;
+  float* c_carry;      // [sl, B, Hs] cell state between the segments of a segmented decode
+  int32_t* tok_carry;  // [B] token fed back by the previous segment's last step
+  int32_t* stop;       // <eos> early exit: [0] stop flag, [1] steps this launch group decoded, [2..66) per-utterance done flags
   size_t bytes;
 };
 SpellerWsFast ws_layout(const las_speller_dims* d, void* base) {
@@ -1225,6 +1239,9 @@ SpellerWsFast ws_layout(const las_speller_dims* d, void* base) {
   w.sync = reinterpret_cast<uint32_t*>(w.flags);
   w.tok_ll = reinterpret_cast<u64*>(w.flags ? w.flags + sync_bytes : nullptr);
   w.h_ll = reinterpret_cast<u64*>(w.flags ? w.flags + sync_bytes + tok_bytes : nullptr);
+  w.c_carry = cv.take<float>((size_t)MAX_SL * d->B * d->Hs);
+  w.tok_carry = cv.take<int32_t>((size_t)d->B);
+  w.stop = cv.take<int32_t>(2 + 64);
   w.bytes = cv.total();
   return w;
 }
@@ -1257,15 +1274,18 @@ int fast_speller_pack(const las_speller_weights* w, const las_speller_dims* d, v
   return LAS_OK;
 }
 
-int fast_speller_decode(const las_decode_io* io, const void* packed_f32, const void* packed_fast, const las_speller_dims* d, int steps,
-                        int decode_mode, int relu, void* ws_f32, void* ws_fast, cudaStream_t st) {
-  LAS_TRY(supported(d));
+// One persistent launch: utterances [b0, b0 + Bc) of the batch, global steps [s_begin, s_begin + s_count).
+//   first_seg: convert enc, compute psi, build the initial input / state (s_begin == 0);
+//   last_seg:  hand the recurrent state back to the caller (io->h_state / c_state / word / context);
+// between segments the state lives in the workspace: h / context / dense word in the parity-0 hand-off buffers (s_count is even
+// for every segment but the last), c and the fed-back token in the carry buffers.
+int fast_speller_decode_segment(const las_decode_io* io, const void* packed_f32, const void* packed_fast, const las_speller_dims* d,
+                                int b0, int Bc, int s_begin, int s_count, bool first_seg, bool last_seg, int decode_mode, int relu,
+                                void* ws_f32, void* ws_fast, cudaStream_t st) {
   const Shape s = shape_of(d);
   const int n_lstm = d->sl * s.ncl;
-  const int nsm = sm_count();
-  LAS_REQUIRE(n_lstm + 1 <= nsm, "LAS_MODE_BF16 speller: %d LSTM CTAs do not fit %d SMs", n_lstm, nsm);
-  // utterances per persistent launch: one attention CTA each, and at most 64 (activation slots hold 64 batch rows)
-  const int max_b = (nsm - n_lstm) < 64 ? (nsm - n_lstm) : 64;
+  LAS_REQUIRE(last_seg || (s_count % 2 == 0), "decoder segments must have an even number of steps (%d)", s_count);
+  LAS_REQUIRE(s_begin % 2 == 0, "decoder segments must start at an even step (%d)", s_begin);
   const SpellerPackFast pk = pack_layout(d, const_cast<void*>(packed_fast));
   // fp32 block of the pack (las_api.cu layout): psi / phi / cd weights and biases in the reference's own shapes
   struct F32View { const float *w_psi, *b_psi, *b_phi, *b_cd; } fv;
@@ -1286,15 +1306,14 @@ int fast_speller_decode(const las_decode_io* io, const void* packed_f32, const v
   float* psi_ws = static_cast<float*>(ws_f32);  // first buffer of the fp32 workspace layout: psi [B,U,D]
   const float* psi = io->psi ? io->psi : psi_ws;
 
-  for (int b0 = 0; b0 < d->B; b0 += max_b) {
-    const int Bc = (d->B - b0) < max_b ? (d->B - b0) : max_b;
+  {
     las_speller_dims dc = *d;
     dc.B = Bc;
     const SpellerWsFast w = ws_layout(&dc, ws_fast);
     DecParams p;
     memset(&p, 0, sizeof(p));
     p.B = Bc; p.U = d->U; p.E = d->E; p.Hs = d->Hs; p.sl = d->sl; p.V = d->V; p.D = d->D;
-    p.steps = steps; p.decode_mode = decode_mode; p.relu = relu; p.gt_steps = io->gt_steps; p.ncl = s.ncl;
+    p.steps = s_count; p.s0 = s_begin; p.decode_mode = decode_mode; p.relu = relu; p.gt_steps = io->gt_steps; p.ncl = s.ncl;
     p.wreg = att_wreg(d) ? 1 : 0;
     p.k_in_smem = att_smem(d, true) <= 220 * 1024;
     {
@@ -1341,9 +1360,13 @@ int fast_speller_decode(const las_decode_io* io, const void* packed_f32, const v
     const size_t so = (size_t)b0;  // batch offset into caller tensors
     p.Bfull = d->B;
     p.b0 = b0;
-    p.c_init = io->c_state;
-    p.h_out = io->h_state;
-    p.c_out = io->c_state;
+    if (first_seg) { p.c_init = io->c_state; p.c_init_rows = d->B; p.c_init_b0 = b0; }
+    else { p.c_init = w.c_carry; p.c_init_rows = Bc; p.c_init_b0 = 0; }
+    if (last_seg) { p.c_out = io->c_state; p.c_out_rows = d->B; p.c_out_b0 = b0; p.h_out = io->h_state; }
+    else { p.c_out = w.c_carry; p.c_out_rows = Bc; p.c_out_b0 = 0; p.h_out = nullptr; }
+    p.tok_init = first_seg ? nullptr : w.tok_carry;
+    p.tok_carry = last_seg ? nullptr : w.tok_carry;
+    p.stop = (io->early_exit && !first_seg) ? w.stop : nullptr;
     p.enc = w.enc_bf16;
     p.psi = psi;
     p.w_phi = pk.w_phi; p.b_phi = fv.b_phi; p.w_cd = pk.w_cd; p.b_cd = fv.b_cd;
@@ -1352,7 +1375,7 @@ int fast_speller_decode(const las_decode_io* io, const void* packed_f32, const v
     p.enc_lengths = io->enc_lengths;
     p.logp = io->logp; p.attn = io->attn; p.tokens = io->tokens;
     p.nll_labels = io->nll_labels; p.nll_terms = io->nll_terms; p.nll_steps = io->nll_steps;
-    p.word_out = io->word; p.ctx_out = io->context;
+    if (last_seg) { p.word_out = io->word; p.ctx_out = io->context; }
     p.sync = w.sync;
     p.h_ll = w.h_ll;
     p.tok_ll = w.tok_ll;
@@ -1360,16 +1383,18 @@ int fast_speller_decode(const las_decode_io* io, const void* packed_f32, const v
     p.ab_flags = g_dec_ab_flags;
     p.word_gather = io->gt_dense ? 0 : (io->gt_index ? 1 : (decode_mode != LAS_DECODE_RAW ? 1 : 0));
     p.sample_seed = io->sample_seed;
-    p.trace = fast_get_trace() ? fast_get_trace() + 512 : nullptr;  // needs 5 roles x 32 steps x 8 stamps behind the recurrence trace
+    p.trace = (fast_get_trace() && first_seg) ? fast_get_trace() + 512 : nullptr;  // needs 5 roles x 32 steps x 8 stamps behind the recurrence trace
 
     {
       ProfScope ps("speller.prepare", st);
-      LAS_TRY(launch_f32_to_bf16(io->enc + so * d->U * d->E, w.enc_bf16, (size_t)Bc * d->U * d->E, st));
+      if (first_seg) LAS_TRY(launch_f32_to_bf16(io->enc + so * d->U * d->E, w.enc_bf16, (size_t)Bc * d->U * d->E, st));
       LAS_CUDA_OK(cudaMemsetAsync(w.flags, 0, w.flag_bytes, st));
-      dec_init_kernel<<<Bc, 256, 0, st>>>(p, io->enc, io->word, io->context, io->h_state);
-      LAS_LAUNCH_OK("dec_init_kernel");
+      if (first_seg) {
+        dec_init_kernel<<<Bc, 256, 0, st>>>(p, io->enc, io->word, io->context, io->h_state);
+        LAS_LAUNCH_OK("dec_init_kernel");
+      }
     }
-    if (!io->psi) {
+    if (!io->psi && first_seg) {
       // psi(enc) once per utterance (model/las_model.py:279 recomputes it every step): the same tcgen05 GEMM as the
       // listener's input projection, bf16 operands (the enc copy made above), fp32 accumulate + bias + relu
       ProfScope pp("speller.psi", st);
@@ -1392,6 +1417,71 @@ int fast_speller_decode(const las_decode_io* io, const void* packed_f32, const v
     cfg.numAttrs = 1;
     LAS_CUDA_OK(cudaLaunchKernelEx(&cfg, speller_decode_persistent_kernel, p));
     count_launch();
+  }
+  return LAS_OK;
+}
+
+int fast_speller_max_group(const las_speller_dims* d) {
+  const Shape s = shape_of(d);
+  const int n_lstm = d->sl * s.ncl, nsm = sm_count();
+  // utterances per persistent launch: one attention CTA each, and at most 64 (activation slots hold 64 batch rows)
+  return (nsm - n_lstm) < 64 ? (nsm - n_lstm) : 64;
+}
+
+int fast_speller_ctas(const las_speller_dims* d) { return d->sl * shape_of(d).ncl + d->B; }
+
+// <eos> bookkeeping of one launch group between / after its segments (io->early_exit)
+int fast_speller_eos_begin(const las_speller_dims* d, int Bc, void* ws_fast, cudaStream_t st) {
+  las_speller_dims dc = *d;
+  dc.B = Bc;
+  const SpellerWsFast w = ws_layout(&dc, ws_fast);
+  LAS_CUDA_OK(cudaMemsetAsync(w.stop, 0, sizeof(int32_t) * (2 + 64), st));  // stop, group_steps, done[64]
+  return LAS_OK;
+}
+int fast_speller_eos_check(const las_decode_io* io, const las_speller_dims* d, int b0, int Bc, int s_begin, int s_end, void* ws_fast,
+                           cudaStream_t st) {
+  las_speller_dims dc = *d;
+  dc.B = Bc;
+  const SpellerWsFast w = ws_layout(&dc, ws_fast);
+  return launch_eos_check(io->tokens, d->B, b0, Bc, s_begin, s_end, io->eos_token, w.stop, st);
+}
+int fast_speller_eos_fill(const las_decode_io* io, const las_speller_dims* d, int b0, int Bc, int steps, void* ws_fast, cudaStream_t st) {
+  las_speller_dims dc = *d;
+  dc.B = Bc;
+  const SpellerWsFast w = ws_layout(&dc, ws_fast);
+  return launch_eos_fill(w.stop, steps, d->B, b0, Bc, d->V, d->U, 1, io->eos_token, io->logp, io->attn, io->tokens, io->nll_terms, io->steps_done, st);
+}
+
+// Segment lengths: `seg` steps each (even), the remainder in the last one.  seg <= 0: one segment.
+static int next_segment(int s_begin, int steps, int seg) {
+  if (seg <= 0 || s_begin + seg >= steps) return steps - s_begin;
+  return seg;
+}
+
+int fast_speller_decode(const las_decode_io* io, const void* packed_f32, const void* packed_fast, const las_speller_dims* d, int steps,
+                        int decode_mode, int relu, void* ws_f32, void* ws_fast, cudaStream_t st) {
+  LAS_TRY(supported(d));
+  const Shape s = shape_of(d);
+  const int n_lstm = d->sl * s.ncl;
+  const int nsm = sm_count();
+  LAS_REQUIRE(n_lstm + 1 <= nsm, "LAS_MODE_BF16 speller: %d LSTM CTAs do not fit %d SMs", n_lstm, nsm);
+  const int max_b = fast_speller_max_group(d);
+  const bool eos = io->early_exit != 0;
+  LAS_REQUIRE(!eos || io->tokens, "<eos> early exit needs io->tokens");
+  int seg = io->segment_steps > 0 ? (io->segment_steps + 1) & ~1 : 0;
+  if (eos && seg == 0) seg = 32;
+  if (eos && io->steps_done) LAS_CUDA_OK(cudaMemsetAsync(io->steps_done, 0, sizeof(int32_t), st));
+  for (int b0 = 0; b0 < d->B; b0 += max_b) {
+    const int Bc = (d->B - b0) < max_b ? (d->B - b0) : max_b;
+    if (eos) LAS_TRY(fast_speller_eos_begin(d, Bc, ws_fast, st));
+    for (int sb = 0; sb < steps;) {
+      const int n = next_segment(sb, steps, seg);
+      LAS_TRY(fast_speller_decode_segment(io, packed_f32, packed_fast, d, b0, Bc, sb, n, sb == 0, sb + n == steps, decode_mode, relu, ws_f32,
+                                          ws_fast, st));
+      if (eos) LAS_TRY(fast_speller_eos_check(io, d, b0, Bc, sb, sb + n, ws_fast, st));
+      sb += n;
+    }
+    if (eos) LAS_TRY(fast_speller_eos_fill(io, d, b0, Bc, steps, ws_fast, st));
   }
   return LAS_OK;
 }

@@ -509,4 +509,53 @@ int launch_label_smoothing(const float* logp, const int32_t* labels, int S, int 
   return LAS_OK;
 }
 
+// ---- <eos> early exit (extension: the reference always runs max_label_len steps, model/las_model.py:205-209)
+// After each segment: has every utterance of this launch group emitted <eos> by now?  If so, raise `stop` (the following segment
+// launches return at once) and record where the group stopped.
+// state [66] int32: [0] stop flag, [1] steps the group decoded, [2..66) per-utterance done flags (zeroed at the start of a group)
+__global__ void eos_check_kernel(const int32_t* tokens, int Bfull, int b0, int Bc, int s_begin, int s_end, int eos, int32_t* state) {
+  int32_t *stop = state, *group_steps = state + 1, *done = state + 2;
+  const int b = threadIdx.x;
+  int d = 1;
+  if (b < Bc) {
+    d = done[b];
+    for (int s = s_begin; s < s_end && !d; ++s) d = tokens[(size_t)s * Bfull + b0 + b] == eos;
+    done[b] = d;
+  }
+  const int all = __syncthreads_and(d);
+  if (threadIdx.x == 0 && *stop == 0) {
+    *group_steps = s_end;
+    if (all) *stop = 1;
+  }
+}
+// steps this group did not decode: tokens = <eos>, log-probs / attention = 0; steps_done (nullable) = max over the groups
+__global__ void eos_fill_kernel(const int32_t* state, int S, int Bfull, int b0, int Bc, int V, int U, int heads, int eos, float* logp, float* attn,
+                                int32_t* tokens, float* nll_terms, int32_t* steps_done) {
+  const int s0 = state[1];
+  if (blockIdx.x == 0 && threadIdx.x == 0 && steps_done) atomicMax(steps_done, s0);
+  const size_t n = (size_t)(S - s0) * Bc;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const int s = s0 + (int)(i / Bc), b = b0 + (int)(i % Bc);
+    const size_t row = (size_t)s * Bfull + b;
+    if (tokens) tokens[row] = eos;
+    if (nll_terms) nll_terms[row] = 0.f;
+    for (int v = 0; v < V; ++v) logp[row * V + v] = 0.f;
+    if (attn)  // [S, heads, B, U]
+      for (int h = 0; h < heads; ++h)
+        for (int u = 0; u < U; ++u) attn[(((size_t)s * heads + h) * Bfull + b) * U + u] = 0.f;
+  }
+}
+
+int launch_eos_check(const int32_t* tokens, int Bfull, int b0, int Bc, int s_begin, int s_end, int eos, int32_t* state, cudaStream_t st) {
+  eos_check_kernel<<<1, 64, 0, st>>>(tokens, Bfull, b0, Bc, s_begin, s_end, eos, state);
+  LAS_LAUNCH_OK("eos_check_kernel");
+  return LAS_OK;
+}
+int launch_eos_fill(const int32_t* state, int S, int Bfull, int b0, int Bc, int V, int U, int heads, int eos, float* logp, float* attn, int32_t* tokens,
+                    float* nll_terms, int32_t* steps_done, cudaStream_t st) {
+  eos_fill_kernel<<<64, 256, 0, st>>>(state, S, Bfull, b0, Bc, V, U, heads, eos, logp, attn, tokens, nll_terms, steps_done);
+  LAS_LAUNCH_OK("eos_fill_kernel");
+  return LAS_OK;
+}
+
 }  // namespace las

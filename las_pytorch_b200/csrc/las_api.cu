@@ -240,6 +240,7 @@ struct SpellerWsF32 {
   float* xin;
   float* h[2];
   float* c;
+  int32_t* eos_state;  // <eos> early exit bookkeeping of one launch group (66 int32)
   size_t bytes;
 };
 static SpellerWsF32 speller_ws_layout_f32(const las_speller_dims* d, void* base) {
@@ -250,6 +251,7 @@ static SpellerWsF32 speller_ws_layout_f32(const las_speller_dims* d, void* base)
   w.h[0] = cv.take<float>((size_t)d->sl * d->B * d->Hs);
   w.h[1] = cv.take<float>((size_t)d->sl * d->B * d->Hs);
   w.c = cv.take<float>((size_t)d->sl * d->B * d->Hs);
+  w.eos_state = cv.take<int32_t>(66);
   w.bytes = cv.total();
   return w;
 }
@@ -349,6 +351,20 @@ static int speller_decode_f32(const las_decode_io* io, const void* packed, const
   if (io->word && io->context) {
     LAS_TRY(launch_copy2d(io->word, V, w.xin, xld, B, V, st));
     LAS_TRY(launch_copy2d(io->context, E, w.xin + V, xld, B, E, st));
+  }
+  if (io->early_exit) {
+    // The fp32 mode is launch-per-step and gains nothing from stopping early; it reproduces the early-exit OUTPUT contract of
+    // las_decode_io (groups of <= 64 utterances, checked every segment, the undecoded tail filled) so that both modes agree.
+    const int seg = io->segment_steps > 0 ? (io->segment_steps + 1) & ~1 : 32;
+    if (io->steps_done) LAS_CUDA_OK(cudaMemsetAsync(io->steps_done, 0, sizeof(int32_t), st));
+    for (int b0 = 0; b0 < B; b0 += 64) {
+      const int Bc = B - b0 < 64 ? B - b0 : 64;
+      LAS_CUDA_OK(cudaMemsetAsync(w.eos_state, 0, sizeof(int32_t) * 66, st));
+      for (int sb = 0; sb < steps; sb += seg)
+        LAS_TRY(launch_eos_check(io->tokens, B, b0, Bc, sb, sb + seg < steps ? sb + seg : steps, io->eos_token, w.eos_state, st));
+      LAS_TRY(launch_eos_fill(w.eos_state, steps, B, b0, Bc, V, U, NH, io->eos_token, io->logp, io->attn, io->tokens, io->nll_terms,
+                              io->steps_done, st));
+    }
   }
   return LAS_OK;
 }
@@ -561,6 +577,7 @@ int las_speller_decode(const las_decode_io* io, const void* packed, const las_sp
   LAS_REQUIRE(!(io->gt_dense || io->gt_index) || io->gt_steps >= steps, "ground truth has %d steps, %d requested", io->gt_steps, steps);
   LAS_REQUIRE(d->cell != LAS_CELL_LSTM || (io->h_state == nullptr) == (io->c_state == nullptr), "h_state and c_state must be given together");
   LAS_REQUIRE((io->word == nullptr) == (io->context == nullptr), "word and context must be given together");
+  LAS_REQUIRE(!io->early_exit || io->tokens, "<eos> early exit needs io->tokens");
   LAS_TRY(device_ok());
   if (workspace_bytes < las_speller_workspace_bytes(d, steps, mode))
     return fail(LAS_ENOMEM, "workspace too small: %zu < %zu", workspace_bytes, las_speller_workspace_bytes(d, steps, mode));
@@ -576,6 +593,55 @@ int las_speller_decode(const las_decode_io* io, const void* packed, const las_sp
                                static_cast<char*>(workspace) + f32w, st);
   }
   return speller_decode_f32(io, packed, d, steps, decode_mode, relu, workspace, st);
+}
+
+int las_pipeline_step(const las_pipeline_args* a, int mode, void* stream) {
+  LAS_REQUIRE(a, "null pointer argument");
+  const bool dec = a->dec_io != nullptr, lis = a->x != nullptr;
+  LAS_REQUIRE(dec || lis, "nothing to do: neither a batch to decode nor a batch to encode");
+  if (!dec)
+    return las_listener_forward_masked(a->x, a->x_lengths, a->listener_packed, a->listener_dims, mode, a->enc, a->enc_lengths, a->listener_ws,
+                                       a->listener_ws_bytes, stream);
+  if (!lis)
+    return las_speller_decode(a->dec_io, a->speller_packed, a->speller_dims, a->steps, a->decode_mode, mode, a->relu, a->speller_ws,
+                              a->speller_ws_bytes, stream);
+  const las_speller_dims* sd = a->speller_dims;
+  const las_listener_dims* ld = a->listener_dims;
+  const bool fast = mode == LAS_MODE_BF16 && sd && ld && n_heads(sd) == 1 && !sd->no_mlp && sd->cell == LAS_CELL_LSTM && ld->cell == LAS_CELL_LSTM &&
+                    a->steps > 0;
+  if (!fast) {  // fp32 mode / variants: the same results, one after the other
+    LAS_TRY(las_speller_decode(a->dec_io, a->speller_packed, sd, a->steps, a->decode_mode, mode, a->relu, a->speller_ws, a->speller_ws_bytes, stream));
+    return las_listener_forward_masked(a->x, a->x_lengths, a->listener_packed, ld, mode, a->enc, a->enc_lengths, a->listener_ws,
+                                       a->listener_ws_bytes, stream);
+  }
+  // argument checks of the two entry points this call stands for
+  LAS_TRY(speller_check(sd));
+  LAS_TRY(listener_check(ld));
+  const las_decode_io* io = a->dec_io;
+  LAS_REQUIRE(a->speller_packed && a->speller_ws && a->listener_packed && a->listener_ws && a->enc, "null pointer argument");
+  LAS_REQUIRE(io->enc && io->logp, "io->enc and io->logp are required");
+  LAS_REQUIRE(a->decode_mode == LAS_DECODE_RAW || a->decode_mode == LAS_DECODE_GREEDY || a->decode_mode == LAS_DECODE_SAMPLE,
+              "decode_mode %d is not supported (0 = raw, 1 = greedy, 2 = sample)", a->decode_mode);
+  LAS_REQUIRE(!(io->gt_dense || io->gt_index) || io->gt_steps >= a->steps, "ground truth has %d steps, %d requested", io->gt_steps, a->steps);
+  LAS_REQUIRE((io->h_state == nullptr) == (io->c_state == nullptr), "h_state and c_state must be given together");
+  LAS_REQUIRE((io->word == nullptr) == (io->context == nullptr), "word and context must be given together");
+  LAS_REQUIRE(!io->early_exit || io->tokens, "<eos> early exit needs io->tokens");
+  LAS_TRY(device_ok());
+  if (a->speller_ws_bytes < las_speller_workspace_bytes(sd, a->steps, mode))
+    return fail(LAS_ENOMEM, "speller workspace too small: %zu < %zu", a->speller_ws_bytes, las_speller_workspace_bytes(sd, a->steps, mode));
+  if (a->listener_ws_bytes < las_listener_workspace_bytes(ld, mode))
+    return fail(LAS_ENOMEM, "listener workspace too small: %zu < %zu", a->listener_ws_bytes, las_listener_workspace_bytes(ld, mode));
+  const size_t f32p = speller_pack_layout_f32(sd, nullptr).bytes;
+  const size_t f32w = speller_ws_layout_f32(sd, nullptr).bytes;
+  return fast_pipeline_step(io, a->speller_packed, static_cast<const char*>(a->speller_packed) + f32p, sd, a->steps, a->decode_mode, a->relu,
+                            a->speller_ws, static_cast<char*>(a->speller_ws) + f32w, a->x, a->x_lengths, a->listener_packed, ld, a->enc,
+                            a->enc_lengths, a->listener_ws, static_cast<cudaStream_t>(stream));
+}
+
+int las_pipeline_overlaps(const las_listener_dims* ld, const las_speller_dims* sd, int steps, int mode) {
+  if (mode != LAS_MODE_BF16 || !ld || !sd || listener_check(ld) != LAS_OK || speller_check(sd) != LAS_OK) return 0;
+  if (n_heads(sd) != 1 || sd->no_mlp || sd->cell != LAS_CELL_LSTM || ld->cell != LAS_CELL_LSTM) return 0;
+  return fast_pipeline_bc(ld, sd, steps) > 0 ? 1 : 0;
 }
 
 int las_nll_sums(const float* logp, const int32_t* labels, int S, int S_lab, int B, int V, int max_label_len, float* out2,

@@ -19,6 +19,23 @@ int fast_speller_decode(const las_decode_io* io, const void* packed_f32, const v
                         const las_speller_dims* d, int steps, int decode_mode, int relu, void* ws_f32, void* ws_fast,
                         cudaStream_t st);
 
+// segments / launch groups of the persistent decoder (fast_speller.cu), stages of the listener (fast_listener.cu), and the
+// serving pipeline that interleaves them (fast_pipeline.cu)
+int fast_speller_decode_segment(const las_decode_io* io, const void* packed_f32, const void* packed_fast, const las_speller_dims* d,
+                                int b0, int Bc, int s_begin, int s_count, bool first_seg, bool last_seg, int decode_mode, int relu,
+                                void* ws_f32, void* ws_fast, cudaStream_t st);
+int fast_speller_max_group(const las_speller_dims* d);
+int fast_speller_ctas(const las_speller_dims* d);  // CTAs of one persistent launch covering d->B utterances
+int fast_listener_stage(const float* x, const int32_t* x_lengths, const void* packed, const las_listener_dims* d, float* enc,
+                        int32_t* enc_lengths, void* ws, int stage, int bc, int* resident, cudaStream_t st);
+int fast_listener_rec_ctas(const las_listener_dims* d, int bc);
+int fast_side_stream(cudaStream_t* s);
+int fast_pipeline_bc(const las_listener_dims* ld, const las_speller_dims* sd, int steps);
+int fast_pipeline_step(const las_decode_io* io, const void* spl_packed_f32, const void* spl_packed_fast, const las_speller_dims* sd, int steps,
+                       int decode_mode, int relu, void* spl_ws_f32, void* spl_ws_fast, const float* x, const int32_t* x_lengths,
+                       const void* lis_packed, const las_listener_dims* ld, float* enc, int32_t* enc_lengths, void* lis_ws, cudaStream_t st);
+void fast_set_option_pipeline(int key, int value);
+
 void fast_set_option(int key, int value);  // test hook: 1 = recurrence A operand in TMEM (default 1)
 void fast_set_trace(long long* dev_buf);
 long long* fast_get_trace();  // test hook: recurrence kernel timeline (64 steps x 8 clock64 stamps)

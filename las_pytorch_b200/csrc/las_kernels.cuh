@@ -80,6 +80,10 @@ int launch_pyramid_lengths(const int32_t* in, int32_t* out, int B, int cap, cuda
 int launch_nll_sums(const float* logp, const int32_t* labels, int S, int S_lab, int B, int V, int max_label_len,
                     float* out2, cudaStream_t st);
 
+// <eos> early exit bookkeeping (las_decode_io.early_exit): `state` = 66 int32 {stop, steps decoded, done[64]} per launch group
+int launch_eos_check(const int32_t* tokens, int Bfull, int b0, int Bc, int s_begin, int s_end, int eos, int32_t* state, cudaStream_t st);
+int launch_eos_fill(const int32_t* state, int S, int Bfull, int b0, int Bc, int V, int U, int heads, int eos, float* logp, float* attn, int32_t* tokens,
+                    float* nll_terms, int32_t* steps_done, cudaStream_t st);
 int launch_label_smoothing(const float* logp, const int32_t* labels, int S, int S_lab, int B, int V, int max_label_len, float ls,
                            float* per_utt, cudaStream_t st);
 

@@ -78,6 +78,14 @@ class _Cache:
         self.packed = {}
         self.work = {}
         self.lock = threading.Lock()
+        self.enqueue_locks = {}
+
+    def enqueue_lock(self, device):
+        """Held while one forward's kernels are being enqueued: the workspace of a (module, device, stream) is reused by every call,
+        which is only safe if two host threads never interleave their launches on it (the work itself is asynchronous; the lock
+        covers host-side enqueue time only).  One lock per device, so DataParallel's per-GPU threads do not serialise each other."""
+        with self.lock:
+            return self.enqueue_locks.setdefault(device.index, threading.RLock())
 
     @staticmethod
     def tensors_key(tensors, mode):
@@ -121,9 +129,15 @@ def _lstm_weight_array(holder, layers, directions):
     return arr, keep
 
 
-def _run_listener(x, holders, input_feature_dim, hidden_size, mode, cache, lengths=None, cell="LSTM", is_replica=False):
-    """x [B,T,F] -> [B, T/2^L, 2H] through `len(holders)` pyramid layers.  With `lengths` ([B] valid frames; extension)
-    returns (enc, enc_lengths [B] int32)."""
+class _Call:
+    """Marshalled arguments of one C-ABI call: ctypes structs, the tensors they point into (kept alive here) and the outputs."""
+
+    def __init__(self, **kw):
+        self.__dict__.update(kw)
+
+
+def _prepare_listener(x, holders, input_feature_dim, hidden_size, mode, cache, lengths=None, cell="LSTM", is_replica=False):
+    """Checks, packed weights, workspace and output buffers of one listener call (the caller holds cache.enqueue_lock)."""
     _require_cuda(x, "input_x")
     lib = _cabi.load_library()
     x = _f32c(x)
@@ -138,41 +152,51 @@ def _run_listener(x, holders, input_feature_dim, hidden_size, mode, cache, lengt
             f"shape '[{b}, {t >> 1}, {f * 2}]' is invalid: timestep {t} is not divisible by 2^{nl} "
             "(model/las_model.py:86-87 halves the time axis in every layer)"
         )
-    with torch.cuda.device(x.device):
-        st = current_stream_ptr(x.device)
-        tensors = _weight_tensors(*holders)
-        for t in tensors:
-            _require_cuda(t, "listener weight")
-            if t.device != x.device:
-                raise RuntimeError(f"listener weights are on {t.device}, input_x on {x.device}")
-        key = _Cache.tensors_key(tensors, mode)
-        packed = cache.lookup(x.device, mode, key, is_replica)
-        if packed is None:
-            arr = (LstmWeights * (2 * nl))()
-            keep = []
-            for l, h in enumerate(holders):
-                a1, k1 = _lstm_weight_array(h, 1, 2)
-                keep.extend(k1)
-                for d in range(2):
-                    arr[2 * l + d] = a1[d]
-            nbytes = lib.las_listener_packed_bytes(C.byref(dims), mode)
-            packed = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=x.device)
-            check(lib.las_listener_pack(arr, C.byref(dims), mode, ptr(packed), packed.numel(), st))
-            cache.store(x.device, mode, key, packed)
-            del keep
-        ws_bytes = lib.las_listener_workspace_bytes(C.byref(dims), mode)
-        ws = cache.workspace(("listener", x.device, mode), ws_bytes, x.device)
-        enc = torch.empty(b, t >> nl, 2 * hidden_size, dtype=torch.float32, device=x.device)
-        if lengths is None:
-            check(lib.las_listener_forward(ptr(x), ptr(packed), C.byref(dims), mode, ptr(enc), ptr(ws), ws.numel(), st))
-            return enc
-        if lengths.numel() != b:
-            raise RuntimeError(f"input_lengths has {lengths.numel()} entries for a batch of {b}")
+    if lengths is not None and lengths.numel() != b:
+        raise RuntimeError(f"input_lengths has {lengths.numel()} entries for a batch of {b}")
+    st = current_stream_ptr(x.device)
+    tensors = _weight_tensors(*holders)
+    for w in tensors:
+        _require_cuda(w, "listener weight")
+        if w.device != x.device:
+            raise RuntimeError(f"listener weights are on {w.device}, input_x on {x.device}")
+    key = _Cache.tensors_key(tensors, mode)
+    packed = cache.lookup(x.device, mode, key, is_replica)
+    if packed is None:
+        arr = (LstmWeights * (2 * nl))()
+        keep = []
+        for l, h in enumerate(holders):
+            a1, k1 = _lstm_weight_array(h, 1, 2)
+            keep.extend(k1)
+            for d in range(2):
+                arr[2 * l + d] = a1[d]
+        nbytes = lib.las_listener_packed_bytes(C.byref(dims), mode)
+        packed = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=x.device)
+        check(lib.las_listener_pack(arr, C.byref(dims), mode, ptr(packed), packed.numel(), st))
+        cache.store(x.device, mode, key, packed)
+        del keep
+    ws_bytes = lib.las_listener_workspace_bytes(C.byref(dims), mode)
+    ws = cache.workspace(("listener", x.device, mode, st.value), ws_bytes, x.device)
+    enc = torch.empty(b, t >> nl, 2 * hidden_size, dtype=torch.float32, device=x.device)
+    lens = enc_lens = None
+    if lengths is not None:
         lens = lengths.to(device=x.device, dtype=torch.int32).contiguous()
         enc_lens = torch.empty(b, dtype=torch.int32, device=x.device)
-        check(lib.las_listener_forward_masked(ptr(x), ptr(lens), ptr(packed), C.byref(dims), mode, ptr(enc), ptr(enc_lens), ptr(ws),
-                                              ws.numel(), st))
-    return enc, enc_lens
+    return _Call(lib=lib, x=x, dims=dims, packed=packed, ws=ws, enc=enc, lens=lens, enc_lens=enc_lens, mode=mode, st=st)
+
+
+def _run_listener(x, holders, input_feature_dim, hidden_size, mode, cache, lengths=None, cell="LSTM", is_replica=False):
+    """x [B,T,F] -> [B, T/2^L, 2H] through `len(holders)` pyramid layers.  With `lengths` ([B] valid frames; extension)
+    returns (enc, enc_lengths [B] int32)."""
+    _require_cuda(x, "input_x")
+    with torch.cuda.device(x.device), cache.enqueue_lock(x.device):
+        c = _prepare_listener(x, holders, input_feature_dim, hidden_size, mode, cache, lengths, cell, is_replica)
+        if c.lens is None:
+            check(c.lib.las_listener_forward(ptr(c.x), ptr(c.packed), C.byref(c.dims), mode, ptr(c.enc), ptr(c.ws), c.ws.numel(), c.st))
+            return c.enc
+        check(c.lib.las_listener_forward_masked(ptr(c.x), ptr(c.lens), ptr(c.packed), C.byref(c.dims), mode, ptr(c.enc), ptr(c.enc_lens),
+                                                ptr(c.ws), c.ws.numel(), c.st))
+    return c.enc, c.enc_lens
 
 
 class LAS(nn.Module):
@@ -202,6 +226,12 @@ class LAS(nn.Module):
                                                           enc_lengths=enc_lengths, nll_labels=nll_labels)
         return raw_pred_seq, attention_record
 
+    def serve(self, want_attention=True):
+        """Cross-batch serving pipeline (extension; free-running decoding = the reference's is_training=False path,
+        model/las_model.py:36-39).  `pipe.submit(x)` enqueues batch i+1's Listener UNDER batch i's decoder and returns batch i's
+        results; `pipe.flush()` decodes the last batch.  Same numbers as calling `forward` batch by batch."""
+        return ServingPipeline(self, want_attention)
+
     def invalidate_packed_weights(self):
         """Drops every cached kernel-layout weight image.  The caches follow parameter identity and version counters, which
         `load_state_dict`, optimizer steps and `.to()` change; an in-place write through `.data` does not -- call this after one."""
@@ -230,6 +260,83 @@ class LAS(nn.Module):
             package["tr_loss"] = tr_loss
             package["val_loss"] = val_loss
         return package
+
+
+class ServingResult:
+    """Outputs of one decoded batch (device tensors, valid once the stream they were enqueued on reaches them)."""
+
+    def __init__(self, logp, attn, tokens, steps_done=None):
+        self.logp, self.attn, self.tokens, self.steps_done = logp, attn, tokens, steps_done
+
+    @property
+    def raw_pred_seq(self):  # the reference's return structure (model/las_model.py:213,238)
+        return list(self.logp.unbind(0))
+
+    @property
+    def attention_record(self):
+        return None if self.attn is None else [list(a.unbind(0)) for a in self.attn.unbind(0)]
+
+
+class ServingPipeline:
+    """Two batches in flight on one GPU: while batch i is being decoded (the persistent decoder owns 128 of the 148 SMs at paper
+    size and is latency-bound), batch i+1 is being encoded -- its recurrences on the SMs the decoder leaves free, its
+    input-projection GEMMs between the decoder's segments (include/las_b200.h `las_pipeline_step`, csrc/fast_pipeline.cu).
+
+        pipe = las.serve()
+        for x in batches:                 # [B,T,F] device tensors
+            out = pipe.submit(x)          # None for the first batch, then the previous batch's ServingResult
+        last = pipe.flush()
+
+    Every batch gets exactly what `las(x, None, 0, is_training=False)` returns for it (bit-identical: the decoder's segments carry
+    its state on the device).  `x` must stay alive and unmodified until the next `submit` / `flush` has been enqueued behind it on
+    the same stream (its listener runs inside that call's work).  Shapes or modes the concurrent schedule does not cover (fp32
+    mode, variants, batches of more than 64 utterances) run the same two steps one after the other."""
+
+    def __init__(self, las, want_attention=True):
+        self.las = las
+        self.want_attention = want_attention
+        self._pending = None  # (enc, enc_lengths) of the batch encoded last and not decoded yet
+
+    def _decode_call(self, enc, enc_lengths):
+        sp = self.las.speller
+        return sp._prepare_decode(enc, sp.max_label_len, enc_lengths=enc_lengths, want_attn=self.want_attention)
+
+    def submit(self, x, input_lengths=None):
+        las = self.las
+        lis, sp = las.listener, las.speller
+        _require_cuda(x, "input_x")
+        holders = [getattr(lis, "pLSTM_layer" + str(i)).BLSTM for i in range(lis.num_layers)]
+        mode = _mode_of(lis.precision)
+        if mode != _mode_of(sp.precision):
+            raise RuntimeError("the serving pipeline needs the listener and the speller in the same precision mode")
+        with torch.cuda.device(x.device), lis._cache.enqueue_lock(x.device), sp._cache.enqueue_lock(x.device):
+            lc = _prepare_listener(x, holders, lis.input_feature_dim, lis.hidden_size, mode, lis._cache, input_lengths, lis.cell,
+                                   getattr(lis, "_is_replica", False))
+            args = _cabi.PipelineArgs()
+            args.x, args.x_lengths, args.listener_packed = lc.x.data_ptr(), (lc.lens.data_ptr() if lc.lens is not None else None), lc.packed.data_ptr()
+            args.listener_dims = C.pointer(lc.dims)
+            args.enc, args.enc_lengths = lc.enc.data_ptr(), (lc.enc_lens.data_ptr() if lc.enc_lens is not None else None)
+            args.listener_ws, args.listener_ws_bytes = lc.ws.data_ptr(), lc.ws.numel()
+            out = None
+            if self._pending is not None:
+                dc = self._decode_call(*self._pending)
+                args.dec_io, args.speller_packed, args.speller_dims = C.pointer(dc.io), dc.packed.data_ptr(), C.pointer(dc.dims)
+                args.steps, args.decode_mode, args.relu = dc.steps, dc.decode_mode, dc.relu
+                args.speller_ws, args.speller_ws_bytes = dc.ws.data_ptr(), dc.ws.numel()
+                out = ServingResult(dc.logp, dc.attn[:, 0] if dc.attn is not None and dc.attn.size(1) == 1 else dc.attn, dc.tokens)
+            check(lc.lib.las_pipeline_step(C.byref(args), mode, lc.st))
+            self._pending = (lc.enc, lc.enc_lens)
+        return out
+
+    def flush(self):
+        """Decodes the batch submitted last; returns its ServingResult (None if nothing is pending)."""
+        if self._pending is None:
+            return None
+        enc, enc_lens = self._pending
+        self._pending = None
+        sp = self.las.speller
+        logp, attn, tokens = sp._decode(enc, sp.max_label_len, enc_lengths=enc_lens, want_attn=self.want_attention)
+        return ServingResult(logp, attn[:, 0] if attn is not None and attn.size(1) == 1 else attn, tokens)
 
 
 def _check_unit(rnn_unit, precision="fp32"):
@@ -416,10 +523,10 @@ class Speller(nn.Module):
 
     def _packed(self, lib, dims, mode, device, st):
         tensors = _weight_tensors(self)
-        for t in tensors:
-            _require_cuda(t, "speller weight")
-            if t.device != device:
-                raise RuntimeError(f"speller weights are on {t.device}, listener_feature on {device}")
+        for w in tensors:
+            _require_cuda(w, "speller weight")
+            if w.device != device:
+                raise RuntimeError(f"speller weights are on {w.device}, listener_feature on {device}")
         key = _Cache.tensors_key(tensors, mode)
         packed = self._cache.lookup(device, mode, key, getattr(self, "_is_replica", False))
         if packed is None:
@@ -444,9 +551,9 @@ class Speller(nn.Module):
             del keep, ts
         return packed
 
-    def _decode(self, enc, steps, gt_dense=None, gt_index=None, state=None, word=None, context=None, enc_lengths=None,
-                want_attn=True, nll_labels=None):
-        """Runs `steps` decoder steps.  Returns (logp [S,B,V], attn [S,B,U] | None, tokens [S,B])."""
+    def _prepare_decode(self, enc, steps, gt_dense=None, gt_index=None, state=None, word=None, context=None, enc_lengths=None,
+                        want_attn=True, nll_labels=None, segment_steps=0, early_exit=False, eos_token=1):
+        """Checks, packed weights, workspace, outputs and the las_decode_io of one decode call (the caller holds the enqueue lock)."""
         _require_cuda(enc, "listener_feature")
         lib = _cabi.load_library()
         enc = _f32c(enc)
@@ -471,46 +578,62 @@ class Speller(nn.Module):
                                ("word", word, (b, self.label_dim)), ("context", context, (b, e))):
             if t is not None and tuple(t.shape) != shape:
                 raise RuntimeError(f"{name} has shape {tuple(t.shape)}; expected {shape}")
-        with torch.cuda.device(dev):
-            st = current_stream_ptr(dev)
-            packed = self._packed(lib, dims, mode, dev, st)
-            ws_bytes = lib.las_speller_workspace_bytes(C.byref(dims), steps, mode)
-            ws = self._cache.workspace(("speller", dev, mode), ws_bytes, dev)
-            logp = torch.empty(steps, b, self.label_dim, dtype=torch.float32, device=dev)
-            attn = torch.empty(steps, self.attention.multi_head, b, u, dtype=torch.float32, device=dev) if want_attn else None
-            tokens = torch.empty(steps, b, dtype=torch.int32, device=dev)
-            io = DecodeIO()
-            io.enc = enc.data_ptr()
-            io.psi = None
-            io.gt_steps = 0
-            if gt_dense is not None:
-                io.gt_dense = gt_dense.data_ptr()
-                io.gt_steps = gt_dense.size(1)
-            if gt_index is not None:
-                io.gt_index = gt_index.data_ptr()
-                io.gt_steps = gt_index.size(1)
-            if enc_lengths is not None:
-                io.enc_lengths = enc_lengths.data_ptr()
-            if int(self.decode_mode) == 2 and gt_dense is None and gt_index is None:
-                # one draw from torch's global generator seeds the device-side generator (reproducible under torch.manual_seed)
-                io.sample_seed = int(torch.randint(0, 2 ** 62, (1,)).item())
-            if state is not None:
-                io.h_state = state[0].data_ptr()
-                io.c_state = state[1].data_ptr() if state[1] is not None else None
-            if word is not None:
-                io.word, io.context = word.data_ptr(), context.data_ptr()
-            self.last_nll_terms = None
-            if nll_labels is not None:
-                # fused NLLLoss(ignore_index=0) terms (solver/solver.py:62,70-77): [S,B], zero where the label is 0 / past the labels
-                nll_labels = nll_labels.to(device=dev, dtype=torch.int32).contiguous()
-                self.last_nll_terms = torch.empty(steps, b, dtype=torch.float32, device=dev)
-                io.nll_labels, io.nll_steps, io.nll_terms = nll_labels.data_ptr(), nll_labels.size(1), self.last_nll_terms.data_ptr()
-            io.logp = logp.data_ptr()
-            io.attn = attn.data_ptr() if attn is not None else None
-            io.tokens = tokens.data_ptr()
-            check(lib.las_speller_decode(C.byref(io), ptr(packed), C.byref(dims), steps, int(self.decode_mode), mode,
-                                         self.attention.relu_flag, ptr(ws), ws.numel(), st))
-        return logp, attn, tokens
+        st = current_stream_ptr(dev)
+        packed = self._packed(lib, dims, mode, dev, st)
+        ws_bytes = lib.las_speller_workspace_bytes(C.byref(dims), steps, mode)
+        ws = self._cache.workspace(("speller", dev, mode, st.value), ws_bytes, dev)
+        logp = torch.empty(steps, b, self.label_dim, dtype=torch.float32, device=dev)
+        attn = torch.empty(steps, self.attention.multi_head, b, u, dtype=torch.float32, device=dev) if want_attn else None
+        tokens = torch.empty(steps, b, dtype=torch.int32, device=dev)
+        keep = [enc, gt_dense, gt_index, enc_lengths, state, word, context]
+        io = DecodeIO()
+        io.enc = enc.data_ptr()
+        io.psi = None
+        io.gt_steps = 0
+        if gt_dense is not None:
+            io.gt_dense = gt_dense.data_ptr()
+            io.gt_steps = gt_dense.size(1)
+        if gt_index is not None:
+            io.gt_index = gt_index.data_ptr()
+            io.gt_steps = gt_index.size(1)
+        if enc_lengths is not None:
+            io.enc_lengths = enc_lengths.data_ptr()
+        if int(self.decode_mode) == 2 and gt_dense is None and gt_index is None:
+            # one draw from torch's global generator seeds the device-side generator (reproducible under torch.manual_seed)
+            io.sample_seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+        if state is not None:
+            io.h_state = state[0].data_ptr()
+            io.c_state = state[1].data_ptr() if state[1] is not None else None
+        if word is not None:
+            io.word, io.context = word.data_ptr(), context.data_ptr()
+        nll_terms = None
+        if nll_labels is not None:
+            # fused NLLLoss(ignore_index=0) terms (solver/solver.py:62,70-77): [S,B], zero where the label is 0 / past the labels
+            nll_labels = nll_labels.to(device=dev, dtype=torch.int32).contiguous()
+            nll_terms = torch.empty(steps, b, dtype=torch.float32, device=dev)
+            io.nll_labels, io.nll_steps, io.nll_terms = nll_labels.data_ptr(), nll_labels.size(1), nll_terms.data_ptr()
+            keep.append(nll_labels)
+        steps_done = None
+        io.segment_steps = int(segment_steps)
+        if early_exit:
+            steps_done = torch.zeros(1, dtype=torch.int32, device=dev)
+            io.early_exit, io.eos_token, io.steps_done = 1, int(eos_token), steps_done.data_ptr()
+        io.logp = logp.data_ptr()
+        io.attn = attn.data_ptr() if attn is not None else None
+        io.tokens = tokens.data_ptr()
+        return _Call(lib=lib, io=io, packed=packed, dims=dims, steps=steps, mode=mode, ws=ws, st=st, logp=logp, attn=attn, tokens=tokens,
+                     nll_terms=nll_terms, steps_done=steps_done, keep=keep, relu=self.attention.relu_flag, decode_mode=int(self.decode_mode))
+
+    def _decode(self, enc, steps, **kw):
+        """Runs `steps` decoder steps.  Returns (logp [S,B,V], attn [S,heads,B,U] | None, tokens [S,B])."""
+        _require_cuda(enc, "listener_feature")
+        with torch.cuda.device(enc.device), self._cache.enqueue_lock(enc.device):
+            c = self._prepare_decode(enc, steps, **kw)
+            self.last_nll_terms = c.nll_terms
+            self.last_steps_done = c.steps_done
+            check(c.lib.las_speller_decode(C.byref(c.io), ptr(c.packed), C.byref(c.dims), steps, c.decode_mode, c.mode, c.relu, ptr(c.ws),
+                                           c.ws.numel(), c.st))
+        return c.logp, c.attn, c.tokens
 
     # ---- reference API ---------------------------------------------------------------------------------
     def forward_step(self, input_word, last_hidden_state, listener_feature):
@@ -531,9 +654,14 @@ class Speller(nn.Module):
         logp, attn, _ = self._decode(listener_feature, 1, state=(h, c), word=word, context=context)
         return logp[0], ((h, c) if lstm else h), context, list(attn[0].unbind(0))
 
-    def forward(self, listener_feature, ground_truth=None, teacher_force_rate=0.9, enc_lengths=None, nll_labels=None):
+    def forward(self, listener_feature, ground_truth=None, teacher_force_rate=0.9, enc_lengths=None, nll_labels=None,
+                early_exit=None):
         """`nll_labels` ([B,S'] label indices; extension) makes the decoder also emit the NLLLoss(ignore_index=0) terms of
-        solver/solver.py:62,70-77 as `self.last_nll_terms` [S,B], so the loss needs no pass over the log-probabilities."""
+        solver/solver.py:62,70-77 as `self.last_nll_terms` [S,B], so the loss needs no pass over the log-probabilities.
+        `early_exit` (extension, default `self.early_exit` = False): free-running decoding stops once every
+        utterance has emitted <eos> (token 1, utils/functions.py:124-125), checked on the device every `self.early_exit_every` steps; the
+        remaining steps are filled with <eos> tokens and zero log-probs, `self.last_steps_done` (device int32[1]) says how many ran.
+        The reference always runs max_label_len steps (model/las_model.py:205-209), which stays the default."""
         if ground_truth is None:
             teacher_force_rate = 0
         # one draw from numpy's global RNG per call, exactly like the reference (:189)
@@ -556,8 +684,12 @@ class Speller(nn.Module):
                 gt_dense = ground_truth.to(device=listener_feature.device, dtype=torch.float32).contiguous()
         if enc_lengths is not None:
             enc_lengths = enc_lengths.to(device=listener_feature.device, dtype=torch.int32).contiguous()
+        if early_exit is None:
+            early_exit = getattr(self, "early_exit", False)
+        early_exit = bool(early_exit) and gt_dense is None and gt_index is None  # teacher forcing decodes every label
         logp, attn, tokens = self._decode(listener_feature, max_step, gt_dense=gt_dense, gt_index=gt_index, enc_lengths=enc_lengths,
-                                          nll_labels=nll_labels)
+                                          nll_labels=nll_labels, early_exit=early_exit, eos_token=getattr(self, "eos_token", 1),
+                                          segment_steps=getattr(self, "early_exit_every", 32) if early_exit else 0)
         self.last_tokens = tokens  # [S,B] int32 argmax per step (device); not part of the reference API
         self.last_logp = logp      # [S,B,V] the buffer raw_pred_seq's entries are views of
         raw_pred_seq = list(logp.unbind(0))

@@ -89,8 +89,13 @@ def test_matches_reference_golden(name, precision):
     margin = srt[..., -1] - srt[..., -2]
     tok = logp.argmax(-1)
     if mode == "tf" and not chaotic_bf16:
-        safe = margin > 10 * tol["logp"] * slack
-        assert np.array_equal(tok[safe], ref_tok[safe])  # argmax bit-exact wherever the oracle's margin is meaningful
+        # argmax bit-exact wherever the oracle's top-2 margin exceeds twice the log-prob tolerance (two log-probs can each move by
+        # the tolerance); the mask is proportional to the tolerance, and must keep a stated share of the positions
+        safe = margin > 2 * tol["logp"] * slack
+        if precision == "fp32":
+            assert safe.mean() >= 0.9, safe.mean()  # (bf16: the default-init goldens have margins of ~4e-3, far below 4e-2; the
+            # share kept at the benchmarked shapes is asserted in tests/test_benchmark_shapes_gpu.py)
+        assert np.array_equal(tok[safe], ref_tok[safe])
     elif precision == "fp32":
         assert (tok == ref_tok).mean() >= 0.99
     elif mode == "greedy":
@@ -121,7 +126,18 @@ def test_against_numpy_oracle_on_seeded_inputs(precision):
     assert np.abs(attn - ref_tf["attn"]).max() <= tol["attn"]
     _, logp_g, _ = run_ours(las, x, labels, c["V"], "greedy")
     agree = (logp_g.argmax(-1) == ref_gr["tokens"]).mean()
-    assert agree >= (0.99 if precision == "fp32" else 0.90), f"greedy agreement {agree:.3f}"
+    floor = 0.99
+    if precision == "bf16":
+        # bf16 GEMM operands move log-probs by ~4e-3, enough to flip a near-tie and send a free-running utterance down another
+        # trajectory.  Calibrate on the spot: the ORACLE with nothing but its 2-D weights rounded to bf16 vs itself (see
+        # tests/test_benchmark_shapes_gpu.py); ours must be no worse than that minus 0.05.
+        sd_b = {k: (torch.from_numpy(v).to(torch.bfloat16).float().numpy() if v.ndim == 2 else v) for k, v in sd.items()}
+        ref_b = O.las_forward(x.numpy(), sd_b, c["L"], c["sl"], S, dtype=np.float64)
+        floor = min(0.99, float((ref_b["tokens"] == ref_gr["tokens"]).mean()) - 0.05)
+        tok = logp_g.argmax(-1)
+        rescored = O.las_forward(x.numpy(), sd, c["L"], c["sl"], S, ground_truth=tok.T, teacher_forced=True, dtype=np.float64)
+        assert np.abs(logp_g - rescored["logp"]).max() <= tol["logp"]  # every step of the trajectory we followed is right
+    assert agree >= floor, f"greedy agreement {agree:.3f} < {floor:.3f}"
     if precision == "fp32":
         assert np.abs(logp_g - ref_gr["logp"]).max() <= tol["logp"]
         assert np.array_equal(las.speller.last_tokens.cpu().numpy(), logp_g.argmax(-1))
@@ -782,3 +798,136 @@ def test_solver_raises_when_the_decoder_is_shorter_than_the_labels():
     x, labels = tl.make_inputs(2, 16, c["F"], 6, c["V"], seed=3)
     with pytest.raises(RuntimeError, match="max_label_len"):
         solver.batch_iterator(x.cuda(), tl.onehot(labels, c["V"]).cuda(), las, None, 0.0, False, 6, 0.0)
+
+
+def _decode_kw(las, enc, steps, **kw):
+    logp, attn, tok = las.speller._decode(enc, steps, **kw)
+    torch.cuda.synchronize()
+    return logp.clone(), attn.clone(), tok.clone()
+
+
+@pytest.mark.parametrize("cfgname,B,T,S", [("small", 5, 64, 30), ("paper", 64, 320, 46), ("odd", 3, 48, 11)])
+def test_bf16_segmented_decode_is_bit_identical(cfgname, B, T, S):
+    """las_decode_io.segment_steps: the persistent decoder's step loop cut into several launches (what the serving pipeline and the
+    <eos> early exit build on) carries h / c / context / fed-back word on the device and must reproduce the single launch bit for
+    bit -- greedy, index and dense teacher forcing, raw feedback (decode_mode 0) and sampling."""
+    if "bf16" not in precisions():
+        pytest.skip("bf16 mode not built")
+    c = tl.CONFIGS[cfgname]
+    x, labels = tl.make_inputs(B, T, c["F"], S, c["V"], seed=91)
+    for dm in (1, 0, 2):
+        las = tl.build_model(cfgname, max_label_len=S, decode_mode=dm, seed=91, gain=3.0, precision="bf16").cuda()
+        enc = las.listener(x.cuda())
+        variants = [dict()]
+        if dm == 1:
+            variants += [dict(gt_index=labels.cuda().to(torch.int32).contiguous()),
+                         dict(gt_dense=tl.onehot(labels, c["V"]).float().cuda().contiguous()),
+                         dict(nll_labels=labels.cuda())]
+        for kw in variants:
+            torch.manual_seed(5)
+            one = _decode_kw(las, enc, S, **kw)
+            for seg in (2, 10, 16):
+                torch.manual_seed(5)
+                many = _decode_kw(las, enc, S, segment_steps=seg, **kw)
+                for a, b in zip(one, many):
+                    assert torch.equal(a, b), (cfgname, dm, list(kw), seg)
+
+
+@pytest.mark.parametrize("precision", precisions())
+def test_eos_early_exit(precision):
+    """Row f4, <eos> early-exit batching (extension; the reference always runs max_label_len steps, model/las_model.py:205-209):
+    decoding stops at the first check after every utterance has emitted <eos>; decoded steps equal the full decode, the rest is
+    filled (<eos> tokens, zero log-probs / attention), steps_done says where it stopped.  No host synchronisation inside."""
+    c = tl.CONFIGS["small"]
+    B, T, S = 6, 64, 96
+    las = tl.build_model("small", max_label_len=S, seed=97, gain=3.0, precision=precision).cuda()
+    x, _ = tl.make_inputs(B, T, c["F"], S, c["V"], seed=97)
+    enc = las.listener(x.cuda())
+    logp, attn, tok = _decode_kw(las, enc, S)
+    t = tok.cpu().numpy()
+    # pick as <eos> a token every utterance emits, as late as possible but before the end
+    best = None
+    for v in range(c["V"]):
+        hit = (t == v)
+        if hit.any(0).all():
+            first_all = int(hit.argmax(0).max()) + 1   # steps needed until every utterance has emitted v
+            if first_all < S - 20 and (best is None or first_all > best[1]):
+                best = (v, first_all)
+    assert best is not None, "no token is emitted by every utterance early enough; change the seed"
+    eos, need = best
+    for every in (8, 32):
+        expect = min(S, -(-need // every) * every)
+        las.speller.eos_token, las.speller.early_exit_every = eos, every
+        preds, attns = las.speller(enc, None, 0.0, early_exit=True)
+        torch.cuda.synchronize()
+        assert int(las.speller.last_steps_done) == expect, (int(las.speller.last_steps_done), expect, need, every)
+        lp, tk = torch.stack(preds), las.speller.last_tokens
+        at = torch.stack([a[0] for a in attns])
+        assert torch.equal(lp[:expect], logp[:expect]) and torch.equal(tk[:expect], tok[:expect]) and torch.equal(at[:expect], attn[:expect, 0])
+        assert bool((tk[expect:] == eos).all()) and float(lp[expect:].abs().max() if expect < S else 0) == 0.0
+        assert float(at[expect:].abs().max() if expect < S else 0) == 0.0
+    # default stays the reference's behaviour: all max_label_len steps
+    preds, _ = las.speller(enc, None, 0.0)
+    assert torch.equal(torch.stack(preds), logp)
+    # teacher forcing ignores the switch
+    np.random.seed(0)
+    labels = torch.randint(2, c["V"], (B, 12)).cuda()
+    p1, _ = las.speller(enc, labels, 1.1, early_exit=True)
+    assert len(p1) == 12
+
+
+@pytest.mark.parametrize("cfgname,B,T,S,overlaps", [("paper", 64, 1600, 300, True), ("small", 32, 1600, 300, True), ("paper", 16, 3000, 600, True),
+                                                    ("small", 4, 64, 12, True), ("odd", 3, 48, 6, None)])
+def test_serving_pipeline_equals_forward(cfgname, B, T, S, overlaps):
+    """LAS.serve(): batch i+1's listener under batch i's decoder (las_pipeline_step).  Every batch must get exactly what LAS.forward
+    gives it on its own -- at the benchmarked shapes (c3, c2, c4), where the concurrent schedule applies, and at small / odd ones."""
+    from las_pytorch_b200 import _cabi
+
+    if "bf16" not in precisions():
+        pytest.skip("bf16 mode not built")
+    c = tl.CONFIGS[cfgname]
+    las = tl.build_model(cfgname, max_label_len=S, seed=17, gain=3.0, precision="bf16").cuda()
+    xs = [tl.make_inputs(B, T, c["F"], S, c["V"], seed=100 + i)[0].cuda() for i in range(4)]
+    want = []
+    for x in xs:
+        preds, attns = las(x, None, 0.0, is_training=False)
+        want.append((torch.stack(preds).clone(), torch.stack([a[0] for a in attns]).clone(), las.speller.last_tokens.clone()))
+    if overlaps is not None:
+        ld = _cabi.ListenerDims(B, T, c["F"], c["H"], c["L"], 0)
+        sd = las.speller._dims(B, T >> c["L"], 2 * c["H"])
+        import ctypes as C
+        assert bool(_cabi.load_library().las_pipeline_overlaps(C.byref(ld), C.byref(sd), S, _cabi.MODE_BF16)) == overlaps
+    for rounds in range(2):  # twice: the pipeline's workspaces / events are reused
+        pipe = las.serve()
+        got = []
+        for x in xs:
+            r = pipe.submit(x)
+            if r is not None:
+                got.append(r)
+        got.append(pipe.flush())
+        assert pipe.flush() is None
+        torch.cuda.synchronize()
+        assert len(got) == len(xs)
+        for (lp, at, tk), r in zip(want, got):
+            assert torch.equal(r.tokens, tk)
+            assert torch.equal(r.logp, lp)
+            assert torch.equal(r.attn, at)
+            assert len(r.raw_pred_seq) == S and r.attention_record[0][0].shape == (B, T >> c["L"])
+
+
+def test_serving_pipeline_fp32_and_masks_fall_back_to_the_same_results():
+    c = tl.CONFIGS["small"]
+    B, T, S = 4, 64, 10
+    for precision in precisions():
+        las = tl.build_model("small", max_label_len=S, seed=19, gain=3.0, precision=precision).cuda()
+        xs = [tl.make_inputs(B, T, c["F"], S, c["V"], seed=200 + i)[0].cuda() for i in range(3)]
+        lens = torch.tensor([64, 50, 33, 20])
+        want = []
+        for x in xs:
+            preds, _ = las(x, None, 0.0, is_training=False, input_lengths=lens)
+            want.append(torch.stack(preds).clone())
+        pipe = las.serve(want_attention=False)
+        got = [pipe.submit(x, input_lengths=lens) for x in xs][1:] + [pipe.flush()]
+        torch.cuda.synchronize()
+        for w, r in zip(want, got):
+            assert torch.equal(r.logp, w) and r.attn is None
