@@ -322,6 +322,24 @@ int make_tmap_bf16_atoms(CUtensorMap* tm, const void* base, long long rows, int 
   return LAS_OK;
 }
 
+// bf16 [B, Tl, Kx] (row pitch Kx, utterance pitch Tl*Kx) seen as {8 k, B, Kx/8, Tl}: one copy of box {8, box_b, Kx/8, 1} lands as
+// [Kx/8][box_b][8] -- the no-swizzle K-major UMMA operand layout (core matrices of 8 rows x 16 bytes, 8-row groups 128 bytes apart,
+// K-adjacent core matrices box_b*16 bytes apart) -- for the time step given by the last coordinate.  Rows beyond B read as zeros.
+int make_tmap_x_core(CUtensorMap* tm, const void* x_bf16, int B, int Tl, int Kx, int box_b) {
+  EncodeTiledFn enc;
+  LAS_TRY(get_encode_fn(&enc));
+  LAS_REQUIRE(Kx % 8 == 0 && (reinterpret_cast<uintptr_t>(x_bf16) & 15) == 0 && box_b <= 256, "TMA core-matrix view needs K %% 8 == 0 (K=%d)", Kx);
+  cuuint64_t gdim[4] = {8, (cuuint64_t)B, (cuuint64_t)(Kx / 8), (cuuint64_t)Tl};
+  cuuint64_t gstr[3] = {(cuuint64_t)Tl * Kx * 2, 16, (cuuint64_t)Kx * 2};
+  cuuint32_t box[4] = {8, (cuuint32_t)box_b, (cuuint32_t)(Kx / 8), 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  const CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x_bf16), gdim, gstr, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(LAS_ECUDA, "cuTensorMapEncodeTiled (core-matrix view) failed with CUresult %d (B=%d Tl=%d K=%d)", (int)r, B, Tl, Kx);
+  return LAS_OK;
+}
+
 int launch_gemm_bf16_tc(const __nv_bfloat16* A, long long lda, const __nv_bfloat16* W, long long ldw, const float* bias, float* C,
                         long long ldc, int M, int N, int K, cudaStream_t st, bool relu) {
   LAS_REQUIRE(M > 0 && N > 0 && K > 0, "bad GEMM shape %dx%dx%d", M, N, K);

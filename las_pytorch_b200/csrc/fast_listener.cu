@@ -13,17 +13,23 @@
 // Gate rows are ordered unit-major / gate-minor (row = 4*unit + gate), so the four gates of a unit sit in four
 // adjacent lanes of one warp after tcgen05.ld and are exchanged with warp shuffles.  The GEMM's weight rows are
 // permuted the same way at pack time, so P[b,t] holds (i,f,g,o) of a unit as one float4.
+#include <cuda.h>
+
 #include "las_fast.cuh"
 #include "las_kernels.cuh"
 #include "umma.cuh"
 
 namespace las {
 
+int make_tmap_x_core(CUtensorMap* tm, const void* x_bf16, int B, int Tl, int Kx, int box_b);  // fast_gemm.cu
+
 namespace {
 
-constexpr int REC_THREADS = 320;  // warps 0-7: epilogue (TMEM lane quadrant = warp % 4, batch half = warp / 4); warp 8: MMA issuer;
-                                  // warp 9: watches the input-projection GEMM's tile flags (when it runs concurrently)
-constexpr int REC_MMA_WARP = 8, REC_POLL_WARP = 9, REC_EPI_THREADS = 256;
+// Warps: 4*EPW epilogue warps (TMEM lane quadrant = warp % 4, batch slice = warp / 4), then the MMA issuer, then the warp that
+// watches the input-projection GEMM's tile flags (when it runs concurrently).  EPW = 2 up to 32 utterances per cluster; the
+// 64-utterance chunk (serving pipeline: one cluster per direction next to the decoder) uses EPW = 4 so that a thread still
+// owns only 4 cells.
+template <int BC> struct RecCfg { static constexpr int EPW = BC >= 64 ? 4 : 2; static constexpr int THREADS = (4 * EPW + 2) * 32; };
 
 struct RecParams {
   const float* P;               // [Tl*Bp, NP] fp32, time-major: row = t*Bp + b; column = dir*4Hp + r*128 + jj*4 + gate
@@ -36,6 +42,13 @@ struct RecParams {
   int B, Tl, H, Hp, CS, nchunks;
   int a_tmem;                   // 1: W_hh slice lives in tensor memory (UMMA .ts form); 0: in shared memory
   long long* trace;             // nullable test hook: [64 steps][8] clock64 stamps from CTA 0
+  // Fused input projection (layer 0, template FX): the K = 2F projection X.W_ih^T is never materialised.  Each step's folded frames
+  // x_t [BC, Kx] arrive by TMA straight in the B-operand layout, W_ih's slice sits in tensor memory next to W_hh's, and the Kx/16
+  // extra MMAs of step s are issued while the CTA still waits for h_{s-1}.
+  CUtensorMap tm_x;             // {8 k, B, Kx/8, Tl} view of the bf16 input [B, Tl, Kx]: a box {8, BC, Kx/8, 1} lands as [Kx/8][BC][8]
+  const __nv_bfloat16* wih_img; // [2][CS][128][Kx] bf16, rows in gate-row order (= the GEMM's packed W_ih)
+  const float* bias;            // [2][CS][128] b_ih + b_hh in gate-row order
+  int Kx;
   int* resident;                // nullable: every CTA adds 1 once it is running (the serving pipeline launches the decoder, which takes
                                 // all but a few SMs, only after this kernel's clusters have been placed)
 };
@@ -57,16 +70,22 @@ __host__ __device__ inline UmmaLayout whh_layout() { return UmmaLayout{0, 2048, 
 // h operand: Bc rows x Hp, INTERLEAVE: [coreK][coreN][8 rows][16 B]
 __host__ __device__ inline UmmaLayout h_layout(int Bc) { return UmmaLayout{0, (uint32_t)Bc * 16u, 128, 0}; }
 
-__host__ __device__ inline uint32_t rec_tmem_cols(int Hp, int BC, int a_tmem) {
-  uint32_t need = (uint32_t)BC + (a_tmem ? (uint32_t)Hp / 2 : 0u), c = 32;
+__host__ __device__ inline uint32_t rec_tmem_cols(int Hp, int BC, int a_tmem, int Kx = 0) {
+  // Kx > 0 (fused input projection): W_ih slice behind W_hh, and two accumulator sets (step s+1's input part is issued while the
+  // epilogue still reads step s's)
+  uint32_t need = (uint32_t)BC * (Kx > 0 ? 2u : 1u) + (a_tmem ? (uint32_t)Hp / 2 : 0u) + (uint32_t)Kx / 2, c = 32;
   while (c < need) c <<= 1;
   return c;
 }
 
-template <int BC, int NACC>
-__global__ void __launch_bounds__(REC_THREADS, 1) lstm_recurrence_cluster_kernel(RecParams p) {
-  constexpr int NB = BC / 8;  // cells per epilogue thread
-  constexpr int HB = BC / 2;  // batch columns per epilogue warp (two warps share a TMEM lane quadrant)
+constexpr int XSLOTS = 4;  // ring of x_t tiles (fused input projection)
+
+template <int BC, int NACC, bool FX>
+__global__ void __launch_bounds__(RecCfg<BC>::THREADS, 1) lstm_recurrence_cluster_kernel(const __grid_constant__ RecParams p) {
+  constexpr int EPW = RecCfg<BC>::EPW;
+  constexpr int REC_MMA_WARP = 4 * EPW, REC_POLL_WARP = 4 * EPW + 1, REC_EPI_THREADS = 4 * EPW * 32;
+  constexpr int HB = BC / EPW;  // batch columns per epilogue warp (EPW warps share a TMEM lane quadrant)
+  constexpr int NB = HB / 4;    // cells per epilogue thread
   // The K loop can be spread round-robin over NACC independent accumulators that the epilogue sums (test hook:
   // las_debug_set_option(4, n)).  tools/microbench.cu: a tcgen05.mma with the A operand in TMEM issues every ~33 cycles
   // whatever N is and whether or not consecutive instructions share an accumulator, so NACC = 1 is the default.
@@ -78,11 +97,14 @@ __global__ void __launch_bounds__(REC_THREADS, 1) lstm_recurrence_cluster_kernel
   uint8_t* sA = base;
   uint8_t* sH0 = base + a_smem_bytes;                         // two h buffers of h_bytes each
   uint8_t* sStage = sH0 + 2 * h_bytes;                        // [2 parities] x (4 coreK x BC x 16 bytes)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sStage + 2 * 4 * BC * 16);
+  const uint32_t x_bytes = FX ? (uint32_t)BC * p.Kx * 2u : 0u;  // one x_t tile: [Kx/8][BC][8] bf16
+  uint8_t* sX = sStage + 2 * 4 * BC * 16;                     // XSLOTS tiles (FX)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sX + XSLOTS * x_bytes);
   uint64_t* h_full = bars;        // [2]
   uint64_t* mma_done = bars + 2;  // [1]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
   int* s_ready = reinterpret_cast<int*>(bars + 4);  // steps (in processing order) whose P rows are known to be stored
+  uint64_t* x_full = bars + 5;    // [XSLOTS]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t r = ptx::cluster_ctarank();
@@ -90,7 +112,7 @@ __global__ void __launch_bounds__(REC_THREADS, 1) lstm_recurrence_cluster_kernel
   const int cluster_id = blockIdx.x / CS;
   const int dir = cluster_id / p.nchunks, chunk = cluster_id % p.nchunks;
   const int b_base = chunk * BC;
-  const uint32_t tcols = rec_tmem_cols(Hp, BC * NACC, p.a_tmem);
+  const uint32_t tcols = rec_tmem_cols(Hp, BC * NACC, p.a_tmem, FX ? p.Kx : 0);
   const uint8_t* w_img = p.whh_img + ((size_t)dir * CS + r) * a_bytes;
 
   // ---- one-time setup: barriers, TMEM, resident W_hh slice
@@ -100,6 +122,8 @@ __global__ void __launch_bounds__(REC_THREADS, 1) lstm_recurrence_cluster_kernel
     ptx::mbar_init(&h_full[0], 1);  // one local arrive.expect_tx per phase; the peers' bulk copies complete the bytes
     ptx::mbar_init(&h_full[1], 1);
     ptx::mbar_init(mma_done, 1);
+    if (FX)
+      for (int i = 0; i < XSLOTS; ++i) ptx::mbar_init(&x_full[i], 1);
     ptx::fence_mbar_init();
     // arm the first use of each h buffer (steps 1 and 2) before any peer can send
     if (p.Tl > 1) ptx::mbar_arrive_expect_tx(&h_full[1], h_bytes);
@@ -117,7 +141,17 @@ __global__ void __launch_bounds__(REC_THREADS, 1) lstm_recurrence_cluster_kernel
   ptx::tc_fence_after();
   const uint32_t tmem = *tmem_slot;
   // TMEM map: A operand (W_hh slice, lane = gate row, 2 bf16 per column) in columns [0, Hp/2), accumulator behind it
-  const uint32_t d_col = p.a_tmem ? (uint32_t)Hp / 2 : 0u;
+  const uint32_t x_col = p.a_tmem ? (uint32_t)Hp / 2 : 0u;       // W_ih slice (FX): Kx/2 columns
+  const uint32_t d_col = x_col + (FX ? (uint32_t)p.Kx / 2 : 0u);
+  if (FX && warp < 4) {
+    const __nv_bfloat16* wx = p.wih_img + ((size_t)(dir * CS + r) * 128 + threadIdx.x) * p.Kx;  // this lane's gate row
+    for (int k0 = 0; k0 < p.Kx; k0 += 16) {
+      const uint4 q0 = *reinterpret_cast<const uint4*>(wx + k0), q1 = *reinterpret_cast<const uint4*>(wx + k0 + 8);
+      const uint32_t v[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+      ptx::tmem_st_32x32b_x8(tmem + ((uint32_t)(warp * 32) << 16) + x_col + k0 / 2, v);
+    }
+    ptx::tmem_st_wait();
+  }
   if (p.a_tmem && warp < 4) {
     const UmmaLayout la = whh_layout();
     const int row = threadIdx.x;
@@ -143,9 +177,46 @@ __global__ void __launch_bounds__(REC_THREADS, 1) lstm_recurrence_cluster_kernel
     const uint32_t idesc = umma_idesc_bf16(128, BC);
     const uint32_t a_addr = ptx::smem_u32(sA);
     const uint32_t h0_addr = ptx::smem_u32(sH0);
-    if (ptx::elect_one()) ptx::mbar_arrive(mma_done);  // step 0: h_{-1} = 0, nothing to multiply
+    const uint32_t x0_addr = ptx::smem_u32(sX);
+    // x_t tile of processing step `st` -> ring slot st % XSLOTS (all CTAs of the cluster read the same tile; it stays in L2)
+    auto load_x = [&](int st) {
+      const int t = dir ? Tl - 1 - st : st;
+      uint64_t* bar = &x_full[st % XSLOTS];
+      ptx::mbar_arrive_expect_tx(bar, x_bytes);
+      asm volatile(
+          "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
+              x0_addr + (uint32_t)(st % XSLOTS) * x_bytes),
+          "l"(reinterpret_cast<uint64_t>(&p.tm_x)), "r"(ptx::smem_u32(bar)), "r"(0), "r"(b_base), "r"(0), "r"(t)
+          : "memory");
+    };
+    if (FX) {
+      if (ptx::elect_one())
+        for (int st = 0; st < XSLOTS - 1 && st < Tl; ++st) load_x(st);
+    } else {
+      if (ptx::elect_one()) ptx::mbar_arrive(mma_done);  // step 0: h_{-1} = 0, nothing to multiply
+    }
     __syncwarp();
-    for (int s = 1; s < Tl; ++s) {
+    for (int s = FX ? 0 : 1; s < Tl; ++s) {
+      const uint32_t acc = tmem + d_col + (FX ? (uint32_t)(s & 1) * (BC * NACC) : 0u);
+      if (FX) {
+        // input part of step s: x_t . W_ih^T into a fresh accumulator, issued before h_{s-1} is here
+        ptx::mbar_wait(&x_full[s % XSLOTS], (uint32_t)((s / XSLOTS) & 1));
+        ptx::tc_fence_after();
+        if (ptx::elect_one()) {
+          const UmmaLayout lx = h_layout(BC);
+          const uint32_t xa = x0_addr + (uint32_t)(s % XSLOTS) * x_bytes;
+#pragma unroll 1
+          for (int ki = 0; ki < p.Kx / 16; ++ki)
+            ptx::umma_bf16_ts(acc, tmem + x_col + ki * 8, umma_smem_desc(lx, xa, ki * 16), idesc, ki > 0);
+          if (s == 0) ptx::umma_commit(mma_done);
+        }
+        __syncwarp();
+        if (s == 0) {
+          if (ptx::elect_one() && XSLOTS - 1 < Tl) load_x(XSLOTS - 1);
+          __syncwarp();
+          continue;
+        }
+      }
       ptx::mbar_wait(&h_full[s & 1], (uint32_t)((((s + 1) >> 1) - 1) & 1));
       if (lane == 0) REC_TRACE(0);
       ptx::tc_fence_after();
@@ -153,16 +224,35 @@ __global__ void __launch_bounds__(REC_THREADS, 1) lstm_recurrence_cluster_kernel
       if (ptx::elect_one()) {
         if (s + 2 < Tl) ptx::mbar_arrive_expect_tx(&h_full[s & 1], h_bytes);  // re-arm for step s+2
         if (p.a_tmem) {
+          if constexpr (NACC == 1) {
+            // Lean issue loop: the issuing thread's own instructions between two tcgen05.mma pace the chain (~40 cycles per
+            // instruction with the descriptor rebuilt each time, ~27 in tools/microbench_mma_insitu.cu's lean loop).  Consecutive K
+            // steps are 8 tensor-memory columns and two core-matrix columns (2 * BC * 16 bytes) apart, so both operands advance by
+            // constants (the descriptor's 14-bit address field cannot carry: shared memory ends below 256 KB).
+            uint64_t bd = umma_smem_desc(lb, b_addr, 0);
+            uint32_t a = tmem;
+            ptx::umma_bf16_ts(acc, a, bd, idesc, FX ? 1u : 0u);
 #pragma unroll 4
-          for (int ki = 0; ki < Hp / 16; ++ki)
-            ptx::umma_bf16_ts(tmem + d_col + (ki % NACC) * BC, tmem + ki * 8, umma_smem_desc(lb, b_addr, ki * 16), idesc, ki >= NACC);
+            for (int ki = 1; ki < Hp / 16; ++ki) {
+              a += 8;
+              bd += 2 * BC;
+              ptx::umma_bf16_ts(acc, a, bd, idesc, 1u);
+            }
+          } else {
+#pragma unroll 4
+            for (int ki = 0; ki < Hp / 16; ++ki)
+              ptx::umma_bf16_ts(acc + (ki % NACC) * BC, tmem + ki * 8, umma_smem_desc(lb, b_addr, ki * 16), idesc,
+                                (FX && (ki % NACC) == 0) ? 1u : (uint32_t)(ki >= NACC));
+          }
         } else {
 #pragma unroll 4
           for (int ki = 0; ki < Hp / 16; ++ki)
-            ptx::umma_bf16(tmem + d_col + (ki % NACC) * BC, umma_smem_desc(la, a_addr, ki * 16), umma_smem_desc(lb, b_addr, ki * 16), idesc,
-                           ki >= NACC);
+            ptx::umma_bf16(acc + (ki % NACC) * BC, umma_smem_desc(la, a_addr, ki * 16), umma_smem_desc(lb, b_addr, ki * 16), idesc,
+                           (FX && (ki % NACC) == 0) ? 1u : (uint32_t)(ki >= NACC));
         }
         ptx::umma_commit(mma_done);
+        // the MMAs of step s-1 are complete (h_s could not have arrived otherwise): its x slot takes the tile of step s + XSLOTS - 1
+        if (FX && s + XSLOTS - 1 < Tl) load_x(s + XSLOTS - 1);
       }
       __syncwarp();
       if (lane == 0) REC_TRACE(1);
@@ -200,7 +290,9 @@ __global__ void __launch_bounds__(REC_THREADS, 1) lstm_recurrence_cluster_kernel
     const bool bit0 = (g & 1) != 0, bit1 = (g & 2) != 0;
     const int j = (int)r * 32 + jj;        // hidden unit
     const int NP = 8 * Hp;
-    const float* pcol = p.P + (size_t)dir * 4 * Hp + (size_t)r * 128 + jj * 4;
+    const float* pcol = FX ? nullptr : p.P + (size_t)dir * 4 * Hp + (size_t)r * 128 + jj * 4;
+    // fused input projection: the accumulator already holds x_t.W_ih^T + h.W_hh^T; only the bias (i,f,g,o of this unit) is added
+    const float4 bias4 = FX ? *reinterpret_cast<const float4*>(p.bias + (size_t)dir * 4 * Hp + (size_t)r * 128 + jj * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
     float c[NB];
     float4 pnext[NB];
     int len[NB];  // valid steps of this thread's utterances: past them the cell keeps its state and emits h = 0
@@ -229,12 +321,12 @@ __global__ void __launch_bounds__(REC_THREADS, 1) lstm_recurrence_cluster_kernel
 #pragma unroll
       for (int m = 0; m < NB; ++m) {
         const int b = b_base + hb * HB + 4 * m + g;
-        pnext[m] = (b < p.B) ? *reinterpret_cast<const float4*>(pcol + ((size_t)t0 * p.Bp + b) * NP) : make_float4(0.f, 0.f, 0.f, 0.f);
+        pnext[m] = (!FX && b < p.B) ? *reinterpret_cast<const float4*>(pcol + ((size_t)t0 * p.Bp + b) * NP) : bias4;
       }
     }
     const uint32_t stage0 = ptx::smem_u32(sStage);
     const uint32_t h0_addr = ptx::smem_u32(sH0);
-    const int dst_per_warp = (CS + 7) / 8;  // destination CTAs each warp serves
+    const int dst_per_warp = (CS + 4 * EPW - 1) / (4 * EPW);  // destination CTAs each warp serves
     for (int s0 = 0; s0 < Tl; s0 += 8) {
     wait_ready(s0 + 20 < Tl ? s0 + 20 : Tl);
     const int s_end = s0 + 8 < Tl ? s0 + 8 : Tl;
@@ -243,7 +335,7 @@ __global__ void __launch_bounds__(REC_THREADS, 1) lstm_recurrence_cluster_kernel
       float4 pc[NB];
 #pragma unroll
       for (int m = 0; m < NB; ++m) pc[m] = pnext[m];
-      if (s + 1 < Tl) {
+      if (!FX && s + 1 < Tl) {
         const int tn = dir ? t - 1 : t + 1;
 #pragma unroll
         for (int m = 0; m < NB; ++m) {
@@ -262,16 +354,16 @@ __global__ void __launch_bounds__(REC_THREADS, 1) lstm_recurrence_cluster_kernel
       ptx::mbar_wait(mma_done, (uint32_t)(s & 1));
       if (tid == 0) REC_TRACE(2);
       uint32_t v[HB];
-      if (s > 0) {
+      if (FX || s > 0) {
         ptx::tc_fence_after();
         constexpr int LDW = HB < 16 ? HB : 16;  // columns per tcgen05.ld
 #pragma unroll
         for (int a = 0; a < NACC; ++a) {
-          if (a == 0 || a < Hp / 16) {  // accumulator `a` was written this step (Hp = 32 has only two K steps)
+          if (a == 0 || (a < Hp / 16 && s > 0)) {  // accumulator `a` was written this step (Hp = 32 has only two K steps; FX step 0: only a = 0)
 #pragma unroll
             for (int c0 = 0; c0 < HB; c0 += LDW) {
               uint32_t t[LDW];
-              const uint32_t addr = tmem + ((uint32_t)(wq * 32) << 16) + d_col + a * BC + hb * HB + c0;
+              const uint32_t addr = tmem + ((uint32_t)(wq * 32) << 16) + d_col + (FX ? (uint32_t)(s & 1) * (BC * NACC) : 0u) + a * BC + hb * HB + c0;
               if constexpr (LDW == 16) ptx::tmem_ld_32x32b_x16(addr, *reinterpret_cast<uint32_t(*)[16]>(t));
               else ptx::tmem_ld_32x32b_x8(addr, *reinterpret_cast<uint32_t(*)[8]>(t));
               ptx::tmem_ld_wait();
@@ -326,7 +418,7 @@ __global__ void __launch_bounds__(REC_THREADS, 1) lstm_recurrence_cluster_kernel
           asm volatile("st.shared.b16 [%0], %1;" ::"r"(sb + off), "h"(*reinterpret_cast<const unsigned short*>(&hb)) : "memory");
         }
         ptx::fence_proxy_async_smem();  // generic-proxy staging writes -> visible to the bulk-copy (async proxy) reads
-        asm volatile("bar.sync 1, 256;" ::: "memory");
+        asm volatile("bar.sync 1, %0;" ::"n"(REC_EPI_THREADS) : "memory");
         if (tid == 0) REC_TRACE(6);
         const int d = warp * dst_per_warp + lane;
         if (lane < dst_per_warp && d < CS) {
@@ -431,6 +523,7 @@ int side_stream(SideStream** out) {
   return LAS_OK;
 }
 int g_rec_a_tmem = 1;              // las_debug_set_option(1, v)
+int g_rec_fuse_x = 1;              // las_debug_set_option(10, v): layer 0's input projection fused into its recurrence (1, default) or a GEMM (0)
 int g_rec_force_bc = 0;            // las_debug_set_option(9, v): batch chunk per recurrence cluster (0 = pick_bc)
 int g_rec_nacc = 0;                // las_debug_set_option(4, v): independent accumulators the K loop is spread over (0 = default)
 
@@ -506,18 +599,18 @@ int shape_ok(const las_listener_dims* d) {
   return LAS_OK;
 }
 
-template <int BC, int NACC>
+template <int BC, int NACC, bool FX>
 int launch_rec(const RecParams& p, cudaStream_t st, bool exclusive_sm) {
-  size_t smem = 1024 + (p.a_tmem ? 0u : 128u * p.Hp * 2) + 2u * BC * p.Hp * 2 + 2 * 4 * BC * 16 + 64;
+  size_t smem = 1024 + (p.a_tmem ? 0u : 128u * p.Hp * 2) + 2u * BC * p.Hp * 2 + 2 * 4 * BC * 16 + (FX ? XSLOTS * (size_t)BC * p.Kx * 2 : 0) + 128;
   // While the GEMM runs concurrently, a GEMM CTA (197 KB of shared memory, all 512 TMEM columns) must never land on an SM that
   // hosts a recurrence CTA (it would wait for tensor memory held by a CTA that waits for the GEMM's tiles): ask for enough
   // shared memory that the two cannot be co-resident.
   if (exclusive_sm && smem < 48 * 1024) smem = 48 * 1024;
-  LAS_CUDA_OK(cudaFuncSetAttribute(lstm_recurrence_cluster_kernel<BC, NACC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  if (p.CS > 8) LAS_CUDA_OK(cudaFuncSetAttribute(lstm_recurrence_cluster_kernel<BC, NACC>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+  LAS_CUDA_OK(cudaFuncSetAttribute(lstm_recurrence_cluster_kernel<BC, NACC, FX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (p.CS > 8) LAS_CUDA_OK(cudaFuncSetAttribute(lstm_recurrence_cluster_kernel<BC, NACC, FX>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(p.CS * 2 * p.nchunks);
-  cfg.blockDim = dim3(p.gemm_flags ? REC_THREADS : REC_THREADS - 32);  // the watcher warp exists only next to a concurrent GEMM
+  cfg.blockDim = dim3(p.gemm_flags ? RecCfg<BC>::THREADS : RecCfg<BC>::THREADS - 32);  // the watcher warp exists only next to a concurrent GEMM
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
   cudaLaunchAttribute at[1];
@@ -527,7 +620,7 @@ int launch_rec(const RecParams& p, cudaStream_t st, bool exclusive_sm) {
   at[0].val.clusterDim.z = 1;
   cfg.attrs = at;
   cfg.numAttrs = 1;
-  LAS_CUDA_OK(cudaLaunchKernelEx(&cfg, lstm_recurrence_cluster_kernel<BC, NACC>, p));
+  LAS_CUDA_OK(cudaLaunchKernelEx(&cfg, lstm_recurrence_cluster_kernel<BC, NACC, FX>, p));
   count_launch();
   return LAS_OK;
 }
@@ -546,6 +639,7 @@ void fast_set_option(int key, int value) {
   if (key == 6) g_rec_overlap = value;
   if (key == 7) g_rec_gemm_ctas = value;
   if (key == 9) g_rec_force_bc = value;
+  if (key == 10) g_rec_fuse_x = value;
   fast_set_option_speller(key, value);
   fast_set_option_gemm(key, value);
   fast_set_option_pipeline(key, value);
@@ -605,18 +699,38 @@ static RecParams rec_params(const las_listener_dims* d, const Geo& g, const List
   rp.a_tmem = g_rec_a_tmem;
   rp.nchunks = (d->B + bc - 1) / bc;
   rp.resident = nullptr;
+  rp.Kx = 0;
+  rp.wih_img = nullptr;
+  rp.bias = nullptr;
+  memset(&rp.tm_x, 0, sizeof(rp.tm_x));
   return rp;
 }
+// switch layer 0's recurrence to the fused input projection
+static int rec_fuse(RecParams& rp, const las_listener_dims* d, const ListenerPackFast& pk, const ListenerWsFast& w, int bc) {
+  rp.Kx = 2 * d->F;
+  rp.wih_img = pk.wih[0];
+  rp.bias = pk.bias[0];
+  rp.P = nullptr;
+  return make_tmap_x_core(&rp.tm_x, w.xb, d->B, d->T / 2, rp.Kx, bc);
+}
 static int launch_rec_bc(const RecParams& rp, int bc, cudaStream_t st, bool exclusive) {
+  if (rp.Kx > 0) {  // fused input projection (layer 0)
+    if (bc == 16) return launch_rec<16, 1, true>(rp, st, exclusive);
+    if (bc == 32) return launch_rec<32, 2, true>(rp, st, exclusive);
+    return launch_rec<64, 1, true>(rp, st, exclusive);
+  }
   if (bc == 16) {
     const int nacc = g_rec_nacc ? g_rec_nacc : 1;  // measured: one accumulator chain is fastest with the A operand in TMEM
-    if (nacc == 1) return launch_rec<16, 1>(rp, st, exclusive);
-    if (nacc == 2) return launch_rec<16, 2>(rp, st, exclusive);
-    return launch_rec<16, 4>(rp, st, exclusive);
+    if (nacc == 1) return launch_rec<16, 1, false>(rp, st, exclusive);
+    if (nacc == 2) return launch_rec<16, 2, false>(rp, st, exclusive);
+    return launch_rec<16, 4, false>(rp, st, exclusive);
   }
-  if (bc == 32) return launch_rec<32, 2>(rp, st, exclusive);
-  return launch_rec<64, 1>(rp, st, exclusive);
+  if (bc == 32) return launch_rec<32, 2, false>(rp, st, exclusive);
+  return launch_rec<64, 1, false>(rp, st, exclusive);
 }
+
+// layer l's input projection can be fused when the A operand is in tensor memory and K = 2F splits into 16-wide MMA steps
+static bool fuse_x(const las_listener_dims* d, int l) { return l == 0 && g_rec_fuse_x && g_rec_a_tmem && (2 * d->F) % 16 == 0 && 2 * d->F <= 256; }
 
 // CTAs the recurrence of this model occupies with batch chunk `bc`
 int fast_listener_rec_ctas(const las_listener_dims* d, int bc) {
@@ -639,12 +753,14 @@ int fast_listener_stage(const float* x, const int32_t* x_lengths, const void* pa
   const LayerGeom q = layer_geom(d, g, w, l);
   if ((stage - 1) % 2 == 0) {
     if (x_lengths) LAS_TRY(launch_pyramid_lengths(l == 0 ? x_lengths : w.len + (size_t)(l - 1) * d->B, w.len + (size_t)l * d->B, d->B, q.Tl, st));
+    if (fuse_x(d, l)) return LAS_OK;  // the recurrence does the projection itself
     snprintf(nm, sizeof(nm), "listener.L%d.input_gemm", l);
     ProfScope ps(nm, st);
     return launch_gemm_listener(q.in, d->B, q.Tl, q.K, pk.wih[l], pk.bias[l], w.P, q.NP, nullptr, 0, st);
   }
   RecParams rp = rec_params(d, g, pk, w, l, enc, x_lengths ? w.len + (size_t)l * d->B : nullptr, bc);
   rp.resident = resident;
+  if (fuse_x(d, l)) LAS_TRY(rec_fuse(rp, d, pk, w, bc));
   snprintf(nm, sizeof(nm), "listener.L%d.recurrence", l);
   {
     ProfScope ps(nm, st);
@@ -683,6 +799,14 @@ int fast_listener_forward(const float* x, const int32_t* x_lengths, const void* 
     // The GEMM emits its tiles in the recurrence's consumption order and flags each one, so it can run next to the recurrence
     // (which occupies 2 * nchunks * CS SMs) on the remaining SMs instead of in front of it.  Needs the two directions' columns
     // to fall on separate column tiles and enough free SMs to be worth it.
+    if (fuse_x(d, l)) {
+      // layer 0: K = 2F = 80 makes the projection's [B*T/2, 8H] fp32 output (419 MB at c3) the cost, not its flops (SURVEY.md
+      // 7.2.3): it is never materialised, the recurrence multiplies x_t itself
+      LAS_TRY(rec_fuse(rp, d, pk, w, bc));
+      ProfScope ps("listener.L0.recurrence", st);
+      LAS_TRY(launch_rec_bc(rp, bc, st, false));
+      continue;
+    }
     const int rec_ctas = 2 * rp.nchunks * g.CS;
     const int gemm_ctas = g_rec_gemm_ctas > 0 ? g_rec_gemm_ctas : sm_count() - rec_ctas - 4;
     const bool overlap = g_rec_overlap && ((q.NP / 2) % 256 == 0) && gemm_ctas >= 32;

@@ -572,6 +572,8 @@ __device__ void attention_role(const DecParams& p, uint8_t* smem, int b) {
   uint8_t* s_bop = reinterpret_cast<uint8_t*>(s_tm + 4);     // [2*nks core-K][2][8 rows][16 B]: row 0 = scores (bf16)
   const int nks = (U + 15) / 16;                              // UMMA K steps over the encoder axis
   const int CU = nks * 8;                                     // TMEM columns of one 128-feature tile of enc^T
+  // warps issuing the context UMMAs, one chain of nks instructions per feature tile (ab_flags bit 10: a single issuer)
+  const int niss = (ntm == 0) ? 0 : ((p.ab_flags & 1024) ? 1 : (ntm < 4 ? ntm : 4));
 
   if (!p.wreg)
     for (int i = tid; i < D * Hs; i += DEC_THREADS) s_wphi[(size_t)(i / Hs) * WPS + (i % Hs)] = p.w_phi[i];
@@ -595,7 +597,7 @@ __device__ void attention_role(const DecParams& p, uint8_t* smem, int b) {
     // enc[b]^T -> tensor memory, once: tile t holds features [128t, 128t+128) as TMEM lanes, encoder steps along the
     // columns (two bf16 per 32-bit column) = the A operand of  ctx^T[E,1] = enc^T[E,U] . score[U,1]
     if (tid == 0) {
-      ptx::mbar_init(ctx_bar, 1);
+      ptx::mbar_init(ctx_bar, (uint32_t)niss);
       ptx::fence_mbar_init();
     }
     if (warp == 0) ptx::tmem_alloc(tmem_slot, 512);
@@ -808,42 +810,41 @@ __device__ void attention_role(const DecParams& p, uint8_t* smem, int b) {
 
     // ---- D: context[e] = sum_u score[u] * enc[b,u,e]  (:293-297); warps 1.. meanwhile evaluate the h half of the
     //         character distribution, W_cd[:, :Hs] . h + b_cd  (16 lanes per output)
-    if (warp == 0) {
-      if (p.ctx_tmem) {
-        // scores (bf16) are row 0 of a 16-row K-major operand in shared memory:
-        // D_t[128 features, 16] = enc^T tile (TMEM) . scores^T ; column 0 of each accumulator is the context
-        ptx::tc_fence_after();
-        if (ptx::elect_one()) {
-          const UmmaLayout lb{0, 256, 128, 0};
-          const uint32_t idesc = umma_idesc_bf16(128, 16);
-          const uint32_t bop = ptx::smem_u32(s_bop);
-          if (p.ab_flags & 512) {  // A/B: descriptors rebuilt per instruction
-            for (int t = 0; t < ntm; ++t)
-              for (int ks = 0; ks < nks; ++ks)
-                ptx::umma_bf16_ts(tmem + ntm * CU + t * 16, tmem + t * CU + ks * 8, umma_smem_desc(lb, bop, ks * 16), idesc, ks != 0);
-          } else {
-            // The issuing thread's own instructions between two tcgen05.mma set the pace of this chain (N = 16: the pipe needs
-            // ~8 cycles per instruction; tools/microbench_mma_insitu.cu reaches ~27 with a lean loop, the per-instruction
-            // descriptor arithmetic cost ~58).  Consecutive K steps are 512 bytes apart in the score operand and 8 columns apart
-            // in tensor memory, so both operands advance by constants: 32 in the descriptor's 16-byte address field (which
-            // cannot carry out of its 14 bits: shared memory ends below 256 KB) and 8 in the tensor-memory address.
-            const uint64_t bd0 = umma_smem_desc(lb, bop, 0);
-            for (int t = 0; t < ntm; ++t) {
-              uint64_t bd = bd0;
-              uint32_t a = tmem + t * CU;
-              const uint32_t dcol = tmem + ntm * CU + t * 16;
+    if (warp < niss) {
+      // scores (bf16) are row 0 of a 16-row K-major operand in shared memory:
+      // D_t[128 features, 16] = enc^T tile (TMEM) . scores^T ; column 0 of each accumulator is the context.
+      // One issuing warp per feature tile (up to four): a chain of N = 16 instructions is paced by its issuing thread (~27-58
+      // cycles per instruction against ~8 in the pipe, tools/microbench_mma_insitu.cu), so independent chains issued from
+      // different warps overlap.  Each issuer commits to ctx_bar (initialised with one arrival per issuer).
+      ptx::tc_fence_after();
+      if (ptx::elect_one()) {
+        const UmmaLayout lb{0, 256, 128, 0};
+        const uint32_t idesc = umma_idesc_bf16(128, 16);
+        const uint32_t bop = ptx::smem_u32(s_bop);
+        if (p.ab_flags & 512) {  // A/B: descriptors rebuilt per instruction
+          for (int t = warp; t < ntm; t += niss)
+            for (int ks = 0; ks < nks; ++ks)
+              ptx::umma_bf16_ts(tmem + ntm * CU + t * 16, tmem + t * CU + ks * 8, umma_smem_desc(lb, bop, ks * 16), idesc, ks != 0);
+        } else {
+          // Consecutive K steps are 512 bytes apart in the score operand and 8 columns apart in tensor memory, so both operands
+          // advance by constants: 32 in the descriptor's 16-byte address field (which cannot carry out of its 14 bits: shared
+          // memory ends below 256 KB) and 8 in the tensor-memory address.
+          const uint64_t bd0 = umma_smem_desc(lb, bop, 0);
+          for (int t = warp; t < ntm; t += niss) {
+            uint64_t bd = bd0;
+            uint32_t a = tmem + t * CU;
+            const uint32_t dcol = tmem + ntm * CU + t * 16;
 #pragma unroll 4
-              for (int ks = 0; ks < nks; ++ks) {
-                ptx::umma_bf16_ts(dcol, a, bd, idesc, ks != 0);
-                a += 8;
-                bd += 32;
-              }
+            for (int ks = 0; ks < nks; ++ks) {
+              ptx::umma_bf16_ts(dcol, a, bd, idesc, ks != 0);
+              a += 8;
+              bd += 32;
             }
           }
-          ptx::umma_commit(ctx_bar);
         }
-        __syncwarp();
+        ptx::umma_commit(ctx_bar);
       }
+      __syncwarp();
     }
     if (p.attn && (tid & 1) == 0) {  // attention record (:292, returned to the caller): off the critical path
 #pragma unroll

@@ -273,8 +273,10 @@ class ServingResult:
         return list(self.logp.unbind(0))
 
     @property
-    def attention_record(self):
-        return None if self.attn is None else [list(a.unbind(0)) for a in self.attn.unbind(0)]
+    def attention_record(self):  # per step: one [B,U] tensor per head (model/las_model.py:214,292,299)
+        if self.attn is None:
+            return None
+        return [[a] if a.dim() == 2 else list(a.unbind(0)) for a in self.attn.unbind(0)]
 
 
 class ServingPipeline:

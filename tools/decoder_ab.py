@@ -23,6 +23,13 @@ def main():
     x, _ = tl.make_inputs(B, T, c["F"], S, c["V"], seed=17)
     enc = las.listener(x.cuda())
     res = {f: [] for f in flags}
+    outs = {}
+    for f in flags:  # same instructions in the same order per accumulator: every variant must be bit-identical to the first
+        lib.las_debug_set_option(5, f)
+        pred, _ = las.speller(enc, None, 0.0)
+        outs[f] = (torch.stack(pred).clone(), las.speller.last_tokens.clone())
+    for f in flags[1:]:
+        print(f"flags={f} vs flags={flags[0]}: bit-identical={all(torch.equal(a, b) for a, b in zip(outs[f], outs[flags[0]]))}")
     for rep in range(4):
         for f in flags:
             lib.las_debug_set_option(5, f)

@@ -19,6 +19,13 @@ def main():
     lis = tl.build_model("paper", max_label_len=4, seed=17, gain=3.0, precision="bf16").listener.cuda()
     x = x.cuda()
     res = [[] for _ in variants]
+    outs = []
+    for v in variants:  # outputs of every variant against the first one
+        for k, val in v.items():
+            lib.las_debug_set_option(k, val)
+        outs.append(lis(x).clone())
+    for v, o in zip(variants[1:], outs[1:]):
+        print(f"{v} vs {variants[0]}: max-abs diff {float((o - outs[0]).abs().max()):.3e}  bit-identical={torch.equal(o, outs[0])}")
     for rep in range(4):
         for i, v in enumerate(variants):
             for k, val in v.items():
