@@ -846,16 +846,11 @@ __device__ void attention_role(const DecParams& p, uint8_t* smem, int b) {
       }
       __syncwarp();
     }
-    if (p.attn && (tid & 1) == 0) {  // attention record (:292, returned to the caller): off the critical path
-#pragma unroll
-      for (int ps = 0; ps < ATT_MAXP; ++ps) {
-        const int u = ps * 256 + (tid >> 1);
-        if (u < U) p.attn[((size_t)(p.s0 + s) * p.Bfull + gb) * U + u] = ev[ps] * inv;
-      }
-    }
-    const bool late_h = hybrid;  // h half of the logits together with the context half, after the publish (measured for the pure
-                                 // tensor-memory path too: -0.07 us/step, but the fed-back token then reaches layer 0 only ~0.4 us
-                                 // before its MMAs finish)
+    // The h half of the logits is evaluated together with the context half, AFTER the context has been published.  It used to run
+    // on warps 1.. while the context UMMAs were in flight, but since those are issued from four warps they finish (~0.9 us) before
+    // that GEMV did, and the publish waited for it: -0.22 us/step (ab_flags bit 12 restores the old order for A/B runs).  The
+    // fed-back token still reaches layer 0 before its MMAs finish.
+    const bool late_h = hybrid || !(p.ab_flags & 4096);
     if (warp != 0 && !late_h) {
       const int part = tid & 15;
       for (int v = (tid - 32) >> 4; v < Vp; v += (DEC_THREADS - 32) / 16) {
@@ -960,6 +955,14 @@ __device__ void attention_role(const DecParams& p, uint8_t* smem, int b) {
           DEC_TRACE_ALL(3);
           if (b == 0) DEC_TRACE(2, 4);
         }
+      }
+    }
+
+    if (p.attn && (tid & 1) == 0) {  // attention record (:292, returned to the caller): off the critical path, after the publish
+#pragma unroll
+      for (int ps = 0; ps < ATT_MAXP; ++ps) {
+        const int u = ps * 256 + (tid >> 1);
+        if (u < U) p.attn[((size_t)(p.s0 + s) * p.Bfull + gb) * U + u] = ev[ps] * inv;
       }
     }
 
