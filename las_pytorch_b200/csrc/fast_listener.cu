@@ -645,6 +645,12 @@ void fast_set_option(int key, int value) {
   fast_set_option_pipeline(key, value);
 }
 
+// Does the cluster-resident recurrence cover this model?  (Otherwise las_api.cu runs the generic path: tensor-core input projection,
+// fp32 recurrent kernel.)
+bool fast_listener_fits(const las_listener_dims* d) {
+  const Geo g = geometry(d->H);
+  return d->cell == LAS_CELL_LSTM && g.ok && (2 * d->F) % 8 == 0 && (4 * d->H) % 8 == 0;
+}
 size_t fast_listener_packed_bytes(const las_listener_dims* d) { return pack_layout(d, nullptr).bytes; }
 size_t fast_listener_workspace_bytes(const las_listener_dims* d) { return ws_layout(d, nullptr).bytes; }
 

@@ -1253,6 +1253,13 @@ SpellerWsFast ws_layout(const las_speller_dims* d, void* base) {
 }  // namespace
 
 bool fast_available() { return true; }
+// Does the persistent decoder hold this model on chip?  (No error message is left behind: the caller falls back to the generic
+// tensor-core path, las_api.cu speller_decode_generic.)
+bool fast_speller_fits(const las_speller_dims* d) {
+  if (d->cell != LAS_CELL_LSTM || d->heads > 1 || d->no_mlp) return false;
+  const bool ok = supported(d) == LAS_OK && d->sl * (d->Hs / DEC_UNITS) + 1 <= sm_count();
+  return ok;
+}
 void fast_set_option_speller(int key, int value) {
   if (key == 2) g_dec_ctx_tmem = value;
   if (key == 5) g_dec_ab_flags = value;

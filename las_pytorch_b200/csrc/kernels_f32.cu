@@ -1,6 +1,8 @@
 // LAS_MODE_FP32 kernels: fp32 operands, fp32 FMA accumulation, precise expf/tanhf.
 // This is the correctness mode (north_star: log-probs within 1e-4 of the reference); it is also the first CUDA
 // path every faster kernel is validated against.  Kernels here are straightforward CUDA-core code.
+#include <cuda_bf16.h>
+
 #include "las_kernels.cuh"
 
 namespace las {
@@ -555,6 +557,91 @@ int launch_eos_fill(const int32_t* state, int S, int Bfull, int b0, int Bc, int 
                     float* nll_terms, int32_t* steps_done, cudaStream_t st) {
   eos_fill_kernel<<<64, 256, 0, st>>>(state, S, Bfull, b0, Bc, V, U, heads, eos, logp, attn, tokens, nll_terms, steps_done);
   LAS_LAUNCH_OK("eos_fill_kernel");
+  return LAS_OK;
+}
+
+// =========================================================================================================
+// Generic tensor-core decoder step (LAS_MODE_BF16 for the shapes / variants the persistent decoder does not hold on chip:
+// 1024-wide cells, GRU / RNN cells; las_api.cu speller_decode_generic): per layer and step
+//     A = bf16([x | h_prev])  ->  tcgen05 GEMM with the packed [R, Kp] bf16 weights (+ bias)  ->  fp32 cell update.
+// Packed rows R: LSTM 4H (i,f,g,o), RNN H, GRU 4H = (r, z, n_x, n_h) -- the n gate's input and hidden parts are kept apart
+// (torch: n = tanh(W_in x + b_in + r * (W_hn h + b_hn))) by giving them separate rows with a zero block each.
+// K columns: x part in [0, Kx), zero padding up to Kxp, h part in [Kxp, Kxp + H), zero padding up to Kp.
+// =========================================================================================================
+__global__ void gen_pack_w_kernel(const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh, __nv_bfloat16* dst, float* bias,
+                                  int cell, int H, int Kx, int Kxp, int Kp) {
+  const int R = (cell == LAS_CELL_RNN) ? H : 4 * H;
+  const size_t n = (size_t)R * Kp;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const int k = (int)(i % Kp), row = (int)(i / Kp);
+    const int blk = row / H, j = row % H;
+    float v = 0.f;
+    // source gate block of this packed row, and which parts (x / h) it carries
+    int src = blk;
+    bool use_x = true, use_h = true;
+    if (cell == LAS_CELL_GRU) {
+      if (blk == 2) use_h = false;                // n_x
+      if (blk == 3) { src = 2; use_x = false; }   // n_h
+    }
+    if (k < Kx) { if (use_x) v = w_ih[((size_t)src * H + j) * Kx + k]; }
+    else if (k >= Kxp && k < Kxp + H) { if (use_h) v = w_hh[((size_t)src * H + j) * H + (k - Kxp)]; }
+    dst[i] = __float2bfloat16_rn(v);
+    if (k == 0) bias[row] = (use_x ? b_ih[src * H + j] : 0.f) + (use_h ? b_hh[src * H + j] : 0.f);
+  }
+}
+int launch_gen_pack_w(const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh, __nv_bfloat16* dst, float* bias, int cell,
+                      int H, int Kx, int Kxp, int Kp, cudaStream_t st) {
+  gen_pack_w_kernel<<<592, 256, 0, st>>>(w_ih, w_hh, b_ih, b_hh, dst, bias, cell, H, Kx, Kxp, Kp);
+  LAS_LAUNCH_OK("gen_pack_w_kernel");
+  return LAS_OK;
+}
+// A[b, :] = bf16([x[b, 0:Kx] | 0 | h[b, 0:H] | 0]); h == nullptr reads as zeros
+__global__ void gen_build_a_kernel(const float* x, long long x_ld, const float* h, long long h_ld, __nv_bfloat16* A, int B, int H, int Kx, int Kxp,
+                                   int Kp) {
+  const size_t n = (size_t)B * Kp;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const int k = (int)(i % Kp), b = (int)(i / Kp);
+    float v = 0.f;
+    if (k < Kx) v = x[(long long)b * x_ld + k];
+    else if (h && k >= Kxp && k < Kxp + H) v = h[(long long)b * h_ld + (k - Kxp)];
+    A[i] = __float2bfloat16_rn(v);
+  }
+}
+int launch_gen_build_a(const float* x, long long x_ld, const float* h, long long h_ld, __nv_bfloat16* A, int B, int H, int Kx, int Kxp, int Kp,
+                       cudaStream_t st) {
+  const size_t n = (size_t)B * Kp;
+  gen_build_a_kernel<<<(unsigned)((n + 255) / 256 < 592 ? (n + 255) / 256 : 592), 256, 0, st>>>(x, x_ld, h, h_ld, A, B, H, Kx, Kxp, Kp);
+  LAS_LAUNCH_OK("gen_build_a_kernel");
+  return LAS_OK;
+}
+// pre [B, R] (biases included) -> cell update in fp32; h_prev nullable (zeros); c nullable for GRU / RNN
+__global__ void gen_cell_kernel(const float* pre, const float* h_prev, long long h_ld, float* c, float* h_out, long long hout_ld, int B, int H,
+                                int cell) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * H) return;
+  const int b = i / H, j = i % H;
+  const int R = (cell == LAS_CELL_RNN) ? H : 4 * H;
+  const float* p = pre + (size_t)b * R;
+  float h;
+  if (cell == LAS_CELL_LSTM) {
+    const float ig = sigmoid_precise(p[j]), fg = sigmoid_precise(p[H + j]), gg = tanhf(p[2 * H + j]), og = sigmoid_precise(p[3 * H + j]);
+    const float cn = fg * c[(size_t)b * H + j] + ig * gg;
+    c[(size_t)b * H + j] = cn;
+    h = og * tanhf(cn);
+  } else if (cell == LAS_CELL_GRU) {
+    const float hp = h_prev ? h_prev[(long long)b * h_ld + j] : 0.f;
+    const float rg = sigmoid_precise(p[j]), zg = sigmoid_precise(p[H + j]);
+    const float ng = tanhf(p[2 * H + j] + rg * p[3 * H + j]);
+    h = (1.0f - zg) * ng + zg * hp;
+  } else {
+    h = tanhf(p[j]);
+  }
+  h_out[(long long)b * hout_ld + j] = h;
+}
+int launch_gen_cell(const float* pre, const float* h_prev, long long h_ld, float* c, float* h_out, long long hout_ld, int B, int H, int cell,
+                    cudaStream_t st) {
+  gen_cell_kernel<<<(B * H + 255) / 256, 256, 0, st>>>(pre, h_prev, h_ld, c, h_out, hout_ld, B, H, cell);
+  LAS_LAUNCH_OK("gen_cell_kernel");
   return LAS_OK;
 }
 

@@ -123,10 +123,45 @@ static ListenerWsF32 listener_ws_layout_f32(const las_listener_dims* d, void* ba
   return w;
 }
 
+// LAS_MODE_BF16 for GRU / RNN cells and hidden sizes the cluster-resident recurrence does not cover: the input projection (the one
+// dense contraction of a layer) runs as a tcgen05 GEMM over bf16 copies of the layer input and of W_ih, the recurrence on the fp32
+// cell kernel.  The bf16 weights follow the fp32 pack, the bf16 activations the fp32 workspace.
+struct ListenerGen {
+  __nv_bfloat16* w[16];  // pack: [2*G*H, K] per layer;  workspace: w[0] = bf16 copy of the current layer's input
+  size_t bytes;
+};
+static bool listener_gen_ok(const las_listener_dims* d) { return (2 * d->F) % 8 == 0 && (4 * d->H) % 8 == 0; }
+static ListenerGen listener_pack_layout_gen(const las_listener_dims* d, void* base) {
+  ListenerGen p;
+  Carver cv(base);
+  for (int l = 0; l < d->L; ++l) {
+    const size_t K = (l == 0) ? 2 * (size_t)d->F : 4 * (size_t)d->H;
+    p.w[l] = cv.take<__nv_bfloat16>(2 * (size_t)n_gates(d->cell) * d->H * K);
+  }
+  p.bytes = cv.total();
+  return p;
+}
+static ListenerGen listener_ws_layout_gen(const las_listener_dims* d, void* base) {
+  ListenerGen p;
+  Carver cv(base);
+  const size_t n0 = (size_t)d->B * d->T * d->F, n1 = (size_t)d->B * (d->T / 2) * 2 * d->H;
+  p.w[0] = cv.take<__nv_bfloat16>(n0 > n1 ? n0 : n1);
+  p.bytes = cv.total();
+  return p;
+}
+
 static int listener_forward_f32(const float* x, const int32_t* x_lengths, const void* packed, const las_listener_dims* d, float* enc,
-                                int32_t* enc_lengths, void* ws, cudaStream_t st) {
+                                int32_t* enc_lengths, void* ws, cudaStream_t st, const void* packed_gen = nullptr, void* ws_gen = nullptr) {
   const ListenerPackF32 pk = listener_pack_layout_f32(d, const_cast<void*>(packed));
   const ListenerWsF32 w = listener_ws_layout_f32(d, ws);
+  const bool gen = packed_gen != nullptr;
+  ListenerGen gp, gw;
+  memset(&gp, 0, sizeof(gp));
+  memset(&gw, 0, sizeof(gw));
+  if (gen) {
+    gp = listener_pack_layout_gen(d, const_cast<void*>(packed_gen));
+    gw = listener_ws_layout_gen(d, ws_gen);
+  }
   const int B = d->B, H = d->H;
   const int GH = n_gates(d->cell) * H;
   const bool lstm = d->cell == LAS_CELL_LSTM;
@@ -144,7 +179,12 @@ static int listener_forward_f32(const float* x, const int32_t* x_lengths, const 
     {
       snprintf(nm, sizeof(nm), "listener.L%d.input_gemm", l);
       ProfScope ps(nm, st);
-      LAS_TRY(launch_sgemm_nt_bias(cur, K, pk.wcat[l], K, pk.bias[l], w.P, 2 * GH, M, 2 * GH, K, false, st));
+      if (gen) {
+        LAS_TRY(launch_f32_to_bf16(cur, gw.w[0], (size_t)M * K, st));
+        LAS_TRY(launch_gemm_bf16_tc(gw.w[0], K, gp.w[l], K, pk.bias[l], w.P, 2 * GH, M, 2 * GH, K, st));
+      } else {
+        LAS_TRY(launch_sgemm_nt_bias(cur, K, pk.wcat[l], K, pk.bias[l], w.P, 2 * GH, M, 2 * GH, K, false, st));
+      }
     }
     snprintf(nm, sizeof(nm), "listener.L%d.recurrence", l);
     ProfScope ps(nm, st);
@@ -256,10 +296,80 @@ static SpellerWsF32 speller_ws_layout_f32(const las_speller_dims* d, void* base)
   return w;
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Speller, LAS_MODE_BF16 beyond what the persistent decoder keeps on chip (1024-wide cells such as the reference's shipped
+// config/librispeech-config.yaml:13-34, GRU / RNN cells, multi_head > 1, use_mlp_in_attention=False): the generic tensor-core
+// path.  Same step structure as the fp32 mode, but every cell's [x | h_prev] . [W_ih | W_hh]^T is ONE tcgen05 GEMM over bf16
+// operands with fp32 accumulation (the weights stream from L2 each step), psi(enc) is a tcgen05 GEMM too, and the cell state,
+// the attention and the character distribution stay fp32 -- north_star's "bf16-GEMM / fp32-state" mode, launch per step.
+// ---------------------------------------------------------------------------------------------------------
+struct GenGeom {
+  int R, Kx[8], Kxp[8], Kp[8], Kp_max;
+};
+static GenGeom gen_geom(const las_speller_dims* d) {
+  GenGeom g;
+  g.R = (d->cell == LAS_CELL_RNN ? 1 : 4) * d->Hs;
+  g.Kp_max = 0;
+  for (int l = 0; l < d->sl; ++l) {
+    g.Kx[l] = (l == 0) ? d->V + d->E : d->Hs;
+    g.Kxp[l] = (g.Kx[l] + 7) & ~7;
+    g.Kp[l] = g.Kxp[l] + ((d->Hs + 7) & ~7);
+    if (g.Kp[l] > g.Kp_max) g.Kp_max = g.Kp[l];
+  }
+  return g;
+}
+struct SpellerPackGen {
+  __nv_bfloat16* w[8];
+  float* bias[8];
+  __nv_bfloat16* w_psi;
+  size_t bytes;
+};
+static SpellerPackGen speller_pack_layout_gen(const las_speller_dims* d, void* base) {
+  SpellerPackGen p;
+  const GenGeom g = gen_geom(d);
+  Carver cv(base);
+  for (int l = 0; l < d->sl; ++l) {
+    p.w[l] = cv.take<__nv_bfloat16>((size_t)g.R * g.Kp[l]);
+    p.bias[l] = cv.take<float>(g.R);
+  }
+  p.w_psi = cv.take<__nv_bfloat16>(d->no_mlp ? 0 : (size_t)d->D * d->E);
+  p.bytes = cv.total();
+  return p;
+}
+struct SpellerWsGen {
+  __nv_bfloat16* a;    // [B, Kp_max] bf16 GEMM operand of the current layer
+  float* pre;          // [B, R] gate pre-activations
+  __nv_bfloat16* enc;  // [B*U, E] bf16 copy for the psi GEMM
+  size_t bytes;
+};
+static SpellerWsGen speller_ws_layout_gen(const las_speller_dims* d, void* base) {
+  SpellerWsGen w;
+  const GenGeom g = gen_geom(d);
+  Carver cv(base);
+  w.a = cv.take<__nv_bfloat16>((size_t)d->B * g.Kp_max);
+  w.pre = cv.take<float>((size_t)d->B * g.R);
+  w.enc = cv.take<__nv_bfloat16>(d->no_mlp ? 0 : (size_t)d->B * d->U * d->E);
+  w.bytes = cv.total();
+  return w;
+}
+// psi GEMM / cell GEMMs read bf16 rows through TMA: 16-byte aligned rows
+static bool gen_ok(const las_speller_dims* d) { return d->no_mlp || d->E % 8 == 0; }
+
 static int speller_decode_f32(const las_decode_io* io, const void* packed, const las_speller_dims* d, int steps,
-                              int decode_mode, int relu, void* ws, cudaStream_t st) {
+                              int decode_mode, int relu, void* ws, cudaStream_t st, const void* packed_gen = nullptr, void* ws_gen = nullptr) {
   const SpellerPackF32 pk = speller_pack_layout_f32(d, const_cast<void*>(packed));
   const SpellerWsF32 w = speller_ws_layout_f32(d, ws);
+  // packed_gen != nullptr: the generic tensor-core path of LAS_MODE_BF16 (see above); everything but the GEMMs is shared
+  const bool gen = packed_gen != nullptr;
+  const GenGeom gg = gen_geom(d);
+  SpellerPackGen gp;
+  SpellerWsGen gw;
+  memset(&gp, 0, sizeof(gp));
+  memset(&gw, 0, sizeof(gw));
+  if (gen) {
+    gp = speller_pack_layout_gen(d, const_cast<void*>(packed_gen));
+    gw = speller_ws_layout_gen(d, ws_gen);
+  }
   const int B = d->B, Hs = d->Hs, V = d->V, E = d->E, U = d->U, D = d->D, sl = d->sl;
   const int xld = V + E;
   const size_t state_n = (size_t)sl * B * Hs;
@@ -270,7 +380,12 @@ static int speller_decode_f32(const las_decode_io* io, const void* packed, const
     psi = io->enc;  // use_mlp_in_attention=False (model/las_model.py:283-285): the keys are the listener features themselves
   } else if (!psi) {
     ProfScope ps("speller.psi", st);
-    LAS_TRY(launch_sgemm_nt_bias(io->enc, E, pk.w_psi, E, pk.b_psi, w.psi, D, B * U, D, E, relu != 0, st));
+    if (gen) {
+      LAS_TRY(launch_f32_to_bf16(io->enc, gw.enc, (size_t)B * U * E, st));
+      LAS_TRY(launch_gemm_bf16_tc(gw.enc, E, gp.w_psi, E, pk.b_psi, w.psi, D, B * U, D, E, st, relu != 0));
+    } else {
+      LAS_TRY(launch_sgemm_nt_bias(io->enc, E, pk.w_psi, E, pk.b_psi, w.psi, D, B * U, D, E, relu != 0, st));
+    }
     psi = w.psi;
   }
   if (io->word && io->context) {
@@ -293,6 +408,14 @@ static int speller_decode_f32(const las_decode_io* io, const void* packed, const
     float* hp = w.h[s & 1];
     float* hn = w.h[(s & 1) ^ 1];
     for (int l = 0; l < sl; ++l) {
+      if (gen) {
+        const float* xin_l = (l == 0) ? w.xin : hn + (size_t)(l - 1) * B * Hs;
+        const float* hp_l = hp + (size_t)l * B * Hs;
+        LAS_TRY(launch_gen_build_a(xin_l, (l == 0) ? xld : Hs, hp_l, Hs, gw.a, B, Hs, gg.Kx[l], gg.Kxp[l], gg.Kp[l], st));
+        LAS_TRY(launch_gemm_bf16_tc(gw.a, gg.Kp[l], gp.w[l], gg.Kp[l], gp.bias[l], gw.pre, gg.R, B, gg.R, gg.Kp[l], st));
+        LAS_TRY(launch_gen_cell(gw.pre, hp_l, Hs, w.c + (size_t)l * B * Hs, hn + (size_t)l * B * Hs, Hs, B, Hs, d->cell, st));
+        continue;
+      }
       CellArgs a;
       memset(&a, 0, sizeof(a));
       a.x = (l == 0) ? w.xin : hn + (size_t)(l - 1) * B * Hs;
@@ -412,7 +535,8 @@ int64_t las_launch_count(int reset) {
 // ---- listener ------------------------------------------------------------------------------------------
 size_t las_listener_packed_bytes(const las_listener_dims* d, int mode) {
   if (listener_check(d) != LAS_OK) return 0;
-  if (mode == LAS_MODE_BF16) return fast_listener_packed_bytes(d);
+  if (mode == LAS_MODE_BF16 && fast_listener_fits(d)) return fast_listener_packed_bytes(d);
+  if (mode == LAS_MODE_BF16) return listener_pack_layout_f32(d, nullptr).bytes + listener_pack_layout_gen(d, nullptr).bytes;
   return listener_pack_layout_f32(d, nullptr).bytes;
 }
 
@@ -425,8 +549,9 @@ int las_listener_pack(const las_lstm_weights* w, const las_listener_dims* d, int
   if (packed_bytes < las_listener_packed_bytes(d, mode))
     return fail(LAS_ENOMEM, "packed buffer too small: %zu < %zu", packed_bytes, las_listener_packed_bytes(d, mode));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  LAS_REQUIRE(mode != LAS_MODE_BF16 || d->cell == LAS_CELL_LSTM, "LAS_MODE_BF16 implements LSTM cells only; use LAS_MODE_FP32 for GRU / RNN");
-  if (mode == LAS_MODE_BF16) return fast_listener_pack(w, d, packed, st);
+  LAS_REQUIRE(mode != LAS_MODE_BF16 || fast_listener_fits(d) || listener_gen_ok(d),
+              "LAS_MODE_BF16 needs 16-byte aligned bf16 rows for TMA: 2F (%d) and 4H (%d) must be multiples of 8; use LAS_MODE_FP32", 2 * d->F, 4 * d->H);
+  if (mode == LAS_MODE_BF16 && fast_listener_fits(d)) return fast_listener_pack(w, d, packed, st);
   const ListenerPackF32 pk = listener_pack_layout_f32(d, packed);
   const size_t H = d->H, GH = (size_t)n_gates(d->cell) * H;
   for (int l = 0; l < d->L; ++l) {
@@ -445,12 +570,20 @@ int las_listener_pack(const las_lstm_weights* w, const las_listener_dims* d, int
       }
     }
   }
+  if (mode == LAS_MODE_BF16) {  // generic path: bf16 copies of [W_ih fwd ; W_ih reverse] behind the fp32 pack
+    const ListenerGen gp = listener_pack_layout_gen(d, static_cast<char*>(packed) + pk.bytes);
+    for (int l = 0; l < d->L; ++l) {
+      const size_t K = (l == 0) ? 2 * (size_t)d->F : 4 * H;
+      LAS_TRY(launch_f32_to_bf16(pk.wcat[l], gp.w[l], 2 * GH * K, st));
+    }
+  }
   return LAS_OK;
 }
 
 size_t las_listener_workspace_bytes(const las_listener_dims* d, int mode) {
   if (listener_check(d) != LAS_OK) return 0;
-  if (mode == LAS_MODE_BF16) return fast_listener_workspace_bytes(d);
+  if (mode == LAS_MODE_BF16 && fast_listener_fits(d)) return fast_listener_workspace_bytes(d);
+  if (mode == LAS_MODE_BF16) return listener_ws_layout_f32(d, nullptr).bytes + listener_ws_layout_gen(d, nullptr).bytes;
   return listener_ws_layout_f32(d, nullptr).bytes;
 }
 
@@ -469,8 +602,13 @@ int las_listener_forward_masked(const float* x, const int32_t* x_lengths, const 
   if (workspace_bytes < las_listener_workspace_bytes(d, mode))
     return fail(LAS_ENOMEM, "workspace too small: %zu < %zu", workspace_bytes, las_listener_workspace_bytes(d, mode));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  LAS_REQUIRE(mode != LAS_MODE_BF16 || d->cell == LAS_CELL_LSTM, "LAS_MODE_BF16 implements LSTM cells only; use LAS_MODE_FP32 for GRU / RNN");
-  if (mode == LAS_MODE_BF16) return fast_listener_forward(x, x_lengths, packed, d, enc, enc_lengths, workspace, st);
+  if (mode == LAS_MODE_BF16 && fast_listener_fits(d)) return fast_listener_forward(x, x_lengths, packed, d, enc, enc_lengths, workspace, st);
+  if (mode == LAS_MODE_BF16) {
+    LAS_REQUIRE(listener_gen_ok(d), "LAS_MODE_BF16 needs 2F (%d) and 4H (%d) to be multiples of 8; use LAS_MODE_FP32", 2 * d->F, 4 * d->H);
+    return listener_forward_f32(x, x_lengths, packed, d, enc, enc_lengths, workspace, st,
+                                static_cast<const char*>(packed) + listener_pack_layout_f32(d, nullptr).bytes,
+                                static_cast<char*>(workspace) + listener_ws_layout_f32(d, nullptr).bytes);
+  }
   return listener_forward_f32(x, x_lengths, packed, d, enc, enc_lengths, workspace, st);
 }
 
@@ -479,7 +617,7 @@ size_t las_speller_packed_bytes(const las_speller_dims* d, int mode) {
   if (speller_check(d) != LAS_OK) return 0;
   // the bf16 pack keeps the fp32 block first (phi/psi/cd and fallbacks read it), then its own layouts
   const size_t f32 = speller_pack_layout_f32(d, nullptr).bytes;
-  if (mode == LAS_MODE_BF16) return f32 + fast_speller_packed_bytes(d);
+  if (mode == LAS_MODE_BF16) return f32 + (fast_speller_fits(d) ? fast_speller_packed_bytes(d) : speller_pack_layout_gen(d, nullptr).bytes);
   return f32;
 }
 
@@ -491,9 +629,8 @@ int las_speller_pack(const las_speller_weights* w, const las_speller_dims* d, in
   LAS_REQUIRE(w->w_cd && w->b_cd, "null output weight pointer");
   LAS_REQUIRE(d->no_mlp || (w->w_phi && w->b_phi && w->w_psi && w->b_psi), "null attention weight pointer");
   LAS_REQUIRE(n_heads(d) == 1 || (w->w_dr && w->b_dr), "multi_head > 1 needs attention.dim_reduce weights");
-  LAS_REQUIRE(mode != LAS_MODE_BF16 || (n_heads(d) == 1 && !d->no_mlp && d->cell == LAS_CELL_LSTM),
-              "LAS_MODE_BF16 implements single-head MLP attention with LSTM cells only; use LAS_MODE_FP32 for multi_head > 1 / "
-              "use_mlp_in_attention=False / GRU / RNN");
+  LAS_REQUIRE(mode != LAS_MODE_BF16 || fast_speller_fits(d) || gen_ok(d),
+              "LAS_MODE_BF16 needs E %% 8 == 0 for the psi GEMM's TMA rows (E=%d); use LAS_MODE_FP32", d->E);
   LAS_TRY(device_ok());
   if (packed_bytes < las_speller_packed_bytes(d, mode))
     return fail(LAS_ENOMEM, "packed buffer too small: %zu < %zu", packed_bytes, las_speller_packed_bytes(d, mode));
@@ -523,7 +660,16 @@ int las_speller_pack(const las_speller_weights* w, const las_speller_dims* d, in
     CP(pk.b_dr, w->b_dr, d->E);
   }
 #undef CP
-  if (mode == LAS_MODE_BF16) return fast_speller_pack(w, d, static_cast<char*>(packed) + pk.bytes, st);
+  if (mode == LAS_MODE_BF16 && fast_speller_fits(d)) return fast_speller_pack(w, d, static_cast<char*>(packed) + pk.bytes, st);
+  if (mode == LAS_MODE_BF16) {  // generic tensor-core path: [W_ih | W_hh] per layer as one bf16 matrix, psi weights in bf16
+    const SpellerPackGen gp = speller_pack_layout_gen(d, static_cast<char*>(packed) + pk.bytes);
+    const GenGeom g = gen_geom(d);
+    for (int l = 0; l < d->sl; ++l) {
+      const las_lstm_weights& s = w->rnn_host[l];
+      LAS_TRY(launch_gen_pack_w(s.w_ih, s.w_hh, s.b_ih, s.b_hh, gp.w[l], gp.bias[l], d->cell, d->Hs, g.Kx[l], g.Kxp[l], g.Kp[l], st));
+    }
+    if (!d->no_mlp) LAS_TRY(launch_f32_to_bf16(w->w_psi, gp.w_psi, (size_t)d->D * d->E, st));
+  }
   return LAS_OK;
 }
 
@@ -561,7 +707,7 @@ int las_attention_forward(const float* state, const float* enc, const float* psi
 size_t las_speller_workspace_bytes(const las_speller_dims* d, int steps, int mode) {
   if (speller_check(d) != LAS_OK || steps < 0) return 0;
   const size_t f32 = speller_ws_layout_f32(d, nullptr).bytes;
-  if (mode == LAS_MODE_BF16) return f32 + fast_speller_workspace_bytes(d, steps);
+  if (mode == LAS_MODE_BF16) return f32 + (fast_speller_fits(d) ? fast_speller_workspace_bytes(d, steps) : speller_ws_layout_gen(d, nullptr).bytes);
   return f32;
 }
 
@@ -583,9 +729,13 @@ int las_speller_decode(const las_decode_io* io, const void* packed, const las_sp
     return fail(LAS_ENOMEM, "workspace too small: %zu < %zu", workspace_bytes, las_speller_workspace_bytes(d, steps, mode));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (steps == 0) return LAS_OK;
-  LAS_REQUIRE(mode != LAS_MODE_BF16 || (n_heads(d) == 1 && !d->no_mlp && d->cell == LAS_CELL_LSTM),
-              "LAS_MODE_BF16 implements single-head MLP attention with LSTM cells only; use LAS_MODE_FP32 for multi_head > 1 / "
-              "use_mlp_in_attention=False / GRU / RNN");
+  if (mode == LAS_MODE_BF16 && !fast_speller_fits(d)) {
+    LAS_REQUIRE(gen_ok(d), "LAS_MODE_BF16 needs E %% 8 == 0 (E=%d); use LAS_MODE_FP32", d->E);
+    const size_t f32p = speller_pack_layout_f32(d, nullptr).bytes;
+    const size_t f32w = speller_ws_layout_f32(d, nullptr).bytes;
+    return speller_decode_f32(io, packed, d, steps, decode_mode, relu, workspace, st, static_cast<const char*>(packed) + f32p,
+                              static_cast<char*>(workspace) + f32w);
+  }
   if (mode == LAS_MODE_BF16) {
     const size_t f32p = speller_pack_layout_f32(d, nullptr).bytes;
     const size_t f32w = speller_ws_layout_f32(d, nullptr).bytes;
@@ -607,8 +757,8 @@ int las_pipeline_step(const las_pipeline_args* a, int mode, void* stream) {
                               a->speller_ws_bytes, stream);
   const las_speller_dims* sd = a->speller_dims;
   const las_listener_dims* ld = a->listener_dims;
-  const bool fast = mode == LAS_MODE_BF16 && sd && ld && n_heads(sd) == 1 && !sd->no_mlp && sd->cell == LAS_CELL_LSTM && ld->cell == LAS_CELL_LSTM &&
-                    a->steps > 0;
+  const bool fast = mode == LAS_MODE_BF16 && sd && ld && speller_check(sd) == LAS_OK && fast_speller_fits(sd) && listener_check(ld) == LAS_OK &&
+                    fast_listener_fits(ld) && a->steps > 0;
   if (!fast) {  // fp32 mode / variants: the same results, one after the other
     LAS_TRY(las_speller_decode(a->dec_io, a->speller_packed, sd, a->steps, a->decode_mode, mode, a->relu, a->speller_ws, a->speller_ws_bytes, stream));
     return las_listener_forward_masked(a->x, a->x_lengths, a->listener_packed, ld, mode, a->enc, a->enc_lengths, a->listener_ws,
@@ -640,7 +790,7 @@ int las_pipeline_step(const las_pipeline_args* a, int mode, void* stream) {
 
 int las_pipeline_overlaps(const las_listener_dims* ld, const las_speller_dims* sd, int steps, int mode) {
   if (mode != LAS_MODE_BF16 || !ld || !sd || listener_check(ld) != LAS_OK || speller_check(sd) != LAS_OK) return 0;
-  if (n_heads(sd) != 1 || sd->no_mlp || sd->cell != LAS_CELL_LSTM || ld->cell != LAS_CELL_LSTM) return 0;
+  if (!fast_speller_fits(sd) || !fast_listener_fits(ld)) return 0;
   return fast_pipeline_bc(ld, sd, steps) > 0 ? 1 : 0;
 }
 

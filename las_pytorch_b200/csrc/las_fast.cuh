@@ -6,12 +6,14 @@ namespace las {
 
 bool fast_available();
 
+bool fast_listener_fits(const las_listener_dims* d);
 size_t fast_listener_packed_bytes(const las_listener_dims* d);
 int fast_listener_pack(const las_lstm_weights* w_host, const las_listener_dims* d, void* packed, cudaStream_t st);
 size_t fast_listener_workspace_bytes(const las_listener_dims* d);
 int fast_listener_forward(const float* x, const int32_t* x_lengths, const void* packed, const las_listener_dims* d, float* enc,
                           int32_t* enc_lengths, void* ws, cudaStream_t st);
 
+bool fast_speller_fits(const las_speller_dims* d);
 size_t fast_speller_packed_bytes(const las_speller_dims* d);
 int fast_speller_pack(const las_speller_weights* w, const las_speller_dims* d, void* packed_fast, cudaStream_t st);
 size_t fast_speller_workspace_bytes(const las_speller_dims* d, int steps);

@@ -1,5 +1,6 @@
 // Internal launch-function declarations shared between translation units.
 #pragma once
+#include <cuda_bf16.h>
 #include "las_common.cuh"
 
 namespace las {
@@ -79,6 +80,14 @@ int launch_pyramid_lengths(const int32_t* in, int32_t* out, int B, int cap, cuda
 
 int launch_nll_sums(const float* logp, const int32_t* labels, int S, int S_lab, int B, int V, int max_label_len,
                     float* out2, cudaStream_t st);
+
+// generic tensor-core decoder step (LAS_MODE_BF16 beyond the persistent decoder's shapes; kernels_f32.cu)
+int launch_gen_pack_w(const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh, __nv_bfloat16* dst, float* bias, int cell,
+                      int H, int Kx, int Kxp, int Kp, cudaStream_t st);
+int launch_gen_build_a(const float* x, long long x_ld, const float* h, long long h_ld, __nv_bfloat16* A, int B, int H, int Kx, int Kxp, int Kp,
+                       cudaStream_t st);
+int launch_gen_cell(const float* pre, const float* h_prev, long long h_ld, float* c, float* h_out, long long hout_ld, int B, int H, int cell,
+                    cudaStream_t st);
 
 // <eos> early exit bookkeeping (las_decode_io.early_exit): `state` = 66 int32 {stop, steps decoded, done[64]} per launch group
 int launch_eos_check(const int32_t* tokens, int Bfull, int b0, int Bc, int s_begin, int s_end, int eos, int32_t* state, cudaStream_t st);

@@ -8,9 +8,10 @@ torch is used only for device memory, the current stream and parameter storage.
 Extra keyword accepted everywhere the reference swallows **kwargs: `precision` = "fp32" | "bf16"
 (LAS_MODE_FP32 / LAS_MODE_BF16; default from $LAS_B200_PRECISION, else "fp32").
 
-Variants of the reference classes: multi_head > 1 (with attention.dim_reduce) and use_mlp_in_attention=False run in the
-fp32 mode only, and so do the GRU / RNN cells (`rnn_unit`; the reference does getattr(nn, rnn_unit.upper()), :69,156) -- the bf16
-mode raises and says so.  decode_mode 2 samples the fed-back word on the device from the reference's distribution
+Variants of the reference classes -- multi_head > 1 (with attention.dim_reduce), use_mlp_in_attention=False, GRU / RNN cells
+(`rnn_unit`; the reference does getattr(nn, rnn_unit.upper()), :69,156) and cells too wide for the persistent decoder (the shipped
+config's 1024) -- run in both modes; in the bf16 mode their GEMMs (input projections, [x | h] . [W_ih | W_hh]^T per cell and step,
+psi) are tcgen05 GEMMs over bf16 operands and everything else stays fp32 (the generic tensor-core path, csrc/las_api.cu).  decode_mode 2 samples the fed-back word on the device from the reference's distribution
 (Categorical(probs=log-probs)) with a counter-based generator seeded from torch's global generator, so runs are
 reproducible under torch.manual_seed but not draw-for-draw equal to the reference.  Not on this path: training/backward.
 """
@@ -346,8 +347,6 @@ def _check_unit(rnn_unit, precision="fp32"):
     unit = str(rnn_unit).upper()
     if unit not in _cabi.CELLS:
         raise NotImplementedError(f"rnn_unit={rnn_unit!r}: LSTM, GRU and RNN cells are implemented (SURVEY.md section 8 row f4)")
-    if unit != "LSTM" and precision != "fp32":
-        raise NotImplementedError(f"rnn_unit={rnn_unit!r} runs in the fp32 mode only; construct the module with precision='fp32'")
     return unit
 
 
@@ -496,10 +495,6 @@ class Speller(nn.Module):
         self.label_dim = vocab_size
         if decode_mode not in (0, 1, 2):
             raise ValueError(f"decode_mode must be 0 (raw), 1 (greedy) or 2 (sample), got {decode_mode}")
-        if (not use_mlp_in_attention or multi_head > 1) and self.precision != "fp32":
-            raise NotImplementedError(
-                "the bf16 mode implements single-head MLP attention only; construct the Speller with precision='fp32' for "
-                "multi_head > 1 / use_mlp_in_attention=False (SURVEY.md section 8 row f4)")
         if hidden_size != 2 * listener_hidden_size:
             raise ValueError(
                 f"hidden_size ({hidden_size}) must equal 2*listener_hidden_size ({2 * listener_hidden_size}): the rnn input is "

@@ -93,8 +93,7 @@ def test_constructor_contract():
     assert gru.pLSTM_layer0.BLSTM.weight_ih_l0.shape == (3 * 16, 80) and gru.pLSTM_layer1.BLSTM.weight_hh_l0_reverse.shape == (48, 16)
     assert list(gru.state_dict()) == list(torch.nn.GRU(80, 16, 1, bidirectional=True).state_dict().__class__(
         (f"pLSTM_layer{i}.BLSTM.{k}", None) for i in range(2) for k in torch.nn.GRU(80, 16, 1, bidirectional=True).state_dict()))
-    with pytest.raises(NotImplementedError):
-        lp.Listener(40, 16, 2, "GRU", True, precision="bf16")  # GRU / RNN cells run in the fp32 mode only
+    assert lp.Listener(40, 16, 2, "GRU", True, precision="bf16").cell == "GRU"  # both modes take GRU / RNN cells
     with pytest.raises(NotImplementedError):
         lp.Listener(40, 16, 2, "QRNN", True)
 

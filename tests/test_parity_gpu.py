@@ -61,11 +61,7 @@ def run_ours(las, x, labels, V, mode):
 @pytest.mark.parametrize("precision", precisions())
 @pytest.mark.parametrize("name", CASES)
 def test_matches_reference_golden(name, precision):
-    variant = tl.CONFIGS[str(np.load(os.path.join(tl.GOLDEN_DIR, name + ".npz"))["cfg"])]
-    if precision == "bf16" and (variant.get("heads", 1) > 1 or not variant.get("use_mlp", True) or variant.get("unit", "LSTM") != "LSTM"):
-        with pytest.raises(NotImplementedError):  # row f4 variants run in the fp32 mode only, and the bf16 mode says so
-            load_case(name, precision)
-        return
+    # (row f4 variants -- multi-head, no-MLP attention, GRU / RNN cells -- run in the bf16 mode through the generic tensor-core path)
     g, cfg, las, mode = load_case(name, precision)
     tol = TOL[precision]
     enc, logp, attn = run_ours(las, torch.from_numpy(g["x"]), torch.from_numpy(g["labels"]).long(), cfg["V"], mode)
@@ -78,6 +74,20 @@ def test_matches_reference_golden(name, precision):
         # noise).  bf16 operand rounding (listener error 7e-2 here) flips the peaked attention onto other frames, so only
         # the listener is held to a (5x) bound in this regime; measured log-prob error is recorded in profiles/ and DESIGN.md.
         slack = 5.0
+    sens = dict(enc=0.0, logp=0.0, attn=0.0)
+    if precision == "bf16" and cfg.get("unit", "LSTM") != "LSTM":
+        # Ungated tanh / GRU recurrences at gain 3 amplify operand rounding far more than the LSTM does: the ORACLE itself, fed
+        # bf16-rounded inputs and 2-D weights (fp64 arithmetic), moves the tiny GRU / RNN goldens by 4e-2 / 5e-2 in the listener and
+        # up to 0.6 in the log-probs.  Calibrate on the spot: the bound is 3x that sensitivity where it exceeds the mode's tolerance.
+        def bf(a):
+            return torch.from_numpy(np.asarray(a, np.float32)).to(torch.bfloat16).float().numpy()
+
+        sd_full = tl.state_dict_numpy(las)
+        sd_b = {k: (bf(v) if v.ndim == 2 else v) for k, v in sd_full.items()}
+        rb = O.las_forward(bf(g["x"]), sd_b, cfg["L"], cfg["sl"], logp.shape[0], ground_truth=g["labels"], teacher_forced=True, dtype=np.float64)
+        sens = dict(enc=float(np.abs(rb["enc"] - g["enc_f64"]).max()), logp=float(np.abs(rb["logp"] - g["logp_f64"]).max()),
+                    attn=float(np.abs(rb["attn"] - g["attn_f64"]).max()))
+    tol = {k: max(tol[k], 3.0 * sens[k]) for k in tol}
     assert enc.shape == g["enc_f64"].shape and logp.shape == g["logp_f64"].shape and attn.shape == g["attn_f64"].shape
     if mode == "tf" or precision == "fp32":
         assert np.abs(enc - g["enc_f64"]).max() <= tol["enc"] * slack
@@ -410,11 +420,10 @@ def test_error_paths_raise_instead_of_falling_back():
     with pytest.raises(ValueError):
         ours.Speller(30, 32, "LSTM", 2, 5, True, 16, "relu", 16, 1, 3)  # decode_mode is 0, 1 or 2 in the reference
     if "bf16" in precisions():
-        with pytest.raises(NotImplementedError, match="fp32"):
-            ours.Speller(30, 32, "LSTM", 2, 5, True, 16, "relu", 16, 2, 1, precision="bf16")  # multi_head in bf16 mode
+        # shapes outside the persistent decoder (here V > 64, its word atom) run on the generic tensor-core path instead of raising
         big_v = ours.Speller(80, 32, "LSTM", 2, 3, True, 16, "relu", 16, 1, 1, precision="bf16").cuda()
-        with pytest.raises(_cabi.LasB200Error, match="vocabular"):  # V > 64 is outside the bf16 decoder's word atom
-            big_v(torch.randn(2, 4, 32, device="cuda"), None, 0.0)
+        preds, _ = big_v(torch.randn(2, 4, 32, device="cuda"), None, 0.0)
+        assert len(preds) == 3 and preds[0].shape == (2, 80) and float((torch.stack(preds).exp().sum(-1) - 1).abs().max()) < 1e-4
     # the library reports a bad status instead of aborting
     lib = _cabi.load_library()
     d = _cabi.ListenerDims(2, 15, 40, 16, 2)
@@ -529,18 +538,18 @@ def test_two_devices_from_two_host_threads():
         assert torch.equal(out[0], lone) and torch.equal(out[1], lone)
 
 
-def test_shipped_config_size_runs_in_fp32_and_bf16_says_what_it_cannot_do():
+def test_shipped_config_size_decodes_in_both_modes():
     """config/librispeech-config.yaml:13-34 ships listener 512x3 / speller 1024x2.  The fp32 path takes any size; the bf16 listener
-    takes H = 512 (16-CTA clusters); the bf16 persistent decoder keeps every LSTM weight on chip, which 1024-wide cells exceed --
-    it must say so instead of running something else."""
-    from las_pytorch_b200 import _cabi
-
+    takes H = 512 (16-CTA clusters); 1024-wide decoder cells (34 MB of LSTM weights) exceed what the persistent decoder keeps on
+    chip, so the bf16 mode decodes them on the generic tensor-core path (weights streamed through a tcgen05 GEMM per cell and
+    step) -- within the bf16 tolerance of the oracle, teacher-forced and re-scored free-running."""
     cfg = dict(F=40, H=512, L=3, sl=2, V=30, D=64)
-    B, T, S = 2, 32, 3
+    B, T, S = 3, 64, 6
     las = tl.build_model(cfg, max_label_len=S, seed=71, gain=2.0, precision="fp32")
     sd = tl.state_dict_numpy(las)
-    x, _ = tl.make_inputs(B, T, cfg["F"], S, cfg["V"], seed=71)
+    x, labels = tl.make_inputs(B, T, cfg["F"], S, cfg["V"], seed=71)
     ref = O.las_forward(x.numpy(), sd, cfg["L"], cfg["sl"], S, dtype=np.float64)
+    ref_tf = O.las_forward(x.numpy(), sd, cfg["L"], cfg["sl"], S, ground_truth=labels.numpy(), teacher_forced=True, dtype=np.float64)
     las = las.cuda()
     preds, _ = las(x.cuda(), None, 0.0, is_training=False)
     assert np.abs(torch.stack(preds).cpu().numpy() - ref["logp"]).max() <= 1e-4
@@ -548,8 +557,18 @@ def test_shipped_config_size_runs_in_fp32_and_bf16_says_what_it_cannot_do():
         lasb = tl.build_model(cfg, max_label_len=S, seed=71, gain=2.0, precision="bf16").cuda()
         enc = lasb.listener(x.cuda())  # H = 512 is within the bf16 listener's range
         assert np.abs(enc.cpu().numpy() - ref["enc"]).max() <= 3e-2
-        with pytest.raises(_cabi.LasB200Error, match="LAS_MODE_FP32"):
-            lasb.speller(enc, None, 0.0)
+        np.random.seed(0)
+        preds, attns = lasb(x.cuda(), labels.cuda(), 1.1, is_training=True)
+        assert np.abs(torch.stack(preds).cpu().numpy() - ref_tf["logp"]).max() <= 2e-2
+        assert np.abs(torch.stack([a[0] for a in attns]).cpu().numpy() - ref_tf["attn"]).max() <= 1e-2
+        preds, _ = lasb(x.cuda(), None, 0.0, is_training=False)
+        logp = torch.stack(preds).cpu().numpy()
+        rescored = O.las_forward(x.numpy(), sd, cfg["L"], cfg["sl"], S, ground_truth=logp.argmax(-1).T, teacher_forced=True, dtype=np.float64)
+        assert np.abs(logp - rescored["logp"]).max() <= 2e-2
+        # forward_step / state hand-over and the <eos> early exit contract work on this path too
+        lasb.speller.eos_token, lasb.speller.early_exit_every = int(logp.argmax(-1)[0, 0]), 2
+        lasb.speller(enc[:1], None, 0.0, early_exit=True)
+        assert int(lasb.speller.last_steps_done) == 2
 
 
 def test_bf16_batch_larger_than_one_decoder_launch():
