@@ -2,13 +2,15 @@
 """bench.py -- LAS forward hot path on B200: audio-seconds per second (RTFx) + microseconds per decoder step.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference|reference-gpu] [--precision bf16|fp32]
-                    [--workload c3|c2|c4|c5]
+                    [--workload c3|c2|c4|c5|yaml]
 
 A "step" is one pass of the hot path (Listener pBLSTM encoder + Speller greedy attention-decoder loop) over one
 synthetic batch.  Workloads are BASELINE.json configs:
     c3 (default, the one the metric is quoted on): paper LAS (256x3 / 512x2), batch 64 x 1600 frames, 300-char greedy
     c2: small LAS (128x2 / 256x2), batch 32 x 1600 frames, 300-char greedy
     c4: paper LAS long-form, batch 16 x 3000 frames, 600-char greedy
+    yaml: the reference's shipped YAML size (listener 512x3, speller 1024x2, batch 16, 576 steps): 34 MB of decoder LSTM weights do
+        not fit on chip, so the bf16 mode decodes on the generic tensor-core path (one tcgen05 GEMM per cell and step)
     c5: paper LAS, ONE global batch of 512 x 1600 frames sharded 512/N per GPU (strong scaling; N = 1/2/4 run the decoder in
         chunks of 64 utterances per persistent launch); the gathered shard tokens are compared with a single-GPU decode
 N > 1 (torchrun, one rank per GPU): every rank runs the same per-GPU batch on its own shard of utterances (weak
@@ -42,6 +44,9 @@ WORKLOADS = {
     "c3": dict(cfg="paper", B=64, T=1600, S=300, desc="paper LAS (listener 256x3 pBLSTM, speller 512x2), batch 64 x 1600 frames, 300-char greedy decode"),
     "c2": dict(cfg="small", B=32, T=1600, S=300, desc="small LAS (listener 128x2, speller 256x2), batch 32 x 1600 frames, 300-char greedy decode"),
     "c4": dict(cfg="paper", B=16, T=3000, S=600, desc="paper LAS long-form, batch 16 x 3000 frames, 600-char greedy decode"),
+    "yaml": dict(cfg="shipped", B=16, T=1600, S=576,
+                 desc="the reference's shipped config/librispeech-config.yaml (listener 512x3, speller 1024x2, batch_size 16, max_label_len 576), "
+                      "1600 frames, 576-char greedy decode"),
     "c5": dict(cfg="paper", B=512, T=1600, S=300, strong=True,
                desc="paper LAS, global batch 512 x 1600 frames sharded 512/N per GPU, 300-char greedy decode"),
 }
@@ -147,7 +152,8 @@ def shared_config(args, wl, world):
             "weights": "random init seed 17, 2-D params x3 (gain-3)",
             "precision": "ours: bf16 GEMM operands, fp32 accumulate / state / softmax (north_star bf16 mode) unless --precision fp32; "
                          "reference arm: fp32 on the host CPU",
-            "l2": "ours: 256 MiB buffer written between timed steps (untimed); reference arm: host CPU, not applicable",
+            "l2": "ours: 256 MiB buffer written between timed steps (inside the timed region when the serving pipeline is on, untimed "
+                  "otherwise); reference arm: host CPU, not applicable",
             "parallelism": "ours: one rank per GPU, utterance shards, no data-path collective; reference arm: rank 0, all host threads"}
 
 
@@ -304,8 +310,8 @@ def main():
 
     for _ in range(args.warmup):
         timed_step(x_dev)
-    if pipe is not None:
-        pipe.flush()
+    # (the serving pipeline stays primed: the last warm-up batch is encoded and waits for its decoder, so that each of the K
+    # timed submissions below does one full listener AND one full decode -- K batches' worth of work inside the timed region)
     barrier()
 
     # ---- timed region 1: device-resident inputs, CUDA events around the K steps, L2 flushed between steps
@@ -328,16 +334,16 @@ def main():
         ms = sum(a.elapsed_time(b) for a, b in evs)
     else:
         # the pipeline keeps two batches in flight (batch i+1's listener under batch i's decoder), so steps cannot be bracketed one
-        # by one: one event pair around exactly K submissions + the drain of the last one.  The 256 MiB L2-flush writes (one per
-        # step, ~0.07 ms each) are INSIDE this region.
+        # by one: one event pair around exactly K submissions in steady state (each = the listener of one batch + the decoder of the
+        # batch before it; the pipeline was primed by the warm-up and is drained after the region).  The 256 MiB L2-flush writes
+        # (one per step, ~0.07 ms each) are INSIDE this region.
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(args.steps):
             flush.zero_()
-            t = timed_step(x_dev)
-            tokens = t if t is not None else tokens
-        tokens = pipe.flush().tokens
+            tokens = timed_step(x_dev)
         e1.record()
+        pipe.flush()
         barrier()
         ms = e0.elapsed_time(e1)
     clocks = sampler.stop()
@@ -436,13 +442,11 @@ def main():
             logp_host[k].copy_(res[1], non_blocking=True)
             out_done[k].record(out_stream)
 
-    for _ in range(min(args.warmup, 3)):  # untimed warm-up of exactly this path: first-use allocations
-        xd[0].copy_(x_host, non_blocking=True)
-        r = api_step(xd[0])
+    for _ in range(min(args.warmup, 3)):  # untimed warm-up of exactly this path: first-use allocations; leaves the pipeline primed
+        xd[2].copy_(x_host, non_blocking=True)
+        r = api_step(xd[2])
         if r is not None:
             ship(r, 0)
-    if pipe is not None:
-        pipe.flush()
     barrier()
     t0 = time.perf_counter()
     with torch.cuda.stream(copy_stream):
@@ -468,18 +472,14 @@ def main():
                 host_checksum += int(tok_host[shipped & 1][0, 0])
             ship(r, shipped & 1)
             shipped += 1
-    if pipe is not None:
-        o = pipe.flush()
-        if shipped >= 2:
-            out_done[shipped & 1].synchronize()
-        ship((o.tokens, o.logp), shipped & 1)
-        shipped += 1
     for k in range(2):
         out_done[k].synchronize()
     host_checksum += int(tok_host[(shipped - 1) & 1][0, 0])
     barrier()
     e2e_s = time.perf_counter() - t0
     assert shipped == args.steps, (shipped, args.steps)
+    if pipe is not None:
+        pipe.flush()
     t_e2e = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
     if dist is not None:
         dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
@@ -539,6 +539,8 @@ def main():
             l = int(name.split(".")[1][1:])
             Tl = T >> (l + 1)
             by = B * Tl * (8 * H * 4.0 + 2 * H * 4.0)
+            if l == 0 and precision == "bf16" and (2 * c["F"]) % 16 == 0:  # fused input projection: x_t (bf16) read instead of P
+                by = B * Tl * (2 * c["F"] * 2.0 + 2 * H * 2.0)
             r = {"bound": "hbm", "achieved": by / dt / 1e9, "peak": peaks["hbm"], "unit": "GB/s", "us_per_serial_step": per_step[name] * 1e3 / Tl}
         elif name == "speller.psi":
             by = n_dec * (B * U * (E * 4.0 + D * 4.0) + D * E * 4.0)
@@ -558,8 +560,9 @@ def main():
 
     out = dict(base, value=value, ms_per_step=ms / args.steps, dtype=("bf16" if precision == "bf16" else "f32"),
                precision=precision, world=world,
-               mode=("serving pipeline (LAS.serve): batch i+1's listener runs under batch i's decoder; K submissions + drain timed with one "
-                     "CUDA-event pair, L2-flush writes included") if pipe is not None else "LAS.forward batch by batch, CUDA events per step",
+               mode=("serving pipeline (LAS.serve): batch i+1's listener runs under batch i's decoder; K steady-state submissions (each = one "
+                     "batch's listener + the previous batch's decoder) timed with one CUDA-event pair, L2-flush writes included")
+               if pipe is not None else "LAS.forward batch by batch, CUDA events per step",
                us_per_decoder_step=1e3 * spl_ms / (n_dec * S * max(1, -(-B // 64))), listener_ms=lis_ms, speller_ms=spl_ms, phase_ms=per_step,
                clocks=clocks, gpu_launches=launches,
                e2e={"value": e2e_value, "unit": "audio-s/s", "h2d_bytes_per_step": x_host.numel() * 4,

@@ -21,7 +21,7 @@ namespace las {
 namespace {
 
 // Residency is a placement matter only (nothing read here is produced by the kernel waited for), so the wait is bounded: after
-// 20 ms the decoder segment is launched regardless and the recurrence simply runs when SMs free up.
+// 1 ms the decoder segment is launched regardless and the recurrence simply runs when SMs free up.
 __global__ void wait_resident_kernel(const int* flag, int target) {
   long long t0, t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
@@ -30,7 +30,7 @@ __global__ void wait_resident_kernel(const int* flag, int target) {
     asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
     if (v >= target) break;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    if (t - t0 > 20000000LL) break;
+    if (t - t0 > 1000000LL) break;
     __nanosleep(100);
   }
 }

@@ -34,6 +34,8 @@ CONFIGS = {
     # README small LAS (listener 128x2, speller 256x2) and the paper-size model
     "small": dict(F=40, H=128, L=2, sl=2, V=30, D=64),
     "paper": dict(F=40, H=256, L=3, sl=2, V=30, D=64),
+    # the reference's shipped config (config/librispeech-config.yaml:13-34): listener 512x3, speller 1024x2
+    "shipped": dict(F=40, H=512, L=3, sl=2, V=30, D=64),
 }
 
 
