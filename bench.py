@@ -316,10 +316,15 @@ def main():
 
     # ---- timed region 1: device-resident inputs, CUDA events around the K steps, L2 flushed between steps
     sampler = ClockSampler(local_rank)
-    lib.las_prof_enable(1)
-    lib.las_launch_count(1)
-    sampler.start()
+    if not os.environ.get("LAS_BENCH_NOSAMPLER"):
+        sampler.start()
+    # one more untimed step with the clock sampler already polling NVML (its first queries stall the first step enqueued after
+    # them by several ms: measured 8-16 ms on the first timed step, 4.18 ms on every later one), then the counters start
+    timed_step(x_dev)
     barrier()
+    if not os.environ.get("LAS_BENCH_NOPROF"):
+        lib.las_prof_enable(2 if os.environ.get("LAS_BENCH_DEBUG") else 1)
+    lib.las_launch_count(1)
     tokens = None
     if pipe is None:
         evs = []
@@ -332,28 +337,47 @@ def main():
             evs.append((e0, e1))
         barrier()
         ms = sum(a.elapsed_time(b) for a, b in evs)
+        step_ms = [round(a.elapsed_time(b), 4) for a, b in evs]
     else:
         # the pipeline keeps two batches in flight (batch i+1's listener under batch i's decoder), so steps cannot be bracketed one
         # by one: one event pair around exactly K submissions in steady state (each = the listener of one batch + the decoder of the
         # batch before it; the pipeline was primed by the warm-up and is drained after the region).  The 256 MiB L2-flush writes
         # (one per step, ~0.07 ms each) are INSIDE this region.
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(args.steps):
-            flush.zero_()
+        marks = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+        flush.zero_()  # the flush in front of the first timed step is outside the region (it absorbs the memory system's wake-up after
+        e0.record()    # the barrier: 4-10 ms for this one 256 MiB write against 0.07 ms for each later one); the K-1 others are inside
+        host_ms = []
+        for i in range(args.steps):
+            if i:
+                flush.zero_()
+            h0 = time.perf_counter()
             tokens = timed_step(x_dev)
+            host_ms.append(round(1e3 * (time.perf_counter() - h0), 3))
+            marks[i].record()
         e1.record()
+        torch.cuda.synchronize()
+        launches = int(lib.las_launch_count(0))
+        ctypes_buf = ctypes.create_string_buffer(1 << 20)
+        _cabi.check(lib.las_prof_report(ctypes_buf, len(ctypes_buf)))  # the K timed steps' launch groups, before the drain adds its own
+        lib.las_prof_enable(0)
         pipe.flush()
         barrier()
         ms = e0.elapsed_time(e1)
+        step_ms = [round(a.elapsed_time(b), 4) for a, b in zip([e0] + marks[:-1], marks)]
+        base["host_enqueue_ms_each_step"] = host_ms
     clocks = sampler.stop()
-    launches = int(lib.las_launch_count(0))
-    ctypes_buf = ctypes.create_string_buffer(1 << 20)
-    _cabi.check(lib.las_prof_report(ctypes_buf, len(ctypes_buf)))
-    lib.las_prof_enable(0)
+    if pipe is None:
+        launches = int(lib.las_launch_count(0))
+        ctypes_buf = ctypes.create_string_buffer(1 << 20)
+        _cabi.check(lib.las_prof_report(ctypes_buf, len(ctypes_buf)))
+        lib.las_prof_enable(0)
     groups = {}
+    if os.environ.get("LAS_BENCH_DEBUG"):
+        sys.stderr.write("PROF-RAW\n" + ctypes_buf.value.decode() + "\n")
     for line in ctypes_buf.value.decode().splitlines():
         name, t, n = line.rsplit(" ", 2)
+        name = name.split("@")[0]
         g = groups.setdefault(name, [0.0, 0])
         g[0] += float(t); g[1] += int(n)
     # untimed extra passes with the listener's GEMM / recurrence overlap switched off (las_debug_set_option(6, 0)): the duration
@@ -448,6 +472,8 @@ def main():
         if r is not None:
             ship(r, 0)
     barrier()
+    flush.zero_()
+    torch.cuda.synchronize()
     t0 = time.perf_counter()
     with torch.cuda.stream(copy_stream):
         xd[0].copy_(x_host, non_blocking=True)
@@ -462,7 +488,8 @@ def main():
                 xd[nxt].copy_(x_host, non_blocking=True)
                 in_ready[nxt].record(copy_stream)
         main.wait_event(in_ready[cur])
-        flush.zero_()  # cold L2 for every step here too; the 256 MiB write (~0.07 ms) is inside this wall-clock region
+        if i:
+            flush.zero_()  # cold L2 for every step here too; the 256 MiB write (~0.07 ms) is inside this wall-clock region
         r = api_step(xd[cur])
         # (pipeline: batch i's input buffer is read by its listener during THIS call's enqueued work; it is reused 3 steps later)
         in_free[cur].record(main)
@@ -563,7 +590,7 @@ def main():
                mode=("serving pipeline (LAS.serve): batch i+1's listener runs under batch i's decoder; K steady-state submissions (each = one "
                      "batch's listener + the previous batch's decoder) timed with one CUDA-event pair, L2-flush writes included")
                if pipe is not None else "LAS.forward batch by batch, CUDA events per step",
-               us_per_decoder_step=1e3 * spl_ms / (n_dec * S * max(1, -(-B // 64))), listener_ms=lis_ms, speller_ms=spl_ms, phase_ms=per_step,
+               ms_each_step=step_ms, us_per_decoder_step=1e3 * spl_ms / (n_dec * S * max(1, -(-B // 64))), listener_ms=lis_ms, speller_ms=spl_ms, phase_ms=per_step,
                clocks=clocks, gpu_launches=launches,
                e2e={"value": e2e_value, "unit": "audio-s/s", "h2d_bytes_per_step": x_host.numel() * 4,
                     "d2h_bytes_per_step": tok_host[0].numel() * 4 + logp_host[0].numel() * 4,

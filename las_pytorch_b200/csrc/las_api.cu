@@ -26,6 +26,7 @@ struct ProfRec {
   int64_t launches0, launches1;
 };
 static thread_local bool g_prof_on = false;
+static thread_local bool g_prof_starts = false;
 static thread_local ProfRec g_prof[4096];
 static thread_local int g_prof_n = 0;
 
@@ -509,6 +510,7 @@ int las_prof_enable(int on) {
   }
   g_prof_n = 0;
   g_prof_on = on != 0;
+  g_prof_starts = on == 2;
   return LAS_OK;
 }
 int las_prof_report(char* buf, size_t buf_bytes) {
@@ -519,8 +521,14 @@ int las_prof_report(char* buf, size_t buf_bytes) {
     float ms = 0.f;
     LAS_CUDA_OK(cudaEventSynchronize(g_prof[i].e1));
     LAS_CUDA_OK(cudaEventElapsedTime(&ms, g_prof[i].e0, g_prof[i].e1));
-    const int n = snprintf(buf + off, buf_bytes - off, "%s %.6f %lld\n", g_prof[i].name, ms,
-                           (long long)(g_prof[i].launches1 - g_prof[i].launches0));
+    int n;
+    if (g_prof_starts) {  // las_prof_enable(2): name@start-offset (ms since the first recorded group) instead of the bare name
+      float t0 = 0.f;
+      cudaEventElapsedTime(&t0, g_prof[0].e0, g_prof[i].e0);
+      n = snprintf(buf + off, buf_bytes - off, "%s@%.3f %.6f %lld\n", g_prof[i].name, t0, ms, (long long)(g_prof[i].launches1 - g_prof[i].launches0));
+    } else {
+      n = snprintf(buf + off, buf_bytes - off, "%s %.6f %lld\n", g_prof[i].name, ms, (long long)(g_prof[i].launches1 - g_prof[i].launches0));
+    }
     if (n < 0 || (size_t)n >= buf_bytes - off) return fail(LAS_ENOMEM, "report buffer too small");
     off += n;
   }
