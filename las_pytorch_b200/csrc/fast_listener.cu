@@ -722,7 +722,7 @@ static int rec_fuse(RecParams& rp, const las_listener_dims* d, const ListenerPac
 static int launch_rec_bc(const RecParams& rp, int bc, cudaStream_t st, bool exclusive) {
   if (rp.Kx > 0) {  // fused input projection (layer 0)
     if (bc == 16) return launch_rec<16, 1, true>(rp, st, exclusive);
-    if (bc == 32) return launch_rec<32, 2, true>(rp, st, exclusive);
+    if (bc == 32) return launch_rec<32, 1, true>(rp, st, exclusive);
     return launch_rec<64, 1, true>(rp, st, exclusive);
   }
   if (bc == 16) {
@@ -731,7 +731,9 @@ static int launch_rec_bc(const RecParams& rp, int bc, cudaStream_t st, bool excl
     if (nacc == 2) return launch_rec<16, 2, false>(rp, st, exclusive);
     return launch_rec<16, 4, false>(rp, st, exclusive);
   }
-  if (bc == 32) return launch_rec<32, 2, false>(rp, st, exclusive);
+  // one accumulator chain for every chunk size: an utterance's result must not depend on how its batch is sharded (the chunk size
+  // follows the batch size), so all variants accumulate in the same order
+  if (bc == 32) return launch_rec<32, 1, false>(rp, st, exclusive);
   return launch_rec<64, 1, false>(rp, st, exclusive);
 }
 

@@ -81,6 +81,13 @@ class _Cache:
         self.lock = threading.Lock()
         self.enqueue_locks = {}
 
+    # copy.deepcopy(model) / pickling a module (torch.save(model)) must not drag device buffers or locks along: a copy starts empty
+    def __deepcopy__(self, memo):
+        return _Cache()
+
+    def __reduce__(self):
+        return (_Cache, ())
+
     def enqueue_lock(self, device):
         """Held while one forward's kernels are being enqueued: the workspace of a (module, device, stream) is reused by every call,
         which is only safe if two host threads never interleave their launches on it (the work itself is asynchronous; the lock

@@ -239,3 +239,11 @@ def test_packed_weight_cache_keys_follow_the_tensors_handed_to_the_pack_call():
     assert cache.lookup(dev, 0, k1, False) == "image"                   # ... and a device replaces only its own
     cache.invalidate()
     assert cache.lookup(dev, 0, k1, False) is None
+    # modules stay deep-copyable and picklable (EMA copies, torch.save(model)): a copied cache starts empty
+    import copy
+    import pickle
+
+    cache.store(dev, 0, k1, "image")
+    las2 = copy.deepcopy(las)
+    assert las2.speller._cache is not las.speller._cache and las2.speller._cache.packed == {}
+    assert pickle.loads(pickle.dumps(cache)).packed == {}
