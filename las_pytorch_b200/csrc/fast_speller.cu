@@ -98,6 +98,7 @@ struct DecParams {
   int ab_flags;     // test hook (las_debug_set_option(5, v)): bit 0 = W_phi from shared memory instead of registers; bit 2 (value 4) = eight 2-D copies per activation part instead of one 3-D copy; bit 5 (value 32) = query GEMV after a CTA-wide barrier (8 lanes per output) instead of per-warp partials; bit 6 (value 64) = LSTM epilogue stores one row per thread from the registers instead of staging + coalesced rows; bit 9 (value 512) = context UMMA descriptors rebuilt per instruction instead of advanced by constants
   unsigned long long sample_seed;  // LAS_DECODE_SAMPLE
   int word_gather;  // 1: the fed-back word is an index (greedy argmax / gt_index); 0: a dense vector (part 1b)
+  int lstm_ts;      // 1: LSTM CTAs use the weights-stationary operand roles (lstm_role_ts); 0: lstm_role
   int ctx_tmem;     // > 0: enc[b]^T is resident in the attention CTA's tensor memory and the context is a UMMA
   int ctx_ntm;      // 128-feature tiles of enc[b]^T held in tensor memory: E/128 = all of them; fewer (long encoders, e.g. U = 375:
                     // 2 of 4) = hybrid, the remaining features are reduced on the CUDA cores from the L2-resident bf16 copy
@@ -495,6 +496,341 @@ __device__ void lstm_role(const DecParams& p, uint8_t* smem, int l, int nb) {
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// LSTM role, weights-stationary operand roles ("TS form")
+// ------------------------------------------------------------------------------------------------------------
+// Same CTA, same data flow and hand-offs as lstm_role, but the two GEMM operands trade places on the critical part:
+//     D[gate row (64 of the 128 TMEM lanes), batch (N = 64)] = W_slice[64(128), K] . act[batch, K]^T
+// so that the layer's critical input weights (context / lower-layer h part, K = 512 -> 256 tensor-memory columns) are the A operand
+// IN TENSOR MEMORY: a tcgen05.mma with A in TMEM issues at its ~32-cycle math floor (N = 64), against ~57 cycles when both
+// operands come from shared memory (tools/microbench.cu: the shared-memory A read is exposed).  The part's 32 instructions were
+// ~1.05 us of each layer's critical path; here ~0.55 us.  The own-h part (ready long before it is needed) stays in the
+// shared-memory form with the same operand roles, so both parts land in accumulators of the same orientation.
+// M = 128 although a CTA owns only 64 gate rows: lanes 64..127 hold zeros / read the atom behind (the instruction costs the same
+// for M = 64 and 128), which keeps the plain lane = row layout.
+// Epilogue: thread = gate row (lane; unit-major / gate-minor, so the four gates of a unit sit in four adjacent lanes), 16 batch
+// columns per warp; a 4x4 transpose inside each 4-lane group (two shuffle stages, as in the listener's recurrence) leaves every
+// lane with (i, f, g, o) of one (unit, batch) cell -- 4 cells per thread, cell state in registers.
+__device__ void lstm_role_ts(const DecParams& p, uint8_t* smem, int l, int nb) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool first = (l == 0), top = (l == p.sl - 1);
+  const int nh = (p.Hs + 63) / 64;
+  const int nc = first ? (p.E + 63) / 64 : (p.Hs + 63) / 64;
+  const int nwd = first ? 1 : 0;
+  const int natoms = nh + nwd + nc;
+  const int NBUF = p.nstages, STAGE_BYTES = p.stage_bytes;
+  const int wslot = NBUF - 1;
+  uint8_t* abuf = smem;                                  // NBUF x STAGE_BYTES activation slots ([64 batch rows x 64 k], SW128)
+  uint8_t* wsm = abuf + (size_t)NBUF * STAGE_BYTES;      // natoms x 8 KB weight atoms ([64 gate rows x 64 k], SW128)
+  float* bias_s = reinterpret_cast<float*>(wsm + (size_t)natoms * WATOM_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(bias_s + DEC_NW);
+  uint64_t* full = bars;
+  uint64_t* part_empty = bars + DEC_MAX_STAGES;
+  uint64_t* tmem_full = part_empty + 1;
+  uint64_t* tmem_empty = tmem_full + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 1);
+  float* s_st = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_slot + 2) + 15) & ~uintptr_t(15));  // [64 batch rows][20]
+  constexpr int EPI_WARPS = 8, EPI_THREADS = EPI_WARPS * 32, PROD_WARP = 2, MMA_WARP = 3;
+  // tensor-memory map: critical weights [0, nc*32), accumulator of the own-h part, accumulator of the critical part (64 columns each)
+  const uint32_t a_cols = (uint32_t)nc * 32u, acc0 = a_cols, acc1 = a_cols + 64u;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < NBUF; ++i) ptx::mbar_init(&full[i], 1);
+    ptx::mbar_init(part_empty, 1);
+    ptx::mbar_init(tmem_full, 1);
+    ptx::mbar_init(tmem_empty, EPI_THREADS);
+    ptx::fence_mbar_init();
+  }
+  if (warp == MMA_WARP) ptx::tmem_alloc(tmem_slot, 512);
+  {  // weight slice + bias -> shared memory
+    const uint4* src = reinterpret_cast<const uint4*>(p.w_img[l] + (size_t)nb * natoms * WATOM_BYTES);
+    uint4* dst = reinterpret_cast<uint4*>(wsm);
+    for (int i = threadIdx.x; i < natoms * WATOM_BYTES / 16; i += DEC_THREADS) dst[i] = src[i];
+    if (threadIdx.x < DEC_NW) bias_s[threadIdx.x] = p.bias[l][nb * DEC_NW + threadIdx.x];
+  }
+  ptx::fence_proxy_async();
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  if (warp < 4) {
+    // critical-part weights: shared-memory atoms (128-byte swizzle undone) -> tensor memory, lane = gate row, two bf16 per column
+    const int row = warp * 32 + lane;
+    const uint8_t* wc = wsm + (size_t)(nh + nwd) * WATOM_BYTES;
+    for (int i = 0; i < nc; ++i) {
+      const uint8_t* rb = wc + (size_t)i * WATOM_BYTES + (row >> 3) * 1024 + (row & 7) * 128;
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+        uint4 q0 = make_uint4(0, 0, 0, 0), q1 = q0;
+        if (row < DEC_NW) {
+          q0 = *reinterpret_cast<const uint4*>(rb + (((2 * kk) ^ (row & 7)) << 4));
+          q1 = *reinterpret_cast<const uint4*>(rb + (((2 * kk + 1) ^ (row & 7)) << 4));
+        }
+        const uint32_t v[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+        ptx::tmem_st_32x32b_x8(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)i * 32u + (uint32_t)kk * 8u, v);
+      }
+    }
+    ptx::tmem_st_wait();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const int S = p.steps;
+  uint32_t* my_ready = counter(p, l);
+  const int trole = (nb == 0 && l == 0) ? 0 : ((nb == 0 && top) ? 1 : -1);
+
+  if (warp == PROD_WARP) {
+    // ============================ TMA producer (as in lstm_role) ============================
+    const uint32_t* own_ctr = counter(p, l);
+    const uint32_t* in_ctr = first ? counter(p, CTR_CTX) : counter(p, l - 1);
+    const uint32_t* word_ctr = counter(p, CTR_WORD);
+    int n = 0;
+    for (int s = 0; s < S; ++s) {
+      const int par = s & 1;
+      if (n > 0) ptx::mbar_wait(part_empty, (uint32_t)((n - 1) & 1));
+      ++n;
+      if (lane == 0) wait_counter(own_ctr, (uint32_t)s * p.ncl);
+      __syncwarp();
+      fence_proxy_async_global();
+      if (ptx::elect_one()) {
+        ptx::mbar_arrive_expect_tx(&full[0], nh * STAGE_BYTES);
+        ptx::tma_load_3d(abuf, &p.tm_h3[l][par], &full[0], 0, 0, 0);
+      }
+      __syncwarp();
+      ptx::mbar_wait(part_empty, (uint32_t)((n - 1) & 1));
+      ++n;
+      if (ptx::elect_one()) ptx::mbar_arrive_expect_tx(&full[0], nc * STAGE_BYTES);
+      __syncwarp();
+      if (lane == 0) {
+        wait_counter(in_ctr, first ? (uint32_t)s * p.B : (uint32_t)(s + 1) * p.ncl);
+        if (trole >= 0) DEC_TRACE(trole, 0);
+        DEC_TRACE_ALL(0);
+      }
+      __syncwarp();
+      fence_proxy_async_global();
+      if (lane == 0 && trole >= 0) DEC_TRACE(4, 6 + trole);
+      {
+        const CUtensorMap* tm3 = first ? &p.tm_x3[par] : &p.tm_h3[l - 1][par ^ 1];
+        if (ptx::elect_one()) ptx::tma_load_3d(abuf, tm3, &full[0], 0, 0, 0);
+        __syncwarp();
+      }
+      if (lane == 0 && trole >= 0) DEC_TRACE(trole, 1);
+      if (first && (p.s0 + s == 0 || !p.word_gather)) {
+        if (lane == 0) wait_counter(word_ctr, (uint32_t)s * p.B);
+        __syncwarp();
+        fence_proxy_async_global();
+        if (ptx::elect_one()) {
+          ptx::mbar_arrive_expect_tx(&full[wslot], STAGE_BYTES);
+          ptx::tma_load_2d(abuf + (size_t)wslot * STAGE_BYTES, &p.tm_w[par], &full[wslot], 0, 0);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp == MMA_WARP) {
+    // ============================ MMA issuer ============================
+    const UmmaLayout lact{1, 0, 1024, (uint32_t)STAGE_BYTES}, lw{1, 0, 1024, WATOM_BYTES};
+    const uint32_t idesc = umma_idesc_bf16(128, 64);  // M = 128 gate-row lanes (64 used), N = 64 batch columns
+    const uint32_t a0 = ptx::smem_u32(abuf), w_addr = ptx::smem_u32(wsm);
+    uint32_t phase0 = 0, phasew = 0;
+    for (int s = 0; s < S; ++s) {
+      const bool wd = first && (p.s0 + s == 0 || !p.word_gather);
+      ptx::mbar_wait(tmem_empty, (uint32_t)((s & 1) ^ 1));
+      ptx::tc_fence_after();
+      // ---- part 0: own h_{s-1}; both operands from shared memory (weights = A, activations = B)
+      ptx::mbar_wait(&full[0], phase0);
+      phase0 ^= 1u;
+      ptx::tc_fence_after();
+      if (ptx::elect_one()) {
+        for (int i = 0; i < nh; ++i) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            ptx::umma_bf16(tmem + acc0, umma_smem_desc(lw, w_addr + i * WATOM_BYTES, k * 16), umma_smem_desc(lact, a0 + i * STAGE_BYTES, k * 16),
+                           idesc, !(i == 0 && k == 0));
+        }
+        ptx::umma_commit(part_empty);
+      }
+      __syncwarp();
+      if (lane == 0 && trole >= 0) DEC_TRACE(trole, 6);
+      // ---- part 1: the critical input; weights from tensor memory, activations from shared memory.  Lean loop: the A operand
+      // advances 8 columns per instruction, the B descriptor 32 bytes inside an atom and one slot between atoms.
+      ptx::mbar_wait(&full[0], phase0);
+      phase0 ^= 1u;
+      ptx::tc_fence_after();
+      if (lane == 0 && trole >= 0) DEC_TRACE(4, 3 + 2 * trole);
+      if (ptx::elect_one()) {
+        uint32_t a = tmem;
+        uint64_t bd_atom = umma_smem_desc(lact, a0, 0);
+        const uint64_t atom_step = (uint64_t)(STAGE_BYTES >> 4);
+        for (int i = 0; i < nc; ++i) {
+          uint64_t bd = bd_atom;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            ptx::umma_bf16_ts(tmem + acc1, a, bd, idesc, !(i == 0 && k == 0));
+            a += 8;
+            bd += 2;
+          }
+          bd_atom += atom_step;
+        }
+        if (!wd) {
+          ptx::umma_commit(part_empty);
+          ptx::umma_commit(tmem_full);
+        }
+      }
+      __syncwarp();
+      if (wd) {  // dense word vector (first step, decode_mode 0, dense teacher forcing): its atom, shared-memory form
+        ptx::mbar_wait(&full[wslot], phasew);
+        phasew ^= 1u;
+        ptx::tc_fence_after();
+        if (ptx::elect_one()) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            ptx::umma_bf16(tmem + acc1, umma_smem_desc(lw, w_addr + nh * WATOM_BYTES, k * 16), umma_smem_desc(lact, a0 + wslot * STAGE_BYTES, k * 16),
+                           idesc, 1u);
+          ptx::umma_commit(part_empty);
+          ptx::umma_commit(tmem_full);
+        }
+        __syncwarp();
+      }
+      if (lane == 0 && trole >= 0) DEC_TRACE(trole, 2);
+    }
+  } else if ((warp & 3) < 2) {
+    // ============================ epilogue: gates, cell state, h ============================
+    const int q = warp & 3, cs = warp >> 2;        // TMEM lane quadrant (gate rows 32q..32q+31), batch slice [16cs, 16cs+16)
+    const int row = q * 32 + lane;                 // gate row of this CTA = 4 * unit + gate
+    const int jj = row >> 2, g = row & 3;
+    const bool bit0 = (g & 1) != 0, bit1 = (g & 2) != 0;
+    const int u = nb * DEC_UNITS + jj;             // hidden unit
+    const bool lead = (warp == 0 && lane == 0);
+    const bool warp_live = cs * 16 < p.B;
+    float c[4];
+    int bm[4];
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+      bm[m] = cs * 16 + 4 * m + g;                 // this thread's cell m: (unit u, batch bm[m])
+      c[m] = (bm[m] < p.B && p.c_init) ? p.c_init[((size_t)l * p.c_init_rows + p.c_init_b0 + bm[m]) * p.Hs + u] : 0.f;
+    }
+    const float4 bias4 = *reinterpret_cast<const float4*>(bias_s + 4 * jj);
+    const uint8_t* watom = wsm + (size_t)nh * WATOM_BYTES;  // layer 0: word atom [64 gate rows x 64 vocabulary entries]
+    for (int s = 0; s < S; ++s) {
+      // bias + (index word) the token's column of W_word for this unit's four gate rows, per cell -- before the accumulators are ready.
+      // The warp's 16 batches are polled by 16 lanes (ONE L2 round trip; four dependent polls per thread cost ~2.4 us and made the
+      // token the critical path) and handed to the cells' owners by shuffles.
+      float4 pb[4];
+      int tokl = -1;
+      const bool gather = first && p.s0 + s > 0 && p.word_gather;
+      if (gather) {
+        const int bb = cs * 16 + (lane & 15);
+        if (bb < p.B)
+          tokl = p.gt_index ? p.gt_index[(size_t)(p.b0 + bb) * p.gt_steps + (p.s0 + s - 1)]
+                            : (s > 0 ? (int)ll_wait(p.tok_ll + (size_t)nb * p.B + bb, (uint32_t)s) : p.tok_init[bb]);
+      }
+#pragma unroll
+      for (int m = 0; m < 4; ++m) {
+        pb[m] = bias4;
+        const int tok = __shfl_sync(0xffffffffu, tokl, 4 * m + g);
+        if (gather && tok >= 0 && tok < p.V) {
+          const uint32_t tok_off = (uint32_t)(tok & 7) * 2u, tok_chunk = (uint32_t)(tok >> 3);
+          float wv[4];
+#pragma unroll
+          for (int gg = 0; gg < 4; ++gg) {
+            const uint32_t rr = (uint32_t)(4 * jj + gg);
+            const uint32_t off = (rr >> 3) * 1024u + (rr & 7u) * 128u + (((tok_chunk ^ (rr & 7u)) & 7u) << 4) + tok_off;
+            wv[gg] = __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(watom + off));
+          }
+          pb[m].x += wv[0]; pb[m].y += wv[1]; pb[m].z += wv[2]; pb[m].w += wv[3];
+        }
+      }
+      if (lead && trole == 0) DEC_TRACE(4, 1);
+      ptx::mbar_wait(tmem_full, (uint32_t)(s & 1));
+      if (lead && trole >= 0) DEC_TRACE(trole, 3);
+      if (lead) DEC_TRACE_ALL(1);
+      ptx::tc_fence_after();
+      float h[4] = {0.f, 0.f, 0.f, 0.f};
+      if (warp_live) {
+        uint32_t x0[16], x1[16];
+        ptx::tmem_ld_32x32b_x16(tmem + ((uint32_t)(q * 32) << 16) + acc0 + cs * 16, x0);
+        ptx::tmem_ld_32x32b_x16(tmem + ((uint32_t)(q * 32) << 16) + acc1 + cs * 16, x1);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+          // lane g holds its gate's pre-activations for batches 4m..4m+3 of the slice; after the 4x4 transpose inside the 4-lane
+          // group it holds all four gates (i,f,g,o) of batch 4m+g
+          float v0 = __uint_as_float(x0[4 * m]) + __uint_as_float(x1[4 * m]), v1 = __uint_as_float(x0[4 * m + 1]) + __uint_as_float(x1[4 * m + 1]),
+                v2 = __uint_as_float(x0[4 * m + 2]) + __uint_as_float(x1[4 * m + 2]), v3 = __uint_as_float(x0[4 * m + 3]) + __uint_as_float(x1[4 * m + 3]);
+          {
+            const float s01 = bit0 ? v0 : v1, s23 = bit0 ? v2 : v3;
+            const float r01 = __shfl_xor_sync(0xffffffffu, s01, 1), r23 = __shfl_xor_sync(0xffffffffu, s23, 1);
+            v0 = bit0 ? r01 : v0; v1 = bit0 ? v1 : r01;
+            v2 = bit0 ? r23 : v2; v3 = bit0 ? v3 : r23;
+          }
+          {
+            const float s02 = bit1 ? v0 : v2, s13 = bit1 ? v1 : v3;
+            const float r02 = __shfl_xor_sync(0xffffffffu, s02, 2), r13 = __shfl_xor_sync(0xffffffffu, s13, 2);
+            v0 = bit1 ? r02 : v0; v2 = bit1 ? v2 : r02;
+            v1 = bit1 ? r13 : v1; v3 = bit1 ? v3 : r13;
+          }
+          const float pi = v0 + pb[m].x, pf = v1 + pb[m].y, pg = v2 + pb[m].z, po = v3 + pb[m].w;
+          const float cn = sigmoid_fast(pf) * c[m] + sigmoid_fast(pi) * tanh_fast(pg);
+          c[m] = cn;
+          h[m] = sigmoid_fast(po) * tanh_fast(cn);
+        }
+      }
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(tmem_empty);
+      const int np = (s + 1) & 1;
+      // hand-off: the 64 x 16 block through shared memory ([batch row][20 floats]), then whole rows per warp (as in lstm_role)
+      if (warp_live) {
+#pragma unroll
+        for (int m = 0; m < 4; ++m) s_st[bm[m] * 20 + jj] = h[m];
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      const int r0 = (cs * 2 + q) * 8;  // this warp's 8 rows
+      if (top) {
+        const uint32_t tag = (uint32_t)(s + 1);
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+          const int rw = r0 + hf * 4 + (lane >> 3), piece = lane & 7;
+          if (rw < p.B) {
+            const float2 v = *reinterpret_cast<const float2*>(s_st + rw * 20 + piece * 2);
+            ll_store2(p.h_ll + (size_t)rw * p.Hs + nb * DEC_UNITS + piece * 2, ll_pack(__float_as_uint(v.x), tag), ll_pack(__float_as_uint(v.y), tag));
+          }
+        }
+      }
+      if (lane < 16) {
+        const int rw = r0 + (lane >> 1), hf = lane & 1;
+        if (rw < p.B) {
+          const float4 y0 = *reinterpret_cast<const float4*>(s_st + rw * 20 + hf * 8), y1 = *reinterpret_cast<const float4*>(s_st + rw * 20 + hf * 8 + 4);
+          const __nv_bfloat162 t0 = __floats2bfloat162_rn(y0.x, y0.y), t1 = __floats2bfloat162_rn(y0.z, y0.w);
+          const __nv_bfloat162 t2 = __floats2bfloat162_rn(y1.x, y1.y), t3 = __floats2bfloat162_rn(y1.z, y1.w);
+          *reinterpret_cast<uint4*>(p.hbuf[l][np] + (size_t)rw * p.Hs + nb * DEC_UNITS + hf * 8) =
+              make_uint4(*reinterpret_cast<const uint32_t*>(&t0), *reinterpret_cast<const uint32_t*>(&t1),
+                         *reinterpret_cast<const uint32_t*>(&t2), *reinterpret_cast<const uint32_t*>(&t3));
+        }
+      }
+      if (s == S - 1) {
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+          if (bm[m] < p.B) {
+            if (p.h_out) p.h_out[((size_t)l * p.Bfull + p.b0 + bm[m]) * p.Hs + u] = h[m];
+            if (p.c_out) p.c_out[((size_t)l * p.c_out_rows + p.c_out_b0 + bm[m]) * p.Hs + u] = c[m];
+          }
+        }
+      }
+      if (lead && trole >= 0) DEC_TRACE(trole, 4);
+      if (lead) DEC_TRACE_ALL(2);
+      asm volatile("bar.sync 1, 256;" ::: "memory");  // all rows stored; the release below is cumulative over the barrier
+      if (lead) {
+        red_release_add(my_ready, 1u);
+        if (trole >= 0) DEC_TRACE(trole, 5);
+        DEC_TRACE_ALL(3);
+      }
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == MMA_WARP) ptx::tmem_dealloc(tmem, 512);
+}
+
+// ------------------------------------------------------------------------------------------------------------
 // attention role (one utterance)
 // ------------------------------------------------------------------------------------------------------------
 // padded psi row (floats): KS % 32 == 8, so that the 8 lanes of a quarter warp (4 encoder steps x 2 halves, 16-byte
@@ -846,14 +1182,16 @@ __device__ void attention_role(const DecParams& p, uint8_t* smem, int b) {
       }
       __syncwarp();
     }
-    // The h half of the logits is evaluated together with the context half, AFTER the context has been published.  It used to run
-    // on warps 1.. while the context UMMAs were in flight, but since those are issued from four warps they finish (~0.9 us) before
-    // that GEMV did, and the publish waited for it: -0.22 us/step (ab_flags bit 12 restores the old order for A/B runs).  The
-    // fed-back token still reaches layer 0 before its MMAs finish.
-    const bool late_h = hybrid || !(p.ab_flags & 4096);
-    if (warp != 0 && !late_h) {
+    // The h half of the logits is evaluated together with the context half, AFTER the context has been published ("late"): the
+    // context UMMAs (four issuing warps) finish in ~0.9 us, sooner than a GEMV squeezed in next to them, and the publish must not
+    // wait for it.  ab_flags bit 12 (4096) selects the alternative for A/B runs: warps 0-3 -- the issuers, one per TMEM lane
+    // quadrant -- read the context out and publish it on their own named barrier while warps 4-15 evaluate the h half
+    // (measured 0.2 us/step slower: that GEMV is bound by the shared-memory pipe and delays the context half behind it).
+    const bool split_h = !hybrid && ntm > 0 && (E >> 3) <= 128 && (p.ab_flags & 4096);
+    const bool late_h = !split_h;
+    if (split_h && warp >= 4) {
       const int part = tid & 15;
-      for (int v = (tid - 32) >> 4; v < Vp; v += (DEC_THREADS - 32) / 16) {
+      for (int v = (tid - 128) >> 4; v < Vp; v += (DEC_THREADS - 128) / 16) {
         float acc = 0.f;
         if (v < V) {
           const uint4* wr = reinterpret_cast<const uint4*>(s_wcd + (size_t)v * WCS);
@@ -907,12 +1245,12 @@ __device__ void attention_role(const DecParams& p, uint8_t* smem, int b) {
         dst[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
       }
     }
-    if (ntm > 0) {
+    if (ntm > 0 && (!split_h || warp < 4)) {
       ptx::mbar_wait(ctx_bar, (uint32_t)(s & 1));
       ptx::tc_fence_after();
       if (tid == 0 && b == 0 && !hybrid) DEC_TRACE(2, 3);
       const int qd = warp & 3;
-      for (int t = warp >> 2; t < ntm; t += NWARP / 4) {
+      for (int t = split_h ? 0 : (warp >> 2); t < ntm; t += split_h ? 1 : NWARP / 4) {
         const uint32_t r = ptx::tmem_ld_32x32b_x1(tmem + ((uint32_t)(qd * 32) << 16) + ntm * CU + t * 16);
         ptx::tmem_ld_wait();
         const int e = t * 128 + qd * 32 + lane;
@@ -933,7 +1271,11 @@ __device__ void attention_role(const DecParams& p, uint8_t* smem, int b) {
         if (last && p.ctx_out) p.ctx_out[(size_t)gb * E + e_cc + ee] = acc;
       }
     }
-    __syncthreads();
+    if (split_h) {
+      if (warp < 4) asm volatile("bar.sync 3, 128;" ::: "memory");  // s_ctx complete: written by warps 0-3 only
+    } else {
+      __syncthreads();
+    }
     // publish the context row (bf16) with 16-byte stores from the first E/8 threads -- few, sector-filling writes keep the
     // release short -- then release: layer 0 starts its context GEMM while the character distribution is evaluated here
     {
@@ -958,6 +1300,7 @@ __device__ void attention_role(const DecParams& p, uint8_t* smem, int b) {
       }
     }
 
+    if (split_h) __syncthreads();  // s_ctx (warps 0-3) and the h half of the logits (warps 4-15) are both in place
     if (p.attn && (tid & 1) == 0) {  // attention record (:292, returned to the caller): off the critical path, after the publish
 #pragma unroll
       for (int ps = 0; ps < ATT_MAXP; ++ps) {
@@ -966,10 +1309,13 @@ __device__ void attention_role(const DecParams& p, uint8_t* smem, int b) {
       }
     }
 
-    // ---- E: logits = W_cd . [h || context] + b_cd: the context half, 16 lanes per output  (:181)
-    {
+    // ---- E: logits = W_cd . [h || context] + b_cd, 16 lanes per output  (:181).  Warp 0 has just issued the release of the context
+    // (its thread 0 stalls ~0.4 us on it), so it takes no part: warps 1-15 hold the 30 output groups, synchronise among themselves
+    // (named barrier, 480 threads) and warp 1 goes on to the feedback; warp 0 only waits for them before it touches the next step's h.
+    constexpr int FW = 1;  // the warp that evaluates the feedback (phase F)
+    if (warp != 0) {
       const int part = tid & 15;
-      for (int v = tid >> 4; v < Vp; v += DEC_THREADS / 16) {
+      for (int v = (tid - 32) >> 4; v < Vp; v += (DEC_THREADS - 32) / 16) {
         float acc = 0.f;
         if (v < V) {
           const uint4* wr = reinterpret_cast<const uint4*>(s_wcd + (size_t)v * WCS);
@@ -992,13 +1338,16 @@ __device__ void attention_role(const DecParams& p, uint8_t* smem, int b) {
         acc += __shfl_xor_sync(0xffffffffu, acc, 8);
         if (part == 0 && v < V) s_logit[v] = late_h ? acc + s_bcd[v] : s_logit[v] + acc;
       }
+      asm volatile("bar.sync 4, %0;" ::"n"(DEC_THREADS - 32) : "memory");   // logits complete (warps 1-15)
+      asm volatile("bar.arrive 5, %0;" ::"n"(DEC_THREADS) : "memory");      // ... and s_h / s_ctx no longer read: warp 0 may move on
+    } else {
+      asm volatile("bar.sync 5, %0;" ::"n"(DEC_THREADS) : "memory");
     }
-    __syncthreads();
-    if (tid == 0 && b == 0) DEC_TRACE(2, 5);
+    if (tid == FW * 32 && b == 0) DEC_TRACE(2, 5);
 
-    // ---- F: warp 0: log_softmax (:182), argmax / teacher forcing (:216-227), the word fed back (:236).  The other
+    // ---- F: warp FW: log_softmax (:182), argmax / teacher forcing (:216-227), the word fed back (:236).  The other
     //         warps go straight on to poll for the next step's h.
-    if (warp == 0) {
+    if (warp == FW) {
       // Greedy feedback first: argmax(log_softmax(z)) = argmax(z), so the token leaves for layer 0 (whose epilogue needs it
       // ~2.5 us after the context was published) before the log-sum-exp, the log-prob stores and the loss term are done.
       const bool early_tok = p.word_gather && !p.gt_index && !p.gt_dense && p.decode_mode != LAS_DECODE_SAMPLE;
@@ -1079,7 +1428,10 @@ __global__ void __launch_bounds__(DEC_THREADS, 1) speller_decode_persistent_kern
   uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
   const int n_lstm = p.sl * p.ncl;
   if (p.stop && *reinterpret_cast<const volatile int32_t*>(p.stop) != 0) return;  // written before this launch: every CTA sees the same value
-  if ((int)blockIdx.x < n_lstm) lstm_role(p, smem, blockIdx.x / p.ncl, blockIdx.x % p.ncl);
+  if ((int)blockIdx.x < n_lstm) {
+    if (p.lstm_ts) lstm_role_ts(p, smem, blockIdx.x / p.ncl, blockIdx.x % p.ncl);
+    else lstm_role(p, smem, blockIdx.x / p.ncl, blockIdx.x % p.ncl);
+  }
   else attention_role(p, smem, blockIdx.x - n_lstm);
 }
 
@@ -1362,6 +1714,9 @@ int fast_speller_decode_segment(const las_decode_io* io, const void* packed_f32,
       LAS_TRY(make_tmap_bf16_box(&p.tm_w[k], w.wbuf[k], Bc, DEC_VP, DEC_VP, rc.box_rows));
     }
     p.tma3d = (d->Hs % 64 == 0 && d->E % 64 == 0 && !(g_dec_ab_flags & 4)) ? 1 : 0;
+    // weights-stationary LSTM CTAs: whole 64-wide atoms, one 3-D copy per part, critical weights within 384 tensor-memory columns
+    // (ab_flags bit 14 = 16384 selects the round-1 operand roles for A/B runs)
+    p.lstm_ts = (p.tma3d && d->Hs <= 768 && d->E <= 768 && !(g_dec_ab_flags & 16384)) ? 1 : 0;
     if (p.tma3d) {
       for (int l = 0; l < d->sl; ++l)
         for (int k = 0; k < 2; ++k) LAS_TRY(make_tmap_bf16_atoms(&p.tm_h3[l][k], w.hbuf[l][k], Bc, d->Hs / 64, d->Hs, rc.box_rows, d->Hs / 64));
