@@ -99,6 +99,8 @@ struct DecParams {
   unsigned long long sample_seed;  // LAS_DECODE_SAMPLE
   int word_gather;  // 1: the fed-back word is an index (greedy argmax / gt_index); 0: a dense vector (part 1b)
   int lstm_ts;      // 1: LSTM CTAs use the weights-stationary operand roles (lstm_role_ts); 0: lstm_role
+  int att_split;    // 2: every utterance is attended by a CLUSTER of two CTAs, each holding half of the encoder steps (long encoders:
+                    // all of enc[b]^T stays in tensor memory; partial softmax / context combined through DSMEM); 1: one CTA
   int ctx_tmem;     // > 0: enc[b]^T is resident in the attention CTA's tensor memory and the context is a UMMA
   int ctx_ntm;      // 128-feature tiles of enc[b]^T held in tensor memory: E/128 = all of them; fewer (long encoders, e.g. U = 375:
                     // 2 of 4) = hybrid, the remaining features are reduced on the CUDA cores from the L2-resident bf16 copy
@@ -610,7 +612,11 @@ __device__ void lstm_role_ts(const DecParams& p, uint8_t* smem, int l, int nb) {
       if (lane == 0 && trole >= 0) DEC_TRACE(4, 6 + trole);
       {
         const CUtensorMap* tm3 = first ? &p.tm_x3[par] : &p.tm_h3[l - 1][par ^ 1];
-        if (ptx::elect_one()) ptx::tma_load_3d(abuf, tm3, &full[0], 0, 0, 0);
+        if (ptx::elect_one()) {
+          if (trole == 0) DEC_TRACE(4, 0);
+          ptx::tma_load_3d(abuf, tm3, &full[0], 0, 0, 0);
+          if (trole == 0) DEC_TRACE(4, 2);
+        }
         __syncwarp();
       }
       if (lane == 0 && trole >= 0) DEC_TRACE(trole, 1);
@@ -842,10 +848,10 @@ __host__ __device__ inline int att_kstride(int D) {
 }
 struct AttLayout {
   int WPS, WCS, KS, Up;
-  size_t o_wcd, o_h, o_hw, o_qp, o_q, o_score, o_logit, o_bphi, o_bcd, o_red, o_part, o_bop, o_k, total;
+  size_t o_wcd, o_h, o_hw, o_qp, o_q, o_score, o_logit, o_bphi, o_bcd, o_red, o_part, o_bop, o_xchg, o_k, total;
 };
 __host__ __device__ inline size_t att_bop_bytes(int U) { return (size_t)((U + 15) / 16) * 512 + 16; }
-__host__ __device__ inline AttLayout att_layout(int Hs, int E, int U, int D, int V, bool k_in, bool wreg, bool hybrid = false) {
+__host__ __device__ inline AttLayout att_layout(int Hs, int E, int U, int D, int V, bool k_in, bool wreg, bool hybrid = false, bool split = false) {
   AttLayout a;
   a.WPS = Hs + 8;          // bf16 row strides: multiples of 8 keep every 16-byte chunk aligned
   a.WCS = Hs + E + 8;
@@ -866,20 +872,32 @@ __host__ __device__ inline AttLayout att_layout(int Hs, int E, int U, int D, int
   a.o_red = take(64 * 4);
   a.o_part = take(4096 * 4);                           // context partial sums, or {mbarrier, TMEM slot, score operand}
   a.o_bop = hybrid ? take(att_bop_bytes(U)) : a.o_part; // hybrid context path: both at once
+  // split attention: {2 mbarriers} + own partial [E + 4] + receive buffers [2 step parities][E + 4] floats
+  a.o_xchg = split ? take(32 + (size_t)3 * (E + 4) * 4) : o;
   a.o_k = o;
   if (k_in) take((size_t)U * a.KS * 4);
   a.total = o;
   return a;
 }
 
-__device__ void attention_role(const DecParams& p, uint8_t* smem, int b) {
+// Half of the encoder steps one CTA of a split pair holds: a whole number of 16-step UMMA K blocks
+__host__ __device__ inline int att_split_half(int U) { return ((U + 1) / 2 + 15) / 16 * 16; }
+
+__device__ void attention_role(const DecParams& p, uint8_t* smem, int b, int rank) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr int NWARP = DEC_THREADS / 32;
-  const int Hs = p.Hs, E = p.E, U = p.U, D = p.D, V = p.V, KC = p.Hs + p.E;
+  const bool split = p.att_split == 2;
+  // Split attention (cluster of two CTAs per utterance): this CTA sees only the encoder steps [ub, ub + U) -- "U" below is the LOCAL
+  // count; `Ulay` (the first half's size) sizes the shared-memory layout of both ranks.
+  const int Utot = p.U;
+  const int Ulay = split ? att_split_half(Utot) : Utot;
+  const int ub = (split && rank) ? Ulay : 0;
+  const int U = split ? (rank ? Utot - Ulay : Ulay) : Utot;
+  const int Hs = p.Hs, E = p.E, D = p.D, V = p.V, KC = p.Hs + p.E;
   const int NT = E / 128;                                     // feature tiles
   const int ntm = p.ctx_tmem ? p.ctx_ntm : 0;                 // ... of which in tensor memory
   const bool hybrid = ntm > 0 && ntm * 128 < E;               // (E need not be a multiple of 128 when ntm = 0)
-  const AttLayout L = att_layout(Hs, E, U, D, V, p.k_in_smem != 0, p.wreg != 0, hybrid);
+  const AttLayout L = att_layout(Hs, E, Ulay, D, V, p.k_in_smem != 0, p.wreg != 0, hybrid, split);
   const int KS = L.KS, WPS = L.WPS, WCS = L.WCS;
   const int gb = p.b0 + b;  // utterance index in the caller's tensors
   __nv_bfloat16* s_wphi = reinterpret_cast<__nv_bfloat16*>(smem);               // [D][WPS]
@@ -917,15 +935,22 @@ __device__ void attention_role(const DecParams& p, uint8_t* smem, int b) {
   for (int i = tid; i < KS; i += DEC_THREADS) s_q[i] = 0.f;
   for (int i = tid; i < D; i += DEC_THREADS) s_bphi[i] = p.b_phi[i];
   for (int i = tid; i < V; i += DEC_THREADS) s_bcd[i] = p.b_cd[i];
-  const float* psib = p.psi + (size_t)gb * U * D;
+  const float* psib = p.psi + ((size_t)gb * Utot + ub) * D;
   if (p.k_in_smem) {
     for (int i = tid; i < U * KS; i += DEC_THREADS) {
       const int u = i / KS, d = i % KS;
       s_k[i] = d < D ? psib[(size_t)u * D + d] : 0.f;
     }
   }
-  const int ulen = p.enc_lengths ? min(max(p.enc_lengths[gb], 1), U) : U;
-  const __nv_bfloat16* encb = p.enc + (size_t)b * U * E;
+  const int ulen_tot = p.enc_lengths ? min(max(p.enc_lengths[gb], 1), Utot) : Utot;
+  const int ulen = min(max(ulen_tot - ub, 0), U);  // (a split pair's second CTA may have nothing valid: its partial sums are zero)
+  const __nv_bfloat16* encb = p.enc + ((size_t)b * Utot + ub) * E;
+  // split attention: exchange area.  Each CTA writes its partial {context[E], max, sum} into its own `s_own` and into the PEER's
+  // receive buffer of the step's parity (st.shared::cluster), one remote mbarrier arrive per warp.
+  uint64_t* xbar = reinterpret_cast<uint64_t*>(smem + L.o_xchg);                 // [2]
+  float* s_own = reinterpret_cast<float*>(smem + L.o_xchg + 32);                 // [E + 4]
+  float* s_recv = s_own + (E + 4);                                               // [2][E + 4]
+  const uint32_t peer = (uint32_t)(rank ^ 1);
   uint32_t* ctx_ctr = counter(p, CTR_CTX);
   uint32_t* word_ctr = counter(p, CTR_WORD);
   uint32_t tmem = 0;
@@ -934,6 +959,10 @@ __device__ void attention_role(const DecParams& p, uint8_t* smem, int b) {
     // columns (two bf16 per 32-bit column) = the A operand of  ctx^T[E,1] = enc^T[E,U] . score[U,1]
     if (tid == 0) {
       ptx::mbar_init(ctx_bar, (uint32_t)niss);
+      if (split) {
+        ptx::mbar_init(&xbar[0], NWARP);
+        ptx::mbar_init(&xbar[1], NWARP);
+      }
       ptx::fence_mbar_init();
     }
     if (warp == 0) ptx::tmem_alloc(tmem_slot, 512);
@@ -961,6 +990,7 @@ __device__ void attention_role(const DecParams& p, uint8_t* smem, int b) {
     ptx::tc_fence_before();
   }
   __syncthreads();
+  if (split) ptx::cluster_sync();  // the peer's exchange barriers are initialised before anything is sent to them
   ptx::tc_fence_after();
 
   const int hchunks = Hs >> 3, kchunks = KC >> 3;  // 16-byte chunks (8 bf16) of a W_phi row / W_cd row
@@ -1074,6 +1104,7 @@ __device__ void attention_role(const DecParams& p, uint8_t* smem, int b) {
     //         steps (:292) with one exchange of warp maxima and one of warp sums
     float ev[ATT_MAXP];
     float lmax = -INFINITY;
+    float m_loc = -INFINITY;  // this CTA's maximum energy (split attention: exchanged with the peer)
     {
       const int half = tid & 1;
 #pragma unroll
@@ -1115,6 +1146,7 @@ __device__ void attention_role(const DecParams& p, uint8_t* smem, int b) {
         m = fmaxf(fmaxf(fmaxf(a.x, a.y), fmaxf(a.z, a.w)), fmaxf(fmaxf(b4.x, b4.y), fmaxf(b4.z, b4.w)));
         m = fmaxf(m, fmaxf(fmaxf(fmaxf(c4.x, c4.y), fmaxf(c4.z, c4.w)), fmaxf(fmaxf(d4.x, d4.y), fmaxf(d4.z, d4.w))));
       }
+      m_loc = m;
       // p[u] = exp(e[u] - max) goes to the context reduction unnormalised (bf16 operand of the UMMA / fp32 for the
       // CUDA-core path); the sum arrives through the same barrier and the 1/sum scaling is applied to the context
       float lsum = 0.f;
@@ -1137,11 +1169,12 @@ __device__ void attention_role(const DecParams& p, uint8_t* smem, int b) {
     __syncthreads();
     if (tid == 0 && b == 0) { DEC_TRACE(3, 6); DEC_TRACE(2, 2); }
     if (tid == 0) DEC_TRACE_ALL(1);
-    float inv;
+    float inv, sum_loc;
     {
       const float4* r4 = reinterpret_cast<const float4*>(s_red + 16);
       const float4 a = r4[0], b4 = r4[1], c4 = r4[2], d4 = r4[3];
-      inv = 1.0f / (((a.x + a.y) + (a.z + a.w)) + ((b4.x + b4.y) + (b4.z + b4.w)) + ((c4.x + c4.y) + (c4.z + c4.w)) + ((d4.x + d4.y) + (d4.z + d4.w)));
+      sum_loc = ((a.x + a.y) + (a.z + a.w)) + ((b4.x + b4.y) + (b4.z + b4.w)) + ((c4.x + c4.y) + (c4.z + c4.w)) + ((d4.x + d4.y) + (d4.z + d4.w));
+      inv = split ? 1.0f : 1.0f / sum_loc;  // split attention: the partial context stays unnormalised until the two halves are combined
     }
 
     // ---- D: context[e] = sum_u score[u] * enc[b,u,e]  (:293-297); warps 1.. meanwhile evaluate the h half of the
@@ -1187,7 +1220,8 @@ __device__ void attention_role(const DecParams& p, uint8_t* smem, int b) {
     // wait for it.  ab_flags bit 12 (4096) selects the alternative for A/B runs: warps 0-3 -- the issuers, one per TMEM lane
     // quadrant -- read the context out and publish it on their own named barrier while warps 4-15 evaluate the h half
     // (measured 0.2 us/step slower: that GEMV is bound by the shared-memory pipe and delays the context half behind it).
-    const bool split_h = !hybrid && ntm > 0 && (E >> 3) <= 128 && (p.ab_flags & 4096);
+    const bool split_h = !split && !hybrid && ntm > 0 && (E >> 3) <= 128 && (p.ab_flags & 4096);
+    const bool owner = !split || rank == 0;  // of a split pair only the first CTA publishes the context and evaluates the logits / feedback
     const bool late_h = !split_h;
     if (split_h && warp >= 4) {
       const int part = tid & 15;
@@ -1255,10 +1289,43 @@ __device__ void attention_role(const DecParams& p, uint8_t* smem, int b) {
         ptx::tmem_ld_wait();
         const int e = t * 128 + qd * 32 + lane;
         const float cv = __uint_as_float(r) * inv;
-        s_ctx[xpos(e)] = cv;
-        if (last && p.ctx_out) p.ctx_out[(size_t)gb * E + e] = cv;
+        if (split) {  // partial context: own copy + the peer's receive buffer of this step's parity
+          s_own[e] = cv;
+          asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(ptx::mapa(ptx::smem_u32(s_recv + (size_t)(s & 1) * (E + 4) + e), peer)), "f"(cv) : "memory");
+        } else {
+          s_ctx[xpos(e)] = cv;
+          if (last && p.ctx_out) p.ctx_out[(size_t)gb * E + e] = cv;
+        }
       }
       ptx::tc_fence_before();
+      if (split) {
+        if (tid == 0) {  // this half's softmax statistics travel with warp 0's arrive
+          s_own[E] = m_loc;
+          s_own[E + 1] = sum_loc;
+          const uint32_t dst = ptx::mapa(ptx::smem_u32(s_recv + (size_t)(s & 1) * (E + 4) + E), peer);
+          asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(dst), "f"(m_loc) : "memory");
+          asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(dst + 4), "f"(sum_loc) : "memory");
+        }
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive_remote(ptx::mapa(ptx::smem_u32(&xbar[s & 1]), peer));  // release.cluster: cumulative over the warp's stores
+      }
+    }
+    float att_scale = inv;  // factor that turns exp(e - local max) into the attention weight
+    if (split) {
+      // combine the two halves: M = max(m0, m1), w_r = exp(m_r - M), S = s0 w0 + s1 w1, context = (c0 w0 + c1 w1) / S
+      ptx::mbar_wait_cluster(&xbar[s & 1], (uint32_t)((s >> 1) & 1));
+      __syncthreads();  // own partial complete as well
+      const float* rv = s_recv + (size_t)(s & 1) * (E + 4);
+      const float m_peer = rv[E], s_peer = rv[E + 1];
+      const float M = fmaxf(m_loc, m_peer);
+      const float w_own = (m_loc == -INFINITY) ? 0.f : __expf(m_loc - M), w_peer = (m_peer == -INFINITY) ? 0.f : __expf(m_peer - M);
+      const float rS = 1.0f / (sum_loc * w_own + s_peer * w_peer);
+      att_scale = w_own * rS;
+      for (int e = tid; e < E; e += DEC_THREADS) {
+        const float cv = (s_own[e] * w_own + rv[e] * w_peer) * rS;
+        s_ctx[xpos(e)] = cv;
+        if (rank == 0 && last && p.ctx_out) p.ctx_out[(size_t)gb * E + e] = cv;
+      }
     }
     if (Ec > 0) {
       __syncthreads();
@@ -1278,7 +1345,7 @@ __device__ void attention_role(const DecParams& p, uint8_t* smem, int b) {
     }
     // publish the context row (bf16) with 16-byte stores from the first E/8 threads -- few, sector-filling writes keep the
     // release short -- then release: layer 0 starts its context GEMM while the character distribution is evaluated here
-    {
+    if (owner) {
       const int npub = E >> 3, nsync = (npub + 31) & ~31;
       if (tid < nsync) {
         if (tid < npub) {
@@ -1305,7 +1372,7 @@ __device__ void attention_role(const DecParams& p, uint8_t* smem, int b) {
 #pragma unroll
       for (int ps = 0; ps < ATT_MAXP; ++ps) {
         const int u = ps * 256 + (tid >> 1);
-        if (u < U) p.attn[((size_t)(p.s0 + s) * p.Bfull + gb) * U + u] = ev[ps] * inv;
+        if (u < U) p.attn[((size_t)(p.s0 + s) * p.Bfull + gb) * Utot + ub + u] = ev[ps] * att_scale;
       }
     }
 
@@ -1313,6 +1380,7 @@ __device__ void attention_role(const DecParams& p, uint8_t* smem, int b) {
     // (its thread 0 stalls ~0.4 us on it), so it takes no part: warps 1-15 hold the 30 output groups, synchronise among themselves
     // (named barrier, 480 threads) and warp 1 goes on to the feedback; warp 0 only waits for them before it touches the next step's h.
     constexpr int FW = 1;  // the warp that evaluates the feedback (phase F)
+    if (!owner) continue;
     if (warp != 0) {
       const int part = tid & 15;
       for (int v = (tid - 32) >> 4; v < Vp; v += (DEC_THREADS - 32) / 16) {
@@ -1417,6 +1485,7 @@ __device__ void attention_role(const DecParams& p, uint8_t* smem, int b) {
   if (p.ctx_tmem) {
     ptx::tc_fence_before();
     __syncthreads();
+    if (split) ptx::cluster_sync();  // no CTA leaves while its peer could still write into its receive buffers
     if (warp == 0) ptx::tmem_dealloc(tmem, 512);
   }
 }
@@ -1432,7 +1501,8 @@ __global__ void __launch_bounds__(DEC_THREADS, 1) speller_decode_persistent_kern
     if (p.lstm_ts) lstm_role_ts(p, smem, blockIdx.x / p.ncl, blockIdx.x % p.ncl);
     else lstm_role(p, smem, blockIdx.x / p.ncl, blockIdx.x % p.ncl);
   }
-  else attention_role(p, smem, blockIdx.x - n_lstm);
+  else if (p.att_split == 2) attention_role(p, smem, (blockIdx.x - n_lstm) >> 1, (blockIdx.x - n_lstm) & 1);
+  else attention_role(p, smem, blockIdx.x - n_lstm, 0);
 }
 
 // ---- pack kernels ------------------------------------------------------------------------------------------
@@ -1532,7 +1602,30 @@ RingCfg ring_cfg(const las_speller_dims* d, int rows) {
   return r;
 }
 bool att_wreg(const las_speller_dims* d) { return d->D <= DEC_THREADS / 8 && d->Hs <= 512 && !(g_dec_ab_flags & 1); }
-size_t att_smem(const las_speller_dims* d, bool k_in, bool hybrid = false) { return att_layout(d->Hs, d->E, d->U, d->D, d->V, k_in, att_wreg(d), hybrid).total + 64; }
+size_t att_smem(const las_speller_dims* d, bool k_in, bool hybrid = false, bool split = false) {
+  return att_layout(d->Hs, d->E, split ? att_split_half(d->U) : d->U, d->D, d->V, k_in, att_wreg(d), hybrid, split).total + 64;
+}
+int g_dec_att_split = 1;  // las_debug_set_option(11, v): 1 = split long encoders over a 2-CTA cluster (default), 0 = never
+// Tensor-memory geometry of the context path for `U` encoder steps per CTA: feature tiles of enc^T that fit the 512 columns
+int ctx_tiles_fit(int U, int E) {
+  if (E % 128 != 0) return 0;
+  const int nks = (U + 15) / 16, NT = E / 128;
+  int ntm = 512 / (nks * 8 + 16);
+  if (ntm > NT) ntm = NT;
+  if (ntm == NT && att_bop_bytes(U) > 4096 * 4) ntm = 0;
+  return ntm;
+}
+// Long encoders: when one CTA cannot hold all of enc[b]^T in tensor memory but half of the encoder steps fit (U <= 448 at E = 512),
+// a cluster of two CTAs attends each utterance (flash-decoding style partial softmax, combined through DSMEM) -- provided the LSTM
+// CTAs pair up (even count) and the chip has room for two attention CTAs per utterance.
+bool att_split_ok(const las_speller_dims* d) {
+  if (!g_dec_att_split || g_dec_ctx_tmem <= 0 || d->E % 128 != 0) return false;
+  const int NT = d->E / 128;
+  if (ctx_tiles_fit(d->U, d->E) == NT) return false;  // one CTA is enough
+  const int n_lstm = d->sl * (d->Hs / DEC_UNITS);
+  return ctx_tiles_fit(att_split_half(d->U), d->E) == NT && (n_lstm % 2 == 0) && n_lstm + 2 <= sm_count() &&
+         att_smem(d, true, false, true) <= 220 * 1024;
+}
 int supported(const las_speller_dims* d) {
   LAS_REQUIRE(d->sl <= MAX_SL, "LAS_MODE_BF16 speller supports at most %d layers (sl=%d)", MAX_SL, d->sl);
   LAS_REQUIRE(d->Hs % 16 == 0 && d->Hs <= 512, "LAS_MODE_BF16 speller needs hidden_size %% 16 == 0 and <= 512 (Hs=%d); use LAS_MODE_FP32", d->Hs);
@@ -1615,6 +1708,7 @@ bool fast_speller_fits(const las_speller_dims* d) {
 void fast_set_option_speller(int key, int value) {
   if (key == 2) g_dec_ctx_tmem = value;
   if (key == 5) g_dec_ab_flags = value;
+  if (key == 11) g_dec_att_split = value;
 }
 
 size_t fast_speller_packed_bytes(const las_speller_dims* d) { return pack_layout(d, nullptr).bytes; }
@@ -1679,17 +1773,17 @@ int fast_speller_decode_segment(const las_decode_io* io, const void* packed_f32,
     p.steps = s_count; p.s0 = s_begin; p.decode_mode = decode_mode; p.relu = relu; p.gt_steps = io->gt_steps; p.ncl = s.ncl;
     p.wreg = att_wreg(d) ? 1 : 0;
     p.k_in_smem = att_smem(d, true) <= 220 * 1024;
-    {
-      const int nks = (d->U + 15) / 16, NT = d->E / 128;
+    p.att_split = att_split_ok(d) ? 2 : 1;
+    if (p.att_split == 2) {
+      p.ctx_ntm = d->E / 128;
+      p.ctx_tmem = 1;
+      p.k_in_smem = 1;
+    } else {
+      const int NT = d->E / 128;
       // all feature tiles of enc[b]^T in tensor memory when they fit its 512 columns (U <= 224 at E = 512); otherwise as many
       // as fit, the rest on the CUDA cores (hybrid; needs the score operand in its own shared-memory region)
-      int ntm = 0;
-      if (d->E % 128 == 0 && g_dec_ctx_tmem > 0) {
-        ntm = 512 / (nks * 8 + 16);
-        if (ntm > NT) ntm = NT;
-        if (ntm == NT && att_bop_bytes(d->U) > 4096 * 4) ntm = 0;
-        if (ntm < NT && (g_dec_ctx_tmem == 2 || (512 % ((d->E - ntm * 128) / 8)) != 0)) ntm = 0;  // option 2: value 2 = no hybrid
-      }
+      int ntm = g_dec_ctx_tmem > 0 ? ctx_tiles_fit(d->U, d->E) : 0;
+      if (ntm > 0 && ntm < NT && (g_dec_ctx_tmem == 2 || (512 % ((d->E - ntm * 128) / 8)) != 0)) ntm = 0;  // option 2: value 2 = no hybrid
       p.ctx_ntm = ntm;
       p.ctx_tmem = ntm > 0;
       const bool hyb = ntm > 0 && ntm < NT;
@@ -1768,19 +1862,26 @@ int fast_speller_decode_segment(const las_decode_io* io, const void* packed_f32,
                                   relu != 0));
     }
     ProfScope ps("speller.steps", st);
-    const size_t smem_l = rc.smem, smem_a = att_smem(d, p.k_in_smem != 0, p.ctx_ntm > 0 && p.ctx_ntm < d->E / 128);
+    const size_t smem_l = rc.smem, smem_a = att_smem(d, p.k_in_smem != 0, p.ctx_ntm > 0 && p.ctx_ntm < d->E / 128, p.att_split == 2);
     const size_t smem = (smem_l > smem_a ? smem_l : smem_a) + 1024;
     LAS_CUDA_OK(cudaFuncSetAttribute(speller_decode_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(n_lstm + Bc);
+    cfg.gridDim = dim3(n_lstm + p.att_split * Bc);
     cfg.blockDim = dim3(DEC_THREADS);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
-    cudaLaunchAttribute at[1];
+    cudaLaunchAttribute at[2];
     at[0].id = cudaLaunchAttributeCooperative;
     at[0].val.cooperative = 1;
     cfg.attrs = at;
     cfg.numAttrs = 1;
+    if (p.att_split == 2) {  // pairs of consecutive CTAs form clusters (the LSTM CTAs' pairing is not used)
+      at[1].id = cudaLaunchAttributeClusterDimension;
+      at[1].val.clusterDim.x = 2;
+      at[1].val.clusterDim.y = 1;
+      at[1].val.clusterDim.z = 1;
+      cfg.numAttrs = 2;
+    }
     LAS_CUDA_OK(cudaLaunchKernelEx(&cfg, speller_decode_persistent_kernel, p));
     count_launch();
   }
@@ -1790,11 +1891,13 @@ int fast_speller_decode_segment(const las_decode_io* io, const void* packed_f32,
 int fast_speller_max_group(const las_speller_dims* d) {
   const Shape s = shape_of(d);
   const int n_lstm = d->sl * s.ncl, nsm = sm_count();
-  // utterances per persistent launch: one attention CTA each, and at most 64 (activation slots hold 64 batch rows)
-  return (nsm - n_lstm) < 64 ? (nsm - n_lstm) : 64;
+  // utterances per persistent launch: one attention CTA each (two for split attention), and at most 64 (activation slots hold
+  // 64 batch rows)
+  const int per = att_split_ok(d) ? 2 : 1;
+  return (nsm - n_lstm) / per < 64 ? (nsm - n_lstm) / per : 64;
 }
 
-int fast_speller_ctas(const las_speller_dims* d) { return d->sl * shape_of(d).ncl + d->B; }
+int fast_speller_ctas(const las_speller_dims* d) { return d->sl * shape_of(d).ncl + (att_split_ok(d) ? 2 : 1) * d->B; }
 
 // <eos> bookkeeping of one launch group between / after its segments (io->early_exit)
 int fast_speller_eos_begin(const las_speller_dims* d, int Bc, void* ws_fast, cudaStream_t st) {

@@ -329,20 +329,3 @@ def label_smoothing_loss(logp_bsv, onehot_bsv, label_smoothing=0.1):
     smooth = ((1.0 - label_smoothing) * true_y + (label_smoothing / class_dim)) * true_y.sum(-1, keepdims=True)
     return float(-np.mean(((smooth * logp_bsv).sum(-1) / seq_len).sum(-1)))
 
-
-# ---- solver epilogue ("next" row f1) ------------------------------------------------------------------------
-def label_smoothing_loss(logp, onehot, label_smoothing=0.1):
-    """solver/solver.py:33-45: logp [B,S,V] log-probs, onehot [B,S,V] (padding rows all zero or one-hot(0))."""
-    logp, onehot = np.asarray(logp, np.float64), np.asarray(onehot, np.float64)
-    rows = onehot.sum(-1, keepdims=True)
-    seq_len = rows.sum(1)                                             # [B,1]
-    smooth = ((1.0 - label_smoothing) * onehot + label_smoothing / onehot.shape[-1]) * rows
-    return float(-np.mean(((smooth * logp).sum(-1) / seq_len).sum(-1)))
-
-
-def nll_ignore0(logp, labels):
-    """nn.NLLLoss(ignore_index=0) as solver/solver.py:62,70-77 applies it: mean of -logp[b,s,label] over labels != 0."""
-    logp, labels = np.asarray(logp, np.float64), np.asarray(labels)
-    picked = np.take_along_axis(logp, labels[..., None].astype(np.int64), axis=-1)[..., 0]
-    keep = labels != 0
-    return float(-(picked * keep).sum() / keep.sum())

@@ -13,7 +13,7 @@ tests/test_oracle_golden.py; model/las_model.py:81-91,178-238,275-297).  Per wor
     margin below the 4e-3 log-prob error bf16 operands cause) and the utterance follows another trajectory.  That is a property
     of bf16 GEMM operands, not of these kernels: the REFERENCE's own op sequence with nothing but its 2-D weights rounded to bf16
     (fp32 arithmetic everywhere) agrees with itself on 0.86 of the characters at c3.  The test therefore computes that number on
-    the spot (`reference_bf16_weights_agreement`) and requires ours to be no worse than it minus 0.05, and >= 0.99 wherever the
+    the spot (`reference_bf16_weights_agreement`) and requires ours to be no worse than it minus 0.05 (1.5/B at small batches), and >= 0.99 wherever the
     rounded reference reaches it; every step of the trajectory we DO follow is held to 2e-2 by the re-scoring check below.
   * re-scoring: the reference, teacher-forced on OUR greedy tokens, reproduces our greedy log-probs within the tolerance
     (checks every step of the trajectory we actually followed, including after a near-tie flip)
@@ -122,7 +122,9 @@ def test_parity_at_benchmark_shape(wl, precision):
     assert safe.mean() >= (0.9 if precision == "fp32" else 0.4) and tf_argmax_safe_ok, rep
     assert rescore_err <= tol["logp"], rep
     assert np.abs(np.exp(logp_gr).sum(-1) - 1).max() < 1e-4 and np.abs(attn.sum(-1) - 1).max() < 1e-4
-    floor = tol["greedy"] if precision == "fp32" else min(tol["greedy"], r["bf16w_agree"] - 0.05)
+    # (slack: 0.05, or 1.5 utterances' worth at small batches -- one utterance that leaves the reference's trajectory early moves the
+    # agreement by up to 1/B)
+    floor = tol["greedy"] if precision == "fp32" else min(tol["greedy"], r["bf16w_agree"] - max(0.05, 1.5 / B))
     assert agree >= floor, rep
     # up to its first divergence every utterance IS the reference's trajectory; utterances that never diverge are identical
     assert (per_utt[first_div == S] == 1.0).all()

@@ -207,7 +207,7 @@ def test_oracle_solver_losses_match_the_reference_values():
     for ls in (0.1, 0.3):
         assert abs(O.label_smoothing_loss(logp, zero_pad, ls) - float(g[f"ls_zero_pad_{ls}"])) < 1e-5
         assert abs(O.label_smoothing_loss(logp, pad0, ls) - float(g[f"ls_pad0_{ls}"])) < 1e-5
-    assert abs(O.nll_ignore0(logp, lab0) - float(g["nll_ignore0"])) < 1e-5
+    assert abs(O.nll_loss_ignore0(logp, lab0) - float(g["nll_ignore0"])) < 1e-5
     assert np.allclose(our_solver.LetterErrorRate(logp.argmax(-1), lab0), g["ler"])
 
 

@@ -342,35 +342,55 @@ def test_bf16_decoder_single_3d_copy_matches_per_atom_copies():
     assert torch.isfinite(p3).all()
 
 
-def test_bf16_long_encoder_hybrid_context_path():
-    """Long encoders (BASELINE config 4: 3000 frames -> U = 375): enc[b]^T no longer fits the attention CTA's tensor memory, so
-    two of the four 128-feature tiles are reduced by the UMMA and the other two on the CUDA cores (hybrid).  Teacher-forced
-    log-probs / attention against the fp64 oracle, and against the CUDA-core-only path (las_debug_set_option(2, 0))."""
+def test_bf16_long_encoder_context_paths():
+    """Long encoders (BASELINE config 4: 3000 frames -> U = 375): enc[b]^T no longer fits ONE attention CTA's tensor memory.
+    Default: a cluster of two CTAs attends each utterance, each with half of the encoder steps fully in tensor memory, partial
+    softmax / context combined through DSMEM (las_debug_set_option(11, 1)).  Alternatives kept for A/B and for shapes the split does
+    not cover: hybrid (two of the four 128-feature tiles on the UMMA, two on the CUDA cores; option 11 = 0) and CUDA cores only
+    (option 2 = 0).  All three against the fp64 oracle -- teacher forced, with a length mask that leaves the second CTA of some
+    pairs nothing to attend, and free running -- and against each other."""
     if "bf16" not in precisions():
         pytest.skip("bf16 path not built")
     from las_pytorch_b200 import _cabi
 
     lib = _cabi.load_library()
     c = tl.CONFIGS["paper"]
-    B, T, S = 3, 3000, 12
+    B, T, S = 5, 3000, 12
     las = tl.build_model("paper", max_label_len=S, seed=71, gain=3.0, precision="bf16")
     sd = tl.state_dict_numpy(las)
     x, labels = tl.make_inputs(B, T, c["F"], S, c["V"], seed=71)
     ref = O.las_forward(x.numpy(), sd, c["L"], c["sl"], S, ground_truth=labels.numpy(), teacher_forced=True, dtype=np.float64)
     las = las.cuda()
     out = {}
-    for opt in (0, 1):
+    variants = {"split": (11, 1, 2, 1), "hybrid": (11, 0, 2, 1), "cuda_cores": (11, 0, 2, 0)}
+    for name, (k1, v1, k2, v2) in variants.items():
         try:
-            lib.las_debug_set_option(2, opt)
-            out[opt] = run_ours(las, x, labels, c["V"], "tf")
+            lib.las_debug_set_option(k1, v1)
+            lib.las_debug_set_option(k2, v2)
+            out[name] = run_ours(las, x, labels, c["V"], "tf")
         finally:
+            lib.las_debug_set_option(11, 1)
             lib.las_debug_set_option(2, 1)
-    for opt in (0, 1):
-        _, logp, attn = out[opt]
-        assert np.abs(logp - ref["logp"]).max() <= TOL["bf16"]["logp"]
-        assert np.abs(attn - ref["attn"]).max() <= TOL["bf16"]["attn"]
-    assert np.abs(out[0][1] - out[1][1]).max() <= 5e-3       # the two context paths differ only by the bf16 rounding of the scores
-    assert not np.array_equal(out[0][1], out[1][1])          # ... and are indeed different code paths
+    for name in variants:
+        _, logp, attn = out[name]
+        assert np.abs(logp - ref["logp"]).max() <= TOL["bf16"]["logp"], name
+        assert np.abs(attn - ref["attn"]).max() <= TOL["bf16"]["attn"], name
+        assert np.abs(attn.sum(-1) - 1).max() < 1e-4, name
+    assert np.abs(out["cuda_cores"][1] - out["hybrid"][1]).max() <= 5e-3  # the context paths differ only by the bf16 rounding of the scores
+    assert np.abs(out["split"][1] - out["hybrid"][1]).max() <= 5e-3
+    assert not np.array_equal(out["cuda_cores"][1], out["hybrid"][1]) and not np.array_equal(out["split"][1], out["hybrid"][1])
+    # length masks: utterance 1 ends inside the first CTA's half (the second CTA's partial sums are all zero), utterance 2 inside the second's
+    enc = las.listener(x.cuda())
+    lens = torch.tensor([375, 100, 250, 192, 193], dtype=torch.int32)
+    ref_m = O.speller_forward(ref["enc"], sd, c["sl"], S, labels.numpy(), 1, np.float64, enc_lengths=lens.numpy())
+    np.random.seed(0)
+    preds, attns = las.speller(enc, labels.cuda(), 1.1, enc_lengths=lens.cuda())
+    attn_m = torch.stack([a[0] for a in attns]).cpu().numpy()
+    for b_, n in enumerate(lens.tolist()):
+        assert float(np.abs(attn_m[:, b_, n:]).max() if n < 375 else 0.0) == 0.0       # nothing attended past the length
+        assert np.abs(attn_m[:, b_, :n].sum(-1) - 1).max() < 1e-4
+    assert np.abs(torch.stack(preds).cpu().numpy() - ref_m["logp"]).max() <= TOL["bf16"]["logp"]
+    assert np.abs(attn_m - ref_m["attn"]).max() <= TOL["bf16"]["attn"]
     _, logp_g, _ = run_ours(las, x, labels, c["V"], "greedy")
     assert np.isfinite(logp_g).all() and np.abs(np.exp(logp_g).sum(-1) - 1).max() < 1e-4
 

@@ -51,6 +51,7 @@ def main():
         print("   att fine (rel. h arrived): " + "  ".join(f"{n}={int(t[3, s, i] - t[3, s, 0])}" for i, n in enumerate(
             ["h", "dot", "shfl", "q sync", "energy", "max sync", "sum sync"])))
         print(f"   L0 epilogue: word column gathered at +{int(t[4, s, 1] - base)} ns")
+        print(f"   L0 producer: elected at +{int(t[4, s, 0] - base)} ns, TMA instruction issued at +{int(t[4, s, 2] - base)} ns")
         print(f"   critical activation part (ns): L0 fenced={int(t[4, s, 6] - base)} landed={int(t[4, s, 3] - base)}  "
               f"L1 fenced={int(t[4, s, 7] - base)} landed={int(t[4, s, 5] - base)}")
         if s == 8:
