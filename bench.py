@@ -451,6 +451,9 @@ def main():
 
     def api_step(x):
         """-> (tokens [S,B] int32, logp [S,B,V]) of a finished batch on the device, or None (pipeline still filling)."""
+        if tf_leg:  # c2: the same two decodes per batch as the device-timed step (listener once, TF + loss, greedy)
+            one_step(x)
+            return las.speller.last_tokens, las.speller.last_logp
         if pipe is None:
             preds, _ = las(x, None, 0.0, is_training=False)
             return las.speller.last_tokens, las.speller.last_logp

@@ -1621,7 +1621,9 @@ int ctx_tiles_fit(int U, int E) {
 bool att_split_ok(const las_speller_dims* d) {
   if (!g_dec_att_split || g_dec_ctx_tmem <= 0 || d->E % 128 != 0) return false;
   const int NT = d->E / 128;
-  if (ctx_tiles_fit(d->U, d->E) == NT) return false;  // one CTA is enough
+  // one CTA is enough ... unless the split is forced (option 11 = 2) or the encoder is long enough that halving the energy /
+  // softmax pass and the context UMMA chains pays for the DSMEM exchange (U > 256: two passes of the 256-step energy loop)
+  if (ctx_tiles_fit(d->U, d->E) == NT && g_dec_att_split != 2 && !(g_dec_att_split == 3 && d->U > 256)) return false;
   const int n_lstm = d->sl * (d->Hs / DEC_UNITS);
   return ctx_tiles_fit(att_split_half(d->U), d->E) == NT && (n_lstm % 2 == 0) && n_lstm + 2 <= sm_count() &&
          att_smem(d, true, false, true) <= 220 * 1024;
