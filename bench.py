@@ -299,6 +299,11 @@ def main():
         las.speller(enc, None, 0.0)
         return las.speller.last_tokens
 
+    if not tf_leg and not use_pipeline:
+        def one_step(x):  # noqa: F811 -- plain LAS.forward (batches beyond one decoder launch group are chunk-pipelined inside it)
+            las(x, None, 0.0, is_training=False)
+            return las.speller.last_tokens
+
     pipe = las.serve() if use_pipeline else None
 
     def timed_step(x):

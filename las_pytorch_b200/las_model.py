@@ -220,6 +220,8 @@ class LAS(nn.Module):
         (utils/data.py:146) and train.py:117 drops it.  When given, the BLSTMs and the attention skip the padding.
         `nll_labels` ([B,S'] label indices; extension) -> `self.speller.last_nll_terms` (see Speller.forward)."""
         enc_lengths = None
+        if not is_training and nll_labels is None and self._chunk_pipelining_applies(batch_data):
+            return self._forward_chunk_pipelined(batch_data, input_lengths)
         if input_lengths is None:
             listener_feature = self.listener(batch_data)
         else:
@@ -233,6 +235,40 @@ class LAS(nn.Module):
             raw_pred_seq, attention_record = self.speller(listener_feature, ground_truth=None, teacher_force_rate=0,
                                                           enc_lengths=enc_lengths, nll_labels=nll_labels)
         return raw_pred_seq, attention_record
+
+    # ---- large free-running batches: the serving pipeline applied INSIDE one forward call ------------------------------------
+    CHUNK = 64  # utterances per persistent decoder launch group (one attention CTA each next to the 64 LSTM CTAs)
+
+    def _chunk_pipelining_applies(self, x):
+        """A free-running batch of more than one decoder launch group (BASELINE config 5: 512 utterances on one GPU) is decoded
+        64 utterances at a time anyway; when the concurrent schedule covers the model, chunk i+1's listener runs under chunk i's
+        decoder.  An utterance's result does not depend on the batch it is in (bit-exact in both modes), so the outputs are the same."""
+        sp, lis = self.speller, self.listener
+        if not x.is_cuda or x.dim() != 3 or x.size(0) <= self.CHUNK or getattr(sp, "early_exit", False):
+            return False
+        if lis.precision != "bf16" or sp.precision != "bf16" or x.size(1) % (1 << lis.num_layers) != 0:
+            return False
+        lib = _cabi.load_library()
+        ld = ListenerDims(self.CHUNK, x.size(1), x.size(2), lis.hidden_size, lis.num_layers, _cabi.CELLS[lis.cell])
+        sd = sp._dims(self.CHUNK, x.size(1) >> lis.num_layers, 2 * lis.hidden_size)
+        return bool(lib.las_pipeline_overlaps(C.byref(ld), C.byref(sd), int(sp.max_label_len), _cabi.MODE_BF16))
+
+    def _forward_chunk_pipelined(self, x, input_lengths):
+        np.random.random_sample()  # Speller.forward's one draw from numpy's global RNG per call (model/las_model.py:189)
+        pipe = ServingPipeline(self, want_attention=True)
+        outs = []
+        for i in range(0, x.size(0), self.CHUNK):
+            r = pipe.submit(x[i:i + self.CHUNK], None if input_lengths is None else input_lengths[i:i + self.CHUNK])
+            if r is not None:
+                outs.append(r)
+        outs.append(pipe.flush())
+        logp = torch.cat([o.logp for o in outs], dim=1)
+        attn = torch.cat([o.attn for o in outs], dim=1)
+        sp = self.speller
+        sp.last_tokens = torch.cat([o.tokens for o in outs], dim=1)
+        sp.last_logp = logp
+        sp.last_nll_terms = sp.last_steps_done = None
+        return list(logp.unbind(0)), [[a] for a in attn.unbind(0)]
 
     def serve(self, want_attention=True):
         """Cross-batch serving pipeline (extension; free-running decoding = the reference's is_training=False path,

@@ -1000,3 +1000,28 @@ def test_bf16_results_do_not_depend_on_the_batch_an_utterance_is_in():
     assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
     parts = torch.cat([lis(x[:7]), lis(x[7:24]), lis(x[24:])], dim=0)
     assert torch.equal(parts, outs[0])
+
+
+def test_large_batch_forward_is_chunk_pipelined_and_identical():
+    """LAS.forward on a free-running batch larger than one decoder launch group (BASELINE config 5) runs chunk i+1's listener under
+    chunk i's decoder; the outputs are bit for bit those of the plain path (forced by `--no-pipeline`-style separate calls)."""
+    if "bf16" not in precisions():
+        pytest.skip("bf16 mode not built")
+    c = tl.CONFIGS["paper"]
+    B, T, S = 150, 256, 16
+    las = tl.build_model("paper", max_label_len=S, seed=17, gain=3.0, precision="bf16").cuda()
+    x, _ = tl.make_inputs(B, T, c["F"], S, c["V"], seed=123)
+    x = x.cuda()
+    assert las._chunk_pipelining_applies(x)
+    np.random.seed(3)
+    preds, attns = las(x, None, 0.0, is_training=False)
+    drawn = np.random.random_sample()
+    tok = las.speller.last_tokens.clone()
+    # the plain path: whole-batch listener, then the decoder in its launch groups
+    enc = las.listener(x)
+    np.random.seed(3)
+    p2, a2 = las.speller(enc, None, 0.0)
+    assert np.random.random_sample() == drawn  # one draw from numpy's global RNG per call either way
+    assert torch.equal(torch.stack(preds), torch.stack(p2))
+    assert torch.equal(torch.stack([a[0] for a in attns]), torch.stack([a[0] for a in a2]))
+    assert torch.equal(tok, las.speller.last_tokens) and tok.shape == (S, B)
