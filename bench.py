@@ -267,6 +267,9 @@ def main():
 
         dist.init_process_group("nccl", device_id=dev)
     lib = _cabi.load_library()
+    if os.environ.get("LAS_PIPE_SPLIT"):  # A/B hook: decoder steps per pipeline segment, e.g. "160,92,48"
+        for l, n in enumerate(os.environ["LAS_PIPE_SPLIT"].split(",")):
+            lib.las_debug_set_option(20 + l, int(n))
     precision = args.precision or ("bf16" if lib.las_mode_available(_cabi.MODE_BF16) else "fp32")
     c = tl.CONFIGS[wl["cfg"]]
     T, S = wl["T"], wl["S"]

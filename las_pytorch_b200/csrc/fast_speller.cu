@@ -931,15 +931,30 @@ __device__ void attention_role(const DecParams& p, uint8_t* smem, int b, int ran
 
   if (!p.wreg)
     for (int i = tid; i < D * Hs; i += DEC_THREADS) s_wphi[(size_t)(i / Hs) * WPS + (i % Hs)] = p.w_phi[i];
-  for (int i = tid; i < V * KC; i += DEC_THREADS) s_wcd[(size_t)(i / KC) * WCS + (i % KC)] = p.w_cd[i];
+  // (prologue copies are vectorised: a segmented decode -- serving pipeline, <eos> early exit -- pays this prologue once per segment)
+  if ((KC & 7) == 0) {
+    const int rc8 = KC >> 3;  // 16-byte chunks per W_cd row; the padded row stride WCS keeps them aligned
+    for (int i = tid; i < V * rc8; i += DEC_THREADS)
+      *reinterpret_cast<uint4*>(s_wcd + (size_t)(i / rc8) * WCS + (i % rc8) * 8) = *reinterpret_cast<const uint4*>(p.w_cd + (size_t)(i / rc8) * KC + (i % rc8) * 8);
+  } else {
+    for (int i = tid; i < V * KC; i += DEC_THREADS) s_wcd[(size_t)(i / KC) * WCS + (i % KC)] = p.w_cd[i];
+  }
   for (int i = tid; i < KS; i += DEC_THREADS) s_q[i] = 0.f;
   for (int i = tid; i < D; i += DEC_THREADS) s_bphi[i] = p.b_phi[i];
   for (int i = tid; i < V; i += DEC_THREADS) s_bcd[i] = p.b_cd[i];
   const float* psib = p.psi + ((size_t)gb * Utot + ub) * D;
   if (p.k_in_smem) {
-    for (int i = tid; i < U * KS; i += DEC_THREADS) {
-      const int u = i / KS, d = i % KS;
-      s_k[i] = d < D ? psib[(size_t)u * D + d] : 0.f;
+    if ((D & 3) == 0 && ((reinterpret_cast<uintptr_t>(psib) & 15) == 0)) {  // rows of D floats -> rows of KS floats (zero padded), 16 bytes at a time
+      const int rd4 = D >> 2, rk4 = KS >> 2;
+      for (int i = tid; i < U * rk4; i += DEC_THREADS) {
+        const int u = i / rk4, c4 = i % rk4;
+        reinterpret_cast<float4*>(s_k)[i] = c4 < rd4 ? *reinterpret_cast<const float4*>(psib + (size_t)u * D + 4 * c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    } else {
+      for (int i = tid; i < U * KS; i += DEC_THREADS) {
+        const int u = i / KS, d = i % KS;
+        s_k[i] = d < D ? psib[(size_t)u * D + d] : 0.f;
+      }
     }
   }
   const int ulen_tot = p.enc_lengths ? min(max(p.enc_lengths[gb], 1), Utot) : Utot;
@@ -974,16 +989,23 @@ __device__ void attention_role(const DecParams& p, uint8_t* smem, int b, int ran
     const int qd = warp & 3;
     for (int t = warp >> 2; t < ntm; t += NWARP / 4) {
       const __nv_bfloat16* col = encb + t * 128 + qd * 32 + lane;
-      for (int ks = 0; ks < nks; ++ks) {
-        uint32_t v[8];
+      // four K blocks (64 encoder steps, 64 two-byte loads) in flight per thread: this strided gather is latency-bound and is paid by
+      // every segment of a segmented decode
+      for (int ks0 = 0; ks0 < nks; ks0 += 4) {
+        uint32_t v[4][8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int u0 = ks * 16 + 2 * i;
-          const unsigned short lo = u0 < U ? *reinterpret_cast<const unsigned short*>(col + (size_t)u0 * E) : 0;
-          const unsigned short hi = u0 + 1 < U ? *reinterpret_cast<const unsigned short*>(col + (size_t)(u0 + 1) * E) : 0;
-          v[i] = (uint32_t)lo | ((uint32_t)hi << 16);
+        for (int j = 0; j < 4; ++j) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int u0 = (ks0 + j) * 16 + 2 * i;
+            const unsigned short lo = u0 < U ? *reinterpret_cast<const unsigned short*>(col + (size_t)u0 * E) : 0;
+            const unsigned short hi = u0 + 1 < U ? *reinterpret_cast<const unsigned short*>(col + (size_t)(u0 + 1) * E) : 0;
+            v[j][i] = (uint32_t)lo | ((uint32_t)hi << 16);
+          }
         }
-        ptx::tmem_st_32x32b_x8(tmem + ((uint32_t)(qd * 32) << 16) + t * CU + ks * 8, v);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (ks0 + j < nks) ptx::tmem_st_32x32b_x8(tmem + ((uint32_t)(qd * 32) << 16) + t * CU + (ks0 + j) * 8, v[j]);
       }
     }
     ptx::tmem_st_wait();

@@ -1025,3 +1025,52 @@ def test_large_batch_forward_is_chunk_pipelined_and_identical():
     assert torch.equal(torch.stack(preds), torch.stack(p2))
     assert torch.equal(torch.stack([a[0] for a in attns]), torch.stack([a[0] for a in a2]))
     assert torch.equal(tok, las.speller.last_tokens) and tok.shape == (S, B)
+
+
+@pytest.mark.parametrize("seed", list(range(24)))
+def test_random_shapes_against_the_oracle(seed):
+    """Randomised sweep over the shape space the persistent kernels select their variants from (hidden sizes / 64-wide atoms, batch
+    sizes that leave TMEM lanes and warp slices empty, 1-3 speller layers, vocabularies up to the 64-wide word atom, encoder lengths
+    across the single-CTA / split-attention boundary, odd step counts, segment lengths): both modes against the fp64 oracle,
+    teacher-forced (index and one-hot) plus re-scored free-running decoding, segmented decode bit-identical to one launch."""
+    rng = np.random.RandomState(1000 + seed)
+    H = int(rng.choice([32, 64, 128, 256]))
+    L = int(rng.choice([1, 2, 3]))
+    sl = int(rng.choice([1, 2, 3]))
+    V = int(rng.choice([5, 30, 42, 64]))
+    D = int(rng.choice([16, 40, 64]))
+    B = int(rng.choice([1, 3, 17, 33, 64]))
+    U = int(rng.choice([3, 20, 70, 230, 300])) if H >= 128 else int(rng.choice([3, 20, 70]))
+    if B * U * H > 64 * 120 * 256:  # keep the numpy oracle in seconds
+        B = max(1, (64 * 120 * 256) // (U * H))
+    T = U << L
+    S = int(rng.choice([1, 2, 5, 9]))
+    cfg = dict(F=40, H=H, L=L, sl=sl, V=V, D=D)
+    x, labels = tl.make_inputs(B, T, cfg["F"], S, V, seed=seed)
+    labels = labels % V
+    ref = None
+    for precision in precisions():
+        las = tl.build_model(cfg, max_label_len=S, seed=seed, gain=2.5, precision=precision)
+        sd = tl.state_dict_numpy(las)
+        if ref is None:
+            ref = O.las_forward(x.numpy(), sd, L, sl, S, ground_truth=labels.numpy(), teacher_forced=True, dtype=np.float64)
+        las = las.cuda()
+        tol = TOL[precision]
+        for gt in (labels.cuda(), tl.onehot(labels, V).cuda()):
+            np.random.seed(0)
+            preds, attns = las(x.cuda(), gt, 1.1, is_training=True)
+            logp = torch.stack(preds).cpu().numpy()
+            attn = torch.stack([a[0] for a in attns]).cpu().numpy()
+            assert np.abs(logp - ref["logp"]).max() <= tol["logp"], (cfg, B, U, S, precision)
+            assert np.abs(attn - ref["attn"]).max() <= tol["attn"], (cfg, B, U, S, precision)
+        preds, _ = las(x.cuda(), None, 0.0, is_training=False)
+        logp_g = torch.stack(preds).cpu().numpy()
+        tok = las.speller.last_tokens.cpu().numpy()
+        assert np.array_equal(tok, logp_g.argmax(-1))
+        rescored = O.las_forward(x.numpy(), sd, L, sl, S, ground_truth=tok.T, teacher_forced=True, dtype=np.float64)
+        assert np.abs(logp_g - rescored["logp"]).max() <= tol["logp"], (cfg, B, U, S, precision)
+        if precision == "bf16" and S >= 4:
+            enc = las.listener(x.cuda())
+            one = _decode_kw(las, enc, S)
+            two = _decode_kw(las, enc, S, segment_steps=2)
+            assert all(torch.equal(a, b) for a, b in zip(one, two)), (cfg, B, U, S)
