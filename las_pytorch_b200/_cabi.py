@@ -124,6 +124,11 @@ def load_library(path: str | None = None):
         fn.argtypes = args
     if lib.las_abi_version() != ABI_VERSION:
         raise LasB200Error(f"ABI version mismatch: library reports {lib.las_abi_version()}, binding expects {ABI_VERSION}")
+    # Shared devices: the listener's input-projection GEMM normally runs CONCURRENTLY with its layer's recurrence, which spin-waits
+    # on the GEMM's tile flags -- that needs both kernels co-resident, which CUDA only gives when the SMs the recurrence leaves free
+    # are really free.  LAS_B200_NO_OVERLAP=1 runs the GEMM in front of the recurrence instead (same results, ~10 % slower listener).
+    if os.environ.get("LAS_B200_NO_OVERLAP", "") not in ("", "0"):
+        lib.las_debug_set_option(6, 0)
     if path is None:
         _lib = lib
     return lib
