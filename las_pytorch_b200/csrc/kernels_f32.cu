@@ -240,7 +240,7 @@ __device__ __forceinline__ float block_reduce_sum(float v, float* red) {
   return r;
 }
 
-__global__ void __launch_bounds__(256) attend_f32_kernel(AttendArgs a) {
+__global__ void __launch_bounds__(1024) attend_f32_kernel(AttendArgs a) {
   extern __shared__ float sm[];
   const int NH = a.heads;
   float* s_state = sm;                 // Hs
@@ -309,7 +309,15 @@ __global__ void __launch_bounds__(256) attend_f32_kernel(AttendArgs a) {
     // context[e] = sum_u score[u] * enc[b,u,e]   (:293-297 / :306-312)
     for (int e = tid; e < a.E; e += blockDim.x) {
       float acc = 0.f;
-      for (int u = 0; u < a.U; ++u) acc = fmaf(s_score[u], encb[(size_t)u * a.E + e], acc);
+      int u = 0;
+      for (; u + 8 <= a.U; u += 8) {  // eight rows in flight; the sum keeps its u-ascending order
+        float x[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) x[j] = encb[(size_t)(u + j) * a.E + e];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc = fmaf(s_score[u + j], x[j], acc);
+      }
+      for (; u < a.U; ++u) acc = fmaf(s_score[u], encb[(size_t)u * a.E + e], acc);
       if (NH == 1) {
         s_ctx[e] = acc;
         a.ctx_out[(size_t)b * a.ctx_ld + e] = acc;
@@ -415,7 +423,9 @@ int launch_attend_f32(const AttendArgs& a, cudaStream_t st) {
   if (smem > 48 * 1024) {
     LAS_CUDA_OK(cudaFuncSetAttribute(attend_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   }
-  attend_f32_kernel<<<a.B, 256, smem, st>>>(a);
+  // one CTA per utterance; wide models get more warps (one context feature per thread, more rows of W_phi / W_cd / psi in flight)
+  const int threads = (a.E >= 1024 || a.Hs >= 1024) ? 1024 : (a.E >= 512 ? 512 : 256);
+  attend_f32_kernel<<<a.B, threads, smem, st>>>(a);
   LAS_LAUNCH_OK("attend_f32_kernel");
   return LAS_OK;
 }
@@ -614,33 +624,34 @@ int launch_gen_build_a(const float* x, long long x_ld, const float* h, long long
   LAS_LAUNCH_OK("gen_build_a_kernel");
   return LAS_OK;
 }
-// pre [B, R] (biases included) -> cell update in fp32; h_prev nullable (zeros); c nullable for GRU / RNN
-__global__ void gen_cell_kernel(const float* pre, const float* h_prev, long long h_ld, float* c, float* h_out, long long hout_ld, int B, int H,
-                                int cell) {
+// Gate pre-activations -> cell update in fp32.  pre(b, r) = pre[b * ldb + r * ldr] (+ bias[r] when given): either [B, R] with the
+// biases already added by the GEMM's epilogue (ldb = R, ldr = 1) or the transposed [R, B] a small-batch GEMM writes (ldb = 1, ldr = B).
+// h_prev nullable (zeros); c is not touched for GRU / RNN.
+__global__ void gen_cell_kernel(const float* pre, long long ldb, long long ldr, const float* bias, const float* h_prev, long long h_ld, float* c,
+                                float* h_out, long long hout_ld, int B, int H, int cell) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * H) return;
   const int b = i / H, j = i % H;
-  const int R = (cell == LAS_CELL_RNN) ? H : 4 * H;
-  const float* p = pre + (size_t)b * R;
+  auto P = [&](int r) { return pre[(long long)b * ldb + (long long)r * ldr] + (bias ? bias[r] : 0.f); };
   float h;
   if (cell == LAS_CELL_LSTM) {
-    const float ig = sigmoid_precise(p[j]), fg = sigmoid_precise(p[H + j]), gg = tanhf(p[2 * H + j]), og = sigmoid_precise(p[3 * H + j]);
+    const float ig = sigmoid_precise(P(j)), fg = sigmoid_precise(P(H + j)), gg = tanhf(P(2 * H + j)), og = sigmoid_precise(P(3 * H + j));
     const float cn = fg * c[(size_t)b * H + j] + ig * gg;
     c[(size_t)b * H + j] = cn;
     h = og * tanhf(cn);
   } else if (cell == LAS_CELL_GRU) {
     const float hp = h_prev ? h_prev[(long long)b * h_ld + j] : 0.f;
-    const float rg = sigmoid_precise(p[j]), zg = sigmoid_precise(p[H + j]);
-    const float ng = tanhf(p[2 * H + j] + rg * p[3 * H + j]);
+    const float rg = sigmoid_precise(P(j)), zg = sigmoid_precise(P(H + j));
+    const float ng = tanhf(P(2 * H + j) + rg * P(3 * H + j));
     h = (1.0f - zg) * ng + zg * hp;
   } else {
-    h = tanhf(p[j]);
+    h = tanhf(P(j));
   }
   h_out[(long long)b * hout_ld + j] = h;
 }
-int launch_gen_cell(const float* pre, const float* h_prev, long long h_ld, float* c, float* h_out, long long hout_ld, int B, int H, int cell,
-                    cudaStream_t st) {
-  gen_cell_kernel<<<(B * H + 255) / 256, 256, 0, st>>>(pre, h_prev, h_ld, c, h_out, hout_ld, B, H, cell);
+int launch_gen_cell(const float* pre, long long ldb, long long ldr, const float* bias, const float* h_prev, long long h_ld, float* c, float* h_out,
+                    long long hout_ld, int B, int H, int cell, cudaStream_t st) {
+  gen_cell_kernel<<<(B * H + 255) / 256, 256, 0, st>>>(pre, ldb, ldr, bias, h_prev, h_ld, c, h_out, hout_ld, B, H, cell);
   LAS_LAUNCH_OK("gen_cell_kernel");
   return LAS_OK;
 }

@@ -341,6 +341,7 @@ struct SpellerWsGen {
   __nv_bfloat16* a;    // [B, Kp_max] bf16 GEMM operand of the current layer
   float* pre;          // [B, R] gate pre-activations
   __nv_bfloat16* enc;  // [B*U, E] bf16 copy for the psi GEMM
+  float* zero;         // [256] zeros: the swapped small-batch GEMM's (unused) per-column bias
   size_t bytes;
 };
 static SpellerWsGen speller_ws_layout_gen(const las_speller_dims* d, void* base) {
@@ -350,6 +351,7 @@ static SpellerWsGen speller_ws_layout_gen(const las_speller_dims* d, void* base)
   w.a = cv.take<__nv_bfloat16>((size_t)d->B * g.Kp_max);
   w.pre = cv.take<float>((size_t)d->B * g.R);
   w.enc = cv.take<__nv_bfloat16>(d->no_mlp ? 0 : (size_t)d->B * d->U * d->E);
+  w.zero = cv.take<float>(256);
   w.bytes = cv.total();
   return w;
 }
@@ -370,6 +372,7 @@ static int speller_decode_f32(const las_decode_io* io, const void* packed, const
   if (gen) {
     gp = speller_pack_layout_gen(d, const_cast<void*>(packed_gen));
     gw = speller_ws_layout_gen(d, ws_gen);
+    LAS_CUDA_OK(cudaMemsetAsync(gw.zero, 0, sizeof(float) * 256, st));
   }
   const int B = d->B, Hs = d->Hs, V = d->V, E = d->E, U = d->U, D = d->D, sl = d->sl;
   const int xld = V + E;
@@ -413,8 +416,16 @@ static int speller_decode_f32(const las_decode_io* io, const void* packed, const
         const float* xin_l = (l == 0) ? w.xin : hn + (size_t)(l - 1) * B * Hs;
         const float* hp_l = hp + (size_t)l * B * Hs;
         LAS_TRY(launch_gen_build_a(xin_l, (l == 0) ? xld : Hs, hp_l, Hs, gw.a, B, Hs, gg.Kx[l], gg.Kxp[l], gg.Kp[l], st));
-        LAS_TRY(launch_gemm_bf16_tc(gw.a, gg.Kp[l], gp.w[l], gg.Kp[l], gp.bias[l], gw.pre, gg.R, B, gg.R, gg.Kp[l], st));
-        LAS_TRY(launch_gen_cell(gw.pre, hp_l, Hs, w.c + (size_t)l * B * Hs, hn + (size_t)l * B * Hs, Hs, B, Hs, d->cell, st));
+        if (B <= 64) {
+          // Small batches: the GEMM's 128 x 256 tiles would leave it R/256 CTAs (16 at R = 4096), each streaming 1 MB of weights.  With
+          // the operands swapped -- "M" = the R weight rows, "N" = the batch -- R/128 CTAs stream half as much each; the result arrives
+          // transposed ([R, B]) and the cell kernel adds the bias.
+          LAS_TRY(launch_gemm_bf16_tc(gp.w[l], gg.Kp[l], gw.a, gg.Kp[l], gw.zero, gw.pre, B, gg.R, B, gg.Kp[l], st));
+          LAS_TRY(launch_gen_cell(gw.pre, 1, B, gp.bias[l], hp_l, Hs, w.c + (size_t)l * B * Hs, hn + (size_t)l * B * Hs, Hs, B, Hs, d->cell, st));
+        } else {
+          LAS_TRY(launch_gemm_bf16_tc(gw.a, gg.Kp[l], gp.w[l], gg.Kp[l], gp.bias[l], gw.pre, gg.R, B, gg.R, gg.Kp[l], st));
+          LAS_TRY(launch_gen_cell(gw.pre, gg.R, 1, nullptr, hp_l, Hs, w.c + (size_t)l * B * Hs, hn + (size_t)l * B * Hs, Hs, B, Hs, d->cell, st));
+        }
         continue;
       }
       CellArgs a;

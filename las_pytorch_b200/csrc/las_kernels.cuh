@@ -86,8 +86,8 @@ int launch_gen_pack_w(const float* w_ih, const float* w_hh, const float* b_ih, c
                       int H, int Kx, int Kxp, int Kp, cudaStream_t st);
 int launch_gen_build_a(const float* x, long long x_ld, const float* h, long long h_ld, __nv_bfloat16* A, int B, int H, int Kx, int Kxp, int Kp,
                        cudaStream_t st);
-int launch_gen_cell(const float* pre, const float* h_prev, long long h_ld, float* c, float* h_out, long long hout_ld, int B, int H, int cell,
-                    cudaStream_t st);
+int launch_gen_cell(const float* pre, long long ldb, long long ldr, const float* bias, const float* h_prev, long long h_ld, float* c, float* h_out,
+                    long long hout_ld, int B, int H, int cell, cudaStream_t st);
 
 // <eos> early exit bookkeeping (las_decode_io.early_exit): `state` = 66 int32 {stop, steps decoded, done[64]} per launch group
 int launch_eos_check(const int32_t* tokens, int Bfull, int b0, int Bc, int s_begin, int s_end, int eos, int32_t* state, cudaStream_t st);
