@@ -17,3 +17,5 @@ timeout 600 ncu --set full --clock-control none --import-source on -k regex:lstm
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:gemm_bf16_tc -s 6 -c 3 -f -o gpurun_out/prof_gemm_$TAG \
   python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-gpu-baseline --no-pipeline > gpurun_out/ncu_gemm_$TAG.log 2>&1; echo "ncu gemm rc=$?"
 ls -la gpurun_out | tail -12
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:speller_decode_persistent -s 5 -c 1 -f -o gpurun_out/prof_decoder_c4_$TAG \
+  python bench.py --workload c4 --steps 1 --warmup 3 --no-cpu-baseline --no-gpu-baseline --no-pipeline > gpurun_out/ncu_dec_c4_$TAG.log 2>&1; echo "ncu dec c4 rc=$?"
