@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- LAS forward hot path on B200: audio-seconds per second (RTFx) + microseconds per decoder step.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference|reference-gpu] [--precision bf16|fp32]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference|reference-gpu] [--precision bf16|fp16|fp32]
                     [--workload c3|c2|c4|c5|yaml]
 
 A "step" is one pass of the hot path (Listener pBLSTM encoder + Speller greedy attention-decoder loop) over one
@@ -207,7 +207,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference", "reference-gpu"])
-    ap.add_argument("--precision", default=None, choices=["bf16", "fp32"])
+    ap.add_argument("--precision", default=None, choices=["bf16", "fp16", "fp32"])
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
     ap.add_argument("--cpu-sample", type=int, default=0, help="utterances in the CPU-baseline sample (0 = the workload's batch, at most 64)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -285,7 +285,7 @@ def main():
     labels_dev = labels.to(dev).to(torch.int32)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
     tf_leg = args.workload == "c2"  # BASELINE.json config 2: "teacher-forced loss + greedy decode of 300 chars"
-    use_pipeline = (not args.no_pipeline) and precision == "bf16" and hasattr(las, "serve") and not tf_leg and B <= 64
+    use_pipeline = (not args.no_pipeline) and precision != "fp32" and hasattr(las, "serve") and not tf_leg and B <= 64
 
     def barrier():
         if dist is not None:
@@ -536,7 +536,7 @@ def main():
     # a GEMM that runs concurrently with its layer's recurrence (on the SMs the recurrence leaves free) adds nothing to the step
     lis_ms = sum(v for k, v in per_step.items() if k.startswith("listener") and not k.endswith(".overlapped"))
     spl_ms = sum(v for k, v in per_step.items() if k.startswith("speller"))
-    esize = 2 if precision == "bf16" else 4
+    esize = 2 if precision != "fp32" else 4
     traffic = {}
     tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")  # dram bytes per launch from `ncu --set full` (tools/ncu_traffic.py)
     if os.path.exists(tp):
@@ -564,7 +564,7 @@ def main():
             l = int(name.split(".")[1][1:])
             M, K = B * (T >> (l + 1)), (2 * c["F"] if l == 0 else 4 * H)
             fl, by = 2.0 * M * K * 8 * H, esize * M * K + esize * 8 * H * K + 4.0 * M * 8 * H
-            if l == 0 or precision != "bf16":  # K = 2F: arithmetic intensity below the ridge -> bound by the fp32 output write
+            if l == 0 or precision == "fp32":  # K = 2F: arithmetic intensity below the ridge -> bound by the fp32 output write
                 r = {"bound": "hbm", "achieved": by / dt / 1e9, "peak": peaks["hbm"], "unit": "GB/s", "tflops": fl / dt / 1e12}
             else:  # isolated launch -> burst peak; a launch timed inside the step -> sustained peak
                 r = {"bound": "tensor", "achieved": fl / dt / 1e12, "peak": peaks["tensor_sustained"] if in_pipeline else peaks["tensor"],
@@ -577,7 +577,7 @@ def main():
             l = int(name.split(".")[1][1:])
             Tl = T >> (l + 1)
             by = B * Tl * (8 * H * 4.0 + 2 * H * 4.0)
-            if l == 0 and precision == "bf16" and (2 * c["F"]) % 16 == 0:  # fused input projection: x_t (bf16) read instead of P
+            if l == 0 and precision != "fp32" and (2 * c["F"]) % 16 == 0:  # fused input projection: x_t (bf16) read instead of P
                 by = B * Tl * (2 * c["F"] * 2.0 + 2 * H * 2.0)
             r = {"bound": "hbm", "achieved": by / dt / 1e9, "peak": peaks["hbm"], "unit": "GB/s", "us_per_serial_step": per_step[name] * 1e3 / Tl}
         elif name == "speller.psi":
@@ -596,7 +596,7 @@ def main():
     rooflines = [r for r in (roof(k) for k in sorted(per_step, key=per_step.get, reverse=True)) if r]
     roofline = rooflines[0] if rooflines else None
 
-    out = dict(base, value=value, ms_per_step=ms / args.steps, dtype=("bf16" if precision == "bf16" else "f32"),
+    out = dict(base, value=value, ms_per_step=ms / args.steps, dtype={"bf16": "bf16", "fp16": "f16", "fp32": "f32"}[precision],
                precision=precision, world=world,
                mode=("serving pipeline (LAS.serve): batch i+1's listener runs under batch i's decoder; K steady-state submissions (each = one "
                      "batch's listener + the previous batch's decoder) timed with one CUDA-event pair, L2-flush writes included")
@@ -631,7 +631,8 @@ def main():
         # (free-running greedy decoding at these weights is chaotic: one near-tie flip changes the rest of an utterance)
         from oracle.las_ref_torch import RefTorchLAS
 
-        sd_b = {k: (v.detach().cpu().to(torch.bfloat16).float().numpy() if v.dim() == 2 else v.detach().cpu().numpy()) for k, v in las.state_dict().items()}
+        rdt = torch.float16 if precision == "fp16" else torch.bfloat16
+        sd_b = {k: (v.detach().cpu().to(rdt).float().numpy() if v.dim() == 2 else v.detach().cpu().numpy()) for k, v in las.state_dict().items()}
         mb = RefTorchLAS(sd_b, c["L"], c["sl"])
         xs = (x_host if not strong else x_global)[:cpu_sample]
         lb, _ = mb.speller(mb.listener(xs), S, None, 1)
@@ -642,7 +643,7 @@ def main():
                          "logp_max_abs": float(np.abs(ours_logp - rescored.numpy()).max()),
                          "logp_max_abs_is": "our greedy log-probs vs the reference teacher-forced on the tokens we fed back (every step)",
                          "logp_max_abs_free_running": float(np.abs(ours_logp - info["logp"].numpy()).max()),
-                         "reference_with_bf16_rounded_weights_token_agreement": cal}
+                         "reference_with_bf16_rounded_weights_token_agreement" if precision != "fp16" else "reference_with_fp16_rounded_weights_token_agreement": cal}
     if world == 1 and not args.no_gpu_baseline:
         try:  # the reference's own op sequence with use_gpu=True on this B200 (torch -> cuDNN / cuBLAS), bounded
             v, info = reference_arm(wl, cpu_sample, 2, 1, device=str(dev), x=x_host if not strong else x_global)

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define LAS_B200_ABI_VERSION 4
+#define LAS_B200_ABI_VERSION 5
 
 enum {
   LAS_OK = 0,
@@ -40,7 +40,10 @@ enum {
 /* Arithmetic mode (north_star: "fp32 mode" 1e-4 / "bf16-GEMM, fp32-state mode" 2e-2). */
 enum {
   LAS_MODE_FP32 = 0, /* fp32 operands, fp32 FMA accumulate everywhere */
-  LAS_MODE_BF16 = 1  /* bf16 GEMM operands on tcgen05 tensor cores, fp32 accumulate, fp32 c/h state, fp32 softmax */
+  LAS_MODE_BF16 = 1, /* bf16 GEMM operands on tcgen05 tensor cores, fp32 accumulate, fp32 c/h state, fp32 softmax */
+  LAS_MODE_F16 = 2   /* the same kernels with IEEE fp16 GEMM operands (10 mantissa bits instead of 7: ~8x smaller operand rounding at the
+                        same speed; the model's operands -- weights, activations in [-1,1], filterbank features -- are far inside fp16's
+                        range, values below 6e-5 lose relative precision).  Everything said about LAS_MODE_BF16 below applies. */
 };
 
 /* Recurrent cell (`rnn_unit`, model/las_model.py:69,156: getattr(nn, rnn_unit.upper())).  Weight rows are torch's:

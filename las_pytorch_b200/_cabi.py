@@ -12,9 +12,10 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "liblas_b200.so")
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 MODE_FP32 = 0
 MODE_BF16 = 1
+MODE_F16 = 2
 DECODE_RAW = 0
 DECODE_GREEDY = 1
 DECODE_SAMPLE = 2

@@ -48,6 +48,7 @@ int g_gemm_direct_store = 0;  // las_debug_set_option(8, 1): row-per-thread glob
 
 struct GemmSched {
   int mode, Bp, nfwd;
+  int f16;          // operand format of A and W: 0 = bf16, 1 = IEEE fp16
   uint32_t* flags;  // nullable: [m_tiles * n_tiles] counters, +1 per epilogue warp that has stored its rows of the tile
 };
 __device__ __forceinline__ void sched_tile(const GemmSched& sc, int i, int m_tiles, int n_tiles, int& m, int& n) {
@@ -107,7 +108,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
   } else if (warp == 1) {
     if (lane == 0) {
       const UmmaLayout la{1, 0, 1024, A_TILE_BYTES}, lb{1, 0, 1024, B_TILE_BYTES};
-      const uint32_t idesc = umma_idesc_bf16(BM, BN);
+      const uint32_t idesc = umma_idesc_bf16(BM, BN, sc.f16);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
@@ -355,7 +356,7 @@ int launch_gemm_bf16_tc(const __nv_bfloat16* A, long long lda, const __nv_bfloat
   const size_t smem = sizeof(GemmSmem) + 1024;
   // per launch, not cached: the attribute belongs to the current device's context and a host thread may serve several devices
   LAS_CUDA_OK(cudaFuncSetAttribute(gemm_bf16_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  gemm_bf16_tc_kernel<<<grid, GEMM_THREADS, smem, st>>>(tm_a, tm_b, tm_c, bias, C, ldc, M, N, K, relu ? 1 : 0, ts ? 1 : 0, GemmSched{0, 0, 0, nullptr});
+  gemm_bf16_tc_kernel<<<grid, GEMM_THREADS, smem, st>>>(tm_a, tm_b, tm_c, bias, C, ldc, M, N, K, relu ? 1 : 0, ts ? 1 : 0, GemmSched{0, 0, 0, op_f16(), nullptr});
   LAS_LAUNCH_OK("gemm_bf16_tc_kernel");
   return LAS_OK;
 }
@@ -403,7 +404,7 @@ int launch_gemm_listener(const __nv_bfloat16* A, int B, int Tl, int K, const __n
   // forward-direction columns are the first half of N; when the halves do not fall on tile boundaries every column tile
   // serves both directions and the natural (front-first) order is kept
   const int nfwd = ((N / 2) % BN == 0) ? (N / 2) / BN : n_tiles;
-  gemm_bf16_tc_kernel<<<grid, GEMM_THREADS, smem, st>>>(tm_a, tm_b, tm_c, bias, C, (long long)N, M, N, K, 0, ts ? 1 : 0, GemmSched{1, Bp, nfwd, flags});
+  gemm_bf16_tc_kernel<<<grid, GEMM_THREADS, smem, st>>>(tm_a, tm_b, tm_c, bias, C, (long long)N, M, N, K, 0, ts ? 1 : 0, GemmSched{1, Bp, nfwd, op_f16(), flags});
   LAS_LAUNCH_OK("gemm_bf16_tc_kernel");
   return LAS_OK;
 }
@@ -510,15 +511,15 @@ int launch_umma_probe(const void* A, const void* B, float* D, int N, int K, int 
   return LAS_OK;
 }
 
-// fp32 -> bf16 (round to nearest even), dense
-__global__ void f32_to_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, size_t n) {
+// fp32 -> 16-bit GEMM operand (bf16 or fp16, round to nearest even), dense
+__global__ void f32_to_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, size_t n, int f16) {
   for (size_t i = (blockIdx.x * (size_t)blockDim.x + threadIdx.x) * 4; i < n; i += (size_t)gridDim.x * blockDim.x * 4) {
     if (i + 3 < n) {
       const float4 v = *reinterpret_cast<const float4*>(src + i);
-      *reinterpret_cast<__nv_bfloat162*>(dst + i) = __floats2bfloat162_rn(v.x, v.y);
-      *reinterpret_cast<__nv_bfloat162*>(dst + i + 2) = __floats2bfloat162_rn(v.z, v.w);
+      *reinterpret_cast<__nv_bfloat162*>(dst + i) = op2_from_f32(v.x, v.y, f16);
+      *reinterpret_cast<__nv_bfloat162*>(dst + i + 2) = op2_from_f32(v.z, v.w, f16);
     } else {
-      for (size_t j = i; j < n; ++j) dst[j] = __float2bfloat16_rn(src[j]);
+      for (size_t j = i; j < n; ++j) dst[j] = op_from_f32(src[j], f16);
     }
   }
 }
@@ -526,7 +527,7 @@ int launch_f32_to_bf16(const float* src, __nv_bfloat16* dst, size_t n, cudaStrea
   if (n == 0) return LAS_OK;
   LAS_REQUIRE((reinterpret_cast<uintptr_t>(src) & 15) == 0 && (reinterpret_cast<uintptr_t>(dst) & 7) == 0, "unaligned cast buffers");
   const size_t blocks = (n / 4 + 255) / 256;
-  f32_to_bf16_kernel<<<(unsigned)(blocks < 2368 ? (blocks ? blocks : 1) : 2368), 256, 0, st>>>(src, dst, n);
+  f32_to_bf16_kernel<<<(unsigned)(blocks < 2368 ? (blocks ? blocks : 1) : 2368), 256, 0, st>>>(src, dst, n, op_f16());
   LAS_LAUNCH_OK("f32_to_bf16_kernel");
   return LAS_OK;
 }

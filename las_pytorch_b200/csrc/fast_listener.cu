@@ -49,6 +49,7 @@ struct RecParams {
   const __nv_bfloat16* wih_img; // [2][CS][128][Kx] bf16, rows in gate-row order (= the GEMM's packed W_ih)
   const float* bias;            // [2][CS][128] b_ih + b_hh in gate-row order
   int Kx;
+  int f16;                      // GEMM operand format: 0 = bf16, 1 = IEEE fp16
   int* resident;                // nullable: every CTA adds 1 once it is running (the serving pipeline launches the decoder, which takes
                                 // all but a few SMs, only after this kernel's clusters have been placed)
 };
@@ -174,7 +175,7 @@ __global__ void __launch_bounds__(RecCfg<BC>::THREADS, 1) lstm_recurrence_cluste
     // The whole warp walks the loop with warp-uniform values (descriptors end up in uniform registers); only the
     // tcgen05 / mbarrier-arrive instructions are predicated on one elected lane.
     const UmmaLayout la = whh_layout(), lb = h_layout(BC);
-    const uint32_t idesc = umma_idesc_bf16(128, BC);
+    const uint32_t idesc = umma_idesc_bf16(128, BC, p.f16);
     const uint32_t a_addr = ptx::smem_u32(sA);
     const uint32_t h0_addr = ptx::smem_u32(sH0);
     const uint32_t x0_addr = ptx::smem_u32(sX);
@@ -414,7 +415,7 @@ __global__ void __launch_bounds__(RecCfg<BC>::THREADS, 1) lstm_recurrence_cluste
         for (int m = 0; m < NB; ++m) {
           const int bl = hb * HB + 4 * m + g;  // batch row within the chunk
           const uint32_t off = (uint32_t)wq * (BC * 16u) + (uint32_t)(bl >> 3) * 128u + (uint32_t)(bl & 7) * 16u + (uint32_t)(jj & 7) * 2u;
-          const __nv_bfloat16 hb = __float2bfloat16_rn(hval[m]);
+          const __nv_bfloat16 hb = op_from_f32(hval[m], p.f16);
           asm volatile("st.shared.b16 [%0], %1;" ::"r"(sb + off), "h"(*reinterpret_cast<const unsigned short*>(&hb)) : "memory");
         }
         ptx::fence_proxy_async_smem();  // generic-proxy staging writes -> visible to the bulk-copy (async proxy) reads
@@ -438,7 +439,7 @@ __global__ void __launch_bounds__(RecCfg<BC>::THREADS, 1) lstm_recurrence_cluste
           if (b < p.B) {
             const size_t o = ((size_t)b * Tl + t) * 2 * p.H + (size_t)dir * p.H + j;
             if (p.out_f32) p.out_f32[o] = hval[m];
-            if (p.out_bf16) p.out_bf16[o] = __float2bfloat16_rn(hval[m]);
+            if (p.out_bf16) p.out_bf16[o] = op_from_f32(hval[m], p.f16);
           }
         }
       }
@@ -454,7 +455,7 @@ __global__ void __launch_bounds__(RecCfg<BC>::THREADS, 1) lstm_recurrence_cluste
 
 // ---- pack kernels ------------------------------------------------------------------------------------------
 // W_ih rows permuted to the recurrence's gate-row order, converted to bf16: dst [8Hp, K]
-__global__ void pack_wih_kernel(const float* w_fwd, const float* w_rev, __nv_bfloat16* dst, int H, int Hp, int K) {
+__global__ void pack_wih_kernel(const float* w_fwd, const float* w_rev, __nv_bfloat16* dst, int H, int Hp, int K, int f16) {
   const size_t n = (size_t)8 * Hp * K;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     const int k = (int)(i % K);
@@ -462,7 +463,7 @@ __global__ void pack_wih_kernel(const float* w_fwd, const float* w_rev, __nv_bfl
     const int dir = row / (4 * Hp), rem = row % (4 * Hp);
     const int unit = rem >> 2, gate = rem & 3;  // rem = r*128 + jj*4 + gate with unit = r*32 + jj
     const float* w = dir ? w_rev : w_fwd;
-    dst[i] = __float2bfloat16_rn(unit < H ? w[(size_t)(gate * H + unit) * K + k] : 0.f);
+    dst[i] = op_from_f32(unit < H ? w[(size_t)(gate * H + unit) * K + k] : 0.f, f16);
   }
 }
 __global__ void pack_bias_kernel(const float* bi_f, const float* bh_f, const float* bi_r, const float* bh_r, float* dst, int H, int Hp) {
@@ -475,7 +476,7 @@ __global__ void pack_bias_kernel(const float* bi_f, const float* bh_f, const flo
   dst[i] = unit < H ? bi[gate * H + unit] + bh[gate * H + unit] : 0.f;
 }
 // W_hh -> per (dir, rank) shared-memory images of the 128 x Hp A operand
-__global__ void pack_whh_kernel(const float* w_fwd, const float* w_rev, uint8_t* img, int H, int Hp, int CS) {
+__global__ void pack_whh_kernel(const float* w_fwd, const float* w_rev, uint8_t* img, int H, int Hp, int CS, int f16) {
   const size_t per = (size_t)128 * Hp;
   const size_t n = 2 * (size_t)CS * per;
   const UmmaLayout la = whh_layout();
@@ -487,7 +488,7 @@ __global__ void pack_whh_kernel(const float* w_fwd, const float* w_rev, uint8_t*
     const int unit = rk * 32 + (row >> 2), gate = row & 3;
     const float* w = dir ? w_rev : w_fwd;
     const float val = (unit < H && k < H) ? w[(size_t)(gate * H + unit) * H + k] : 0.f;
-    *reinterpret_cast<__nv_bfloat16*>(img + ((size_t)dir * CS + rk) * per * 2 + umma_offset(la, row, k)) = __float2bfloat16_rn(val);
+    *reinterpret_cast<__nv_bfloat16*>(img + ((size_t)dir * CS + rk) * per * 2 + umma_offset(la, row, k)) = op_from_f32(val, f16);
   }
 }
 
@@ -662,11 +663,11 @@ int fast_listener_pack(const las_lstm_weights* w, const las_listener_dims* d, vo
     const int K = (l == 0) ? 2 * d->F : 4 * d->H;
     const las_lstm_weights &f = w[2 * l], &r = w[2 * l + 1];
     LAS_REQUIRE(f.w_ih && f.w_hh && f.b_ih && f.b_hh && r.w_ih && r.w_hh && r.b_ih && r.b_hh, "null weight pointer in layer %d", l);
-    pack_wih_kernel<<<592, 256, 0, st>>>(f.w_ih, r.w_ih, pk.wih[l], d->H, g.Hp, K);
+    pack_wih_kernel<<<592, 256, 0, st>>>(f.w_ih, r.w_ih, pk.wih[l], d->H, g.Hp, K, op_f16());
     LAS_LAUNCH_OK("pack_wih_kernel");
     pack_bias_kernel<<<(8 * g.Hp + 255) / 256, 256, 0, st>>>(f.b_ih, f.b_hh, r.b_ih, r.b_hh, pk.bias[l], d->H, g.Hp);
     LAS_LAUNCH_OK("pack_bias_kernel");
-    pack_whh_kernel<<<592, 256, 0, st>>>(f.w_hh, r.w_hh, pk.whh[l], d->H, g.Hp, g.CS);
+    pack_whh_kernel<<<592, 256, 0, st>>>(f.w_hh, r.w_hh, pk.whh[l], d->H, g.Hp, g.CS, op_f16());
     LAS_LAUNCH_OK("pack_whh_kernel");
   }
   return LAS_OK;
@@ -705,6 +706,7 @@ static RecParams rec_params(const las_listener_dims* d, const Geo& g, const List
   rp.a_tmem = g_rec_a_tmem;
   rp.nchunks = (d->B + bc - 1) / bc;
   rp.resident = nullptr;
+  rp.f16 = op_f16();
   rp.Kx = 0;
   rp.wih_img = nullptr;
   rp.bias = nullptr;

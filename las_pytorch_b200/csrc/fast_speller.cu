@@ -98,6 +98,7 @@ struct DecParams {
   int ab_flags;     // test hook (las_debug_set_option(5, v)): bit 0 = W_phi from shared memory instead of registers; bit 2 (value 4) = eight 2-D copies per activation part instead of one 3-D copy; bit 5 (value 32) = query GEMV after a CTA-wide barrier (8 lanes per output) instead of per-warp partials; bit 6 (value 64) = LSTM epilogue stores one row per thread from the registers instead of staging + coalesced rows; bit 9 (value 512) = context UMMA descriptors rebuilt per instruction instead of advanced by constants
   unsigned long long sample_seed;  // LAS_DECODE_SAMPLE
   int word_gather;  // 1: the fed-back word is an index (greedy argmax / gt_index); 0: a dense vector (part 1b)
+  int f16;          // GEMM operand format: 0 = bf16 (LAS_MODE_BF16), 1 = IEEE fp16 (LAS_MODE_F16)
   int lstm_ts;      // 1: LSTM CTAs use the weights-stationary operand roles (lstm_role_ts); 0: lstm_role
   int att_split;    // 2: every utterance is attended by a CLUSTER of two CTAs, each holding half of the encoder steps (long encoders:
                     // all of enc[b]^T stays in tensor memory; partial softmax / context combined through DSMEM); 1: one CTA
@@ -186,9 +187,9 @@ __device__ __forceinline__ uint4 lds128(const void* ptr) {
   return v;
 }
 // dot product of 8 bf16 weights (one 16-byte chunk) with 8 fp32 activations
-__device__ __forceinline__ float dot8(const uint4& w, const float4& x0, const float4& x1, float acc) {
+__device__ __forceinline__ float dot8(const uint4& w, const float4& x0, const float4& x1, float acc, int f16) {
   const __nv_bfloat162* w2 = reinterpret_cast<const __nv_bfloat162*>(&w);
-  const float2 a = __bfloat1622float2(w2[0]), b = __bfloat1622float2(w2[1]), c = __bfloat1622float2(w2[2]), d = __bfloat1622float2(w2[3]);
+  const float2 a = op2_to_f32(w2[0], f16), b = op2_to_f32(w2[1], f16), c = op2_to_f32(w2[2], f16), d = op2_to_f32(w2[3], f16);
   acc = fmaf(a.x, x0.x, acc); acc = fmaf(a.y, x0.y, acc); acc = fmaf(b.x, x0.z, acc); acc = fmaf(b.y, x0.w, acc);
   acc = fmaf(c.x, x1.x, acc); acc = fmaf(c.y, x1.y, acc); acc = fmaf(d.x, x1.z, acc); acc = fmaf(d.y, x1.w, acc);
   return acc;
@@ -197,6 +198,7 @@ __device__ __forceinline__ float dot8(const uint4& w, const float4& x0, const fl
 // ------------------------------------------------------------------------------------------------------------
 // LSTM role
 // ------------------------------------------------------------------------------------------------------------
+template <int F16>
 __device__ void lstm_role(const DecParams& p, uint8_t* smem, int l, int nb) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool first = (l == 0), top = (l == p.sl - 1);
@@ -316,7 +318,7 @@ __device__ void lstm_role(const DecParams& p, uint8_t* smem, int l, int nb) {
   } else if (warp == MMA_WARP) {
     // ============================ MMA issuer ============================
     const UmmaLayout la{1, 0, 1024, (uint32_t)STAGE_BYTES}, lb{1, 0, 1024, WATOM_BYTES};
-    const uint32_t idesc = umma_idesc_bf16(128, DEC_NW);
+    const uint32_t idesc = umma_idesc_bf16(128, DEC_NW, F16);
     const uint32_t a0 = ptx::smem_u32(abuf), w_addr = ptx::smem_u32(wsm);
     uint32_t phase_bits = 0;  // per-slot phase parity
     for (int s = 0; s < S; ++s) {
@@ -398,7 +400,7 @@ __device__ void lstm_role(const DecParams& p, uint8_t* smem, int l, int nb) {
           for (int i = 0; i < 16; ++i) {  // + W_word[c0 + i, tok]: the one-hot word times the word atom, without the GEMM
             const uint32_t rr = (uint32_t)(c0 + i);
             const uint32_t off = (rr >> 3) * 1024u + (rr & 7u) * 128u + (((tok_chunk ^ (rr & 7u)) & 7u) << 4) + tok_off;
-            pb[i] += __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(watom + off));
+            pb[i] += op_to_f32(*reinterpret_cast<const __nv_bfloat16*>(watom + off), F16);
           }
         }
       }
@@ -451,8 +453,8 @@ __device__ void lstm_role(const DecParams& p, uint8_t* smem, int l, int nb) {
           const int row = r0 + (lane >> 1), hf = lane & 1;
           if (row < p.B) {
             const float4 x0 = *reinterpret_cast<const float4*>(s_st + row * 20 + hf * 8), x1 = *reinterpret_cast<const float4*>(s_st + row * 20 + hf * 8 + 4);
-            const __nv_bfloat162 t0 = __floats2bfloat162_rn(x0.x, x0.y), t1 = __floats2bfloat162_rn(x0.z, x0.w);
-            const __nv_bfloat162 t2 = __floats2bfloat162_rn(x1.x, x1.y), t3 = __floats2bfloat162_rn(x1.z, x1.w);
+            const __nv_bfloat162 t0 = op2_from_f32(x0.x, x0.y, F16), t1 = op2_from_f32(x0.z, x0.w, F16);
+            const __nv_bfloat162 t2 = op2_from_f32(x1.x, x1.y, F16), t3 = op2_from_f32(x1.z, x1.w, F16);
             *reinterpret_cast<uint4*>(p.hbuf[l][np] + (size_t)row * p.Hs + nb * DEC_UNITS + hf * 8) =
                 make_uint4(*reinterpret_cast<const uint32_t*>(&t0), *reinterpret_cast<const uint32_t*>(&t1),
                            *reinterpret_cast<const uint32_t*>(&t2), *reinterpret_cast<const uint32_t*>(&t3));
@@ -467,7 +469,7 @@ __device__ void lstm_role(const DecParams& p, uint8_t* smem, int l, int nb) {
           ll_store2(dst, ll_pack(__float_as_uint(h[0]), tag), ll_pack(__float_as_uint(h[1]), tag));
           ll_store2(dst + 2, ll_pack(__float_as_uint(h[2]), tag), ll_pack(__float_as_uint(h[3]), tag));
         }
-        const __nv_bfloat162 t0 = __floats2bfloat162_rn(h[0], h[1]), t1 = __floats2bfloat162_rn(h[2], h[3]);
+        const __nv_bfloat162 t0 = op2_from_f32(h[0], h[1], F16), t1 = op2_from_f32(h[2], h[3], F16);
         *reinterpret_cast<uint2*>(p.hbuf[l][np] + (size_t)b * p.Hs + u0) =
             make_uint2(*reinterpret_cast<const uint32_t*>(&t0), *reinterpret_cast<const uint32_t*>(&t1));
         }
@@ -512,6 +514,7 @@ __device__ void lstm_role(const DecParams& p, uint8_t* smem, int l, int nb) {
 // Epilogue: thread = gate row (lane; unit-major / gate-minor, so the four gates of a unit sit in four adjacent lanes), 16 batch
 // columns per warp; a 4x4 transpose inside each 4-lane group (two shuffle stages, as in the listener's recurrence) leaves every
 // lane with (i, f, g, o) of one (unit, batch) cell -- 4 cells per thread, cell state in registers.
+template <int F16>
 __device__ void lstm_role_ts(const DecParams& p, uint8_t* smem, int l, int nb) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool first = (l == 0), top = (l == p.sl - 1);
@@ -634,7 +637,7 @@ __device__ void lstm_role_ts(const DecParams& p, uint8_t* smem, int l, int nb) {
   } else if (warp == MMA_WARP) {
     // ============================ MMA issuer ============================
     const UmmaLayout lact{1, 0, 1024, (uint32_t)STAGE_BYTES}, lw{1, 0, 1024, WATOM_BYTES};
-    const uint32_t idesc = umma_idesc_bf16(128, 64);  // M = 128 gate-row lanes (64 used), N = 64 batch columns
+    const uint32_t idesc = umma_idesc_bf16(128, 64, F16);  // M = 128 gate-row lanes (64 used), N = 64 batch columns
     const uint32_t a0 = ptx::smem_u32(abuf), w_addr = ptx::smem_u32(wsm);
     uint32_t phase0 = 0, phasew = 0;
     for (int s = 0; s < S; ++s) {
@@ -740,7 +743,7 @@ __device__ void lstm_role_ts(const DecParams& p, uint8_t* smem, int l, int nb) {
           for (int gg = 0; gg < 4; ++gg) {
             const uint32_t rr = (uint32_t)(4 * jj + gg);
             const uint32_t off = (rr >> 3) * 1024u + (rr & 7u) * 128u + (((tok_chunk ^ (rr & 7u)) & 7u) << 4) + tok_off;
-            wv[gg] = __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(watom + off));
+            wv[gg] = op_to_f32(*reinterpret_cast<const __nv_bfloat16*>(watom + off), F16);
           }
           pb[m].x += wv[0]; pb[m].y += wv[1]; pb[m].z += wv[2]; pb[m].w += wv[3];
         }
@@ -814,8 +817,8 @@ __device__ void lstm_role_ts(const DecParams& p, uint8_t* smem, int l, int nb) {
         const int rw = r0 + (lane >> 1), hf = lane & 1;
         if (rw < p.B) {
           const float4 y0 = *reinterpret_cast<const float4*>(s_st + rw * 20 + hf * 8), y1 = *reinterpret_cast<const float4*>(s_st + rw * 20 + hf * 8 + 4);
-          const __nv_bfloat162 t0 = __floats2bfloat162_rn(y0.x, y0.y), t1 = __floats2bfloat162_rn(y0.z, y0.w);
-          const __nv_bfloat162 t2 = __floats2bfloat162_rn(y1.x, y1.y), t3 = __floats2bfloat162_rn(y1.z, y1.w);
+          const __nv_bfloat162 t0 = op2_from_f32(y0.x, y0.y, F16), t1 = op2_from_f32(y0.z, y0.w, F16);
+          const __nv_bfloat162 t2 = op2_from_f32(y1.x, y1.y, F16), t3 = op2_from_f32(y1.z, y1.w, F16);
           *reinterpret_cast<uint4*>(p.hbuf[l][np] + (size_t)rw * p.Hs + nb * DEC_UNITS + hf * 8) =
               make_uint4(*reinterpret_cast<const uint32_t*>(&t0), *reinterpret_cast<const uint32_t*>(&t1),
                          *reinterpret_cast<const uint32_t*>(&t2), *reinterpret_cast<const uint32_t*>(&t3));
@@ -892,6 +895,7 @@ __host__ __device__ inline AttLayout att_layout(int Hs, int E, int U, int D, int
 // Half of the encoder steps one CTA of a split pair holds: a whole number of 16-step UMMA K blocks
 __host__ __device__ inline int att_split_half(int U) { return ((U + 1) / 2 + 15) / 16 * 16; }
 
+template <int F16>
 __device__ void attention_role(const DecParams& p, uint8_t* smem, int b, int rank) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr int NWARP = DEC_THREADS / 32;
@@ -1067,8 +1071,8 @@ __device__ void attention_role(const DecParams& p, uint8_t* smem, int b, int ran
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const float4 x0 = hx[2 * j], x1 = hx[2 * j + 1];
-        a0 = dot8(wq[j], x0, x1, a0);
-        a1 = dot8(wq[4 + j], x0, x1, a1);
+        a0 = dot8(wq[j], x0, x1, a0, F16);
+        a1 = dot8(wq[4 + j], x0, x1, a1, F16);
       }
       s_qp[warp * 64 + lane] = a0;
       s_qp[warp * 64 + 32 + lane] = a1;
@@ -1100,11 +1104,11 @@ __device__ void attention_role(const DecParams& p, uint8_t* smem, int b, int ran
           for (int j = 0; j < 8; j += 2) {
             if (part + 8 * j < hchunks) {
               const float4* xv = xchunk(s_h, part + 8 * j);
-              acc = dot8(wq[j], xv[0], xv[8], acc);
+              acc = dot8(wq[j], xv[0], xv[8], acc, F16);
             }
             if (part + 8 * (j + 1) < hchunks) {
               const float4* xv = xchunk(s_h, part + 8 * (j + 1));
-              acc2 = dot8(wq[j + 1], xv[0], xv[8], acc2);
+              acc2 = dot8(wq[j + 1], xv[0], xv[8], acc2, F16);
             }
           }
           acc += acc2;
@@ -1113,7 +1117,7 @@ __device__ void attention_role(const DecParams& p, uint8_t* smem, int b, int ran
 #pragma unroll 4
           for (int c = part; c < hchunks; c += 8) {
             const float4* xv = xchunk(s_h, c);
-            acc = dot8(lds128(wr + c), xv[0], xv[8], acc);
+            acc = dot8(lds128(wr + c), xv[0], xv[8], acc, F16);
           }
         }
         if (tid == 0 && b == 0) DEC_TRACE(3, 1);
@@ -1188,7 +1192,7 @@ __device__ void attention_role(const DecParams& p, uint8_t* smem, int b, int ran
           lsum += ev[ps];
           const int u = ps * 256 + (tid >> 1);
           if (u < U) {
-            if (ntm > 0) *reinterpret_cast<__nv_bfloat16*>(s_bop + (u >> 3) * 256 + (u & 7) * 2) = __float2bfloat16_rn(ev[ps]);
+            if (ntm > 0) *reinterpret_cast<__nv_bfloat16*>(s_bop + (u >> 3) * 256 + (u & 7) * 2) = op_from_f32(ev[ps], F16);
             if (Ec > 0) s_score[u] = ev[ps];
           }
         }
@@ -1219,7 +1223,7 @@ __device__ void attention_role(const DecParams& p, uint8_t* smem, int b, int ran
       ptx::tc_fence_after();
       if (ptx::elect_one()) {
         const UmmaLayout lb{0, 256, 128, 0};
-        const uint32_t idesc = umma_idesc_bf16(128, 16);
+        const uint32_t idesc = umma_idesc_bf16(128, 16, F16);
         const uint32_t bop = ptx::smem_u32(s_bop);
         if (p.ab_flags & 512) {  // A/B: descriptors rebuilt per instruction
           for (int t = warp; t < ntm; t += niss)
@@ -1267,7 +1271,7 @@ __device__ void attention_role(const DecParams& p, uint8_t* smem, int b, int ran
 #pragma unroll 4
           for (int c = part; c < hchunks; c += 16) {
             const float4* xv = xchunk(s_h, c);
-            acc = dot8(lds128(wr + c), xv[0], xv[8], acc);
+            acc = dot8(lds128(wr + c), xv[0], xv[8], acc, F16);
           }
         }
         acc += __shfl_xor_sync(0xffffffffu, acc, 1);
@@ -1303,7 +1307,7 @@ __device__ void attention_role(const DecParams& p, uint8_t* smem, int b, int ran
             const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&v[j]);
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-              const float2 f = __bfloat1622float2(h2[i]);
+              const float2 f = op2_to_f32(h2[i], F16);
               acc[2 * i] = fmaf(a, f.x, acc[2 * i]);
               acc[2 * i + 1] = fmaf(a, f.y, acc[2 * i + 1]);
             }
@@ -1326,7 +1330,7 @@ __device__ void attention_role(const DecParams& p, uint8_t* smem, int b, int ran
         const float cv = __uint_as_float(r) * inv;
         if (direct_pub) {
           // publish straight from the registers: lanes 8j..8j+7 hold 8 consecutive features -> lane 8j stores their 16 bytes
-          const uint32_t mine = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(cv));
+          const uint32_t mine = (uint32_t)__bfloat16_as_ushort(op_from_f32(cv, F16));
           const uint32_t nb1 = __shfl_down_sync(0xffffffffu, mine, 1);
           const uint32_t pair = mine | (nb1 << 16);                        // valid in even lanes: features (e, e+1)
           const uint32_t p1 = __shfl_down_sync(0xffffffffu, pair, 2), p2 = __shfl_down_sync(0xffffffffu, pair, 4), p3 = __shfl_down_sync(0xffffffffu, pair, 6);
@@ -1401,8 +1405,8 @@ __device__ void attention_role(const DecParams& p, uint8_t* smem, int b, int ran
         if (tid < npub) {
           const float4* xv = xchunk(s_ctx, tid);
           const float4 lo = xv[0], hi = xv[8];
-          const __nv_bfloat162 p0 = __floats2bfloat162_rn(lo.x, lo.y), p1 = __floats2bfloat162_rn(lo.z, lo.w);
-          const __nv_bfloat162 p2 = __floats2bfloat162_rn(hi.x, hi.y), p3 = __floats2bfloat162_rn(hi.z, hi.w);
+          const __nv_bfloat162 p0 = op2_from_f32(lo.x, lo.y, F16), p1 = op2_from_f32(lo.z, lo.w, F16);
+          const __nv_bfloat162 p2 = op2_from_f32(hi.x, hi.y, F16), p3 = op2_from_f32(hi.z, hi.w, F16);
           *reinterpret_cast<uint4*>(xr + 8 * tid) =
               make_uint4(*reinterpret_cast<const uint32_t*>(&p0), *reinterpret_cast<const uint32_t*>(&p1),
                          *reinterpret_cast<const uint32_t*>(&p2), *reinterpret_cast<const uint32_t*>(&p3));
@@ -1440,13 +1444,13 @@ __device__ void attention_role(const DecParams& p, uint8_t* smem, int b, int ran
 #pragma unroll 4
           for (int c = part; c < kchunks - hchunks; c += 16) {
             const float4* xv = xchunk(s_ctx, c);
-            acc = dot8(lds128(wr + hchunks + c), xv[0], xv[8], acc);
+            acc = dot8(lds128(wr + hchunks + c), xv[0], xv[8], acc, F16);
           }
           if (late_h) {  // the h half was not evaluated during the context reduction
 #pragma unroll 4
             for (int c = part; c < hchunks; c += 16) {
               const float4* xv = xchunk(s_h, c);
-              acc = dot8(lds128(wr + c), xv[0], xv[8], acc);
+              acc = dot8(lds128(wr + c), xv[0], xv[8], acc, F16);
             }
           }
         }
@@ -1524,7 +1528,7 @@ __device__ void attention_role(const DecParams& p, uint8_t* smem, int b, int ran
             else val = (i == bi) ? 1.f : 0.f;
             if (last && p.word_out) p.word_out[(size_t)gb * V + i] = val;
           }
-          wr_next[i] = __float2bfloat16_rn(val);
+          wr_next[i] = op_from_f32(val, F16);
         }
         __syncwarp();
         if (lane == 0) red_release_add(word_ctr, 1u);
@@ -1540,6 +1544,7 @@ __device__ void attention_role(const DecParams& p, uint8_t* smem, int b, int ran
   }
 }
 
+template <int F16>
 __global__ void __launch_bounds__(DEC_THREADS, 1) speller_decode_persistent_kernel(const __grid_constant__ DecParams p) {
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment (SWIZZLE_128B atoms) as an offset from the __shared__ symbol, so that the compiler keeps the
@@ -1548,16 +1553,16 @@ __global__ void __launch_bounds__(DEC_THREADS, 1) speller_decode_persistent_kern
   const int n_lstm = p.sl * p.ncl;
   if (p.stop && *reinterpret_cast<const volatile int32_t*>(p.stop) != 0) return;  // written before this launch: every CTA sees the same value
   if ((int)blockIdx.x < n_lstm) {
-    if (p.lstm_ts) lstm_role_ts(p, smem, blockIdx.x / p.ncl, blockIdx.x % p.ncl);
-    else lstm_role(p, smem, blockIdx.x / p.ncl, blockIdx.x % p.ncl);
+    if (p.lstm_ts) lstm_role_ts<F16>(p, smem, blockIdx.x / p.ncl, blockIdx.x % p.ncl);
+    else lstm_role<F16>(p, smem, blockIdx.x / p.ncl, blockIdx.x % p.ncl);
   }
-  else if (p.att_split == 2) attention_role(p, smem, (blockIdx.x - n_lstm) >> 1, (blockIdx.x - n_lstm) & 1);
-  else attention_role(p, smem, blockIdx.x - n_lstm, 0);
+  else if (p.att_split == 2) attention_role<F16>(p, smem, (blockIdx.x - n_lstm) >> 1, (blockIdx.x - n_lstm) & 1);
+  else attention_role<F16>(p, smem, blockIdx.x - n_lstm, 0);
 }
 
 // ---- pack kernels ------------------------------------------------------------------------------------------
 // LSTM layer weights -> per-CTA swizzled atoms.  K order: [h part (Hs) | input part], each padded to 64-wide atoms.
-__global__ void pack_dec_w_kernel(const float* w_ih, const float* w_hh, uint8_t* img, int l, int Hs, int E, int V, int ncl) {
+__global__ void pack_dec_w_kernel(const float* w_ih, const float* w_hh, uint8_t* img, int l, int Hs, int E, int V, int ncl, int f16) {
   const int nh = (Hs + 63) / 64;
   const int nx = (l == 0) ? (DEC_VP + E + 63) / 64 : (Hs + 63) / 64;
   const int natoms = nh + nx;
@@ -1585,7 +1590,7 @@ __global__ void pack_dec_w_kernel(const float* w_ih, const float* w_hh, uint8_t*
     }
     const size_t off = ((size_t)nb * natoms + at) * WATOM_BYTES + (size_t)(rr >> 3) * 1024 + (rr & 7) * 128 + ((((kk >> 3) ^ (rr & 7)) & 7) << 4) +
                        (kk & 7) * 2;
-    *reinterpret_cast<__nv_bfloat16*>(img + off) = __float2bfloat16_rn(val);
+    *reinterpret_cast<__nv_bfloat16*>(img + off) = op_from_f32(val, f16);
   }
 }
 __global__ void pack_dec_bias_kernel(const float* b_ih, const float* b_hh, float* dst, int Hs) {
@@ -1602,12 +1607,12 @@ __global__ void dec_init_kernel(DecParams p, const float* enc_f32, const float* 
   __nv_bfloat16* xr = p.xbuf[0] + (size_t)b * p.E;
   __nv_bfloat16* wr = p.wbuf[0] + (size_t)b * DEC_VP;
   for (int i = threadIdx.x; i < DEC_VP + p.E; i += blockDim.x) {
-    if (i < DEC_VP) wr[i] = __float2bfloat16_rn((i < p.V) ? (word_in ? word_in[(size_t)gb * p.V + i] : (i == 0 ? 1.f : 0.f)) : 0.f);  // <sos> = index 0
-    else xr[i - DEC_VP] = __float2bfloat16_rn(ctx_in ? ctx_in[(size_t)gb * p.E + (i - DEC_VP)] : enc_f32[(size_t)gb * p.U * p.E + (i - DEC_VP)]);  // enc[:,0,:]
+    if (i < DEC_VP) wr[i] = op_from_f32((i < p.V) ? (word_in ? word_in[(size_t)gb * p.V + i] : (i == 0 ? 1.f : 0.f)) : 0.f, p.f16);  // <sos> = index 0
+    else xr[i - DEC_VP] = op_from_f32(ctx_in ? ctx_in[(size_t)gb * p.E + (i - DEC_VP)] : enc_f32[(size_t)gb * p.U * p.E + (i - DEC_VP)], p.f16);  // enc[:,0,:]
   }
   for (int l = 0; l < p.sl; ++l)
     for (int i = threadIdx.x; i < p.Hs; i += blockDim.x)
-      p.hbuf[l][0][(size_t)b * p.Hs + i] = __float2bfloat16_rn(h_in ? h_in[((size_t)l * p.Bfull + gb) * p.Hs + i] : 0.f);
+      p.hbuf[l][0][(size_t)b * p.Hs + i] = op_from_f32(h_in ? h_in[((size_t)l * p.Bfull + gb) * p.Hs + i] : 0.f, p.f16);
 }
 
 int g_dec_ctx_tmem = 1;  // las_debug_set_option(2, v)
@@ -1772,7 +1777,7 @@ int fast_speller_pack(const las_speller_weights* w, const las_speller_dims* d, v
   const Shape s = shape_of(d);
   for (int l = 0; l < d->sl; ++l) {
     const las_lstm_weights& lw = w->rnn_host[l];
-    pack_dec_w_kernel<<<592, 256, 0, st>>>(lw.w_ih, lw.w_hh, pk.w_img[l], l, d->Hs, d->E, d->V, s.ncl);
+    pack_dec_w_kernel<<<592, 256, 0, st>>>(lw.w_ih, lw.w_hh, pk.w_img[l], l, d->Hs, d->E, d->V, s.ncl, op_f16());
     LAS_LAUNCH_OK("pack_dec_w_kernel");
     pack_dec_bias_kernel<<<(4 * d->Hs + 255) / 256, 256, 0, st>>>(lw.b_ih, lw.b_hh, pk.bias[l], d->Hs);
     LAS_LAUNCH_OK("pack_dec_bias_kernel");
@@ -1893,6 +1898,7 @@ int fast_speller_decode_segment(const las_decode_io* io, const void* packed_f32,
     p.tok_ll = w.tok_ll;
     // the fed-back word is an index (greedy argmax / index teacher forcing) unless a dense vector is asked for
     p.ab_flags = g_dec_ab_flags;
+    p.f16 = op_f16();
     p.word_gather = io->gt_dense ? 0 : (io->gt_index ? 1 : (decode_mode != LAS_DECODE_RAW ? 1 : 0));
     p.sample_seed = io->sample_seed;
     p.trace = (fast_get_trace() && first_seg) ? fast_get_trace() + 512 : nullptr;  // needs 5 roles x 32 steps x 8 stamps behind the recurrence trace
@@ -1916,7 +1922,9 @@ int fast_speller_decode_segment(const las_decode_io* io, const void* packed_f32,
     ProfScope ps("speller.steps", st);
     const size_t smem_l = rc.smem, smem_a = att_smem(d, p.k_in_smem != 0, p.ctx_ntm > 0 && p.ctx_ntm < d->E / 128, p.att_split == 2);
     const size_t smem = (smem_l > smem_a ? smem_l : smem_a) + 1024;
-    LAS_CUDA_OK(cudaFuncSetAttribute(speller_decode_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // the operand format is a template parameter: the conversions sit in the GEMV inner loops (a run-time branch there cost 20 %)
+    auto kern = p.f16 ? speller_decode_persistent_kernel<1> : speller_decode_persistent_kernel<0>;
+    LAS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(n_lstm + p.att_split * Bc);
     cfg.blockDim = dim3(DEC_THREADS);
@@ -1934,7 +1942,7 @@ int fast_speller_decode_segment(const las_decode_io* io, const void* packed_f32,
       at[1].val.clusterDim.z = 1;
       cfg.numAttrs = 2;
     }
-    LAS_CUDA_OK(cudaLaunchKernelEx(&cfg, speller_decode_persistent_kernel, p));
+    LAS_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, p));
     count_launch();
   }
   return LAS_OK;

@@ -579,7 +579,7 @@ int launch_eos_fill(const int32_t* state, int S, int Bfull, int b0, int Bc, int 
 // K columns: x part in [0, Kx), zero padding up to Kxp, h part in [Kxp, Kxp + H), zero padding up to Kp.
 // =========================================================================================================
 __global__ void gen_pack_w_kernel(const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh, __nv_bfloat16* dst, float* bias,
-                                  int cell, int H, int Kx, int Kxp, int Kp) {
+                                  int cell, int H, int Kx, int Kxp, int Kp, int f16) {
   const int R = (cell == LAS_CELL_RNN) ? H : 4 * H;
   const size_t n = (size_t)R * Kp;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
@@ -595,32 +595,32 @@ __global__ void gen_pack_w_kernel(const float* w_ih, const float* w_hh, const fl
     }
     if (k < Kx) { if (use_x) v = w_ih[((size_t)src * H + j) * Kx + k]; }
     else if (k >= Kxp && k < Kxp + H) { if (use_h) v = w_hh[((size_t)src * H + j) * H + (k - Kxp)]; }
-    dst[i] = __float2bfloat16_rn(v);
+    dst[i] = op_from_f32(v, f16);
     if (k == 0) bias[row] = (use_x ? b_ih[src * H + j] : 0.f) + (use_h ? b_hh[src * H + j] : 0.f);
   }
 }
 int launch_gen_pack_w(const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh, __nv_bfloat16* dst, float* bias, int cell,
                       int H, int Kx, int Kxp, int Kp, cudaStream_t st) {
-  gen_pack_w_kernel<<<592, 256, 0, st>>>(w_ih, w_hh, b_ih, b_hh, dst, bias, cell, H, Kx, Kxp, Kp);
+  gen_pack_w_kernel<<<592, 256, 0, st>>>(w_ih, w_hh, b_ih, b_hh, dst, bias, cell, H, Kx, Kxp, Kp, op_f16());
   LAS_LAUNCH_OK("gen_pack_w_kernel");
   return LAS_OK;
 }
 // A[b, :] = bf16([x[b, 0:Kx] | 0 | h[b, 0:H] | 0]); h == nullptr reads as zeros
 __global__ void gen_build_a_kernel(const float* x, long long x_ld, const float* h, long long h_ld, __nv_bfloat16* A, int B, int H, int Kx, int Kxp,
-                                   int Kp) {
+                                   int Kp, int f16) {
   const size_t n = (size_t)B * Kp;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     const int k = (int)(i % Kp), b = (int)(i / Kp);
     float v = 0.f;
     if (k < Kx) v = x[(long long)b * x_ld + k];
     else if (h && k >= Kxp && k < Kxp + H) v = h[(long long)b * h_ld + (k - Kxp)];
-    A[i] = __float2bfloat16_rn(v);
+    A[i] = op_from_f32(v, f16);
   }
 }
 int launch_gen_build_a(const float* x, long long x_ld, const float* h, long long h_ld, __nv_bfloat16* A, int B, int H, int Kx, int Kxp, int Kp,
                        cudaStream_t st) {
   const size_t n = (size_t)B * Kp;
-  gen_build_a_kernel<<<(unsigned)((n + 255) / 256 < 592 ? (n + 255) / 256 : 592), 256, 0, st>>>(x, x_ld, h, h_ld, A, B, H, Kx, Kxp, Kp);
+  gen_build_a_kernel<<<(unsigned)((n + 255) / 256 < 592 ? (n + 255) / 256 : 592), 256, 0, st>>>(x, x_ld, h, h_ld, A, B, H, Kx, Kxp, Kp, op_f16());
   LAS_LAUNCH_OK("gen_build_a_kernel");
   return LAS_OK;
 }

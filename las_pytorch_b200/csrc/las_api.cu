@@ -19,6 +19,12 @@ int fail(int code, const char* fmt, ...) {
 }
 void count_launch(int n) { g_launches += n; }
 
+// tensor-core modes (same kernels; they differ in the 16-bit operand format) and the calling thread's current one
+static inline bool tc_mode(int mode) { return mode == LAS_MODE_BF16 || mode == LAS_MODE_F16; }
+static thread_local int g_op_f16 = 0;
+void set_operand_mode(int mode) { g_op_f16 = (mode == LAS_MODE_F16) ? 1 : 0; }
+int op_f16() { return g_op_f16; }
+
 // ---- profiling registry (thread-local) ------------------------------------------------------------------
 struct ProfRec {
   char name[48];
@@ -513,7 +519,7 @@ extern "C" {
 int las_abi_version(void) { return LAS_B200_ABI_VERSION; }
 const char* las_last_error(void) { return err_buf(); }
 int las_device_check(void) { return device_ok(); }
-int las_mode_available(int mode) { return mode == LAS_MODE_FP32 || (mode == LAS_MODE_BF16 && fast_available()); }
+int las_mode_available(int mode) { return mode == LAS_MODE_FP32 || (tc_mode(mode) && fast_available()); }
 int las_prof_enable(int on) {
   for (int i = 0; i < g_prof_n; ++i) {
     cudaEventDestroy(g_prof[i].e0);
@@ -554,23 +560,24 @@ int64_t las_launch_count(int reset) {
 // ---- listener ------------------------------------------------------------------------------------------
 size_t las_listener_packed_bytes(const las_listener_dims* d, int mode) {
   if (listener_check(d) != LAS_OK) return 0;
-  if (mode == LAS_MODE_BF16 && fast_listener_fits(d)) return fast_listener_packed_bytes(d);
-  if (mode == LAS_MODE_BF16) return listener_pack_layout_f32(d, nullptr).bytes + listener_pack_layout_gen(d, nullptr).bytes;
+  if (tc_mode(mode) && fast_listener_fits(d)) return fast_listener_packed_bytes(d);
+  if (tc_mode(mode)) return listener_pack_layout_f32(d, nullptr).bytes + listener_pack_layout_gen(d, nullptr).bytes;
   return listener_pack_layout_f32(d, nullptr).bytes;
 }
 
 int las_listener_pack(const las_lstm_weights* w, const las_listener_dims* d, int mode, void* packed, size_t packed_bytes,
                       void* stream) {
+  set_operand_mode(mode);
   LAS_TRY(listener_check(d));
   LAS_REQUIRE(w && packed, "null weights / packed buffer");
-  LAS_REQUIRE(mode == LAS_MODE_FP32 || mode == LAS_MODE_BF16, "unknown mode %d", mode);
+  LAS_REQUIRE(mode == LAS_MODE_FP32 || tc_mode(mode), "unknown mode %d", mode);
   LAS_TRY(device_ok());
   if (packed_bytes < las_listener_packed_bytes(d, mode))
     return fail(LAS_ENOMEM, "packed buffer too small: %zu < %zu", packed_bytes, las_listener_packed_bytes(d, mode));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  LAS_REQUIRE(mode != LAS_MODE_BF16 || fast_listener_fits(d) || listener_gen_ok(d),
+  LAS_REQUIRE(!tc_mode(mode) || fast_listener_fits(d) || listener_gen_ok(d),
               "LAS_MODE_BF16 needs 16-byte aligned bf16 rows for TMA: 2F (%d) and 4H (%d) must be multiples of 8; use LAS_MODE_FP32", 2 * d->F, 4 * d->H);
-  if (mode == LAS_MODE_BF16 && fast_listener_fits(d)) return fast_listener_pack(w, d, packed, st);
+  if (tc_mode(mode) && fast_listener_fits(d)) return fast_listener_pack(w, d, packed, st);
   const ListenerPackF32 pk = listener_pack_layout_f32(d, packed);
   const size_t H = d->H, GH = (size_t)n_gates(d->cell) * H;
   for (int l = 0; l < d->L; ++l) {
@@ -589,7 +596,7 @@ int las_listener_pack(const las_lstm_weights* w, const las_listener_dims* d, int
       }
     }
   }
-  if (mode == LAS_MODE_BF16) {  // generic path: bf16 copies of [W_ih fwd ; W_ih reverse] behind the fp32 pack
+  if (tc_mode(mode)) {  // generic path: bf16 copies of [W_ih fwd ; W_ih reverse] behind the fp32 pack
     const ListenerGen gp = listener_pack_layout_gen(d, static_cast<char*>(packed) + pk.bytes);
     for (int l = 0; l < d->L; ++l) {
       const size_t K = (l == 0) ? 2 * (size_t)d->F : 4 * H;
@@ -601,8 +608,8 @@ int las_listener_pack(const las_lstm_weights* w, const las_listener_dims* d, int
 
 size_t las_listener_workspace_bytes(const las_listener_dims* d, int mode) {
   if (listener_check(d) != LAS_OK) return 0;
-  if (mode == LAS_MODE_BF16 && fast_listener_fits(d)) return fast_listener_workspace_bytes(d);
-  if (mode == LAS_MODE_BF16) return listener_ws_layout_f32(d, nullptr).bytes + listener_ws_layout_gen(d, nullptr).bytes;
+  if (tc_mode(mode) && fast_listener_fits(d)) return fast_listener_workspace_bytes(d);
+  if (tc_mode(mode)) return listener_ws_layout_f32(d, nullptr).bytes + listener_ws_layout_gen(d, nullptr).bytes;
   return listener_ws_layout_f32(d, nullptr).bytes;
 }
 
@@ -614,15 +621,16 @@ int las_listener_forward(const float* x, const void* packed, const las_listener_
 int las_listener_forward_masked(const float* x, const int32_t* x_lengths, const void* packed, const las_listener_dims* d,
                                 int mode, float* enc, int32_t* enc_lengths, void* workspace, size_t workspace_bytes,
                                 void* stream) {
+  set_operand_mode(mode);
   LAS_TRY(listener_check(d));
   LAS_REQUIRE(x && packed && enc && workspace, "null pointer argument");
-  LAS_REQUIRE(mode == LAS_MODE_FP32 || mode == LAS_MODE_BF16, "unknown mode %d", mode);
+  LAS_REQUIRE(mode == LAS_MODE_FP32 || tc_mode(mode), "unknown mode %d", mode);
   LAS_TRY(device_ok());
   if (workspace_bytes < las_listener_workspace_bytes(d, mode))
     return fail(LAS_ENOMEM, "workspace too small: %zu < %zu", workspace_bytes, las_listener_workspace_bytes(d, mode));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (mode == LAS_MODE_BF16 && fast_listener_fits(d)) return fast_listener_forward(x, x_lengths, packed, d, enc, enc_lengths, workspace, st);
-  if (mode == LAS_MODE_BF16) {
+  if (tc_mode(mode) && fast_listener_fits(d)) return fast_listener_forward(x, x_lengths, packed, d, enc, enc_lengths, workspace, st);
+  if (tc_mode(mode)) {
     LAS_REQUIRE(listener_gen_ok(d), "LAS_MODE_BF16 needs 2F (%d) and 4H (%d) to be multiples of 8; use LAS_MODE_FP32", 2 * d->F, 4 * d->H);
     return listener_forward_f32(x, x_lengths, packed, d, enc, enc_lengths, workspace, st,
                                 static_cast<const char*>(packed) + listener_pack_layout_f32(d, nullptr).bytes,
@@ -636,19 +644,20 @@ size_t las_speller_packed_bytes(const las_speller_dims* d, int mode) {
   if (speller_check(d) != LAS_OK) return 0;
   // the bf16 pack keeps the fp32 block first (phi/psi/cd and fallbacks read it), then its own layouts
   const size_t f32 = speller_pack_layout_f32(d, nullptr).bytes;
-  if (mode == LAS_MODE_BF16) return f32 + (fast_speller_fits(d) ? fast_speller_packed_bytes(d) : speller_pack_layout_gen(d, nullptr).bytes);
+  if (tc_mode(mode)) return f32 + (fast_speller_fits(d) ? fast_speller_packed_bytes(d) : speller_pack_layout_gen(d, nullptr).bytes);
   return f32;
 }
 
 int las_speller_pack(const las_speller_weights* w, const las_speller_dims* d, int mode, void* packed, size_t packed_bytes,
                      void* stream) {
+  set_operand_mode(mode);
   LAS_TRY(speller_check(d));
   LAS_REQUIRE(w && packed && w->rnn_host, "null weights / packed buffer");
-  LAS_REQUIRE(mode == LAS_MODE_FP32 || mode == LAS_MODE_BF16, "unknown mode %d", mode);
+  LAS_REQUIRE(mode == LAS_MODE_FP32 || tc_mode(mode), "unknown mode %d", mode);
   LAS_REQUIRE(w->w_cd && w->b_cd, "null output weight pointer");
   LAS_REQUIRE(d->no_mlp || (w->w_phi && w->b_phi && w->w_psi && w->b_psi), "null attention weight pointer");
   LAS_REQUIRE(n_heads(d) == 1 || (w->w_dr && w->b_dr), "multi_head > 1 needs attention.dim_reduce weights");
-  LAS_REQUIRE(mode != LAS_MODE_BF16 || fast_speller_fits(d) || gen_ok(d),
+  LAS_REQUIRE(!tc_mode(mode) || fast_speller_fits(d) || gen_ok(d),
               "LAS_MODE_BF16 needs E %% 8 == 0 for the psi GEMM's TMA rows (E=%d); use LAS_MODE_FP32", d->E);
   LAS_TRY(device_ok());
   if (packed_bytes < las_speller_packed_bytes(d, mode))
@@ -679,8 +688,8 @@ int las_speller_pack(const las_speller_weights* w, const las_speller_dims* d, in
     CP(pk.b_dr, w->b_dr, d->E);
   }
 #undef CP
-  if (mode == LAS_MODE_BF16 && fast_speller_fits(d)) return fast_speller_pack(w, d, static_cast<char*>(packed) + pk.bytes, st);
-  if (mode == LAS_MODE_BF16) {  // generic tensor-core path: [W_ih | W_hh] per layer as one bf16 matrix, psi weights in bf16
+  if (tc_mode(mode) && fast_speller_fits(d)) return fast_speller_pack(w, d, static_cast<char*>(packed) + pk.bytes, st);
+  if (tc_mode(mode)) {  // generic tensor-core path: [W_ih | W_hh] per layer as one bf16 matrix, psi weights in bf16
     const SpellerPackGen gp = speller_pack_layout_gen(d, static_cast<char*>(packed) + pk.bytes);
     const GenGeom g = gen_geom(d);
     for (int l = 0; l < d->sl; ++l) {
@@ -694,6 +703,7 @@ int las_speller_pack(const las_speller_weights* w, const las_speller_dims* d, in
 
 int las_psi_precompute(const float* enc, const float* w_psi, const float* b_psi, int B, int U, int E, int D, int relu,
                        float* psi, void* stream) {
+  set_operand_mode(LAS_MODE_BF16);
   LAS_REQUIRE(enc && w_psi && b_psi && psi, "null pointer argument");
   LAS_REQUIRE(B > 0 && U > 0 && E > 0 && D > 0, "bad dims (B=%d U=%d E=%d D=%d)", B, U, E, D);
   LAS_TRY(device_ok());
@@ -726,17 +736,18 @@ int las_attention_forward(const float* state, const float* enc, const float* psi
 size_t las_speller_workspace_bytes(const las_speller_dims* d, int steps, int mode) {
   if (speller_check(d) != LAS_OK || steps < 0) return 0;
   const size_t f32 = speller_ws_layout_f32(d, nullptr).bytes;
-  if (mode == LAS_MODE_BF16) return f32 + (fast_speller_fits(d) ? fast_speller_workspace_bytes(d, steps) : speller_ws_layout_gen(d, nullptr).bytes);
+  if (tc_mode(mode)) return f32 + (fast_speller_fits(d) ? fast_speller_workspace_bytes(d, steps) : speller_ws_layout_gen(d, nullptr).bytes);
   return f32;
 }
 
 int las_speller_decode(const las_decode_io* io, const void* packed, const las_speller_dims* d, int steps, int decode_mode,
                        int mode, int relu, void* workspace, size_t workspace_bytes, void* stream) {
+  set_operand_mode(mode);
   LAS_TRY(speller_check(d));
   LAS_REQUIRE(io && packed && workspace, "null pointer argument");
   LAS_REQUIRE(io->enc && io->logp, "io->enc and io->logp are required");
   LAS_REQUIRE(steps >= 0, "steps must be >= 0");
-  LAS_REQUIRE(mode == LAS_MODE_FP32 || mode == LAS_MODE_BF16, "unknown mode %d", mode);
+  LAS_REQUIRE(mode == LAS_MODE_FP32 || tc_mode(mode), "unknown mode %d", mode);
   LAS_REQUIRE(decode_mode == LAS_DECODE_RAW || decode_mode == LAS_DECODE_GREEDY || decode_mode == LAS_DECODE_SAMPLE,
               "decode_mode %d is not supported (0 = raw, 1 = greedy, 2 = sample)", decode_mode);
   LAS_REQUIRE(!(io->gt_dense || io->gt_index) || io->gt_steps >= steps, "ground truth has %d steps, %d requested", io->gt_steps, steps);
@@ -748,14 +759,14 @@ int las_speller_decode(const las_decode_io* io, const void* packed, const las_sp
     return fail(LAS_ENOMEM, "workspace too small: %zu < %zu", workspace_bytes, las_speller_workspace_bytes(d, steps, mode));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (steps == 0) return LAS_OK;
-  if (mode == LAS_MODE_BF16 && !fast_speller_fits(d)) {
+  if (tc_mode(mode) && !fast_speller_fits(d)) {
     LAS_REQUIRE(gen_ok(d), "LAS_MODE_BF16 needs E %% 8 == 0 (E=%d); use LAS_MODE_FP32", d->E);
     const size_t f32p = speller_pack_layout_f32(d, nullptr).bytes;
     const size_t f32w = speller_ws_layout_f32(d, nullptr).bytes;
     return speller_decode_f32(io, packed, d, steps, decode_mode, relu, workspace, st, static_cast<const char*>(packed) + f32p,
                               static_cast<char*>(workspace) + f32w);
   }
-  if (mode == LAS_MODE_BF16) {
+  if (tc_mode(mode)) {
     const size_t f32p = speller_pack_layout_f32(d, nullptr).bytes;
     const size_t f32w = speller_ws_layout_f32(d, nullptr).bytes;
     return fast_speller_decode(io, packed, static_cast<const char*>(packed) + f32p, d, steps, decode_mode, relu, workspace,
@@ -765,6 +776,7 @@ int las_speller_decode(const las_decode_io* io, const void* packed, const las_sp
 }
 
 int las_pipeline_step(const las_pipeline_args* a, int mode, void* stream) {
+  set_operand_mode(mode);
   LAS_REQUIRE(a, "null pointer argument");
   const bool dec = a->dec_io != nullptr, lis = a->x != nullptr;
   LAS_REQUIRE(dec || lis, "nothing to do: neither a batch to decode nor a batch to encode");
@@ -776,7 +788,7 @@ int las_pipeline_step(const las_pipeline_args* a, int mode, void* stream) {
                               a->speller_ws_bytes, stream);
   const las_speller_dims* sd = a->speller_dims;
   const las_listener_dims* ld = a->listener_dims;
-  const bool fast = mode == LAS_MODE_BF16 && sd && ld && speller_check(sd) == LAS_OK && fast_speller_fits(sd) && listener_check(ld) == LAS_OK &&
+  const bool fast = tc_mode(mode) && sd && ld && speller_check(sd) == LAS_OK && fast_speller_fits(sd) && listener_check(ld) == LAS_OK &&
                     fast_listener_fits(ld) && a->steps > 0;
   if (!fast) {  // fp32 mode / variants: the same results, one after the other
     LAS_TRY(las_speller_decode(a->dec_io, a->speller_packed, sd, a->steps, a->decode_mode, mode, a->relu, a->speller_ws, a->speller_ws_bytes, stream));
@@ -808,7 +820,7 @@ int las_pipeline_step(const las_pipeline_args* a, int mode, void* stream) {
 }
 
 int las_pipeline_overlaps(const las_listener_dims* ld, const las_speller_dims* sd, int steps, int mode) {
-  if (mode != LAS_MODE_BF16 || !ld || !sd || listener_check(ld) != LAS_OK || speller_check(sd) != LAS_OK) return 0;
+  if (!tc_mode(mode) || !ld || !sd || listener_check(ld) != LAS_OK || speller_check(sd) != LAS_OK) return 0;
   if (!fast_speller_fits(sd) || !fast_listener_fits(ld)) return 0;
   return fast_pipeline_bc(ld, sd, steps) > 0 ? 1 : 0;
 }
@@ -830,6 +842,7 @@ int las_label_smoothing_terms(const float* logp, const int32_t* labels, int S, i
 }
 
 int las_debug_gemm_bf16(const void* a, const void* w, const float* bias, float* c, int M, int N, int K, void* stream) {
+  set_operand_mode(LAS_MODE_BF16);
   LAS_REQUIRE(a && w && bias && c, "null pointer argument");
   LAS_TRY(device_ok());
   return launch_gemm_bf16_tc(static_cast<const __nv_bfloat16*>(a), K, static_cast<const __nv_bfloat16*>(w), K, bias, c, N, M, N, K,
@@ -844,6 +857,7 @@ int las_debug_set_trace(void* dev_buf) {
   return LAS_OK;
 }
 int las_debug_umma_probe(const void* a, const void* b, float* d, int N, int K, int a_sw128, int b_sw128, int variant, void* stream) {
+  set_operand_mode(LAS_MODE_BF16);
   LAS_REQUIRE(a && b && d, "null pointer argument");
   LAS_TRY(device_ok());
   return launch_umma_probe(a, b, d, N, K, a_sw128, b_sw128, variant, static_cast<cudaStream_t>(stream));

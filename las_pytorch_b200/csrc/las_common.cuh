@@ -3,6 +3,7 @@
 
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <stdarg.h>
@@ -60,6 +61,37 @@ struct Carver {
 };
 
 int sm_count();  // cached per device
+
+// 16-bit GEMM operand format of the tensor-core modes: bf16 (LAS_MODE_BF16) or IEEE fp16 (LAS_MODE_F16: same kernels, same speed, 10
+// mantissa bits instead of 7; the model's operands -- weights, activations in [-1,1], filterbank features -- sit far inside fp16's
+// range).  The C-ABI entry points record the mode of the call on the calling thread; the launchers read it when they fill kernel
+// parameters.  Operand buffers are typed __nv_bfloat16 throughout (16-bit containers); `f16` says how the bits are produced / read.
+void set_operand_mode(int mode);
+int op_f16();
+#ifdef __CUDACC__
+__device__ __forceinline__ __nv_bfloat16 op_from_f32(float x, int f16) {
+  if (f16) {
+    const __half h = __float2half_rn(x);
+    return *reinterpret_cast<const __nv_bfloat16*>(&h);
+  }
+  return __float2bfloat16_rn(x);
+}
+__device__ __forceinline__ __nv_bfloat162 op2_from_f32(float a, float b, int f16) {
+  if (f16) {
+    const __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<const __nv_bfloat162*>(&h);
+  }
+  return __floats2bfloat162_rn(a, b);
+}
+__device__ __forceinline__ float op_to_f32(__nv_bfloat16 v, int f16) {
+  if (f16) return __half2float(*reinterpret_cast<const __half*>(&v));
+  return __bfloat162float(v);
+}
+__device__ __forceinline__ float2 op2_to_f32(__nv_bfloat162 v, int f16) {
+  if (f16) return __half22float2(*reinterpret_cast<const __half2*>(&v));
+  return __bfloat1622float2(v);
+}
+#endif
 
 // ---- optional per-phase device timing (bench.py roofline): cudaEvent pairs around named launch groups ----
 // Disabled by default (zero overhead beyond one thread-local load).  las_prof_enable(1) turns it on for the

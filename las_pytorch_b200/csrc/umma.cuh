@@ -302,9 +302,10 @@ __device__ __forceinline__ uint64_t umma_smem_desc(const UmmaLayout& L, uint32_t
          (type << 61);
 }
 
-// 32-bit instruction descriptor: bf16 A/B (both K-major), fp32 accumulate, shape M x N
-__host__ __device__ __forceinline__ uint32_t umma_idesc_bf16(uint32_t M, uint32_t N) {
-  return (1u << 4) /* D = f32 */ | (1u << 7) /* A = bf16 */ | (1u << 10) /* B = bf16 */ | ((N >> 3) << 17) | ((M >> 4) << 24);
+// 32-bit instruction descriptor: bf16 (or, f16 != 0, IEEE fp16) A/B, both K-major, fp32 accumulate, shape M x N
+__host__ __device__ __forceinline__ uint32_t umma_idesc_bf16(uint32_t M, uint32_t N, int f16 = 0) {
+  const uint32_t fmt = f16 ? 0u : 1u;  // kind::f16 operand format field: 0 = F16, 1 = BF16
+  return (1u << 4) /* D = f32 */ | (fmt << 7) /* A */ | (fmt << 10) /* B */ | ((N >> 3) << 17) | ((M >> 4) << 24);
 }
 
 }  // namespace las

@@ -5,8 +5,9 @@ Same class names, constructor arguments, `forward` signatures, return structures
 Attention :249-318); the arithmetic is done by the sm_100a kernels behind the C ABI (include/las_b200.h).
 torch is used only for device memory, the current stream and parameter storage.
 
-Extra keyword accepted everywhere the reference swallows **kwargs: `precision` = "fp32" | "bf16"
-(LAS_MODE_FP32 / LAS_MODE_BF16; default from $LAS_B200_PRECISION, else "fp32").
+Extra keyword accepted everywhere the reference swallows **kwargs: `precision` = "fp32" | "bf16" | "fp16"
+(LAS_MODE_FP32 / LAS_MODE_BF16 / LAS_MODE_F16 -- the tensor-core kernels with bf16 or IEEE fp16 GEMM operands; default from
+$LAS_B200_PRECISION, else "fp32").
 
 Variants of the reference classes -- multi_head > 1 (with attention.dim_reduce), use_mlp_in_attention=False, GRU / RNN cells
 (`rnn_unit`; the reference does getattr(nn, rnn_unit.upper()), :69,156) and cells too wide for the persistent decoder (the shipped
@@ -29,7 +30,7 @@ from . import _cabi
 from ._cabi import DecodeIO, ListenerDims, LstmWeights, SpellerDims, SpellerWeights, check, current_stream_ptr, ptr
 from .params import LinearWeights, LSTMWeights
 
-_MODES = {"fp32": _cabi.MODE_FP32, "bf16": _cabi.MODE_BF16}
+_MODES = {"fp32": _cabi.MODE_FP32, "bf16": _cabi.MODE_BF16, "fp16": _cabi.MODE_F16}
 
 
 def _default_precision():
@@ -246,12 +247,12 @@ class LAS(nn.Module):
         sp, lis = self.speller, self.listener
         if not x.is_cuda or x.dim() != 3 or x.size(0) <= self.CHUNK or getattr(sp, "early_exit", False):
             return False
-        if lis.precision != "bf16" or sp.precision != "bf16" or x.size(1) % (1 << lis.num_layers) != 0:
+        if lis.precision == "fp32" or sp.precision != lis.precision or x.size(1) % (1 << lis.num_layers) != 0:
             return False
         lib = _cabi.load_library()
         ld = ListenerDims(self.CHUNK, x.size(1), x.size(2), lis.hidden_size, lis.num_layers, _cabi.CELLS[lis.cell])
         sd = sp._dims(self.CHUNK, x.size(1) >> lis.num_layers, 2 * lis.hidden_size)
-        return bool(lib.las_pipeline_overlaps(C.byref(ld), C.byref(sd), int(sp.max_label_len), _cabi.MODE_BF16))
+        return bool(lib.las_pipeline_overlaps(C.byref(ld), C.byref(sd), int(sp.max_label_len), _mode_of(sp.precision)))
 
     def _forward_chunk_pipelined(self, x, input_lengths):
         np.random.random_sample()  # Speller.forward's one draw from numpy's global RNG per call (model/las_model.py:189)
