@@ -296,11 +296,29 @@ def main():
         """One pass of the hot path over one batch: listener, (c2: teacher-forced decode with the fused NLL loss,) greedy decode."""
         enc = las.listener(x)
         if tf_leg:
-            np.random.seed(0)
-            las.speller(enc, labels_dev, 1.1, nll_labels=labels_dev)
-            one_step.loss = las.speller.last_nll_terms.sum() / float(labels_dev.numel())
+            # c2: the teacher-forced decode (with the fused NLL loss) and the greedy decode read the same listener features and are
+            # independent: they are issued on two streams and -- 32 LSTM + 32 attention CTAs each at the small model -- run
+            # concurrently as two persistent kernels (LAS_BENCH_SERIAL_LEGS=1: one after the other on the caller's stream)
+            cur = torch.cuda.current_stream(dev)
+            serial = bool(os.environ.get("LAS_BENCH_SERIAL_LEGS"))
+            if not serial:
+                one_step.fork.record(cur)
+                one_step.side.wait_event(one_step.fork)
+            with torch.cuda.stream(cur if serial else one_step.side):
+                np.random.seed(0)
+                las.speller(enc, labels_dev, 1.1, nll_labels=labels_dev)
+                one_step.loss = las.speller.last_nll_terms.sum() / float(labels_dev.numel())
+                if not serial:
+                    one_step.join.record(one_step.side)
+            las.speller(enc, None, 0.0)
+            if not serial:
+                cur.wait_event(one_step.join)
+                enc.record_stream(one_step.side)
+            return las.speller.last_tokens
         las.speller(enc, None, 0.0)
         return las.speller.last_tokens
+
+    one_step.side, one_step.fork, one_step.join = torch.cuda.Stream(device=dev), torch.cuda.Event(), torch.cuda.Event()
 
     if not tf_leg and not use_pipeline:
         def one_step(x):  # noqa: F811 -- plain LAS.forward (batches beyond one decoder launch group are chunk-pipelined inside it)
