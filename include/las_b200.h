@@ -281,7 +281,9 @@ int las_debug_set_trace(void* dev_buf);
  * activation part instead of one 3-D copy); key 6: listener input-projection GEMM concurrent with the recurrence (1, default) or in
  * front of it (0); key 7: persistent CTAs of that concurrent GEMM (0 = auto); key 8: tcgen05 GEMM epilogue with row-per-thread
  * global stores (1) instead of shared-memory staging + TMA stores (0, default); key 9: batch chunk per recurrence cluster (16 / 32 /
- * 64; 0 = automatic); keys 20 + l: decoder steps of the serving pipeline's segment l (0 = proportional to the layer's time steps). */
+ * 64; 0 = automatic); key 12: generic tensor-core decoder step fused (1, default: one launch per stacked-cell layer + a cluster of CTAs
+ * per utterance for the attention) or as separate GEMM / cell / operand kernels with one attention CTA per utterance (0); key 13: CTAs per
+ * utterance of that attention cluster (1 / 2 / 4 / 8; 0 = by batch size); keys 20 + l: decoder steps of the serving pipeline's segment l (0 = proportional to the layer's time steps). */
 int las_debug_set_option(int key, int value);
 
 #ifdef __cplusplus

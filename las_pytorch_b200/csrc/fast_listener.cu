@@ -644,6 +644,7 @@ void fast_set_option(int key, int value) {
   fast_set_option_speller(key, value);
   fast_set_option_gemm(key, value);
   fast_set_option_pipeline(key, value);
+  fast_set_option_gen(key, value);
 }
 
 // Does the cluster-resident recurrence cover this model?  (Otherwise las_api.cu runs the generic path: tensor-core input projection,

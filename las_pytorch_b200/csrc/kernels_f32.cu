@@ -4,6 +4,7 @@
 #include <cuda_bf16.h>
 
 #include "las_kernels.cuh"
+#include "attend_tail.cuh"
 
 namespace las {
 
@@ -219,27 +220,6 @@ int launch_lstm_cell_f32(const CellArgs* args, int ndir, int B, int H, cudaStrea
 // :216-227 (teacher forcing / raw / greedy feedback), :236 (next input = [word || context]).
 // smem: state[Hs] q[D] score[U] vec[Hs+E] logits[V] red[32]
 // =========================================================================================================
-__device__ __forceinline__ float block_reduce_max(float v, float* red) {
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  v = warp_max(v);
-  __syncthreads();
-  if (lane == 0) red[wid] = v;
-  __syncthreads();
-  float r = red[0];
-  for (int i = 1; i < nw; ++i) r = fmaxf(r, red[i]);
-  return r;
-}
-__device__ __forceinline__ float block_reduce_sum(float v, float* red) {
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  v = warp_sum(v);
-  __syncthreads();
-  if (lane == 0) red[wid] = v;
-  __syncthreads();
-  float r = 0.f;
-  for (int i = 0; i < nw; ++i) r += red[i];  // fixed order -> deterministic
-  return r;
-}
-
 __global__ void __launch_bounds__(1024) attend_f32_kernel(AttendArgs a) {
   extern __shared__ float sm[];
   const int NH = a.heads;
@@ -321,6 +301,7 @@ __global__ void __launch_bounds__(1024) attend_f32_kernel(AttendArgs a) {
       if (NH == 1) {
         s_ctx[e] = acc;
         a.ctx_out[(size_t)b * a.ctx_ld + e] = acc;
+        if (a.op_out) a.op_out[(size_t)b * a.op_ld + a.V + e] = op_from_f32(acc, a.op_f16);
       } else {
         s_ctxh[hd * a.E + e] = acc;
       }
@@ -338,6 +319,7 @@ __global__ void __launch_bounds__(1024) attend_f32_kernel(AttendArgs a) {
         p += a.b_dr[e];
         s_ctx[e] = p;
         a.ctx_out[(size_t)b * a.ctx_ld + e] = p;
+        if (a.op_out) a.op_out[(size_t)b * a.op_ld + a.V + e] = op_from_f32(p, a.op_f16);
       }
     }
   }
@@ -355,66 +337,7 @@ __global__ void __launch_bounds__(1024) attend_f32_kernel(AttendArgs a) {
     if (lane == 0) s_logit[v] = p + a.b_cd[v];
   }
   __syncthreads();
-  float lm = -INFINITY;
-  for (int v = tid; v < a.V; v += blockDim.x) lm = fmaxf(lm, s_logit[v]);
-  lm = block_reduce_max(lm, s_red);
-  float ls = 0.f;
-  for (int v = tid; v < a.V; v += blockDim.x) ls += expf(s_logit[v] - lm);
-  ls = block_reduce_sum(ls, s_red);
-  const float lse = lm + logf(ls);
-  for (int v = tid; v < a.V; v += blockDim.x) {
-    const float lp = s_logit[v] - lse;
-    s_logit[v] = lp;
-    a.logp_out[(size_t)b * a.V + v] = lp;
-  }
-  __syncthreads();
-  if (a.nll_term_out && tid == 0) {  // NLLLoss(ignore_index=0) term of this (step, utterance)
-    const int lab = a.nll_label_step ? a.nll_label_step[(size_t)b * a.nll_label_ld] : 0;
-    a.nll_term_out[b] = (lab > 0 && lab < a.V) ? -s_logit[lab] : 0.f;
-  }
-
-  // argmax (lowest index wins ties, as torch.topk / argmax do on a row)   (:225)
-  int best = 0;
-  if (wid == 0) {
-    float bv = -INFINITY;
-    int bi = 0x7fffffff;
-    for (int v = lane; v < a.V; v += 32) {
-      const float x = s_logit[v];
-      if (x > bv) { bv = x; bi = v; }
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
-      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-      if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
-    }
-    best = bi;
-    if (lane == 0) {
-      // decode_mode 2 (:229-234): the word fed back (and reported) is a draw from Categorical(probs = log-probs)
-      if (a.decode_mode == LAS_DECODE_SAMPLE && !a.gt_dense_step && !a.gt_index_step)
-        best = las_sample_logp_as_probs(s_logit, a.V, las_uniform(a.sample_seed, (uint32_t)a.step, (uint32_t)b));
-      s_red[0] = __int_as_float(best);
-      if (a.token_out) a.token_out[b] = best;
-    }
-  }
-  __syncthreads();
-  best = __float_as_int(s_red[0]);
-
-  // next input word   (:216-227)
-  if (a.word_out) {
-    float* wo = a.word_out + (size_t)b * a.word_ld;
-    if (a.gt_dense_step) {
-      const float* g = a.gt_dense_step + (long long)b * a.gt_ld;
-      for (int v = tid; v < a.V; v += blockDim.x) wo[v] = g[v];
-    } else if (a.gt_index_step) {
-      const int gi = a.gt_index_step[(size_t)b * a.gt_index_ld];
-      for (int v = tid; v < a.V; v += blockDim.x) wo[v] = (v == gi) ? 1.f : 0.f;
-    } else if (a.decode_mode == LAS_DECODE_RAW) {
-      for (int v = tid; v < a.V; v += blockDim.x) wo[v] = s_logit[v];
-    } else {
-      for (int v = tid; v < a.V; v += blockDim.x) wo[v] = (v == best) ? 1.f : 0.f;
-    }
-  }
+  attend_tail(a, b, s_logit, s_red);
 }
 
 int launch_attend_f32(const AttendArgs& a, cudaStream_t st) {

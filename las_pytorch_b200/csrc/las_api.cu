@@ -348,6 +348,7 @@ struct SpellerWsGen {
   float* pre;          // [B, R] gate pre-activations
   __nv_bfloat16* enc;  // [B*U, E] bf16 copy for the psi GEMM
   float* zero;         // [256] zeros: the swapped small-batch GEMM's (unused) per-column bias
+  __nv_bfloat16* a2;   // [sl][2][B, Kp_max]: per layer, the operand rows of even / odd steps (fused step, gen_step.cu)
   size_t bytes;
 };
 static SpellerWsGen speller_ws_layout_gen(const las_speller_dims* d, void* base) {
@@ -358,6 +359,7 @@ static SpellerWsGen speller_ws_layout_gen(const las_speller_dims* d, void* base)
   w.pre = cv.take<float>((size_t)d->B * g.R);
   w.enc = cv.take<__nv_bfloat16>(d->no_mlp ? 0 : (size_t)d->B * d->U * d->E);
   w.zero = cv.take<float>(256);
+  w.a2 = cv.take<__nv_bfloat16>((size_t)d->sl * 2 * d->B * g.Kp_max);
   w.bytes = cv.total();
   return w;
 }
@@ -413,11 +415,34 @@ static int speller_decode_f32(const las_decode_io* io, const void* packed, const
     LAS_CUDA_OK(cudaMemsetAsync(w.c, 0, sizeof(float) * state_n, st));
   }
 
+  // Fused generic step (gen_step.cu): per layer the 16-bit operand rows [x | h_prev] of even / odd steps live in abuf[l][parity]; the
+  // kernels that produce x and h write them there directly.  Step 0's rows are built from the initial state here.
+  const bool fused = gen && gen_step_fused(B);
+  const bool cluster_att = gen && NH == 1 && gen_step_fused(1);
+  GenStepMaps maps[8];
+  __nv_bfloat16* abuf[8][2];
+  if (fused) {
+    LAS_CUDA_OK(cudaMemsetAsync(gw.a2, 0, sizeof(__nv_bfloat16) * (size_t)sl * 2 * B * gg.Kp_max, st));
+    for (int l = 0; l < sl; ++l) {
+      for (int q = 0; q < 2; ++q) abuf[l][q] = gw.a2 + (size_t)(l * 2 + q) * B * gg.Kp_max;
+      LAS_TRY(gen_step_make_maps(&maps[l], gp.w[l], abuf[l][0], abuf[l][1], gg.R, d->cell == LAS_CELL_RNN ? 1 : 4, B, gg.Kp[l]));
+      LAS_TRY(launch_gen_build_a(l == 0 ? w.xin : w.h[0], l == 0 ? xld : Hs, w.h[0] + (size_t)l * B * Hs, Hs, abuf[l][0], B, Hs, gg.Kx[l],
+                                 gg.Kxp[l], gg.Kp[l], st));
+    }
+  }
+
   ProfScope ps_steps("speller.steps", st);
   for (int s = 0; s < steps; ++s) {
     float* hp = w.h[s & 1];
     float* hn = w.h[(s & 1) ^ 1];
     for (int l = 0; l < sl; ++l) {
+      if (fused) {
+        const int q = s & 1;
+        LAS_TRY(launch_gen_cell_step(maps[l], q, gp.bias[l], w.c + (size_t)l * B * Hs, hp + (size_t)l * B * Hs, Hs, hn + (size_t)l * B * Hs, Hs,
+                                     abuf[l][q ^ 1] + gg.Kxp[l], gg.Kp[l], l + 1 < sl ? abuf[l + 1][q] : nullptr, l + 1 < sl ? gg.Kp[l + 1] : 0, B,
+                                     Hs, d->cell, gg.Kxp[l], gg.Kp[l], true, st));
+        continue;
+      }
       if (gen) {
         const float* xin_l = (l == 0) ? w.xin : hn + (size_t)(l - 1) * B * Hs;
         const float* hp_l = hp + (size_t)l * B * Hs;
@@ -483,7 +508,13 @@ static int speller_decode_f32(const las_decode_io* io, const void* packed, const
       t.nll_label_step = (io->nll_labels && s < io->nll_steps) ? io->nll_labels + s : nullptr;
       t.nll_label_ld = io->nll_steps;
     }
-    LAS_TRY(launch_attend_f32(t, st));
+    if (fused) {
+      t.op_out = abuf[0][(s & 1) ^ 1];
+      t.op_ld = gg.Kp[0];
+      t.op_f16 = op_f16();
+    }
+    if (cluster_att) LAS_TRY(launch_attend_cluster(t, true, st));
+    else LAS_TRY(launch_attend_f32(t, st));
   }
   if (io->h_state && (io->c_state || d->cell != LAS_CELL_LSTM)) {
     LAS_CUDA_OK(cudaMemcpyAsync(io->h_state, w.h[steps & 1], sizeof(float) * state_n, cudaMemcpyDeviceToDevice, st));

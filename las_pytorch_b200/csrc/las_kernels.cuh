@@ -67,8 +67,14 @@ struct AttendArgs {
   const int32_t* nll_label_step;  // nullable [B] stride nll_label_ld: label of this step for the fused NLL term
   int nll_label_ld;
   float* nll_term_out;            // nullable [B]
+  // generic tensor-core path: the next step's layer-0 GEMM operand row [word V | context E] in the 16-bit operand format
+  __nv_bfloat16* op_out;          // nullable [B, >= V+E] row stride op_ld
+  long long op_ld;
+  int op_f16;
 };
 int launch_attend_f32(const AttendArgs& a, cudaStream_t st);
+// same step, heads == 1: a cluster of up to 8 CTAs per utterance (gen_step.cu); pdl = programmatic dependent launch
+int launch_attend_cluster(const AttendArgs& a, bool pdl, cudaStream_t st);
 
 // xin[b, 0:V] = onehot(0), xin[b, V:V+E] = enc[b, 0, :]   (model/las_model.py:193-198)
 int launch_speller_init(float* xin, int xin_ld, const float* enc, int B, int U, int E, int V, cudaStream_t st);

@@ -1012,6 +1012,60 @@ def test_bf16_results_do_not_depend_on_the_batch_an_utterance_is_in():
     assert torch.equal(parts, outs[0])
 
 
+def test_bf16_generic_step_fused_equals_unfused_and_is_batch_independent():
+    """The generic tensor-core decoder step (1024-wide cells, csrc/gen_step.cu) as one launch per stacked-cell layer + a cluster of CTAs
+    per utterance for the attention, against the same step as separate GEMM / cell / operand kernels with one attention CTA per
+    utterance (las_debug_set_option(12, 0)): the two sum in different orders, so they agree to fp32 round-off of the same bf16 products,
+    not bit for bit.  The fused step picks its cluster size (8 / 4 / 2 / 1 CTAs per utterance) and its GEMM's N from the batch size:
+    an utterance's result must not depend on either."""
+    if "bf16" not in precisions():
+        pytest.skip("bf16 mode not built")
+    from las_pytorch_b200 import _cabi
+
+    lib = _cabi.load_library()
+    c = tl.CONFIGS["shipped"]
+    B, T, S = 80, 200, 8
+    las = tl.build_model("shipped", max_label_len=S, seed=5, gain=2.0, precision="bf16").cuda()
+    x, labels = tl.make_inputs(B, T, c["F"], S, c["V"], seed=5)
+    enc = las.listener(x.cuda())
+    lens = torch.tensor([enc.shape[1] - (i % 5) for i in range(B)], dtype=torch.int32, device="cuda")
+
+    def run(e, **kw):
+        torch.manual_seed(11)
+        np.random.seed(0)
+        preds, attns = las.speller(e, kw.pop("gt", None), kw.pop("rate", 0.0), **kw)
+        return torch.stack(preds), torch.stack([a[0] for a in attns]), las.speller.last_tokens.clone()
+
+    cases = {"greedy": dict(), "masked": dict(enc_lengths=lens), "index_tf": dict(gt=labels.cuda(), rate=1.1),
+             "dense_tf": dict(gt=tl.onehot(labels, c["V"]).cuda(), rate=1.1)}
+    fused = {k: run(enc, **dict(v)) for k, v in cases.items()}
+    try:
+        lib.las_debug_set_option(12, 0)
+        unfused = {k: run(enc, **dict(v)) for k, v in cases.items()}
+    finally:
+        lib.las_debug_set_option(12, 1)
+    for k in cases:
+        assert float((fused[k][0] - unfused[k][0]).abs().max()) <= 2e-3, k
+        assert float((fused[k][1] - unfused[k][1]).abs().max()) <= 1e-3, k
+        assert float((fused[k][2] == unfused[k][2]).float().mean()) >= 0.97, k
+        assert float((fused[k][0].exp().sum(-1) - 1).abs().max()) < 1e-4 and float((fused[k][1].sum(-1) - 1).abs().max()) < 1e-4
+    # masked encoder steps get exactly zero attention
+    U = enc.shape[1]
+    for b in (1, 4, 79):
+        assert float(fused["masked"][1][:, b, U - (b % 5):].abs().max()) == 0.0
+    # 3 utterances (8 CTAs each), 20 (4), 40 (2), 80 (1): the same bits
+    for n in (3, 20, 40):
+        part = run(enc[:n].contiguous())
+        assert torch.equal(part[0], fused["greedy"][0][:, :n]) and torch.equal(part[1], fused["greedy"][1][:, :n]), n
+    try:
+        for cs in (1, 2, 4, 8):
+            lib.las_debug_set_option(13, cs)
+            part = run(enc[:16].contiguous())
+            assert torch.equal(part[0], fused["greedy"][0][:, :16]), cs
+    finally:
+        lib.las_debug_set_option(13, 0)
+
+
 def test_large_batch_forward_is_chunk_pipelined_and_identical():
     """LAS.forward on a free-running batch larger than one decoder launch group (BASELINE config 5) runs chunk i+1's listener under
     chunk i's decoder; the outputs are bit for bit those of the plain path (forced by `--no-pipeline`-style separate calls)."""
