@@ -30,17 +30,34 @@ __device__ __forceinline__ float block_reduce_sum(float v, float* red) {
 // s_logit[V] holds the raw logits of utterance b (already visible to the whole CTA); s_red is a 32-float scratch.
 __device__ __forceinline__ void attend_tail(const AttendArgs& a, int b, float* s_logit, float* s_red) {
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  float lm = -INFINITY;
-  for (int v = tid; v < a.V; v += blockDim.x) lm = fmaxf(lm, s_logit[v]);
-  lm = block_reduce_max(lm, s_red);
-  float ls = 0.f;
-  for (int v = tid; v < a.V; v += blockDim.x) ls += expf(s_logit[v] - lm);
-  ls = block_reduce_sum(ls, s_red);
-  const float lse = lm + logf(ls);
-  for (int v = tid; v < a.V; v += blockDim.x) {
-    const float lp = s_logit[v] - lse;
-    s_logit[v] = lp;
-    a.logp_out[(size_t)b * a.V + v] = lp;
+  if (a.V <= 128) {  // character-level vocabularies: one warp, no block barriers
+    if (wid == 0) {
+      float lm = -INFINITY;
+      for (int v = lane; v < a.V; v += 32) lm = fmaxf(lm, s_logit[v]);
+      lm = warp_max(lm);
+      float ls = 0.f;
+      for (int v = lane; v < a.V; v += 32) ls += expf(s_logit[v] - lm);
+      ls = warp_sum(ls);
+      const float lse = lm + logf(ls);
+      for (int v = lane; v < a.V; v += 32) {
+        const float lp = s_logit[v] - lse;
+        s_logit[v] = lp;
+        a.logp_out[(size_t)b * a.V + v] = lp;
+      }
+    }
+  } else {
+    float lm = -INFINITY;
+    for (int v = tid; v < a.V; v += blockDim.x) lm = fmaxf(lm, s_logit[v]);
+    lm = block_reduce_max(lm, s_red);
+    float ls = 0.f;
+    for (int v = tid; v < a.V; v += blockDim.x) ls += expf(s_logit[v] - lm);
+    ls = block_reduce_sum(ls, s_red);
+    const float lse = lm + logf(ls);
+    for (int v = tid; v < a.V; v += blockDim.x) {
+      const float lp = s_logit[v] - lse;
+      s_logit[v] = lp;
+      a.logp_out[(size_t)b * a.V + v] = lp;
+    }
   }
   __syncthreads();
   if (a.nll_term_out && tid == 0) {  // NLLLoss(ignore_index=0) term of this (step, utterance)

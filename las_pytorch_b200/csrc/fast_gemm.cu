@@ -305,6 +305,30 @@ int make_tmap_bf16_box(CUtensorMap* tm, const void* base, long long rows, long l
   return make_tmap_bf16(tm, base, rows, cols, ld, box_rows);
 }
 
+// General 16-bit tensor map, 128-byte swizzle: dims / box innermost first (dims[0] = box[0] = 64 elements), strides in bytes for
+// dimensions 1..rank-1.
+int make_tmap_bf16_nd(CUtensorMap* tm, const void* base, int rank, const unsigned long long* dims, const unsigned long long* strides,
+                      const unsigned* box) {
+  EncodeTiledFn enc;
+  LAS_TRY(get_encode_fn(&enc));
+  LAS_REQUIRE(rank >= 2 && rank <= 5 && (reinterpret_cast<uintptr_t>(base) & 15) == 0, "bad tensor map request (rank=%d)", rank);
+  cuuint64_t gdim[5], gstr[4];
+  cuuint32_t bx[5], estr[5] = {1, 1, 1, 1, 1};
+  for (int i = 0; i < rank; ++i) {
+    gdim[i] = dims[i];
+    bx[i] = box[i];
+    if (i) {
+      LAS_REQUIRE(strides[i - 1] % 16 == 0, "TMA needs 16-byte aligned strides (dimension %d: %llu bytes)", i, strides[i - 1]);
+      gstr[i - 1] = strides[i - 1];
+    }
+  }
+  const CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(LAS_ECUDA, "cuTensorMapEncodeTiled (rank %d) failed with CUresult %d", rank, (int)r);
+  return LAS_OK;
+}
+
 // The same row-major bf16 matrix [rows, 64*atoms] seen as {64 k, rows, atoms}: one copy of box {64, box_rows, box_atoms}
 // lands as box_atoms consecutive 128-byte-swizzled [box_rows x 64] atoms, i.e. what box_atoms 2-D copies would write.
 int make_tmap_bf16_atoms(CUtensorMap* tm, const void* base, long long rows, int atoms, long long ld, int box_rows, int box_atoms) {

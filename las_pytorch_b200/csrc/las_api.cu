@@ -320,7 +320,7 @@ static GenGeom gen_geom(const las_speller_dims* d) {
   for (int l = 0; l < d->sl; ++l) {
     g.Kx[l] = (l == 0) ? d->V + d->E : d->Hs;
     g.Kxp[l] = (g.Kx[l] + 7) & ~7;
-    g.Kp[l] = g.Kxp[l] + ((d->Hs + 7) & ~7);
+    g.Kp[l] = (g.Kxp[l] + d->Hs + 63) & ~63;  // (whole 64-column K blocks: gen_step.cu fetches them by block index)
     if (g.Kp[l] > g.Kp_max) g.Kp_max = g.Kp[l];
   }
   return g;
@@ -418,14 +418,14 @@ static int speller_decode_f32(const las_decode_io* io, const void* packed, const
   // Fused generic step (gen_step.cu): per layer the 16-bit operand rows [x | h_prev] of even / odd steps live in abuf[l][parity]; the
   // kernels that produce x and h write them there directly.  Step 0's rows are built from the initial state here.
   const bool fused = gen && gen_step_fused(B);
-  const bool cluster_att = gen && NH == 1 && gen_step_fused(1);
+  const bool cluster_att = gen && NH == 1 && E % 4 == 0 && gen_step_fused(1);
   GenStepMaps maps[8];
   __nv_bfloat16* abuf[8][2];
   if (fused) {
     LAS_CUDA_OK(cudaMemsetAsync(gw.a2, 0, sizeof(__nv_bfloat16) * (size_t)sl * 2 * B * gg.Kp_max, st));
     for (int l = 0; l < sl; ++l) {
       for (int q = 0; q < 2; ++q) abuf[l][q] = gw.a2 + (size_t)(l * 2 + q) * B * gg.Kp_max;
-      LAS_TRY(gen_step_make_maps(&maps[l], gp.w[l], abuf[l][0], abuf[l][1], gg.R, d->cell == LAS_CELL_RNN ? 1 : 4, B, gg.Kp[l]));
+      LAS_TRY(gen_step_make_maps(&maps[l], gp.w[l], abuf[l][0], abuf[l][1], Hs, d->cell == LAS_CELL_RNN ? 1 : 4, B, gg.Kxp[l], gg.Kp[l]));
       LAS_TRY(launch_gen_build_a(l == 0 ? w.xin : w.h[0], l == 0 ? xld : Hs, w.h[0] + (size_t)l * B * Hs, Hs, abuf[l][0], B, Hs, gg.Kx[l],
                                  gg.Kxp[l], gg.Kp[l], st));
     }
@@ -440,7 +440,7 @@ static int speller_decode_f32(const las_decode_io* io, const void* packed, const
         const int q = s & 1;
         LAS_TRY(launch_gen_cell_step(maps[l], q, gp.bias[l], w.c + (size_t)l * B * Hs, hp + (size_t)l * B * Hs, Hs, hn + (size_t)l * B * Hs, Hs,
                                      abuf[l][q ^ 1] + gg.Kxp[l], gg.Kp[l], l + 1 < sl ? abuf[l + 1][q] : nullptr, l + 1 < sl ? gg.Kp[l + 1] : 0, B,
-                                     Hs, d->cell, gg.Kxp[l], gg.Kp[l], true, st));
+                                     Hs, d->cell, gg.Kxp[l], gg.Kp[l], true, st, l));
         continue;
       }
       if (gen) {

@@ -58,16 +58,20 @@ int launch_gemm_listener(const __nv_bfloat16* A, int B, int Tl, int K, const __n
 int launch_umma_probe(const void* A, const void* B, float* D, int N, int K, int a_sw128, int b_sw128, int variant, cudaStream_t st);
 int launch_f32_to_bf16(const float* src, __nv_bfloat16* dst, size_t n, cudaStream_t st);
 int make_tmap_bf16_box(CUtensorMap* tm, const void* base, long long rows, long long cols, long long ld, int box_rows);
+int make_tmap_bf16_nd(CUtensorMap* tm, const void* base, int rank, const unsigned long long* dims, const unsigned long long* strides,
+                      const unsigned* box);
 
 // gen_step.cu: fused generic decoder step (stacked-cell layer = one launch; see the file header)
 struct GenStepMaps {
-  CUtensorMap w, a[2];  // packed weights [R, Kp]; the layer's operand rows [B, Kp] of even / odd steps
+  CUtensorMap w, a[2];  // packed weights [R, Kp]; the layer's operand rows [B, Kp] of even / odd steps (per-stage box)
+  CUtensorMap a_ind[2], a_dep[2];  // the same rows, one box for all independent / all dependent K blocks
 };
 bool gen_step_fused(int B);
-int gen_step_make_maps(GenStepMaps* m, const __nv_bfloat16* w, const __nv_bfloat16* act0, const __nv_bfloat16* act1, int R, int G, int B, int Kp);
+int gen_step_make_maps(GenStepMaps* m, const __nv_bfloat16* w, const __nv_bfloat16* act0, const __nv_bfloat16* act1, int H, int G, int B, int Kxp,
+                       int Kp);
 int launch_gen_cell_step(const GenStepMaps& m, int parity, const float* bias, float* c, const float* h_prev, long long h_ld, float* h_out,
                          long long hout_ld, __nv_bfloat16* o1, long long o1_ld, __nv_bfloat16* o2, long long o2_ld, int B, int H, int cell,
-                         int Kxp, int Kp, bool pdl, cudaStream_t st);
+                         int Kxp, int Kp, bool pdl, cudaStream_t st, int trace_slot = 0);
 void fast_set_option_gen(int key, int value);
 
 }  // namespace las

@@ -71,6 +71,7 @@ struct AttendArgs {
   __nv_bfloat16* op_out;          // nullable [B, >= V+E] row stride op_ld
   long long op_ld;
   int op_f16;
+  long long* trace;               // nullable test hook (attend_cluster_kernel): clock64 stamps of CTA 0
 };
 int launch_attend_f32(const AttendArgs& a, cudaStream_t st);
 // same step, heads == 1: a cluster of up to 8 CTAs per utterance (gen_step.cu); pdl = programmatic dependent launch
