@@ -1044,6 +1044,25 @@ def test_bf16_generic_step_fused_equals_unfused_and_is_batch_independent():
         unfused = {k: run(enc, **dict(v)) for k, v in cases.items()}
     finally:
         lib.las_debug_set_option(12, 1)
+    # raw feedback (decode_mode 0), sampling (decode_mode 2) and the fused NLL terms go through the same operand-row outputs
+    extra = {}
+    for dm, kw in ((0, dict()), (2, dict()), (1, dict(nll_labels=labels[:16].cuda()))):
+        m = tl.build_model("shipped", max_label_len=S, decode_mode=dm, seed=5, gain=2.0, precision="bf16").cuda()
+        outs = []
+        for opt in (1, 0):
+            lib.las_debug_set_option(12, opt)
+            try:
+                torch.manual_seed(11)
+                np.random.seed(0)
+                preds, _ = m.speller(enc[:16].contiguous(), None, 0.0, **dict(kw))
+                outs.append((torch.stack(preds), m.speller.last_tokens.clone(),
+                             m.speller.last_nll_terms.clone() if kw else None))
+            finally:
+                lib.las_debug_set_option(12, 1)
+        extra[dm if not kw else "nll"] = outs
+    assert float((extra[0][0][0] - extra[0][1][0]).abs().max()) <= 5e-3          # raw: the log-probs themselves are fed back
+    assert float((extra[2][0][1] == extra[2][1][1]).float().mean()) >= 0.9      # same counter-based draws unless a CDF edge moves
+    assert float((extra["nll"][0][2] - extra["nll"][1][2]).abs().max()) <= 2e-3
     for k in cases:
         assert float((fused[k][0] - unfused[k][0]).abs().max()) <= 2e-3, k
         assert float((fused[k][1] - unfused[k][1]).abs().max()) <= 1e-3, k
