@@ -105,6 +105,7 @@ struct DecParams {
   int ctx_tmem;     // > 0: enc[b]^T is resident in the attention CTA's tensor memory and the context is a UMMA
   int ctx_ntm;      // 128-feature tiles of enc[b]^T held in tensor memory: E/128 = all of them; fewer (long encoders, e.g. U = 375:
                     // 2 of 4) = hybrid, the remaining features are reduced on the CUDA cores from the L2-resident bf16 copy
+  int groups, gsz;  // utterance groups pipelined through the LSTM CTAs (1, or 2 groups of gsz = 32 rows: lstm_role_ts) -- see lstm_role_ts
   int nstages, stage_bytes;  // activation slots: [64 batch rows x 64 bf16], 128-byte swizzled; last slot = word atom
   long long* trace;  // nullable test hook: [3 roles][32 steps][8] globaltimer stamps (layer-0 CTA 0, top-layer CTA 0, attention CTA 0)
 };
@@ -146,7 +147,7 @@ __device__ __forceinline__ void wait_counter(const uint32_t* ctr, uint32_t targe
   (void)ld_acquire(ctr);
 }
 __device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
-__device__ __forceinline__ uint32_t* counter(const DecParams& p, int idx) { return p.sync + idx * 32; }
+__device__ __forceinline__ uint32_t* counter(const DecParams& p, int idx, int grp = 0) { return p.sync + (grp * N_CTR + idx) * 32; }
 
 // flag-in-data slots: one aligned 8-byte store carries the value and the step tag, so the consumer needs no fence
 __device__ __forceinline__ u64 ll_pack(uint32_t value, uint32_t tag) { return ((u64)tag << 32) | value; }
@@ -580,16 +581,23 @@ __device__ void lstm_role_ts(const DecParams& p, uint8_t* smem, int l, int nb) {
   __syncthreads();
   ptx::tc_fence_after();
   const int S = p.steps;
-  uint32_t* my_ready = counter(p, l);
+  // Utterance groups (p.groups = 2 x p.gsz = 32 rows at batch 64): the decoder step is a ring of three stages (layer 0 -> layer 1 ->
+  // attention -> layer 0) and with the whole batch in lockstep every stage idles two thirds of the time.  The LSTM CTAs therefore serve
+  // the groups alternately -- iteration it = s * groups + grp -- with per-group counters, 32-row activation boxes and N = 32 MMAs, while
+  // the attention CTAs (one per utterance anyway) simply follow their group's counters.  Every buffer is indexed by utterance row, a
+  // thread's cells all belong to one group, and an output column's sum does not depend on N: bit-identical to groups = 1.
+  const int G = p.groups, GSZ = p.gsz;
   const int trole = (nb == 0 && l == 0) ? 0 : ((nb == 0 && top) ? 1 : -1);
 
   if (warp == PROD_WARP) {
     // ============================ TMA producer (as in lstm_role) ============================
-    const uint32_t* own_ctr = counter(p, l);
-    const uint32_t* in_ctr = first ? counter(p, CTR_CTX) : counter(p, l - 1);
-    const uint32_t* word_ctr = counter(p, CTR_WORD);
     int n = 0;
-    for (int s = 0; s < S; ++s) {
+    for (int it = 0; it < S * G; ++it) {
+      const int s = it / G, grp = it - s * G, row0 = grp * GSZ;
+      const int Bg = min(p.B - row0, GSZ);  // utterances of this group
+      const uint32_t* own_ctr = counter(p, l, grp);
+      const uint32_t* in_ctr = first ? counter(p, CTR_CTX, grp) : counter(p, l - 1, grp);
+      const uint32_t* word_ctr = counter(p, CTR_WORD, grp);
       const int par = s & 1;
       if (n > 0) ptx::mbar_wait(part_empty, (uint32_t)((n - 1) & 1));
       ++n;
@@ -598,7 +606,7 @@ __device__ void lstm_role_ts(const DecParams& p, uint8_t* smem, int l, int nb) {
       fence_proxy_async_global();
       if (ptx::elect_one()) {
         ptx::mbar_arrive_expect_tx(&full[0], nh * STAGE_BYTES);
-        ptx::tma_load_3d(abuf, &p.tm_h3[l][par], &full[0], 0, 0, 0);
+        ptx::tma_load_3d(abuf, &p.tm_h3[l][par], &full[0], 0, row0, 0);
       }
       __syncwarp();
       ptx::mbar_wait(part_empty, (uint32_t)((n - 1) & 1));
@@ -606,30 +614,30 @@ __device__ void lstm_role_ts(const DecParams& p, uint8_t* smem, int l, int nb) {
       if (ptx::elect_one()) ptx::mbar_arrive_expect_tx(&full[0], nc * STAGE_BYTES);
       __syncwarp();
       if (lane == 0) {
-        wait_counter(in_ctr, first ? (uint32_t)s * p.B : (uint32_t)(s + 1) * p.ncl);
-        if (trole >= 0) DEC_TRACE(trole, 0);
-        DEC_TRACE_ALL(0);
+        wait_counter(in_ctr, first ? (uint32_t)s * Bg : (uint32_t)(s + 1) * p.ncl);
+        if (trole >= 0 && grp == 0) DEC_TRACE(trole, 0);
+        if (grp == 0) DEC_TRACE_ALL(0);
       }
       __syncwarp();
       fence_proxy_async_global();
-      if (lane == 0 && trole >= 0) DEC_TRACE(4, 6 + trole);
+      if (lane == 0 && trole >= 0 && grp == 0) DEC_TRACE(4, 6 + trole);
       {
         const CUtensorMap* tm3 = first ? &p.tm_x3[par] : &p.tm_h3[l - 1][par ^ 1];
         if (ptx::elect_one()) {
-          if (trole == 0) DEC_TRACE(4, 0);
-          ptx::tma_load_3d(abuf, tm3, &full[0], 0, 0, 0);
-          if (trole == 0) DEC_TRACE(4, 2);
+          if (trole == 0 && grp == 0) DEC_TRACE(4, 0);
+          ptx::tma_load_3d(abuf, tm3, &full[0], 0, row0, 0);
+          if (trole == 0 && grp == 0) DEC_TRACE(4, 2);
         }
         __syncwarp();
       }
-      if (lane == 0 && trole >= 0) DEC_TRACE(trole, 1);
+      if (lane == 0 && trole >= 0 && grp == 0) DEC_TRACE(trole, 1);
       if (first && (p.s0 + s == 0 || !p.word_gather)) {
-        if (lane == 0) wait_counter(word_ctr, (uint32_t)s * p.B);
+        if (lane == 0) wait_counter(word_ctr, (uint32_t)s * Bg);
         __syncwarp();
         fence_proxy_async_global();
         if (ptx::elect_one()) {
           ptx::mbar_arrive_expect_tx(&full[wslot], STAGE_BYTES);
-          ptx::tma_load_2d(abuf + (size_t)wslot * STAGE_BYTES, &p.tm_w[par], &full[wslot], 0, 0);
+          ptx::tma_load_2d(abuf + (size_t)wslot * STAGE_BYTES, &p.tm_w[par], &full[wslot], 0, row0);
         }
         __syncwarp();
       }
@@ -637,12 +645,13 @@ __device__ void lstm_role_ts(const DecParams& p, uint8_t* smem, int l, int nb) {
   } else if (warp == MMA_WARP) {
     // ============================ MMA issuer ============================
     const UmmaLayout lact{1, 0, 1024, (uint32_t)STAGE_BYTES}, lw{1, 0, 1024, WATOM_BYTES};
-    const uint32_t idesc = umma_idesc_bf16(128, 64, F16);  // M = 128 gate-row lanes (64 used), N = 64 batch columns
+    const uint32_t idesc = umma_idesc_bf16(128, (uint32_t)GSZ, F16);  // M = 128 gate-row lanes (64 used), N = the group's batch columns
     const uint32_t a0 = ptx::smem_u32(abuf), w_addr = ptx::smem_u32(wsm);
     uint32_t phase0 = 0, phasew = 0;
-    for (int s = 0; s < S; ++s) {
+    for (int it = 0; it < S * G; ++it) {
+      const int s = it / G, grp = it - s * G;
       const bool wd = first && (p.s0 + s == 0 || !p.word_gather);
-      ptx::mbar_wait(tmem_empty, (uint32_t)((s & 1) ^ 1));
+      ptx::mbar_wait(tmem_empty, (uint32_t)((it & 1) ^ 1));
       ptx::tc_fence_after();
       // ---- part 0: own h_{s-1}; both operands from shared memory (weights = A, activations = B)
       ptx::mbar_wait(&full[0], phase0);
@@ -658,13 +667,13 @@ __device__ void lstm_role_ts(const DecParams& p, uint8_t* smem, int l, int nb) {
         ptx::umma_commit(part_empty);
       }
       __syncwarp();
-      if (lane == 0 && trole >= 0) DEC_TRACE(trole, 6);
+      if (lane == 0 && trole >= 0 && grp == 0) DEC_TRACE(trole, 6);
       // ---- part 1: the critical input; weights from tensor memory, activations from shared memory.  Lean loop: the A operand
       // advances 8 columns per instruction, the B descriptor 32 bytes inside an atom and one slot between atoms.
       ptx::mbar_wait(&full[0], phase0);
       phase0 ^= 1u;
       ptx::tc_fence_after();
-      if (lane == 0 && trole >= 0) DEC_TRACE(4, 3 + 2 * trole);
+      if (lane == 0 && trole >= 0 && grp == 0) DEC_TRACE(4, 3 + 2 * trole);
       if (ptx::elect_one()) {
         uint32_t a = tmem;
         uint64_t bd_atom = umma_smem_desc(lact, a0, 0);
@@ -699,7 +708,7 @@ __device__ void lstm_role_ts(const DecParams& p, uint8_t* smem, int l, int nb) {
         }
         __syncwarp();
       }
-      if (lane == 0 && trole >= 0) DEC_TRACE(trole, 2);
+      if (lane == 0 && trole >= 0 && grp == 0) DEC_TRACE(trole, 2);
     }
   } else if ((warp & 3) < 2) {
     // ============================ epilogue: gates, cell state, h ============================
@@ -709,7 +718,9 @@ __device__ void lstm_role_ts(const DecParams& p, uint8_t* smem, int l, int nb) {
     const bool bit0 = (g & 1) != 0, bit1 = (g & 2) != 0;
     const int u = nb * DEC_UNITS + jj;             // hidden unit
     const bool lead = (warp == 0 && lane == 0);
-    const bool warp_live = cs * 16 < p.B;
+    const bool warp_has_rows = cs * 16 < p.B;
+    const int my_grp = (cs * 16) / GSZ;           // the group this thread's cells belong to
+    const uint32_t acc_col = (uint32_t)(cs * 16 - my_grp * GSZ);
     float c[4];
     int bm[4];
 #pragma unroll
@@ -719,13 +730,16 @@ __device__ void lstm_role_ts(const DecParams& p, uint8_t* smem, int l, int nb) {
     }
     const float4 bias4 = *reinterpret_cast<const float4*>(bias_s + 4 * jj);
     const uint8_t* watom = wsm + (size_t)nh * WATOM_BYTES;  // layer 0: word atom [64 gate rows x 64 vocabulary entries]
-    for (int s = 0; s < S; ++s) {
+    for (int it = 0; it < S * G; ++it) {
+      const int s = it / G, grp = it - s * G;
+      const bool warp_live = warp_has_rows && grp == my_grp;
+      uint32_t* my_ready = counter(p, l, grp);
       // bias + (index word) the token's column of W_word for this unit's four gate rows, per cell -- before the accumulators are ready.
       // The warp's 16 batches are polled by 16 lanes (ONE L2 round trip; four dependent polls per thread cost ~2.4 us and made the
       // token the critical path) and handed to the cells' owners by shuffles.
       float4 pb[4];
       int tokl = -1;
-      const bool gather = first && p.s0 + s > 0 && p.word_gather;
+      const bool gather = first && p.s0 + s > 0 && p.word_gather && warp_live;
       if (gather) {
         const int bb = cs * 16 + (lane & 15);
         if (bb < p.B)
@@ -748,16 +762,16 @@ __device__ void lstm_role_ts(const DecParams& p, uint8_t* smem, int l, int nb) {
           pb[m].x += wv[0]; pb[m].y += wv[1]; pb[m].z += wv[2]; pb[m].w += wv[3];
         }
       }
-      if (lead && trole == 0) DEC_TRACE(4, 1);
-      ptx::mbar_wait(tmem_full, (uint32_t)(s & 1));
-      if (lead && trole >= 0) DEC_TRACE(trole, 3);
-      if (lead) DEC_TRACE_ALL(1);
+      if (lead && trole == 0 && grp == 0) DEC_TRACE(4, 1);
+      ptx::mbar_wait(tmem_full, (uint32_t)(it & 1));
+      if (lead && trole >= 0 && grp == 0) DEC_TRACE(trole, 3);
+      if (lead && grp == 0) DEC_TRACE_ALL(1);
       ptx::tc_fence_after();
       float h[4] = {0.f, 0.f, 0.f, 0.f};
       if (warp_live) {
         uint32_t x0[16], x1[16];
-        ptx::tmem_ld_32x32b_x16(tmem + ((uint32_t)(q * 32) << 16) + acc0 + cs * 16, x0);
-        ptx::tmem_ld_32x32b_x16(tmem + ((uint32_t)(q * 32) << 16) + acc1 + cs * 16, x1);
+        ptx::tmem_ld_32x32b_x16(tmem + ((uint32_t)(q * 32) << 16) + acc0 + acc_col, x0);
+        ptx::tmem_ld_32x32b_x16(tmem + ((uint32_t)(q * 32) << 16) + acc1 + acc_col, x1);
         ptx::tmem_ld_wait();
 #pragma unroll
         for (int m = 0; m < 4; ++m) {
@@ -802,7 +816,7 @@ __device__ void lstm_role_ts(const DecParams& p, uint8_t* smem, int l, int nb) {
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");
       const int r0 = (cs * 2 + q) * 8;  // this warp's 8 rows
-      if (top && !direct_ll) {
+      if (top && !direct_ll && warp_live) {
         const uint32_t tag = (uint32_t)(s + 1);
 #pragma unroll
         for (int hf = 0; hf < 2; ++hf) {
@@ -813,7 +827,7 @@ __device__ void lstm_role_ts(const DecParams& p, uint8_t* smem, int l, int nb) {
           }
         }
       }
-      if (lane < 16) {
+      if (lane < 16 && warp_live) {
         const int rw = r0 + (lane >> 1), hf = lane & 1;
         if (rw < p.B) {
           const float4 y0 = *reinterpret_cast<const float4*>(s_st + rw * 20 + hf * 8), y1 = *reinterpret_cast<const float4*>(s_st + rw * 20 + hf * 8 + 4);
@@ -824,7 +838,7 @@ __device__ void lstm_role_ts(const DecParams& p, uint8_t* smem, int l, int nb) {
                          *reinterpret_cast<const uint32_t*>(&t2), *reinterpret_cast<const uint32_t*>(&t3));
         }
       }
-      if (s == S - 1) {
+      if (s == S - 1 && warp_live) {
 #pragma unroll
         for (int m = 0; m < 4; ++m) {
           if (bm[m] < p.B) {
@@ -833,13 +847,13 @@ __device__ void lstm_role_ts(const DecParams& p, uint8_t* smem, int l, int nb) {
           }
         }
       }
-      if (lead && trole >= 0) DEC_TRACE(trole, 4);
-      if (lead) DEC_TRACE_ALL(2);
+      if (lead && trole >= 0 && grp == 0) DEC_TRACE(trole, 4);
+      if (lead && grp == 0) DEC_TRACE_ALL(2);
       asm volatile("bar.sync 1, 256;" ::: "memory");  // all rows stored; the release below is cumulative over the barrier
       if (lead) {
         red_release_add(my_ready, 1u);
-        if (trole >= 0) DEC_TRACE(trole, 5);
-        DEC_TRACE_ALL(3);
+        if (trole >= 0 && grp == 0) DEC_TRACE(trole, 5);
+        if (grp == 0) DEC_TRACE_ALL(3);
       }
     }
   }
@@ -979,8 +993,9 @@ __device__ void attention_role(const DecParams& p, uint8_t* smem, int b, int ran
   float* s_own = reinterpret_cast<float*>(smem + L.o_xchg + 32);                 // [E + 4]
   float* s_recv = s_own + (E + 4);                                               // [2][E + 4]
   const uint32_t peer = (uint32_t)(rank ^ 1);
-  uint32_t* ctx_ctr = counter(p, CTR_CTX);
-  uint32_t* word_ctr = counter(p, CTR_WORD);
+  const int grp = (p.groups > 1) ? b / p.gsz : 0;  // (see lstm_role_ts: the LSTM CTAs serve the utterance groups alternately)
+  uint32_t* ctx_ctr = counter(p, CTR_CTX, grp);
+  uint32_t* word_ctr = counter(p, CTR_WORD, grp);
   uint32_t tmem = 0;
   if (p.ctx_tmem) {
     // enc[b]^T -> tensor memory, once: tile t holds features [128t, 128t+128) as TMEM lanes, encoder steps along the
@@ -1660,6 +1675,7 @@ bool att_wreg(const las_speller_dims* d) { return d->D <= DEC_THREADS / 8 && d->
 size_t att_smem(const las_speller_dims* d, bool k_in, bool hybrid = false, bool split = false) {
   return att_layout(d->Hs, d->E, split ? att_split_half(d->U) : d->U, d->D, d->V, k_in, att_wreg(d), hybrid, split).total + 64;
 }
+int g_dec_groups = 1;     // las_debug_set_option(19, v): 1 = two utterance groups pipelined through the LSTM CTAs (default), 0 = lockstep
 int g_dec_att_split = 1;  // las_debug_set_option(11, v): 1 = split long encoders over a 2-CTA cluster (default), 0 = never
 // Tensor-memory geometry of the context path for `U` encoder steps per CTA: feature tiles of enc^T that fit the 512 columns
 int ctx_tiles_fit(int U, int E) {
@@ -1739,7 +1755,7 @@ SpellerWsFast ws_layout(const las_speller_dims* d, void* base) {
     for (int k = 0; k < 2; ++k) w.hbuf[l][k] = cv.take<__nv_bfloat16>((size_t)d->B * d->Hs);
   for (int k = 0; k < 2; ++k) w.xbuf[k] = cv.take<__nv_bfloat16>((size_t)d->B * d->E);
   for (int k = 0; k < 2; ++k) w.wbuf[k] = cv.take<__nv_bfloat16>((size_t)d->B * DEC_VP);
-  const size_t sync_bytes = sizeof(uint32_t) * 32 * N_CTR, tok_bytes = align_up(sizeof(u64) * (size_t)d->B * (d->Hs / DEC_UNITS), 256);
+  const size_t sync_bytes = sizeof(uint32_t) * 32 * N_CTR * 2 /* utterance groups */, tok_bytes = align_up(sizeof(u64) * (size_t)d->B * (d->Hs / DEC_UNITS), 256);
   w.flag_bytes = sync_bytes + tok_bytes + sizeof(u64) * (size_t)d->B * d->Hs;
   w.flags = cv.take<uint8_t>(w.flag_bytes);
   w.sync = reinterpret_cast<uint32_t*>(w.flags);
@@ -1766,6 +1782,7 @@ void fast_set_option_speller(int key, int value) {
   if (key == 2) g_dec_ctx_tmem = value;
   if (key == 5) g_dec_ab_flags = value;
   if (key == 11) g_dec_att_split = value;
+  if (key == 19) g_dec_groups = value;
 }
 
 size_t fast_speller_packed_bytes(const las_speller_dims* d) { return pack_layout(d, nullptr).bytes; }
@@ -1847,7 +1864,16 @@ int fast_speller_decode_segment(const las_decode_io* io, const void* packed_f32,
       p.k_in_smem = att_smem(d, true, hyb) <= 220 * 1024;
       if (hyb && att_smem(d, p.k_in_smem != 0, true) > 220 * 1024) { p.ctx_ntm = 0; p.ctx_tmem = 0; p.k_in_smem = att_smem(d, true, false) <= 220 * 1024; }
     }
-    const RingCfg rc = ring_cfg(d, Bc);
+    RingCfg rc = ring_cfg(d, Bc);
+    // weights-stationary LSTM CTAs: whole 64-wide atoms, one 3-D copy per part, critical weights within 384 tensor-memory columns
+    // (ab_flags bit 14 = 16384 selects the round-1 operand roles for A/B runs)
+    p.tma3d = (d->Hs % 64 == 0 && d->E % 64 == 0 && !(g_dec_ab_flags & 4)) ? 1 : 0;
+    p.lstm_ts = (p.tma3d && d->Hs <= 768 && d->E <= 768 && !(g_dec_ab_flags & 16384)) ? 1 : 0;
+    // two utterance groups of 32 pipelined through the LSTM CTAs (lstm_role_ts) when the launch has more than 32 utterances
+    p.groups = (p.lstm_ts && Bc > 32 && g_dec_groups != 0) ? 2 : 1;
+    p.gsz = p.groups == 2 ? 32 : 64;
+    rc.box_rows = p.gsz;
+    rc.stage_bytes = rc.box_rows * 128;
     p.nstages = rc.nstages;
     p.stage_bytes = rc.stage_bytes;
     for (int l = 0; l < d->sl; ++l) {
@@ -1864,10 +1890,6 @@ int fast_speller_decode_segment(const las_decode_io* io, const void* packed_f32,
       LAS_TRY(make_tmap_bf16_box(&p.tm_x[k], w.xbuf[k], Bc, d->E, d->E, rc.box_rows));
       LAS_TRY(make_tmap_bf16_box(&p.tm_w[k], w.wbuf[k], Bc, DEC_VP, DEC_VP, rc.box_rows));
     }
-    p.tma3d = (d->Hs % 64 == 0 && d->E % 64 == 0 && !(g_dec_ab_flags & 4)) ? 1 : 0;
-    // weights-stationary LSTM CTAs: whole 64-wide atoms, one 3-D copy per part, critical weights within 384 tensor-memory columns
-    // (ab_flags bit 14 = 16384 selects the round-1 operand roles for A/B runs)
-    p.lstm_ts = (p.tma3d && d->Hs <= 768 && d->E <= 768 && !(g_dec_ab_flags & 16384)) ? 1 : 0;
     if (p.tma3d) {
       for (int l = 0; l < d->sl; ++l)
         for (int k = 0; k < 2; ++k) LAS_TRY(make_tmap_bf16_atoms(&p.tm_h3[l][k], w.hbuf[l][k], Bc, d->Hs / 64, d->Hs, rc.box_rows, d->Hs / 64));
