@@ -283,7 +283,10 @@ int las_debug_set_trace(void* dev_buf);
  * global stores (1) instead of shared-memory staging + TMA stores (0, default); key 9: batch chunk per recurrence cluster (16 / 32 /
  * 64; 0 = automatic); key 12: generic tensor-core decoder step fused (1, default: one launch per stacked-cell layer + a cluster of CTAs
  * per utterance for the attention) or as separate GEMM / cell / operand kernels with one attention CTA per utterance (0); key 13: CTAs per
- * utterance of that attention cluster (1 / 2 / 4 / 8; 0 = by batch size); keys 20 + l: decoder steps of the serving pipeline's segment l (0 = proportional to the layer's time steps). */
+ * utterance of that attention cluster (1 / 2 / 4 / 8; 0 = by batch size); key 15: M = 64 (1, default) or M = 128 (0) MMAs in the fused cell
+ * kernel; key 16: programmatic dependent launch between the fused step's kernels (1, default) or plain stream order (0); key 18: the last
+ * layer's kernel triggers the attention kernel at its start (1, default) or after its own dependency (0); key 19: two utterance groups
+ * pipelined through the persistent decoder's LSTM CTAs (1, default) or the whole batch in lockstep (0); keys 20 + l: decoder steps of the serving pipeline's segment l (0 = proportional to the layer's time steps). */
 int las_debug_set_option(int key, int value);
 
 #ifdef __cplusplus
