@@ -94,13 +94,15 @@ int fast_pipeline_step(const las_decode_io* io, const void* spl_packed_f32, cons
   cudaStream_t side = nullptr;
   LAS_TRY(fast_side_stream(&side));
   const int L = ld->L;
-  // decoder segment lengths: proportional to the layers' time steps (T/2, T/4, ...), even, the remainder in the last one
+  // decoder segment lengths: proportional to the layers' recurrence times -- their time steps (T/2, T/4, ...), layer 0 a little cheaper
+  // per step (fused input projection: 2.25 vs 2.55 us in the 64-utterance form) --, even, the remainder in the last one
   int seg[8], used = 0;
   {
+    auto weight = [&](int l) { return (double)(ld->T >> (l + 1)) * (l == 0 ? 0.88 : 1.0); };
     double tot = 0;
-    for (int l = 0; l < L; ++l) tot += (double)(ld->T >> (l + 1));
+    for (int l = 0; l < L; ++l) tot += weight(l);
     for (int l = 0; l < L; ++l) {
-      int n = g_pipe_split[l] > 0 ? g_pipe_split[l] : (int)(steps * (double)(ld->T >> (l + 1)) / tot);
+      int n = g_pipe_split[l] > 0 ? g_pipe_split[l] : (int)(steps * weight(l) / tot);
       n &= ~1;
       if (n < 2) n = 2;
       if (l == L - 1 || used + n > steps - 2 * (L - 1 - l)) n = (l == L - 1) ? steps - used : ((steps - used - 2 * (L - 1 - l)) & ~1);
