@@ -418,7 +418,8 @@ static int speller_decode_f32(const las_decode_io* io, const void* packed, const
   // Fused generic step (gen_step.cu): per layer the 16-bit operand rows [x | h_prev] of even / odd steps live in abuf[l][parity]; the
   // kernels that produce x and h write them there directly.  Step 0's rows are built from the initial state here.
   const bool fused = gen && gen_step_fused(B);
-  const bool cluster_att = gen && NH == 1 && E % 4 == 0 && gen_step_fused(1);
+  // (the cluster kernel is plain fp32 arithmetic: the fp32 mode uses it as well; multi-head attention keeps the one-CTA kernel)
+  const bool cluster_att = NH == 1 && E % 4 == 0 && gen_step_fused(1);
   GenStepMaps maps[8];
   __nv_bfloat16* abuf[8][2];
   if (fused) {
@@ -513,7 +514,7 @@ static int speller_decode_f32(const las_decode_io* io, const void* packed, const
       t.op_ld = gg.Kp[0];
       t.op_f16 = op_f16();
     }
-    if (cluster_att) LAS_TRY(launch_attend_cluster(t, true, st));
+    if (cluster_att) LAS_TRY(launch_attend_cluster(t, gen, st));
     else LAS_TRY(launch_attend_f32(t, st));
   }
   if (io->h_state && (io->c_state || d->cell != LAS_CELL_LSTM)) {
