@@ -879,6 +879,42 @@ def test_bf16_segmented_decode_is_bit_identical(cfgname, B, T, S):
                     assert torch.equal(a, b), (cfgname, dm, list(kw), seg)
 
 
+@pytest.mark.parametrize("cfgname,B,T,S", [("paper", 64, 320, 40), ("paper", 33, 160, 24), ("small", 47, 128, 30)])
+def test_bf16_utterance_groups_equal_lockstep(cfgname, B, T, S):
+    """Launches with more than 32 utterances run as two groups pipelined through the persistent decoder's LSTM CTAs (per-group
+    counters, 32-row activation boxes, N = 32 MMAs: csrc/fast_speller.cu lstm_role_ts).  Every buffer is indexed by utterance row and a
+    column's sum does not depend on N, so the outputs must equal the lockstep form (las_debug_set_option(19, 0)) bit for bit -- in
+    every feedback mode, with length masks, segmented, and for group sizes 32 + 32, 32 + 1 and 32 + 15."""
+    if "bf16" not in precisions():
+        pytest.skip("bf16 mode not built")
+    from las_pytorch_b200 import _cabi
+
+    lib = _cabi.load_library()
+    c = tl.CONFIGS[cfgname]
+    x, labels = tl.make_inputs(B, T, c["F"], S, c["V"], seed=23)
+    for dm in (1, 0, 2):
+        las = tl.build_model(cfgname, max_label_len=S, decode_mode=dm, seed=23, gain=3.0, precision="bf16").cuda()
+        enc = las.listener(x.cuda())
+        U = enc.shape[1]
+        lens = torch.tensor([U - (i % 7) for i in range(B)], dtype=torch.int32, device="cuda")
+        variants = [dict(), dict(enc_lengths=lens), dict(segment_steps=10)]
+        if dm == 1:
+            variants += [dict(gt_index=labels.cuda().to(torch.int32).contiguous()),
+                         dict(gt_dense=tl.onehot(labels, c["V"]).float().cuda().contiguous()),
+                         dict(nll_labels=labels.cuda())]
+        for kw in variants:
+            outs = []
+            for groups in (1, 0):
+                lib.las_debug_set_option(19, groups)
+                try:
+                    torch.manual_seed(5)
+                    outs.append(_decode_kw(las, enc, S, **kw))
+                finally:
+                    lib.las_debug_set_option(19, 1)
+            for a, b in zip(*outs):
+                assert torch.equal(a, b), (cfgname, B, dm, list(kw))
+
+
 @pytest.mark.parametrize("precision", precisions())
 def test_eos_early_exit(precision):
     """Row f4, <eos> early-exit batching (extension; the reference always runs max_label_len steps, model/las_model.py:205-209):
