@@ -80,6 +80,8 @@ def trace():
     lib.las_debug_set_option(1, opt)
     nacc = int(_s.argv[3]) if len(_s.argv) > 3 else 0
     lib.las_debug_set_option(4, nacc)
+    if len(_s.argv) > 4:  # utterances per recurrence cluster (16 / 32 / 64): 64 is the form that runs under the decoder
+        lib.las_debug_set_option(9, int(_s.argv[4]))
     print(f"recurrence A operand in TMEM: {opt}; accumulators: {nacc or 'default'}")
     ref = tl.build_model("paper", max_label_len=4, seed=17, gain=3.0, precision="fp32").listener.cuda()(x)
     out = lis(x)
